@@ -1,0 +1,243 @@
+/*
+ * b200slam.h — the C ABI of the B200-native 2-D laser SLAM front-end hot path.
+ *
+ * This is the drop-in boundary.  The reference
+ * (xiangli0608/Creating-2D-laser-slam-from-scratch) has no C ABI; its seams are C++ class
+ * methods called in-process.  Every entry point below names the reference method it stands in
+ * for (file:line relative to /root/reference).  A reference-side façade with the reference's own
+ * signatures is in include/b200slam/karto_facade.hpp; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; all arrays are caller-owned HOST memory
+ *     unless the name says `_device`.
+ *   - every function returns a b2s_status (0 = OK); exceptions of the reference map to codes.
+ *   - a handle is single-threaded like the reference's ScanMatcher (Mapper.h:1273-1278 shares
+ *     m_pCorrelationGrid / m_pGridLookup); DISTINCT handles may be used concurrently
+ *     (one CUDA stream each).
+ *   - "batch" = B independent scan-matches, each with its OWN correlation grid.
+ *   - poses are (x, y, heading) doubles; covariances are row-major 3x3 doubles.
+ *   - the product path is CUDA only: if no device is usable every compute entry point returns
+ *     B2S_ERR_NO_DEVICE.  There is no CPU fallback.
+ */
+#ifndef B200SLAM_H
+#define B200SLAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_ABI_VERSION 1
+
+typedef enum b2s_status {
+  B2S_OK = 0,
+  B2S_ERR_BAD_PARAMS = 1,   /* ScanMatcher::Create -> NULL (Mapper.cpp:130-145); smear out of range (Mapper.h:1045-1053) */
+  B2S_ERR_OUT_OF_RANGE = 2, /* karto::Exception "Index out of range" (Karto.h:4492-4498) */
+  B2S_ERR_NO_BEST_POSE = 3, /* std::runtime_error "Unable to find best position" (Mapper.cpp:486) */
+  B2S_ERR_CUDA = 4,         /* a CUDA runtime call failed; see b2s_last_error() */
+  B2S_ERR_NO_DEVICE = 5,    /* no CUDA device: the product path never falls back to the CPU */
+  B2S_ERR_BAD_STATE = 6,    /* call order violated (e.g. correlate before scans are set) */
+  B2S_ERR_TOO_LARGE = 7     /* batch / beam count / window exceeds what the handle was created for */
+} b2s_status;
+
+/* ScanMatcher::Create arguments (Mapper.cpp:126-127) + the 8 tuning values the matcher reads from its
+ * Mapper through friend access (Mapper.cpp:206,238-239,250,256,279-280,405-411).  Values are the ones
+ * STORED in the Mapper: setParamDistanceVariancePenalty/AngleVariancePenalty square their argument
+ * (Mapper.cpp:1919-1927) — do that before filling this struct.  Defaults: Mapper.cpp:1569-1652. */
+typedef struct b2s_matcher_params {
+  double search_size;                /* CorrelationSearchSpaceDimension, m */
+  double resolution;                 /* CorrelationSearchSpaceResolution, m/cell */
+  double smear_deviation;            /* CorrelationSearchSpaceSmearDeviation, m */
+  double range_threshold;            /* LaserRangeFinder range threshold, m */
+  double distance_variance_penalty;  /* default 0.3^2 */
+  double angle_variance_penalty;     /* default (20 deg)^2 */
+  double fine_search_angle_offset;   /* default 0.2 deg */
+  double coarse_search_angle_offset; /* default 20 deg */
+  double coarse_angle_resolution;    /* default 2 deg */
+  double minimum_angle_penalty;      /* default 0.9 */
+  double minimum_distance_penalty;   /* default 0.5 */
+  int32_t use_response_expansion;    /* default 0 */
+  int32_t reserved;
+} b2s_matcher_params;
+
+/* The part of karto::LaserRangeFinder (Karto.h:3700-4184) the hot path reads. */
+typedef struct b2s_laser {
+  int32_t n_readings; /* LaserRangeFinder::GetNumberOfRangeReadings (1081 for Hokuyo_UTM_30LX; a Custom
+                         sensor yields round((max-min)/res) WITHOUT +1, Karto.h:4158-4160) */
+  int32_t reserved;
+  double min_angle;          /* rad */
+  double angular_resolution; /* rad */
+  double min_range;          /* m */
+  double max_range;          /* m */
+  double range_threshold;    /* m */
+  double offset_pose[3];     /* sensor pose in the robot frame (Sensor::GetOffsetPose) */
+} b2s_laser;
+
+/* CorrelationGrid geometry (Mapper.h:900-1118, Karto.h:4381-4767). */
+typedef struct b2s_grid_info {
+  int32_t width, height; /* allocation incl. smear border */
+  int32_t width_step;    /* AlignValue(width, 8) (Karto.h:4442) */
+  int32_t data_size;     /* width_step * height bytes */
+  int32_t roi_x, roi_y, roi_w, roi_h;
+  int32_t kernel_size;   /* smear kernel side, 2*round(2*sigma/res)+1 */
+  int32_t search_side;   /* m_pSearchSpaceProbs side = round(search_size/res)+1 */
+} b2s_grid_info;
+
+/* CorrelateScan arguments (Mapper.cpp:309-317), shared by every match of a batch. */
+typedef struct b2s_search {
+  double offset_x, offset_y;   /* rSearchSpaceOffset */
+  double res_x, res_y;         /* rSearchSpaceResolution */
+  double angle_offset;         /* searchAngleOffset */
+  double angle_res;            /* searchAngleResolution */
+  int32_t do_penalize;
+  int32_t fine;                /* doingFineMatch */
+} b2s_search;
+
+typedef struct b2s_match_result {
+  double response;   /* return value of CorrelateScan / MatchScan, clamped to <= 1 */
+  double pose[3];    /* rMean */
+  double cov[9];     /* rCovariance, row-major */
+  int32_t status;    /* per-match b2s_status (B2S_ERR_NO_BEST_POSE ...) */
+  int32_t tie_count; /* averagePoseCount (Mapper.cpp:459-471) */
+} b2s_match_result;
+
+typedef struct b2s_matcher b2s_matcher; /* opaque: replaces karto::ScanMatcher* */
+
+/* ---------------------------------------------------------------- library */
+int b2s_abi_version(void);
+const char *b2s_last_error(void);              /* thread-local text of the last failure */
+int b2s_device_count(void);                    /* 0 when no usable CUDA device */
+
+/* ---------------------------------------------------------------- K1: Karto correlative scan matcher */
+
+/* ScanMatcher::Create (Mapper.cpp:126-172).  `max_batch` matches share one handle; `max_angles`
+ * bounds nAngles of any later search (0 = derive from params).  `cuda_stream` may be NULL
+ * (the handle then creates its own non-blocking stream) or a cudaStream_t owned by the caller. */
+b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser *laser, int device,
+                              int max_batch, int max_base_scans, void *cuda_stream, b2s_matcher **out);
+void b2s_matcher_destroy(b2s_matcher *m);      /* ScanMatcher::~ScanMatcher (Mapper.cpp:119-124) */
+b2s_status b2s_matcher_grid_info(const b2s_matcher *m, b2s_grid_info *out);
+
+/* The scans being matched: B x (ranges[n_readings], robot pose).  Replaces building B
+ * LocalizedRangeScan objects + SetOdometricPose/SetCorrectedPose (karto_slam.cc:437-440).
+ * Point readings are derived on the device as LocalizedRangeScan::Update does (Karto.h:5362-5428). */
+b2s_status b2s_matcher_set_scans(b2s_matcher *m, int batch, const double *ranges, const double *poses);
+
+/* MatchScan steps 1-4 + AddScans (Mapper.cpp:195-225, 699-811; Mapper.h:971-1005): centre grid b on scan
+ * b's sensor pose and rasterise + smear its `n_base` base scans.  base_ranges: [batch][n_base][n_readings],
+ * base_poses: [batch][n_base][3]. */
+b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_ranges, const double *base_poses);
+
+/* Alternative to add_scans for callers that keep grids themselves: upload ready-made correlation grids
+ * ([batch][data_size] bytes) and their world offsets ([batch][2], CoordinateConverter::SetOffset). */
+b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const double *offsets);
+
+/* ScanMatcher::CorrelateScan (Mapper.cpp:309-523) for every match of the batch; centers: [batch][3].
+ * For fine=1 results[b].cov is IN/OUT exactly like rCovariance (only cov[8] is overwritten, Mapper.cpp:648,691). */
+b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, const b2s_search *search,
+                                      b2s_match_result *results);
+
+/* ScanMatcher::MatchScan (Mapper.cpp:184-291): coarse sweep (+ optional response expansion) + fine sweep.
+ * Requires set_scans + add_scans (or set_grids). */
+b2s_status b2s_matcher_match_scan(b2s_matcher *m, int do_penalize, int do_refine, b2s_match_result *results);
+
+/* One-call host-buffer form (what a reference node's MatchScan call costs end to end):
+ * set_scans + add_scans + match_scan. */
+b2s_status b2s_matcher_match_scan_host(b2s_matcher *m, int batch, const double *ranges, const double *poses,
+                                       int n_base, const double *base_ranges, const double *base_poses,
+                                       int do_penalize, int do_refine, b2s_match_result *results);
+
+/* Inspection (parity tests; also ScanMatcher::GetCorrelationGrid, Mapper.h:1192). */
+b2s_status b2s_matcher_get_grid(b2s_matcher *m, int b, uint8_t *out_bytes, double out_offset[2]);
+b2s_status b2s_matcher_get_point_readings(b2s_matcher *m, int b, double *out_xy /* [n_readings][2] */);
+/* GridIndexLookup::ComputeOffsets (Karto.h:6409-6501): out[n_angles][n_readings]; INT32_MAX = INVALID_SCAN */
+b2s_status b2s_matcher_compute_offsets(b2s_matcher *m, int b, double angle_center, double angle_offset,
+                                       double angle_res, int32_t *out, int32_t *out_n_angles);
+/* integer numerators of GetResponse (Mapper.cpp:819-856) of the LAST correlate_scan sweep for match b,
+ * in the reference's loop order out[nY][nX][nAngles] (Mapper.cpp:373-424). */
+b2s_status b2s_matcher_get_response_sums(b2s_matcher *m, int b, int32_t *out, int32_t dims[3]);
+
+/* Device time (ms, CUDA events on the handle's stream) of the stages of the LAST correlate_scan call:
+ * out[0] = offsets/LUT, out[1] = response sweep, out[2] = reduce (max / tie-average / covariance),
+ * out[3] = number of sweep kernel launches. */
+b2s_status b2s_matcher_last_timing(b2s_matcher *m, double out[4]);
+b2s_status b2s_matcher_sync(b2s_matcher *m);
+/* 0 = automatic, 1 = force the generic global-memory gather kernel, 2 = force the shared-memory window kernel */
+b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which);
+
+/* ---------------------------------------------------------------- K2c: karto::OccupancyGrid */
+
+typedef struct b2s_occ_grid_info {
+  int32_t width, height, width_step, data_size;
+  double offset[2];  /* CoordinateConverter offset = bounding-box minimum (Karto.h:5821) */
+  double resolution;
+  uint64_t cell_visits; /* Bresenham cells touched incl. end cells */
+} b2s_occ_grid_info;
+
+typedef struct b2s_occ_grid b2s_occ_grid; /* opaque: replaces karto::OccupancyGrid* */
+
+/* OccupancyGrid::CreateFromScans (Karto.h:5659-5673, 5804-5990): n_scans x (ranges, robot pose).
+ * Returns B2S_OK with *out == NULL when n_scans == 0 (the reference returns NULL). */
+b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, const double *ranges,
+                                          const double *poses, double resolution, int device,
+                                          void *cuda_stream, b2s_occ_grid **out);
+b2s_status b2s_occ_grid_info_get(const b2s_occ_grid *g, b2s_occ_grid_info *out);
+/* cells: uint8 {0 unknown, 100 occupied, 255 free}; pass/hit: uint32 counters; any pointer may be NULL */
+b2s_status b2s_occ_grid_copy(b2s_occ_grid *g, uint8_t *cells, uint32_t *pass, uint32_t *hit);
+/* nav_msgs/OccupancyGrid payload as SlamKarto::updateMap fills it (karto_slam.cc:546-569):
+ * int8 {-1,100,0}, row-major width x height (no width_step padding) */
+b2s_status b2s_occ_grid_copy_ros(b2s_occ_grid *g, int8_t *out);
+b2s_status b2s_occ_grid_last_timing(b2s_occ_grid *g, double out[2]); /* ms: ray-trace kernel, threshold kernel */
+void b2s_occ_grid_destroy(b2s_occ_grid *g);
+
+/* ---------------------------------------------------------------- K2a / K3: Hector log-odds grid map */
+
+typedef struct b2s_hector_map b2s_hector_map; /* opaque: replaces hectorslam::GridMap (OccGridMapP) */
+
+/* GridMap(mapResolution, size, offset) (GridMapBase.h:54-66, MapRepMultiMap.h:63-67): size x size cells,
+ * start_x/start_y in [0,1] (fraction of the map at which the world origin sits). */
+b2s_status b2s_hector_map_create(int size_x, int size_y, float resolution, float start_x, float start_y,
+                                 int device, void *cuda_stream, b2s_hector_map **out);
+void b2s_hector_map_destroy(b2s_hector_map *m);
+/* GridMapLogOddsFunctions::setUpdateFreeFactor / setUpdateOccupiedFactor (GridMapLogOdds.h:116-134) */
+b2s_status b2s_hector_map_set_factors(b2s_hector_map *m, float update_free, float update_occupied);
+/* OccGridMapBase::updateByScan (OccGridMapBase.h:118-168): points are the DataContainer in map-cell units
+ * ([n][2] float, already scaled by 1/resolution as hector_slam.cc:320-362 does), origo = sensor origin in the
+ * same frame, pose = robot pose in WORLD coordinates (x, y, heading). */
+b2s_status b2s_hector_map_update_by_scan(b2s_hector_map *m, const float *points, int n_points,
+                                         const float origo[2], const float world_pose[3]);
+/* ScanMatcher::matchData (ScanMatcher.h:60-98) on ONE grid level: Gauss-Newton scan-to-map alignment.
+ * begin_world_pose in, new world pose + 3x3 Hessian ("covariance") out. */
+b2s_status b2s_hector_map_match_data(b2s_hector_map *m, const float *points, int n_points,
+                                     const float begin_world_pose[3], int max_iterations,
+                                     float out_world_pose[3], float out_cov[9]);
+/* raw cells: logOdds float + updateIndex int per cell (GridMapLogOdds.h:37-75) */
+b2s_status b2s_hector_map_copy(b2s_hector_map *m, float *log_odds, int32_t *update_index);
+/* nav_msgs/OccupancyGrid payload as HectorMappingRos::publishMap does (hector_slam.cc:254-317) */
+b2s_status b2s_hector_map_copy_ros(b2s_hector_map *m, int8_t *out);
+b2s_status b2s_hector_map_last_timing(b2s_hector_map *m, double out[2]);
+
+/* ---------------------------------------------------------------- K2b: GMapping hit/visit map */
+
+typedef struct b2s_gmap b2s_gmap; /* opaque: replaces GMapping::ScanMatcherMap (gmapping.cc:135) */
+
+/* ScanMatcherMap(center, xmin, ymin, xmax, ymax, delta) (map.h:117-140): note the (cells >> 5) patch rounding. */
+b2s_status b2s_gmap_create(double center_x, double center_y, double xmin, double ymin, double xmax, double ymax,
+                           double delta, int device, void *cuda_stream, b2s_gmap **out);
+void b2s_gmap_destroy(b2s_gmap *g);
+b2s_status b2s_gmap_size(const b2s_gmap *g, int32_t size_xy[2]);
+/* GMapping::ComputeMap (gmapping.cc:171-242) for one scan: ranges[n], angles[n] (beam angles in the laser
+ * frame), laser pose in world, max_range / max_urange. */
+b2s_status b2s_gmap_compute_map(b2s_gmap *g, const double *ranges, const double *angles, int n,
+                                const double laser_pose[3], double max_range, double max_urange);
+/* PointAccumulator per cell (map.h:17-48): n, visits, acc.x, acc.y */
+b2s_status b2s_gmap_copy(b2s_gmap *g, int32_t *n, int32_t *visits, float *acc_x, float *acc_y);
+/* the published map (gmapping.cc:141-159): -1 unknown, 100 if n/visits > 0.25 else 0 */
+b2s_status b2s_gmap_copy_ros(b2s_gmap *g, int8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SLAM_H */

@@ -1,0 +1,159 @@
+"""TEST INFRASTRUCTURE — ctypes binding of oracle/libslam_oracle.so, the plain-C CPU restatement
+(karto_oracle.c / gmapping_oracle.c / hector_oracle.c).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module; the product never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+
+abi = importlib.import_module("creating-2d-laser-slam-from-scratch_b200.abi")
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libslam_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("karto_oracle.c", "gmapping_oracle.c", "hector_oracle.c",
+                                             "oracle_common.h", "Makefile")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libslam_oracle.so"])
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_round.restype = C.c_double
+        L.orc_round.argtypes = [C.c_double]
+        L.orc_normalize_angle.restype = C.c_double
+        L.orc_normalize_angle.argtypes = [C.c_double]
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _d(a):
+    return _p(a, C.c_double)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class PortMatcher:
+    """Stateful convenience wrapper with the same call sequence as the product handle / RefSession."""
+
+    def __init__(self, params, laser):
+        self.L = lib()
+        self.p = params
+        self.l = laser
+        self.g = abi.GridInfo()
+        rc = self.L.orc_matcher_layout(C.byref(params), C.byref(self.g))
+        if rc:
+            raise ValueError(f"orc_matcher_layout -> {abi.STATUS_NAMES[rc]}")
+        self.n = laser.n_readings
+        self.grid = np.zeros(self.g.data_size, dtype=np.uint8)
+        self.grid_off = np.zeros(2)
+        self.last_sums = None
+
+    def kernel(self):
+        k = self.g.kernel_size
+        K = np.zeros(k * k, dtype=np.uint8)
+        self.L.orc_smear_kernel(C.c_double(self.p.resolution), C.c_double(self.p.smear_deviation), k, _p(K, C.c_uint8))
+        return K.reshape(k, k)
+
+    def sensor_pose(self, robot_pose):
+        out = np.zeros(3)
+        off = f64(list(self.l.offset_pose))
+        self.L.orc_sensor_pose(_d(f64(robot_pose)), _d(off), _d(out))
+        return out
+
+    def point_readings(self, ranges, robot_pose):
+        out = np.zeros((self.n, 2))
+        self.L.orc_point_readings(C.byref(self.l), _d(f64(ranges)), _d(f64(robot_pose)), _d(out))
+        return out
+
+    def find_valid_points(self, pts, viewpoint):
+        pts = f64(pts)
+        out = np.zeros_like(pts)
+        n = self.L.orc_find_valid_points(_d(pts), len(pts), _d(f64(viewpoint)), _d(out))
+        return out[:n].copy()
+
+    def set_scan(self, ranges, robot_pose):
+        self.ranges = f64(ranges)
+        self.robot_pose = f64(robot_pose)
+        self.sp = self.sensor_pose(robot_pose)
+        self.pts = self.point_readings(ranges, robot_pose)
+
+    def add_scans(self, base_ranges, base_poses):
+        br, bp = f64(base_ranges).reshape(-1, self.n), f64(base_poses).reshape(-1, 3)
+        self.L.orc_grid_offset(C.byref(self.g), C.c_double(self.p.resolution), _d(self.sp), _d(self.grid_off))
+        self.L.orc_add_scans(C.byref(self.p), C.byref(self.l), C.byref(self.g), _d(self.grid_off),
+                             _p(self.grid, C.c_uint8), len(br), _d(br), _d(bp), _d(self.sp[:2].copy()))
+
+    def compute_offsets(self, angle_center, angle_offset, angle_res):
+        na = abi.n_steps(angle_offset, angle_res)
+        lut = np.zeros((na, self.n), dtype=np.int32)
+        self.L.orc_compute_offsets(C.byref(self.g), C.c_double(self.p.resolution), _d(self.grid_off), _d(self.ranges),
+                                   _d(self.pts), self.n, _d(self.sp), C.c_double(angle_center),
+                                   C.c_double(angle_offset), C.c_double(angle_res), _p(lut, C.c_int32))
+        return lut
+
+    def correlate_scan(self, center, search, cov_in=None, want_sums=False):
+        res = abi.MatchResult()
+        if cov_in is not None:
+            for i, v in enumerate(np.asarray(cov_in, dtype=np.float64).reshape(9)):
+                res.cov[i] = v
+        nx, ny = abi.n_steps(search.offset_x, search.res_x), abi.n_steps(search.offset_y, search.res_y)
+        na = abi.n_steps(search.angle_offset, search.angle_res)
+        sums = np.zeros((ny, nx, na), dtype=np.int32) if want_sums else None
+        rc = self.L.orc_correlate_scan(C.byref(self.p), C.byref(self.g), _d(self.grid_off), _p(self.grid, C.c_uint8),
+                                       _d(self.ranges), _d(self.pts), self.n, _d(self.sp), _d(f64(center)),
+                                       C.byref(search), C.byref(res), _p(sums, C.c_int32) if want_sums else None)
+        self.last_sums = sums
+        return rc, res
+
+    def match_scan(self, ranges, robot_pose, base_ranges, base_poses, do_penalize=True, do_refine=True):
+        br, bp = f64(base_ranges).reshape(-1, self.n), f64(base_poses).reshape(-1, 3)
+        res = abi.MatchResult()
+        rc = self.L.orc_match_scan(C.byref(self.p), C.byref(self.l), _d(f64(ranges)), _d(f64(robot_pose)), len(br),
+                                   _d(br), _d(bp), int(do_penalize), int(do_refine), C.byref(res),
+                                   _p(self.grid, C.c_uint8), _d(self.grid_off))
+        return rc, res
+
+
+def occupancy_grid(laser, ranges, poses, resolution):
+    L = lib()
+    r, p = f64(ranges).reshape(-1, laser.n_readings), f64(poses).reshape(-1, 3)
+    info = abi.OccGridInfo()
+    L.orc_occ_dimensions(C.byref(laser), len(r), _d(r), _d(p), C.c_double(resolution), C.byref(info))
+    n = info.data_size
+    pas, hit, cells = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint8)
+    L.orc_occ_create_from_scans(C.byref(laser), len(r), _d(r), _d(p), C.byref(info), _p(pas, C.c_uint32),
+                                _p(hit, C.c_uint32), _p(cells, C.c_uint8))
+    h, s = info.height, info.width_step
+    return dict(width=info.width, height=h, width_step=s, offset=np.array(info.offset[:]),
+                cell_visits=int(info.cell_visits), cells=cells.reshape(h, s), passes=pas.reshape(h, s),
+                hits=hit.reshape(h, s))
+
+
+def trace_line(w, h, x0, y0, x1, y1):
+    cap = abs(x1 - x0) + abs(y1 - y0) + 4
+    out = np.zeros((cap, 2), dtype=np.int32)
+    n = lib().orc_trace_line_cells(w, h, x0, y0, x1, y1, _p(out, C.c_int32), cap)
+    return out[:n].copy()
+
+
+def result_tuple(res):
+    return res.response, np.array(res.pose[:]), np.array(res.cov[:]).reshape(3, 3)

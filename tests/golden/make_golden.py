@@ -1,0 +1,147 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libkarto_ref.so, asserts enabled).
+
+Run in the build container only (needs /root/reference to have been compiled by `make -C oracle ref`):
+    python tests/golden/make_golden.py
+The vectors pin the C restatement (oracle/karto_oracle.c) and, through it, the CUDA path.
+Every array is produced by the reference's own code; this script only chooses inputs.
+"""
+import hashlib
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("creating-2d-laser-slam-from-scratch_b200")
+synth = pkg.synth
+from oracle import ref  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+D = ref.KT_PI_180
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def small_case():
+    """Full dumps on a small problem: Sick LMS200 preset (361 beams, 0.5 deg), 11x11 cell search space."""
+    laser = synth.Laser(type=2, n_readings=361, min_angle=synth.deg2rad(-90), max_angle=synth.deg2rad(90),
+                        angular_resolution=synth.deg2rad(0.5), min_range=0.0, max_range=80.0, range_threshold=6.0)
+    out = {}
+    for tag, dropout in (("clean", 0.0), ("dropout", 0.03)):
+        mc = synth.make_match_case(11 if dropout == 0 else 12, laser, dropout=dropout, max_xy=0.15, max_th_deg=5)
+        p = ref.default_matcher_params(0.5, 0.05, 0.03, 6.0)
+        s = ref.RefSession(p, laser)
+        assert s.n_readings == 361
+        b = s.add_scan(mc.base_ranges, mc.base_pose)
+        c = s.add_scan(mc.ranges, mc.odom_pose)
+        s.set_grid_from_scans(c, [b])
+        gi = s.grid_info()
+        sp = s.sensor_pose(c)
+        A, R = 10 * D, 1 * D
+        out.update({
+            f"{tag}_base_ranges": mc.base_ranges, f"{tag}_base_pose": mc.base_pose, f"{tag}_ranges": mc.ranges,
+            f"{tag}_pose": mc.odom_pose, f"{tag}_grid": s.grid(), f"{tag}_grid_offset": gi["offset"],
+            f"{tag}_grid_info": np.array([gi[k] for k in ("width", "height", "width_step", "data_size", "roi_x",
+                                                         "roi_y", "roi_w", "roi_h", "kernel_size")], np.int32),
+            f"{tag}_kernel": s.kernel(), f"{tag}_points": s.point_readings(c),
+            f"{tag}_valid_points_base": s.find_valid_points(b, sp[:2]),
+            f"{tag}_lut": s.compute_offsets(c, sp[2], A, R),
+            f"{tag}_sums": s.response_sums(c, sp, (0.25, 0.25), (0.05, 0.05), A, R),
+        })
+        for pen in (0, 1):
+            r = s.correlate_scan(c, sp, (0.25, 0.25), (0.05, 0.05), A, R, do_penalize=bool(pen), fine=False)
+            out[f"{tag}_corr_pen{pen}"] = np.concatenate([[r[0]], r[1], r[2].ravel()])
+            rf = s.correlate_scan(c, r[1], (0.05, 0.05), (0.05, 0.05), 1 * D, 0.2 * D, do_penalize=bool(pen),
+                                  fine=True, cov_in=r[2])
+            out[f"{tag}_fine_pen{pen}"] = np.concatenate([[rf[0]], rf[1], rf[2].ravel()])
+        m = s.match_scan(c, [b])
+        out[f"{tag}_match"] = np.concatenate([[m[0]], m[1], m[2].ravel()])
+        og = s.occupancy_grid([b, c], 0.05)
+        out[f"{tag}_occ_dims"] = np.array([og["width"], og["height"], og["width_step"]], np.int32)
+        out[f"{tag}_occ_offset"] = og["offset"]
+        out[f"{tag}_occ_pass"] = og["passes"]
+        out[f"{tag}_occ_hit"] = og["hits"]
+        out[f"{tag}_occ_cells"] = og["cells"]
+        s.close()
+    np.savez_compressed(os.path.join(HERE, "karto_small.npz"), **out)
+
+
+def cfg1_case():
+    """BASELINE cfg 1: Hokuyo UTM-30LX (1081 beams), 31x31x181 direct CorrelateScan; digests + results."""
+    out = {}
+    laser = synth.Laser()
+    A, R = 22.5 * D, 0.25 * D
+    for seed in range(4):
+        mc = synth.make_match_case(seed, laser, dropout=0.01 if seed == 3 else 0.0)
+        p = ref.default_matcher_params(1.5, 0.05, 0.03, 9.25)
+        s = ref.RefSession(p, laser)
+        b = s.add_scan(mc.base_ranges, mc.base_pose)
+        c = s.add_scan(mc.ranges, mc.odom_pose)
+        s.set_grid_from_scans(c, [b])
+        sp = s.sensor_pose(c)
+        grid, lut = s.grid(), s.compute_offsets(c, sp[2], A, R)
+        sums = s.response_sums(c, sp, (0.75, 0.75), (0.05, 0.05), A, R)
+        r = s.correlate_scan(c, sp, (0.75, 0.75), (0.05, 0.05), A, R, True, False)
+        m = s.match_scan(c, [b])
+        t = f"s{seed}"
+        out.update({
+            f"{t}_base_ranges": mc.base_ranges, f"{t}_base_pose": mc.base_pose, f"{t}_ranges": mc.ranges,
+            f"{t}_pose": mc.odom_pose, f"{t}_grid_sha": np.array(sha(grid)), f"{t}_lut_sha": np.array(sha(lut)),
+            f"{t}_sums_sha": np.array(sha(sums)), f"{t}_sums_max_per_angle": sums.max(axis=(0, 1)),
+            f"{t}_sums_center_plane": sums[:, :, 90].copy(), f"{t}_grid_nonzero": np.array(int((grid > 0).sum())),
+            f"{t}_corr": np.concatenate([[r[0]], r[1], r[2].ravel()]),
+            f"{t}_match": np.concatenate([[m[0]], m[1], m[2].ravel()]),
+        })
+        s.close()
+    np.savez_compressed(os.path.join(HERE, "karto_cfg1.npz"), **out)
+
+
+def multi_base_case():
+    """AddScans with 12 base scans along a short trajectory + Karto occupancy grid of all of them; custom laser
+    (exercises the 'no +1' beam-count quirk, Karto.h:4158-4160: -90..90 @1deg -> 180 beams)."""
+    laser = synth.Laser(type=0, n_readings=180, min_angle=synth.deg2rad(-90), max_angle=synth.deg2rad(90),
+                        angular_resolution=synth.deg2rad(1.0), min_range=0.05, max_range=25.0, range_threshold=8.0,
+                        offset_pose=(0.12, -0.03, 0.05))
+    world, poses, ranges = synth.make_trajectory(5, 13, laser, step_xy=0.2, step_th_deg=4.0)
+    p = ref.default_matcher_params(0.8, 0.1, 0.1, 8.0, use_response_expansion=1)
+    s = ref.RefSession(p, laser)
+    assert s.n_readings == 180, s.n_readings
+    ids = [s.add_scan(ranges[i], poses[i]) for i in range(13)]
+    odom = poses[12] + np.array([0.11, -0.07, 0.04])
+    s.set_pose(ids[12], odom)
+    m = s.match_scan(ids[12], ids[:12])
+    gi = s.grid_info()
+    og = s.occupancy_grid(ids, 0.1)
+    np.savez_compressed(os.path.join(HERE, "karto_multibase.npz"), ranges=ranges, poses=poses, odom=odom,
+                        grid=s.grid(), grid_offset=gi["offset"], match=np.concatenate([[m[0]], m[1], m[2].ravel()]),
+                        sensor_pose=s.sensor_pose(ids[12]),
+                        occ_dims=np.array([og["width"], og["height"], og["width_step"]], np.int32),
+                        occ_offset=og["offset"], occ_pass=og["passes"], occ_hit=og["hits"], occ_cells=og["cells"])
+    s.close()
+
+
+def trace_lines():
+    rng = np.random.default_rng(42)
+    segs = rng.integers(-8, 72, size=(400, 4)).astype(np.int32)
+    cells, lens = [], []
+    for x0, y0, x1, y1 in segs:
+        c = ref.trace_line(64, 48, int(x0), int(y0), int(x1), int(y1))
+        cells.append(c)
+        lens.append(len(c))
+    np.savez_compressed(os.path.join(HERE, "karto_tracelines.npz"), segs=segs, lens=np.array(lens, np.int32),
+                        cells=np.concatenate(cells).astype(np.int16))
+
+
+if __name__ == "__main__":
+    assert ref.available(), "run `make -C oracle ref` first"
+    small_case()
+    cfg1_case()
+    multi_base_case()
+    trace_lines()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
