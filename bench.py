@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  (N > 1: launched by torchrun, one rank per GPU; RANK / LOCAL_RANK / WORLD_SIZE from the env)
+
+Workload (config.workload = "cfg2"): B = 1024 synthetic 1081-beam scans per GPU (Hokuyo UTM-30LX model), each
+matched against its own 0.05 m correlation grid (one base scan, 20.05 m x 20.05 m ROI) with a direct
+ScanMatcher::CorrelateScan over a 31 x 31 x 181 window (+-0.75 m @0.05 m, +-22.5 deg @0.25 deg), doPenalize=true
+(SURVEY.md §8(d) cfg 2).  A "step" is one pass of the hot path over that batch.
+
+  value : scan-matches/s with scans + grids already resident in HBM; timed region = K x b2s_matcher_correlate_scan
+          (lookup tables + response sweep + best/tie-average/covariance + result D2H), CUDA events on the launching
+          stream, barrier + synchronize on both sides, max over ranks.
+  e2e   : the same metric through the host-buffer C-ABI calls a reference node would make
+          (set_scans + add_scans (rasterise base scans) + correlate_scan) from PINNED host buffers, H2D + D2H inside
+          the timed region.
+  roofline : algorithmic bytes A1 = nX*nY*nA*N = 188 030 221 B per match x matches per launch
+          / average k_sweep_window duration (CUDA events inside the library, same stream), against the measured HBM
+          copy bandwidth in MEASURED_PEAKS.json.  K1 is an on-chip-gather kernel: the bytes are served from shared
+          memory, so this is an EFFECTIVE bandwidth; `smem_gather` reports the same work against the
+          shared-memory bank ceiling, which is the resource that actually binds.
+  cpu_baseline : the reference's own single-threaded CorrelateScan (oracle/_ref, unmodified open_karto, -O2 -DNDEBUG)
+          on a bounded sample of the same workload, rank 0 / N = 1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "creating-2d-laser-slam-from-scratch_b200"
+D = 0.01745329251994329577
+NX = NY = 31
+NA = 181
+NBEAMS = 1081
+A1_BYTES = NX * NY * NA * NBEAMS  # 188 030 221 algorithmic bytes per scan-match
+KERNELS_PER_STEP = 5  # k_offsets, k_bases, k_sweep_window, k_sweep_generic (fall-through), k_reduce
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--cpu-sample", type=int, default=48, help="matches timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_workload(synth, batch, rank):
+    cases = [synth.make_match_case(1_000_000 + rank * batch + i) for i in range(batch)]
+    ranges = np.stack([c.ranges for c in cases])
+    poses = np.stack([c.odom_pose for c in cases])
+    bran = np.stack([c.base_ranges for c in cases])[:, None, :]
+    bpos = np.stack([c.base_pose for c in cases])[:, None, :]
+    return ranges, poses, bran, bpos
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag, self.proc = gpu_index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(pkg, n_sample, ranges, poses, bran, bpos):
+    """The reference's own single-threaded CorrelateScan on the first n_sample matches of the workload."""
+    from oracle import ref
+    synth = pkg.synth
+    A, R = 22.5 * D, 0.25 * D
+    if ref.available(ndebug=True):
+        kind, secs = "reference", []
+        s = ref.RefSession(ref.default_matcher_params(1.5, 0.05, 0.03, 9.25), synth.Laser(), ndebug=True)
+        for i in range(n_sample):
+            b = s.add_scan(bran[i, 0], bpos[i, 0])
+            c = s.add_scan(ranges[i], poses[i])
+            s.set_grid_from_scans(c, [b])
+            secs.append(float(s.time_correlate(c, s.sensor_pose(c), (0.75, 0.75), (0.05, 0.05), A, R, True, False, 1)[0]))
+        s.close()
+    else:
+        from oracle import port
+        kind, secs = "port", []
+        abi = pkg.abi
+        for i in range(n_sample):
+            pm = port.PortMatcher(abi.matcher_params(1.5, 0.05, 0.03, 9.25), abi.laser_from(synth.Laser()))
+            pm.set_scan(ranges[i], poses[i])
+            pm.add_scans(bran[i], bpos[i])
+            t = time.perf_counter()
+            pm.correlate_scan(pm.sp, abi.Search(0.75, 0.75, 0.05, 0.05, A, R, 1, 0))
+            secs.append(time.perf_counter() - t)
+    secs = np.array(secs)
+    return {"value": float(1.0 / np.median(secs)), "unit": "scan-matches/s", "cores": 1, "kind": kind,
+            "sample": f"{n_sample} of the {len(ranges)} cfg2 matches, ScanMatcher::CorrelateScan 31x31x181, "
+                      f"median {np.median(secs) * 1e3:.1f} ms/match, g++ -O2 -DNDEBUG, 1 thread",
+            "host": host_desc()}
+
+
+def host_desc():
+    try:
+        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        model = "unknown"
+    return f"{model} x{os.cpu_count()}"
+
+
+def _ref_worker(args):
+    """One process = one reference ScanMatcher session (the reference is single-threaded and not re-entrant)."""
+    seeds, reps = args
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module(PKG)
+    from oracle import port, ref
+    A, R = 22.5 * D, 0.25 * D
+    cases = [pkg.synth.make_match_case(s) for s in seeds]
+    done = 0
+    if ref.available(ndebug=True):
+        s = ref.RefSession(ref.default_matcher_params(1.5, 0.05, 0.03, 9.25), pkg.synth.Laser(), ndebug=True)
+        ids = []
+        for c in cases:
+            ids.append((s.add_scan(c.base_ranges, c.base_pose), s.add_scan(c.ranges, c.odom_pose)))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for b, c in ids:
+                s.set_grid_from_scans(c, [b])
+                s.correlate_scan(c, s.sensor_pose(c), (0.75, 0.75), (0.05, 0.05), A, R, True, False)
+                done += 1
+        return done, time.perf_counter() - t0, "reference"
+    abi = pkg.abi
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for c in cases:
+            pm = port.PortMatcher(abi.matcher_params(1.5, 0.05, 0.03, 9.25), abi.laser_from(pkg.synth.Laser()))
+            pm.set_scan(c.ranges, c.odom_pose)
+            pm.add_scans(c.base_ranges, c.base_pose)
+            pm.correlate_scan(pm.sp, abi.Search(0.75, 0.75, 0.05, 0.05, A, R, 1, 0))
+            done += 1
+    return done, time.perf_counter() - t0, "port"
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on all host cores (one single-threaded
+    ScanMatcher per process), same metric/config; each step is a bounded sample (one match per worker)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    ctx = mp.get_context("spawn")
+    per_step = 1
+    with ctx.Pool(cores) as pool:
+        def step(k):
+            jobs = [([2_000_000 + k * cores + w], per_step) for w in range(cores)]
+            t0 = time.perf_counter()
+            out = pool.map(_ref_worker, jobs)
+            return sum(o[0] for o in out), time.perf_counter() - t0, out[0][2]
+        for k in range(args.warmup):
+            step(k)
+        t_total, n_total, kind = 0.0, 0, "reference"
+        for k in range(args.steps):
+            n, t, kind = step(args.warmup + k)
+            n_total += n
+            t_total += t
+    value = n_total / t_total
+    line = {"impl": "reference", "metric": "scan-matches/s (1081-beam, 31x31x181 window)", "value": value,
+            "unit": "scan-matches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 gather + i32 sum, f64 pose", "data": "synthetic",
+            "config": {"workload": "cfg2", "beams": NBEAMS, "window": [NX, NY, NA], "grid_res_m": 0.05,
+                       "sample_matches_per_step": cores * per_step},
+            "cpu_baseline": {"value": value, "unit": "scan-matches/s", "cores": cores, "kind": kind,
+                             "sample": f"{cores * per_step} matches per step (one per worker process), "
+                                       f"{args.steps} steps; process pool incl. grid build", "host": host_desc()},
+            "e2e": {"value": value, "unit": "scan-matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module(PKG)
+    abi, synth = pkg.abi, pkg.synth
+    M = pkg.load("matcher")
+
+    B = args.batch
+    ranges, poses, bran, bpos = make_workload(synth, B, rank)
+    stream = torch.cuda.Stream(device=local)  # a real (non-default) stream shared with the library, so that
+    torch.cuda.set_stream(stream)             # torch.cuda.Event brackets exactly the library's launches
+    m = M.ScanMatcher(abi.matcher_params(1.5, 0.05, 0.03, 9.25), abi.laser_from(synth.Laser()), max_batch=B,
+                      max_base_scans=1, device=local, stream=stream.cuda_stream)
+    se = abi.Search(0.75, 0.75, 0.05, 0.05, 22.5 * D, 0.25 * D, 1, 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------ resident-in-HBM arm ("value")
+    m.set_scans(ranges, poses)
+    m.add_scans(bran, bpos)
+    m.sync()
+    for _ in range(args.warmup):
+        out = m.correlate_scan(poses, se)
+    assert (out[3] == 0).all() and m.last_timing()["path"] == 2
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sweep_ms, lut_ms, red_ms = [], [], []
+    e0.record(stream)
+    for _ in range(args.steps):
+        out = m.correlate_scan(poses, se)
+        t = m.last_timing()
+        sweep_ms.append(t["sweep_ms"]); lut_ms.append(t["lut_ms"]); red_ms.append(t["reduce_ms"])
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t_ms = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ------------------------------------------------------------ end-to-end arm (host buffers, pinned)
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, C.cast(t.data_ptr(), C.POINTER(C.c_double))
+
+    keep = [pinned(x) for x in (ranges, poses, bran, bpos)]
+    pr, pp, pbr, pbp = (k[1] for k in keep)
+    res = (abi.MatchResult * B)()
+    L = M.lib()
+
+    def e2e_step():
+        M.check(L.b2s_matcher_set_scans(m.h, B, pr, pp))
+        M.check(L.b2s_matcher_add_scans(m.h, 1, pbr, pbp))
+        M.check(L.b2s_matcher_correlate_scan(m.h, pp, C.byref(se), res))
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e3.record(stream)
+    barrier()
+    t_e = torch.tensor([e2.elapsed_time(e3)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t_e.item()) * 1e-3)
+    sampler.stop()
+    h2d = int(ranges.nbytes + poses.nbytes + bran.nbytes + bpos.nbytes + poses.nbytes)
+    d2h = int(C.sizeof(abi.MatchResult) * B)
+    e2e_resp = np.frombuffer(res, dtype=np.uint8).copy()  # the step's result was read back on the host
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        sweep = float(np.mean(sweep_ms))
+        achieved = A1_BYTES * B / (sweep * 1e-3) / 1e9
+        clocks = sampler.summary()
+        sm_clk = (clocks["sm_mhz"] or 1965.0) * 1e6
+        smem_ceiling = 148 * 32 * sm_clk  # 4-byte bank accesses / s
+        line = {
+            "metric": "scan-matches/s (1081-beam, 31x31x181 window)", "value": value, "unit": "scan-matches/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 gather + i32 sum, f64 pose", "data": "synthetic",
+            "config": {"workload": "cfg2", "batch_per_gpu": B, "beams": NBEAMS, "window": [NX, NY, NA],
+                       "grid_res_m": 0.05, "grid_bytes": 165240, "base_scans": 1, "parallelism": f"batch-shard x{world}",
+                       "l2_policy": f"inputs larger than L2 ({B} grids x 165 KB = {B * 165240 / 1e6:.0f} MB resident, "
+                                    f"{B * NA * NBEAMS * 4 / 1e6:.0f} MB LUT, {B * NA * NX * NY * 4 / 1e6:.0f} MB volume per step)"},
+            "e2e": {"value": e2e_value, "unit": "scan-matches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "includes": "set_scans + add_scans (rasterise) + correlate_scan from pinned host buffers"},
+            "gpu_launches": args.steps * KERNELS_PER_STEP,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_sweep_window", "kernel_ms": sweep, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": A1_BYTES * B,
+                         "note": "K1 is not DRAM-bound: the algorithmic bytes are served from shared memory "
+                                 "(effective bandwidth); see smem_gather",
+                         "smem_gather": {"lookups_per_s": A1_BYTES * B / (sweep * 1e-3),
+                                         "bank_ceiling_per_s": smem_ceiling,
+                                         "frac_of_bank_ceiling": A1_BYTES * B / (sweep * 1e-3) / smem_ceiling,
+                                         "lookups_per_clk_per_sm": A1_BYTES * B / (sweep * 1e-3) / (148 * sm_clk)}},
+            "stage_ms": {"lut": float(np.mean(lut_ms)), "sweep": sweep, "reduce": float(np.mean(red_ms))},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(pkg, min(args.cpu_sample, B), ranges, poses, bran, bpos)
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

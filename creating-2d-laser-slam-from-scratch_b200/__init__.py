@@ -7,4 +7,9 @@ ctypes harness used by tests/ and bench.py plus the synthetic workload generator
 """
 from . import abi, synth  # noqa: F401
 
-__all__ = ["abi", "synth"]
+
+
+def load(name: str):
+    """Import a harness submodule that binds libb200slam.so (matcher, occgrid, hector, gmapping) on demand."""
+    import importlib
+    return importlib.import_module(f"{__name__}.{name}")

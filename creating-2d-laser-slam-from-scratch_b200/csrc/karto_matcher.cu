@@ -1,0 +1,1386 @@
+// K1 — Karto correlative scan matcher on B200 (sm_100a).  Product code: CUDA only, no CPU fallback.
+//
+// Reference behaviour (paths relative to /root/reference/lesson6/lib/open_karto):
+//   ScanMatcher::Create / MatchScan / CorrelateScan / GetResponse / AddScans / FindValidPoints  src/Mapper.cpp:126-856
+//   CorrelationGrid (smear kernel, ROI)                                   include/open_karto/Mapper.h:900-1118
+//   GridIndexLookup::ComputeOffsets, Grid<T>, CoordinateConverter          include/open_karto/Karto.h:6409-6501, 4209-4767
+//   LocalizedRangeScan::Update (point readings)                            include/open_karto/Karto.h:5362-5428
+//
+// Data layout in HBM (per handle, B = batch capacity, N = beams):
+//   grids   [B][grid_pitch] u8      one correlation grid per match, same flat row-major layout as the reference
+//                                   (index = x + y*width_step); grid_pitch = data_size rounded up to 128 B (+pad, zero)
+//   lut     [B][nA][N]      i32     per-angle flat offsets (GridIndexLookup), INT32_MAX = INVALID_SCAN
+//   sums    [B][nA][nY][nX] i32     integer numerators of GetResponse for the whole (x,y,theta) volume
+//   probs   [B][side*side]  f64     per-cell maximum over theta (m_pSearchSpaceProbs)
+//
+// Kernels:
+//   k_scan_points      point readings + scan-local points                              (fp64, O(B*N))
+//   k_add_scan         FindValidPoints state machine + rasterise + max-smear           (byte atomics, O(B*S*N))
+//   k_offsets          per-angle lookup tables                                         (fp64 -> i32)
+//   k_sweep_window     THE HOT KERNEL: whole grid staged into shared memory by TMA bulk copy; one warp per
+//                      angle, one lane per candidate row; each 32-bit shared-memory word feeds 4 adjacent-x
+//                      candidates (byte-permute into packed u16 accumulators)           (int, smem-gather bound)
+//   k_sweep_generic    any lattice / any grid size: one warp per (x,y) candidate, lanes over beams,
+//                      gathers from global memory through L1/L2
+//   k_reduce           penalties, best response, tie-averaged pose, positional covariance (fp64, one CTA per match)
+//   k_angular_cov      fine-stage angular covariance (re-evaluates GetResponse at the best cell)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2s {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &s) { g_last_error = s; }
+std::string &last_error_ref() { return g_last_error; }
+
+// ----------------------------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// PRMT, default mode: selector nibble bit 3 replicates the sign bit of the selected byte.  Grid bytes are
+// <= 100 < 128, so a "sign-replicated" byte is 0x00: one PRMT extracts two bytes into packed u16 lanes.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// per-byte atomic max on a u8 array (no native byte atomics): CAS on the containing aligned word
+__device__ __forceinline__ void atomic_max_u8(uint8_t *base, int idx, uint32_t val) {
+  uint32_t *w = reinterpret_cast<uint32_t *>(base + (idx & ~3));
+  uint32_t shift = (idx & 3) * 8;
+  uint32_t v = val << shift;
+  uint32_t old = *w, assumed;
+  do {
+    if (((old >> shift) & 0xffu) >= val) return;
+    assumed = old;
+    old = atomicCAS(w, assumed, __vmaxu4(assumed, v));
+  } while (assumed != old);
+}
+
+// ----------------------------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------------------------
+
+struct SweepDims {
+  int nx = 0, ny = 0, na = 0;
+};
+
+}  // namespace b2s
+
+using namespace b2s;
+
+struct b2s_matcher {
+  b2s_matcher_params p;
+  b2s_laser l;
+  b2s_grid_info g;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int max_batch = 0, max_base = 0;
+  int batch = 0, n = 0, n_base = 0;
+  bool scans_set = false, grids_set = false;
+  bool smear_degenerate = false;  // an off-centre kernel value reaches 100: AddScan becomes order-dependent
+  size_t grid_pitch = 0;
+  int force_kernel = 0;
+  int num_sms = 148;
+  int smem_optin = 0;
+
+  uint8_t *d_kernel = nullptr;
+  double *d_ranges = nullptr, *d_poses = nullptr, *d_sensor = nullptr, *d_pts = nullptr, *d_local = nullptr;
+  uint8_t *d_grids = nullptr;
+  double *d_grid_off = nullptr;
+  double *d_base_ranges = nullptr, *d_base_poses = nullptr, *d_base_pts = nullptr;
+  size_t base_cap = 0;
+  int32_t *d_lut = nullptr;
+  size_t lut_cap = 0;
+  int32_t *d_sums = nullptr;
+  size_t sums_cap = 0;
+  int32_t *d_bases = nullptr;  // [B][ny*nx] candidate base indices
+  size_t bases_cap = 0;
+  int32_t *d_flags = nullptr;  // [B] per-match: bit0 lattice regular stride-1, bits 8.. status
+  double *d_probs = nullptr;
+  double *d_centers = nullptr;
+  b2s_match_result *d_results = nullptr;
+  b2s_match_result *h_results = nullptr;  // pinned
+  int *d_work = nullptr;                   // persistent-CTA work counter
+  SweepDims last;
+  b2s_search last_search;
+  bool have_sweep = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double last_ms[4] = {0, 0, 0, 0};
+  int last_path = 0;
+};
+
+namespace b2s {
+
+// ----------------------------------------------------------------------------------------------
+// k_scan_points: LocalizedRangeScan::Update unfiltered points (Karto.h:5362-5404) and, optionally, the
+// scan-local points of GridIndexLookup::ComputeOffsets (Karto.h:6423-6434, Transform::InverseTransformPose
+// Karto.h:2894-2901).  One block per scan.
+// ----------------------------------------------------------------------------------------------
+__global__ void k_scan_points(const double *__restrict__ ranges, const double *__restrict__ poses, b2s_laser l,
+                              double *__restrict__ sensor, double *__restrict__ pts, double *__restrict__ local) {
+  const int b = blockIdx.x;
+  const int n = l.n_readings;
+  __shared__ double sp[3];
+  __shared__ double inv[6];
+  __shared__ double tr[3];
+  if (threadIdx.x == 0) {
+    double robot[3] = {poses[3 * b], poses[3 * b + 1], poses[3 * b + 2]};
+    double out[3];
+    sensor_pose_of(robot, l.offset_pose, out);
+    sp[0] = out[0]; sp[1] = out[1]; sp[2] = out[2];
+    if (sensor) { sensor[3 * b] = out[0]; sensor[3 * b + 1] = out[1]; sensor[3 * b + 2] = out[2]; }
+    if (out[0] == 0.0 && out[1] == 0.0 && out[2] == 0.0) {
+      inv[0] = 1; inv[1] = 0; inv[2] = 0; inv[3] = 0; inv[4] = 1; inv[5] = 0;
+      tr[0] = tr[1] = tr[2] = 0;
+    } else {
+      double radians = 0.0 - out[2];
+      double c = cos(radians), s = sin(radians), omc = 1.0 - c;
+      inv[0] = 0.0 * omc + c;
+      inv[1] = 0.0 * 0.0 * omc - 1.0 * s;
+      inv[2] = 0.0 * 1.0 * omc + 0.0 * s;
+      inv[3] = 0.0 * 0.0 * omc + 1.0 * s;
+      inv[4] = 0.0 * omc + c;
+      inv[5] = 0.0 * 1.0 * omc - 0.0 * s;
+      tr[0] = out[0]; tr[1] = out[1]; tr[2] = out[2] - 0.0;
+    }
+  }
+  __syncthreads();
+  const double dh = normalize_angle(0.0 - tr[2]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double r = ranges[(size_t)b * n + i];
+    double angle = sp[2] + l.min_angle + (double)(uint32_t)i * l.angular_resolution;
+    double x = sp[0] + (r * cos(angle));
+    double y = sp[1] + (r * sin(angle));
+    pts[((size_t)b * n + i) * 2] = x;
+    pts[((size_t)b * n + i) * 2 + 1] = y;
+    if (local) {
+      double dx = x - tr[0], dy = y - tr[1];
+      local[((size_t)b * n + i) * 2] = inv[0] * dx + inv[1] * dy + inv[2] * dh;
+      local[((size_t)b * n + i) * 2 + 1] = inv[3] * dx + inv[4] * dy + inv[5] * dh;
+    }
+  }
+}
+
+// MatchScan steps 2-4 (Mapper.cpp:212-220): grid offset so that the ROI centre is the scan's sensor position
+__global__ void k_grid_offsets(const double *__restrict__ sensor, double *__restrict__ grid_off, int batch, int roi_w,
+                               int roi_h, double resolution) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  grid_off[2 * b] = sensor[3 * b] - (0.5 * (double)(roi_w - 1) * resolution);
+  grid_off[2 * b + 1] = sensor[3 * b + 1] - (0.5 * (double)(roi_h - 1) * resolution);
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_add_scan: ScanMatcher::AddScan (Mapper.cpp:716-748) for one (match, base scan) per block:
+// thread 0 runs the FindValidPoints state machine (Mapper.cpp:756-811) over points staged in shared memory,
+// then all threads rasterise the valid points and max-stamp the smear kernel (Mapper.h:971-1005).
+// The result is a per-byte maximum, hence independent of the order in which points / scans are applied,
+// EXCEPT when an off-centre kernel value equals 100 (sigma ~ 10*res); that case takes k_add_scans_seq.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void find_valid_points(const double *px, const double *py, int n, double vx, double vy,
+                                                  uint8_t *valid) {
+  const double min_sq = 0.1 * 0.1;
+  int trailing = 0;
+  double fx = 0.0, fy = 0.0;
+  bool first_time = true;
+  for (int it = 0; it < n; it++) {
+    double cx = px[it], cy = py[it];
+    if (first_time && !isnan(cx) && !isnan(cy)) {
+      fx = cx; fy = cy;
+      first_time = false;
+    }
+    double dx = fx - cx, dy = fy - cy;
+    if (dx * dx + dy * dy > min_sq) {
+      double a = vy - fy;
+      double bb = fx - vx;
+      double c = fy * vx - fx * vy;
+      double ss = cx * a + cy * bb + c;
+      fx = cx; fy = cy;
+      if (ss < 0.0) {
+        trailing = it;
+      } else {
+        for (; trailing != it; ++trailing) valid[trailing] = 1;
+      }
+    }
+  }
+}
+
+__global__ void k_add_scan(const double *__restrict__ base_pts, const double *__restrict__ sensor,
+                           const double *__restrict__ grid_off, uint8_t *__restrict__ grids, size_t grid_pitch,
+                           const uint8_t *__restrict__ kernel, b2s_grid_info g, double scale, int n, int n_base) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *px = reinterpret_cast<double *>(smem_raw);
+  double *py = px + n;
+  uint8_t *valid = reinterpret_cast<uint8_t *>(py + n);
+  const int bs = blockIdx.x;  // b * n_base + s
+  const int b = bs / n_base;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    px[i] = base_pts[((size_t)bs * n + i) * 2];
+    py[i] = base_pts[((size_t)bs * n + i) * 2 + 1];
+    valid[i] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) find_valid_points(px, py, n, sensor[3 * b], sensor[3 * b + 1], valid);
+  __syncthreads();
+  const double ox = grid_off[2 * b], oy = grid_off[2 * b + 1];
+  uint8_t *grid = grids + (size_t)b * grid_pitch;
+  const int half = g.kernel_size / 2;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (!valid[i]) continue;
+    double gxd = kround((px[i] - ox) * scale);
+    double gyd = kround((py[i] - oy) * scale);
+    // IsUpTo on static_cast<int>: non-finite / out-of-int-range values are rejected
+    if (!(gxd >= 0.0 && gxd < (double)g.roi_w) || !(gyd >= 0.0 && gyd < (double)g.roi_h)) continue;
+    int gx = (int)gxd + g.roi_x, gy = (int)gyd + g.roi_y;
+    for (int j = -half; j <= half; j++)
+      for (int k = -half; k <= half; k++) {
+        uint32_t kv = kernel[(k + half) + g.kernel_size * (j + half)];
+        if (kv) atomic_max_u8(grid, (gx + k) + (gy + j) * g.width_step, kv);
+      }
+  }
+}
+
+// exact sequential AddScans for the degenerate smear kernel (see above): one thread per match
+__global__ void k_add_scans_seq(const double *__restrict__ base_pts, const double *__restrict__ sensor,
+                                const double *__restrict__ grid_off, uint8_t *__restrict__ grids, size_t grid_pitch,
+                                const uint8_t *__restrict__ kernel, b2s_grid_info g, double scale, int n, int n_base,
+                                int batch, uint8_t *__restrict__ valid_scratch) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  uint8_t *grid = grids + (size_t)b * grid_pitch;
+  uint8_t *valid = valid_scratch + (size_t)b * n;
+  const int half = g.kernel_size / 2;
+  for (int s = 0; s < n_base; s++) {
+    const double *p = base_pts + ((size_t)(b * n_base + s) * n) * 2;
+    // FindValidPoints on strided xy pairs
+    const double min_sq = 0.1 * 0.1;
+    const double vx = sensor[3 * b], vy = sensor[3 * b + 1];
+    for (int i = 0; i < n; i++) valid[i] = 0;
+    int trailing = 0;
+    double fx = 0.0, fy = 0.0;
+    bool first_time = true;
+    for (int it = 0; it < n; it++) {
+      double cx = p[2 * it], cy = p[2 * it + 1];
+      if (first_time && !isnan(cx) && !isnan(cy)) { fx = cx; fy = cy; first_time = false; }
+      double dx = fx - cx, dy = fy - cy;
+      if (dx * dx + dy * dy > min_sq) {
+        double a = vy - fy, bb = fx - vx, c = fy * vx - fx * vy;
+        double ss = cx * a + cy * bb + c;
+        fx = cx; fy = cy;
+        if (ss < 0.0) trailing = it;
+        else for (; trailing != it; ++trailing) valid[trailing] = 1;
+      }
+    }
+    for (int i = 0; i < n; i++) {
+      if (!valid[i]) continue;
+      double gxd = kround((p[2 * i] - grid_off[2 * b]) * scale);
+      double gyd = kround((p[2 * i + 1] - grid_off[2 * b + 1]) * scale);
+      if (!(gxd >= 0.0 && gxd < (double)g.roi_w) || !(gyd >= 0.0 && gyd < (double)g.roi_h)) continue;
+      int gx = (int)gxd + g.roi_x, gy = (int)gyd + g.roi_y;
+      int idx = gx + gy * g.width_step;
+      if (grid[idx] == GRID_OCCUPIED) continue;  // Mapper.cpp:734-738
+      grid[idx] = GRID_OCCUPIED;
+      for (int j = -half; j <= half; j++)
+        for (int k = -half; k <= half; k++) {
+          uint8_t kv = kernel[(k + half) + g.kernel_size * (j + half)];
+          uint8_t *c = grid + (gx + k) + (gy + j) * g.width_step;
+          if (kv > *c) *c = kv;
+        }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_offsets: GridIndexLookup::ComputeOffsets (Karto.h:6455-6501).  One block per (match, angle).
+// ----------------------------------------------------------------------------------------------
+__global__ void k_offsets(const double *__restrict__ ranges, const double *__restrict__ local,
+                          const double *__restrict__ grid_off, const double *__restrict__ centers, int center_stride,
+                          double angle_center_override, int use_override, double angle_offset, double angle_res,
+                          int n_angles, int n, int width_step, double scale, int32_t *__restrict__ lut) {
+  const int b = blockIdx.x / n_angles, k = blockIdx.x % n_angles;
+  const double center = use_override ? angle_center_override : centers[(size_t)b * center_stride + 2];
+  const double start = center - angle_offset;
+  const double angle = start + (double)(uint32_t)k * angle_res;
+  const double cosine = cos(angle), sine = sin(angle);
+  const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double r = ranges[(size_t)b * n + i];
+    int32_t v;
+    if (isnan(r) || isinf(r)) {
+      v = INVALID_SCAN;
+    } else {
+      double lx = local[((size_t)b * n + i) * 2], ly = local[((size_t)b * n + i) * 2 + 1];
+      double ox = __dsub_rn(__dmul_rn(cosine, lx), __dmul_rn(sine, ly));
+      double oy = __dadd_rn(__dmul_rn(sine, lx), __dmul_rn(cosine, ly));
+      // WorldToGrid(offset + rGridOffset): ((o + off) - off) * scale (Karto.h:6491, 4239-4251)
+      int32_t gx = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(ox, gox), gox), scale)));
+      int32_t gy = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(oy, goy), goy), scale)));
+      v = (int32_t)((uint32_t)gx + (uint32_t)gy * (uint32_t)width_step);  // Grid<T>::GridIndex, no ROI
+    }
+    lut[((size_t)b * n_angles + k) * n + i] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_bases: candidate lattice of CorrelateScan (Mapper.cpp:338-358, 373-386) -> flat base index per (iy, ix).
+// flags[b]: bit0 = lattice is the regular stride-1 raster base00 + ix + iy*width_step;
+//           bit1 = some candidate fell outside the grid (reference throws karto::Exception, Karto.h:4490-4499)
+// ----------------------------------------------------------------------------------------------
+__global__ void k_bases(const double *__restrict__ centers, const double *__restrict__ grid_off, b2s_search s,
+                        b2s_grid_info g, double scale, int nx, int ny, int32_t *__restrict__ bases,
+                        int32_t *__restrict__ flags) {
+  const int b = blockIdx.x;
+  __shared__ int irregular, oob;
+  if (threadIdx.x == 0) { irregular = 0; oob = 0; }
+  __syncthreads();
+  const double cx = centers[3 * b], cy = centers[3 * b + 1];
+  const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
+  const double start_x = -s.offset_x, start_y = -s.offset_y;
+  const int32_t gx0 = world_to_grid_1(cx + start_x, gox, scale) + g.roi_x;
+  const int32_t gy0 = world_to_grid_1(cy + start_y, goy, scale) + g.roi_y;
+  for (int c = threadIdx.x; c < nx * ny; c += blockDim.x) {
+    int iy = c / nx, ix = c % nx;
+    double y = start_y + (double)(uint32_t)iy * s.res_y;
+    double x = start_x + (double)(uint32_t)ix * s.res_x;
+    int32_t gx = world_to_grid_1(cx + x, gox, scale) + g.roi_x;  // CorrelationGrid::GridIndex (Mapper.h:941-947)
+    int32_t gy = world_to_grid_1(cy + y, goy, scale) + g.roi_y;
+    if (!(gx >= 0 && gx < g.width && gy >= 0 && gy < g.height)) oob = 1;
+    if (gx != gx0 + ix || gy != gy0 + iy) irregular = 1;
+    bases[(size_t)b * nx * ny + c] = gx + gy * g.width_step;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flags[b] = (irregular ? 0 : 1) | (oob ? 2 : 0);
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_sweep_generic: integer numerators of GetResponse (Mapper.cpp:819-856) for every candidate.
+// One warp per (x,y) candidate, looping over all angles; lanes stride over beams; grid + LUT read from
+// global memory (L1/L2).  Handles any lattice and any grid size.  mode 0: all matches; mode 1: only matches
+// whose lattice is NOT regular (the window kernel did the others).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict__ grids, size_t grid_pitch,
+                                                       int data_size, const int32_t *__restrict__ lut,
+                                                       const int32_t *__restrict__ bases,
+                                                       const int32_t *__restrict__ flags, int mode, int n, int na,
+                                                       int ncell, int32_t *__restrict__ sums) {
+  const int b = blockIdx.y;
+  const int f = flags[b];
+  if (f & 2) return;
+  if (mode == 1 && (f & 1)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= ncell) return;
+  const uint8_t *grid = grids + (size_t)b * grid_pitch;
+  const int32_t base = bases[(size_t)b * ncell + c];
+  for (int k = 0; k < na; k++) {
+    const int32_t *offs = lut + ((size_t)b * na + k) * n;
+    int32_t sum = 0;
+    for (int i = lane; i < n; i += 32) {
+      int32_t o = __ldg(offs + i);
+      if (o == INVALID_SCAN) continue;
+      int32_t idx = (int32_t)((uint32_t)base + (uint32_t)o);
+      if (idx >= 0 && idx < data_size) sum += __ldg(grid + idx);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) sums[((size_t)b * na + k) * ncell + c] = sum;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_sweep_window — the hot kernel (stride-1 lattices, grid fits in shared memory).
+//
+// For a fixed angle k and beam i, the cells read by all (ix, iy) candidates form the nY x nX window of the
+// grid whose origin is  o = base00 + lut[k][i]  (flat index; rows are width_step apart).  So
+//     sums[k][iy][ix] = SUM_i grid[o_i + iy*width_step + ix].
+// A persistent CTA stages one match's whole grid into shared memory with TMA bulk copies and its warps take
+// (angle, 32x32 window tile) work items.  Within a warp lane r owns candidate row r: per beam it loads the 9
+// aligned 32-bit words covering its 32 candidate bytes and, with two PRMTs per word, spreads them into packed
+// u16 accumulators (bytes 0,2 -> "lo", bytes 1,3 -> "hi"; the PRMT selector also absorbs the byte alignment of
+// o_i, which is identical for all rows because width_step % 8 == 0).  u16 lanes are flushed to 32-bit sums
+// every 512 beams (100 * 512 < 65536).  One shared-memory word therefore serves 4 candidates, and the only
+// other per-beam costs are one warp shuffle (offset broadcast) and a handful of integer ops.
+//
+// Flat-index semantics of the reference are kept bit-exactly: rows wrap exactly as `base + offset` does, and
+// positions outside [0, data_size) read zeros (guard bands + redirect of fully-outside rows).
+// Lanes 16..31 fetch their 9 words rotated by one so that the two half-warps hit odd / even banks
+// (width_step/4 is even, so rows r and r+16 would otherwise always collide).
+// ----------------------------------------------------------------------------------------------
+constexpr int WIN_THREADS = 512;
+constexpr int WIN_WARPS = WIN_THREADS / 32;
+constexpr int WIN_GUARD = 128;       // zero bytes before and after the grid image in shared memory
+constexpr int WIN_FLUSH = 512;       // beams between u16 -> u32 flushes
+constexpr int32_t WIN_SKIP = -(1 << 29);
+
+__device__ __forceinline__ void win_accumulate(const uint8_t *__restrict__ sgrid, int a, uint32_t sel_lo,
+                                               uint32_t sel_hi, int hi_half, uint32_t (&lo)[8], uint32_t (&hi)[8]) {
+  // a = byte address (within sgrid) of this lane's row start, already redirected if out of range
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>(sgrid + (a & ~3)) + hi_half;
+  uint32_t v[9];
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = wp[j];
+  v[8] = wp[8 - 9 * hi_half];
+  // half 0: v[j] = word j.            pairs (v[j], v[j+1]) = x-word j, j = 0..7
+  // half 1: v[j] = word j+1 (j<8), v[8] = word 0.  pairs (v[j], v[j+1]) j=0..6 = x-word j+1; (v[8], v[0]) = x-word 0
+#pragma unroll
+  for (int j = 0; j < 7; j++) {
+    lo[j] += prmt(v[j], v[j + 1], sel_lo);
+    hi[j] += prmt(v[j], v[j + 1], sel_hi);
+  }
+  uint32_t pa = hi_half ? v[8] : v[7];
+  uint32_t pb = hi_half ? v[0] : v[8];
+  lo[7] += prmt(pa, pb, sel_lo);
+  hi[7] += prmt(pa, pb, sel_hi);
+}
+
+__global__ void __launch_bounds__(WIN_THREADS, 1)
+    k_sweep_window(const uint8_t *__restrict__ grids, size_t grid_pitch, int data_size, int copy_bytes,
+                   const int32_t *__restrict__ lut, const int32_t *__restrict__ bases,
+                   const int32_t *__restrict__ flags, int batch, int n, int na, int nx, int ny, int width_step,
+                   int32_t *__restrict__ sums, int *__restrict__ work_counter) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint8_t *sgrid = smem;  // [WIN_GUARD zeros][grid image copy_bytes][WIN_GUARD zeros]
+  __shared__ uint64_t bar;
+  __shared__ int s_match, s_item;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = (nx + 31) >> 5, tiles_y = (ny + 31) >> 5;
+  const int items = na * tiles_x * tiles_y;
+  const int hi_half = lane >> 4;
+
+  // zero the guard bands once
+  for (int i = threadIdx.x; i < WIN_GUARD / 4; i += blockDim.x) {
+    reinterpret_cast<uint32_t *>(sgrid)[i] = 0;
+    reinterpret_cast<uint32_t *>(sgrid + WIN_GUARD + copy_bytes)[i] = 0;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  while (true) {
+    if (threadIdx.x == 0) {
+      s_match = atomicAdd(work_counter, 1);
+      s_item = 0;
+    }
+    __syncthreads();
+    const int b = s_match;
+    if (b >= batch) break;
+    const int f = flags[b];
+    if ((f & 2) || !(f & 1)) {  // out-of-range lattice (error) or irregular lattice (generic kernel takes it)
+      __syncthreads();
+      continue;
+    }
+    // ---- stage this match's grid: TMA bulk copies, 32 KB each, one mbarrier phase ----
+    if (threadIdx.x == 0) {
+      fence_proxy_async();  // earlier generic-proxy reads of sgrid are ordered before the async-proxy writes
+      mbar_expect_tx(&bar, (uint32_t)copy_bytes);
+      const uint8_t *src = grids + (size_t)b * grid_pitch;
+      for (int off = 0; off < copy_bytes; off += 32768) {
+        int len = min(32768, copy_bytes - off);
+        bulk_g2s(sgrid + WIN_GUARD + off, src + off, (uint32_t)len, &bar);
+      }
+    }
+    mbar_wait(&bar, parity);
+    parity ^= 1;
+
+    const int32_t base00 = bases[(size_t)b * nx * ny];
+    const int32_t *blut = lut + (size_t)b * na * n;
+    int32_t *bsums = sums + (size_t)b * na * nx * ny;
+
+    while (true) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&s_item, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= items) break;
+      const int k = item / (tiles_x * tiles_y);
+      const int t = item % (tiles_x * tiles_y);
+      const int ty = t / tiles_x, tx = t % tiles_x;
+      const int32_t tile_org = base00 + ty * 32 * width_step + tx * 32;
+      const int row_off = lane * width_step;
+
+      uint32_t acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) acc[j] = 0;
+      const int32_t *offs = blut + (size_t)k * n;
+
+      for (int i0 = 0; i0 < n; i0 += WIN_FLUSH) {
+        uint32_t lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { lo[j] = 0; hi[j] = 0; }
+        const int i1 = min(n, i0 + WIN_FLUSH);
+        for (int ib = i0; ib < i1; ib += 32) {
+          // lane j fetches beam ib+j's offset; INVALID_SCAN and exhausted lanes become a far-negative origin
+          int32_t my = WIN_SKIP;
+          if (ib + lane < i1) {
+            int32_t o = __ldg(offs + ib + lane);
+            if (o != INVALID_SCAN) my = (int32_t)((uint32_t)tile_org + (uint32_t)o);
+          }
+          const int cnt = min(32, i1 - ib);
+          for (int j = 0; j < cnt; j++) {
+            const int32_t o = __shfl_sync(0xffffffffu, my, j);
+            const int32_t idx = o + row_off;  // flat index of this lane's row start
+            // rows entirely outside [0, data_size) read the leading zero guard instead
+            const bool in = ((uint32_t)idx + 35u) < ((uint32_t)data_size + 35u);
+            const int a = in ? (WIN_GUARD + idx) : 0;
+            const uint32_t sh = (uint32_t)o & 3u;  // == idx & 3 (width_step % 4 == 0); uniform in the warp
+            const uint32_t sel_lo = 0x8280u + sh * 0x0101u;  // bytes sh, sh+2 -> u16 lanes
+            const uint32_t sel_hi = 0x8381u + sh * 0x0101u;  // bytes sh+1, sh+3
+            win_accumulate(sgrid, a, sel_lo, sel_hi, hi_half, lo, hi);
+          }
+        }
+        // flush packed u16 partial sums into 32-bit accumulators
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          acc[4 * j + 0] += lo[j] & 0xffffu;
+          acc[4 * j + 1] += hi[j] & 0xffffu;
+          acc[4 * j + 2] += lo[j] >> 16;
+          acc[4 * j + 3] += hi[j] >> 16;
+        }
+      }
+      // ---- write this lane's row.  Slot j holds x-word j (lanes 0..15) or x-word (j+1)%8 (lanes 16..31) ----
+      const int iy = ty * 32 + lane;
+      if (iy < ny) {
+        int32_t *dst = bsums + ((size_t)k * ny + iy) * nx + tx * 32;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int xw = hi_half ? ((j + 1) & 7) : j;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int ix = xw * 4 + q;
+            if (tx * 32 + ix < nx) dst[ix] = (int32_t)acc[4 * j + q];
+          }
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with sgrid before the next match's copy is issued
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_reduce: the fp64 tail of CorrelateScan (Mapper.cpp:397-523): penalties, best response, per-cell maxima,
+// tie-averaged pose, positional covariance.  One CTA per match.  Candidate order of the reference is
+// (iy, ix, k) with linear index (iy*nx + ix)*na + k; ties are summed sequentially in that order when there are
+// at most RED_MAX_TIES of them (bit-identical to the reference), otherwise by a fixed-order tree.
+// ----------------------------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_TIES = 512;
+
+__device__ __forceinline__ double candidate_response(int32_t isum, int n, bool do_penalize, double sq_xy,
+                                                     double angle, double center_h, const b2s_matcher_params &p) {
+  double response = (double)isum;
+  response /= (double)((uint32_t)n * (uint32_t)GRID_OCCUPIED);  // Mapper.cpp:852
+  if (do_penalize && !double_equal(response, 0.0)) {
+    double dpen = 1.0 - (DISTANCE_PENALTY_GAIN * sq_xy / p.distance_variance_penalty);
+    dpen = dmax(dpen, p.minimum_distance_penalty);
+    double sq_a = (angle - center_h) * (angle - center_h);
+    double apen = 1.0 - (ANGLE_PENALTY_GAIN * sq_a / p.angle_variance_penalty);
+    apen = dmax(apen, p.minimum_angle_penalty);
+    response *= (dpen * apen);
+  }
+  return response;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+    k_reduce(const int32_t *__restrict__ sums, const double *__restrict__ centers, const int32_t *__restrict__ flags,
+             b2s_matcher_params p, b2s_search s, b2s_grid_info g, double scale, int n, int nx, int ny, int na,
+             double *__restrict__ probs_all, b2s_match_result *__restrict__ results) {
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int ncell = nx * ny;
+  b2s_match_result *res = results + b;
+  if (flags[b] & 2) {
+    if (tid == 0) res->status = B2S_ERR_OUT_OF_RANGE;
+    return;
+  }
+  const int32_t *bs = sums + (size_t)b * na * ncell;
+  const double cx = centers[3 * b], cy = centers[3 * b + 1], ch = centers[3 * b + 2];
+  const double start_x = -s.offset_x, start_y = -s.offset_y, start_a = ch - s.angle_offset;
+  const int pstep = (g.search_side + 7) & ~7;
+  double *probs = probs_all + (size_t)b * pstep * g.search_side;
+  const double pox = cx - s.offset_x, poy = cy - s.offset_y;  // Mapper.cpp:332-333
+
+  __shared__ double red[RED_THREADS];
+  __shared__ int s_err, s_count;
+  __shared__ int tie_idx[RED_MAX_TIES];
+  __shared__ double s_best;
+  if (tid == 0) { s_err = 0; s_count = 0; }
+  if (!s.fine)
+    for (int i = tid; i < pstep * g.search_side; i += RED_THREADS) probs[i] = 0.0;  // Clear (Mapper.cpp:329)
+  __syncthreads();
+
+  // ---- pass 1: best response + per-cell maxima (Mapper.cpp:430-451) ----
+  double best = -1.0;
+  for (int c = tid; c < ncell; c += RED_THREADS) {
+    const int iy = c / nx, ix = c % nx;
+    const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
+    const double sq = x * x + y * y;
+    double cell_best = -1.0;
+    for (int k = 0; k < na; k++) {
+      const double angle = start_a + (double)(uint32_t)k * s.angle_res;
+      const double r = candidate_response(bs[(size_t)k * ncell + c], n, s.do_penalize, sq, angle, ch, p);
+      cell_best = dmax(cell_best, r);
+    }
+    best = dmax(best, cell_best);
+    if (!s.fine) {
+      const int32_t px = world_to_grid_1(cx + x, pox, scale), py = world_to_grid_1(cy + y, poy, scale);
+      if (!(px >= 0 && px < g.search_side && py >= 0 && py < g.search_side)) {
+        s_err = 1;  // GetDataPointer -> GridIndex throws (Karto.h:4553-4557)
+      } else {
+        // distinct candidates can share a probs cell only on degenerate lattices; max is order-free
+        unsigned long long *pp = reinterpret_cast<unsigned long long *>(probs + px + (size_t)py * pstep);
+        atomicMax(pp, (unsigned long long)__double_as_longlong(dmax(cell_best, 0.0)));
+      }
+    }
+  }
+  red[tid] = best;
+  __syncthreads();
+  for (int d = RED_THREADS / 2; d > 0; d >>= 1) {
+    if (tid < d) red[tid] = dmax(red[tid], red[tid + d]);
+    __syncthreads();
+  }
+  if (tid == 0) s_best = red[0];
+  __syncthreads();
+  best = s_best;
+  if (s_err) {
+    if (tid == 0) res->status = B2S_ERR_OUT_OF_RANGE;
+    return;
+  }
+
+  // ---- pass 2: poses tied with the best (Mapper.cpp:455-487) ----
+  double ax = 0, ay = 0, tx = 0, ty = 0;
+  int cnt = 0;
+  for (int c = tid; c < ncell; c += RED_THREADS) {
+    const int iy = c / nx, ix = c % nx;
+    const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
+    const double sq = x * x + y * y;
+    for (int k = 0; k < na; k++) {
+      const double angle = start_a + (double)(uint32_t)k * s.angle_res;
+      const double r = candidate_response(bs[(size_t)k * ncell + c], n, s.do_penalize, sq, angle, ch, p);
+      if (double_equal(r, best)) {
+        const double h = normalize_angle(angle);
+        ax += cx + x; ay += cy + y; tx += cos(h); ty += sin(h);
+        cnt++;
+        int slot = atomicAdd(&s_count, 1);
+        if (slot < RED_MAX_TIES) tie_idx[slot] = c * na + k;
+      }
+    }
+  }
+  __syncthreads();
+  const int total = s_count;
+  double mean[3];
+  if (total == 0) {
+    if (tid == 0) res->status = B2S_ERR_NO_BEST_POSE;  // Mapper.cpp:484-487
+    return;
+  }
+  if (total <= RED_MAX_TIES) {
+    // rank-sort the tie list by reference linear index, then one thread sums in that exact order
+    __shared__ int sorted[RED_MAX_TIES];
+    for (int i = tid; i < total; i += RED_THREADS) {
+      int v = tie_idx[i], rank = 0;
+      for (int j = 0; j < total; j++) rank += (tie_idx[j] < v);
+      sorted[rank] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double sx = 0, sy = 0, cxs = 0, sys = 0;
+      for (int i = 0; i < total; i++) {
+        int v = sorted[i];
+        int c = v / na, k = v % na;
+        int iy = c / nx, ix = c % nx;
+        double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
+        double h = normalize_angle(start_a + (double)(uint32_t)k * s.angle_res);
+        sx += cx + x; sy += cy + y; cxs += cos(h); sys += sin(h);
+      }
+      red[0] = sx; red[1] = sy; red[2] = cxs; red[3] = sys;
+    }
+    __syncthreads();
+  } else {
+    // fixed-order tree reduction (deterministic; differs from the sequential sum only in the last bits)
+    __shared__ double r4[4][RED_THREADS];
+    r4[0][tid] = ax; r4[1][tid] = ay; r4[2][tid] = tx; r4[3][tid] = ty;
+    __syncthreads();
+    for (int d = RED_THREADS / 2; d > 0; d >>= 1) {
+      if (tid < d)
+        for (int q = 0; q < 4; q++) r4[q][tid] += r4[q][tid + d];
+      __syncthreads();
+    }
+    if (tid == 0) { red[0] = r4[0][0]; red[1] = r4[1][0]; red[2] = r4[2][0]; red[3] = r4[3][0]; }
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  {
+    double sx = red[0], sy = red[1], cxs = red[2], sys = red[3];
+    sx /= total; sy /= total; cxs /= total; sys /= total;
+    mean[0] = sx; mean[1] = sy; mean[2] = atan2(sys, cxs);
+  }
+  // ---- covariance ----
+  if (!s.fine) {
+    // ComputePositionalCovariance (Mapper.cpp:535-630), sequential in the reference's order
+    double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    int err = 0;
+    if (best < KT_TOLERANCE) {
+      cov[0] = MAX_VARIANCE; cov[4] = MAX_VARIANCE;
+      cov[8] = 4 * (s.angle_res * s.angle_res);
+    } else {
+      double axx = 0, axy = 0, ayy = 0, norm = 0;
+      const double dx = mean[0] - cx, dy = mean[1] - cy;
+      for (int iy = 0; iy < ny && !err; iy++) {
+        const double y = start_y + (double)(uint32_t)iy * s.res_y;
+        for (int ix = 0; ix < nx; ix++) {
+          const double x = start_x + (double)(uint32_t)ix * s.res_x;
+          const int32_t px = world_to_grid_1(cx + x, pox, scale), py = world_to_grid_1(cy + y, poy, scale);
+          if (!(px >= 0 && px < g.search_side && py >= 0 && py < g.search_side)) { err = 1; break; }
+          const double response = probs[px + (size_t)py * pstep];
+          if (response >= (best - 0.1)) {
+            norm += response;
+            axx += ((x - dx) * (x - dx) * response);
+            axy += ((x - dx) * (y - dy) * response);
+            ayy += ((y - dy) * (y - dy) * response);
+          }
+        }
+      }
+      if (norm > KT_TOLERANCE) {
+        double vxx = axx / norm, vxy = axy / norm, vyy = ayy / norm;
+        const double vthth = 4 * (s.angle_res * s.angle_res);
+        vxx = dmax(vxx, 0.1 * (s.res_x * s.res_x));
+        vyy = dmax(vyy, 0.1 * (s.res_y * s.res_y));
+        const double mult = 1.0 / best;
+        cov[0] = vxx * mult; cov[1] = vxy * mult; cov[3] = vxy * mult; cov[4] = vyy * mult; cov[8] = vthth;
+      }
+      if (double_equal(cov[0], 0.0)) cov[0] = MAX_VARIANCE;
+      if (double_equal(cov[4], 0.0)) cov[4] = MAX_VARIANCE;
+    }
+    if (err) { res->status = B2S_ERR_OUT_OF_RANGE; return; }
+    for (int i = 0; i < 9; i++) res->cov[i] = cov[i];
+  }
+  res->pose[0] = mean[0]; res->pose[1] = mean[1]; res->pose[2] = mean[2];
+  // un-clamped best goes through `response` for k_angular_cov; it clamps afterwards.  Coarse: clamp here.
+  res->response = s.fine ? best : (best > 1.0 ? 1.0 : best);  // Mapper.cpp:514-517
+  res->status = B2S_OK;
+  res->tie_count = total;
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_angular_cov: ComputeAngularCovariance (Mapper.cpp:641-692).  One CTA per match; warps over angles,
+// lanes over beams (GetResponse at the best cell), then thread 0 accumulates in angle order.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_angular_cov(const uint8_t *__restrict__ grids, size_t grid_pitch, b2s_grid_info g,
+                  const double *__restrict__ grid_off, const int32_t *__restrict__ lut,
+                  const double *__restrict__ centers, b2s_search s, double scale, int n, int na,
+                  b2s_match_result *__restrict__ results) {
+  const int b = blockIdx.x;
+  b2s_match_result *res = results + b;
+  if (res->status != B2S_OK) return;
+  extern __shared__ double s_resp[];  // [na]
+  __shared__ int32_t s_base;
+  __shared__ int s_bad;
+  const double best = res->response;
+  if (threadIdx.x == 0) {
+    int32_t gx = world_to_grid_1(res->pose[0], grid_off[2 * b], scale) + g.roi_x;
+    int32_t gy = world_to_grid_1(res->pose[1], grid_off[2 * b + 1], scale) + g.roi_y;
+    s_bad = !(gx >= 0 && gx < g.width && gy >= 0 && gy < g.height);
+    s_base = gx + gy * g.width_step;
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (threadIdx.x == 0) res->status = B2S_ERR_OUT_OF_RANGE;
+    return;
+  }
+  const uint8_t *grid = grids + (size_t)b * grid_pitch;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < na; k += nw) {
+    const int32_t *offs = lut + ((size_t)b * na + k) * n;
+    int32_t sum = 0;
+    for (int i = lane; i < n; i += 32) {
+      int32_t o = offs[i];
+      if (o == INVALID_SCAN) continue;
+      int32_t idx = (int32_t)((uint32_t)s_base + (uint32_t)o);
+      if (idx >= 0 && idx < g.data_size) sum += grid[idx];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) {
+      double r = (double)sum;
+      r /= (double)((uint32_t)n * (uint32_t)GRID_OCCUPIED);
+      s_resp[k] = r;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double ch = centers[3 * b + 2];
+  const double best_angle = normalize_angle_difference(res->pose[2], ch);
+  const double start = ch - s.angle_offset;
+  double norm = 0.0, acc = 0.0;
+  for (int k = 0; k < na; k++) {
+    const double angle = start + (double)(uint32_t)k * s.angle_res;
+    const double response = s_resp[k];
+    if (response >= (best - 0.1)) {
+      norm += response;
+      acc += ((angle - best_angle) * (angle - best_angle) * response);
+    }
+  }
+  if (norm > KT_TOLERANCE) {
+    if (acc < KT_TOLERANCE) acc = s.angle_res * s.angle_res;
+    acc /= norm;
+  } else {
+    acc = 1000 * (s.angle_res * s.angle_res);
+  }
+  res->cov[8] = acc;
+  if (best > 1.0) res->response = 1.0;
+}
+
+// fine-stage search centre = coarse mean (Mapper.cpp:278): copy result poses into the centre array
+__global__ void k_results_to_centers(const b2s_match_result *__restrict__ results, double *__restrict__ centers,
+                                     int batch) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  centers[3 * b] = results[b].pose[0];
+  centers[3 * b + 1] = results[b].pose[1];
+  centers[3 * b + 2] = results[b].pose[2];
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+
+static b2s_status layout_from_params(const b2s_matcher_params *p, b2s_grid_info *g) {
+  // ScanMatcher::Create (Mapper.cpp:126-172) + CorrelationGrid ctor (Mapper.h:920-1027) + Grid::Resize (Karto.h:4438)
+  if (p->resolution <= 0 || p->search_size <= 0 || p->smear_deviation < 0 || p->range_threshold <= 0)
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "ScanMatcher::Create: invalid parameters");
+  uint32_t side = cast_u32(kround(p->search_size / p->resolution) + 1);
+  uint32_t margin = cast_u32(ceil(p->range_threshold / p->resolution));
+  int32_t grid_size = (int32_t)(side + 2 * margin);
+  int32_t half_kernel = cast_i32(kround(2.0 * p->smear_deviation / p->resolution));
+  uint32_t border = (uint32_t)(half_kernel + 1);
+  g->width = grid_size + 2 * (int32_t)border;
+  g->height = grid_size + 2 * (int32_t)border;
+  g->width_step = (int32_t)(((size_t)g->width + 7) & ~(size_t)7);
+  g->data_size = g->width_step * g->height;
+  g->roi_x = g->roi_y = (int32_t)border;
+  g->roi_w = g->roi_h = grid_size;
+  g->kernel_size = 2 * half_kernel + 1;
+  g->search_side = (int32_t)side;
+  double resolution = 1.0 / (1.0 / p->resolution);
+  double min_dev = 0.5 * resolution, max_dev = 10 * resolution;  // Mapper.h:1041-1053 throws
+  if (!(p->smear_deviation >= min_dev && p->smear_deviation <= max_dev))
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "Mapper Error: smear deviation must be within [0.5, 10] x resolution");
+  return B2S_OK;
+}
+
+template <class T>
+static b2s_status dev_alloc(T **p, size_t count) {
+  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T)));
+  return B2S_OK;
+}
+
+template <class T>
+static b2s_status ensure_cap(T **p, size_t *cap, size_t count) {
+  if (count <= *cap && *p) return B2S_OK;
+  if (*p) B2S_CUDA_CHECK(cudaFree(*p));
+  *p = nullptr;
+  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T)));
+  *cap = count;
+  return B2S_OK;
+}
+
+static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool centers_on_device);
+
+}  // namespace b2s
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int b2s_abi_version(void) { return B2S_ABI_VERSION; }
+const char *b2s_last_error(void) { return b2s::last_error_ref().c_str(); }
+int b2s_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser *laser, int device, int max_batch,
+                              int max_base_scans, void *cuda_stream, b2s_matcher **out) {
+  if (!params || !laser || !out || max_batch <= 0 || laser->n_readings < 0 || max_base_scans < 0)
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_matcher_create: null/negative argument");
+  *out = nullptr;
+  b2s_grid_info g;
+  b2s_status st = layout_from_params(params, &g);
+  if (st) return st;
+  if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
+  B2S_CUDA_CHECK(cudaSetDevice(device));
+  b2s_matcher *m = new (std::nothrow) b2s_matcher();
+  if (!m) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
+  m->p = *params; m->l = *laser; m->g = g; m->device = device;
+  m->max_batch = max_batch; m->max_base = max_base_scans; m->n = laser->n_readings;
+  cudaDeviceProp prop;
+  B2S_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  m->num_sms = prop.multiProcessorCount;
+  m->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cuda_stream) {
+    m->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  } else {
+    B2S_CUDA_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    m->own_stream = true;
+  }
+  for (auto &e : m->ev) B2S_CUDA_CHECK(cudaEventCreate(&e));
+  // smear kernel on the host with glibc, exactly CorrelationGrid::CalculateKernel (Mapper.h:1032-1087)
+  {
+    int ks = g.kernel_size, half = ks / 2;
+    std::vector<uint8_t> K((size_t)ks * ks);
+    double resolution = 1.0 / (1.0 / params->resolution);
+    for (int i = -half; i <= half; i++)
+      for (int j = -half; j <= half; j++) {
+        double d = hypot(i * resolution, j * resolution);
+        double z = exp(-0.5 * pow(d / params->smear_deviation, 2));
+        uint32_t kv = cast_u32(kround(z * GRID_OCCUPIED));
+        K[(i + half) + ks * (j + half)] = (uint8_t)kv;
+        if ((i != 0 || j != 0) && kv >= (uint32_t)GRID_OCCUPIED) m->smear_degenerate = true;
+      }
+    st = dev_alloc(&m->d_kernel, K.size());
+    if (st) return st;
+    B2S_CUDA_CHECK(cudaMemcpy(m->d_kernel, K.data(), K.size(), cudaMemcpyHostToDevice));
+  }
+  const size_t B = (size_t)max_batch, N = (size_t)std::max(m->n, 1);
+  m->grid_pitch = (((size_t)g.data_size + 16) + 127) & ~(size_t)127;
+  const int pstep = (g.search_side + 7) & ~7;
+  if ((st = dev_alloc(&m->d_ranges, B * N))) return st;
+  if ((st = dev_alloc(&m->d_poses, B * 3))) return st;
+  if ((st = dev_alloc(&m->d_sensor, B * 3))) return st;
+  if ((st = dev_alloc(&m->d_pts, B * N * 2))) return st;
+  if ((st = dev_alloc(&m->d_local, B * N * 2))) return st;
+  if ((st = dev_alloc(&m->d_grids, B * m->grid_pitch))) return st;
+  if ((st = dev_alloc(&m->d_grid_off, B * 2))) return st;
+  if ((st = dev_alloc(&m->d_flags, B))) return st;
+  if ((st = dev_alloc(&m->d_probs, B * (size_t)pstep * g.search_side))) return st;
+  if ((st = dev_alloc(&m->d_centers, B * 3))) return st;
+  if ((st = dev_alloc(&m->d_results, B))) return st;
+  if ((st = dev_alloc(&m->d_work, 1))) return st;
+  B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m->h_results), B * sizeof(b2s_match_result)));
+  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_grids, 0, B * m->grid_pitch, m->stream));
+  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_results, 0, B * sizeof(b2s_match_result), m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return B2S_OK;
+}
+
+void b2s_matcher_destroy(b2s_matcher *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  void *ptrs[] = {m->d_kernel, m->d_ranges, m->d_poses, m->d_sensor, m->d_pts, m->d_local, m->d_grids,
+                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_sums, m->d_bases,
+                  m->d_flags, m->d_probs, m->d_centers, m->d_results, m->d_work};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (m->h_results) cudaFreeHost(m->h_results);
+  for (auto &e : m->ev)
+    if (e) cudaEventDestroy(e);
+  if (m->own_stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+b2s_status b2s_matcher_grid_info(const b2s_matcher *m, b2s_grid_info *out) {
+  if (!m || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  *out = m->g;
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which) {
+  if (!m || which < 0 || which > 2) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad kernel selector");
+  m->force_kernel = which;
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_sync(b2s_matcher *m) {
+  if (!m) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null handle");
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_set_scans(b2s_matcher *m, int batch, const double *ranges, const double *poses) {
+  if (!m || !ranges || !poses) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (batch <= 0 || batch > m->max_batch) B2S_FAIL(B2S_ERR_TOO_LARGE, "batch exceeds the handle's max_batch");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  m->batch = batch;
+  const size_t n = (size_t)m->n;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_ranges, ranges, sizeof(double) * batch * n, cudaMemcpyHostToDevice, m->stream));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_poses, poses, sizeof(double) * batch * 3, cudaMemcpyHostToDevice, m->stream));
+  k_scan_points<<<batch, 256, 0, m->stream>>>(m->d_ranges, m->d_poses, m->l, m->d_sensor, m->d_pts, m->d_local);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  m->scans_set = true;
+  m->grids_set = false;
+  m->have_sweep = false;
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_ranges, const double *base_poses) {
+  if (!m || n_base < 0 || (n_base > 0 && (!base_ranges || !base_poses))) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (!m->scans_set) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_set_scans must precede b2s_matcher_add_scans");
+  if (n_base > m->max_base) B2S_FAIL(B2S_ERR_TOO_LARGE, "n_base exceeds the handle's max_base_scans");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int B = m->batch;
+  const size_t n = (size_t)m->n;
+  const double resolution = 1.0 / (1.0 / m->p.resolution);
+  const double scale = 1.0 / m->p.resolution;  // CorrelationGrid ctor SetScale (Mapper.h:1020)
+  k_grid_offsets<<<ceil_div(B, 128), 128, 0, m->stream>>>(m->d_sensor, m->d_grid_off, B, m->g.roi_w, m->g.roi_h,
+                                                          resolution);
+  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_grids, 0, (size_t)B * m->grid_pitch, m->stream));  // Grid::Clear
+  m->n_base = n_base;
+  if (n_base > 0 && n > 0) {
+    const size_t need = (size_t)B * n_base;
+    if (need > m->base_cap) {
+      for (double **p : {&m->d_base_ranges, &m->d_base_poses, &m->d_base_pts})
+        if (*p) { B2S_CUDA_CHECK(cudaFree(*p)); *p = nullptr; }
+      b2s_status st;
+      if ((st = dev_alloc(&m->d_base_ranges, need * n))) return st;
+      if ((st = dev_alloc(&m->d_base_poses, need * 3))) return st;
+      if ((st = dev_alloc(&m->d_base_pts, need * n * 2))) return st;
+      m->base_cap = need;
+    }
+    B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_base_ranges, base_ranges, sizeof(double) * need * n, cudaMemcpyHostToDevice, m->stream));
+    B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_base_poses, base_poses, sizeof(double) * need * 3, cudaMemcpyHostToDevice, m->stream));
+    k_scan_points<<<(unsigned)need, 256, 0, m->stream>>>(m->d_base_ranges, m->d_base_poses, m->l, nullptr, m->d_base_pts, nullptr);
+    if (!m->smear_degenerate) {
+      size_t smem = n * (2 * sizeof(double) + 1) + 16;
+      if (smem > 48 * 1024)
+        B2S_CUDA_CHECK(cudaFuncSetAttribute(k_add_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_add_scan<<<(unsigned)need, 128, smem, m->stream>>>(m->d_base_pts, m->d_sensor, m->d_grid_off, m->d_grids,
+                                                           m->grid_pitch, m->d_kernel, m->g, scale, (int)n, n_base);
+    } else {
+      uint8_t *scratch = nullptr;
+      B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)B * n, m->stream));
+      k_add_scans_seq<<<ceil_div(B, 32), 32, 0, m->stream>>>(m->d_base_pts, m->d_sensor, m->d_grid_off, m->d_grids,
+                                                             m->grid_pitch, m->d_kernel, m->g, scale, (int)n, n_base,
+                                                             B, scratch);
+      B2S_CUDA_CHECK(cudaFreeAsync(scratch, m->stream));
+    }
+    B2S_CUDA_CHECK(cudaGetLastError());
+  }
+  m->grids_set = true;
+  m->have_sweep = false;
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const double *offsets) {
+  if (!m || !grids || !offsets) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (!m->scans_set) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_set_scans must precede b2s_matcher_set_grids");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int B = m->batch;
+  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_grids, 0, (size_t)B * m->grid_pitch, m->stream));
+  B2S_CUDA_CHECK(cudaMemcpy2DAsync(m->d_grids, m->grid_pitch, grids, (size_t)m->g.data_size, (size_t)m->g.data_size, B,
+                                   cudaMemcpyHostToDevice, m->stream));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_grid_off, offsets, sizeof(double) * 2 * B, cudaMemcpyHostToDevice, m->stream));
+  m->grids_set = true;
+  m->have_sweep = false;
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_get_grid(b2s_matcher *m, int b, uint8_t *out_bytes, double out_offset[2]) {
+  if (!m || b < 0 || b >= m->batch || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "no grid for this match");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  if (out_bytes)
+    B2S_CUDA_CHECK(cudaMemcpyAsync(out_bytes, m->d_grids + (size_t)b * m->grid_pitch, (size_t)m->g.data_size,
+                                   cudaMemcpyDeviceToHost, m->stream));
+  if (out_offset)
+    B2S_CUDA_CHECK(cudaMemcpyAsync(out_offset, m->d_grid_off + 2 * b, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_get_point_readings(b2s_matcher *m, int b, double *out_xy) {
+  if (!m || !out_xy || b < 0 || b >= m->batch || !m->scans_set) B2S_FAIL(B2S_ERR_BAD_STATE, "no scan for this match");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(out_xy, m->d_pts + (size_t)b * m->n * 2, sizeof(double) * 2 * m->n,
+                                 cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_compute_offsets(b2s_matcher *m, int b, double angle_center, double angle_offset,
+                                       double angle_res, int32_t *out, int32_t *out_n_angles) {
+  if (!m || !out || b < 0 || b >= m->batch) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad argument");
+  if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
+  if (angle_res == 0.0) B2S_FAIL(B2S_ERR_BAD_PARAMS, "angle resolution must be non-zero");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int na = n_steps(angle_offset, angle_res);
+  const size_t n = (size_t)m->n;
+  int32_t *tmp = nullptr;
+  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&tmp), sizeof(int32_t) * std::max<size_t>(na * n, 1)));
+  // one-match launch on the slices of match b
+  k_offsets<<<na, 256, 0, m->stream>>>(m->d_ranges + (size_t)b * n, m->d_local + (size_t)b * n * 2,
+                                       m->d_grid_off + 2 * b, nullptr, 0, angle_center, 1, angle_offset, angle_res, na,
+                                       (int)n, m->g.width_step, 1.0 / m->p.resolution, tmp);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, sizeof(int32_t) * na * n, cudaMemcpyDeviceToHost, m->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  cudaFree(tmp);
+  B2S_CUDA_CHECK(e);
+  if (out_n_angles) *out_n_angles = na;
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, const b2s_search *search,
+                                      b2s_match_result *results) {
+  if (!m || !centers || !search || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int B = m->batch;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_centers, centers, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, m->stream));
+  if (search->fine) {  // rCovariance is IN/OUT for the fine stage (Mapper.cpp:648)
+    for (int b = 0; b < B; b++) m->h_results[b] = results[b];
+    B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_results, m->h_results, sizeof(b2s_match_result) * B, cudaMemcpyHostToDevice, m->stream));
+  }
+  b2s_status st = run_correlate(m, search, true);
+  if (st) return st;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  std::memcpy(results, m->h_results, sizeof(b2s_match_result) * B);
+  for (int i = 1; i < 3; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, m->ev[i - 1], m->ev[i]) == cudaSuccess) m->last_ms[i - 1] = ms;
+  }
+  {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->last_ms[2] = ms;
+  }
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_match_scan(b2s_matcher *m, int do_penalize, int do_refine, b2s_match_result *results) {
+  if (!m || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int B = m->batch;
+  if (m->n == 0) {  // Mapper.cpp:199-209: no readings -> pose passthrough, maximum covariance
+    std::vector<double> sp((size_t)3 * B);
+    B2S_CUDA_CHECK(cudaMemcpyAsync(sp.data(), m->d_sensor, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, m->stream));
+    B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    for (int b = 0; b < B; b++) {
+      std::memset(&results[b], 0, sizeof(b2s_match_result));
+      for (int i = 0; i < 3; i++) results[b].pose[i] = sp[3 * b + i];
+      results[b].cov[0] = MAX_VARIANCE; results[b].cov[4] = MAX_VARIANCE;
+      results[b].cov[8] = 4 * (m->p.coarse_angle_resolution * m->p.coarse_angle_resolution);
+    }
+    return B2S_OK;
+  }
+  const double resolution = 1.0 / (1.0 / m->p.resolution);
+  b2s_search coarse;
+  coarse.offset_x = 0.5 * ((double)m->g.search_side - 1) * resolution;  // Mapper.cpp:228-230
+  coarse.offset_y = coarse.offset_x;
+  coarse.res_x = 2 * resolution;  // Mapper.cpp:233-234
+  coarse.res_y = 2 * resolution;
+  coarse.angle_offset = m->p.coarse_search_angle_offset;
+  coarse.angle_res = m->p.coarse_angle_resolution;
+  coarse.do_penalize = do_penalize;
+  coarse.fine = 0;
+  // search centre = scan (sensor) pose (Mapper.cpp:237)
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_centers, m->d_sensor, sizeof(double) * 3 * B, cudaMemcpyDeviceToDevice, m->stream));
+  b2s_status st = run_correlate(m, &coarse, true);
+  if (st) return st;
+  if (m->p.use_response_expansion) {  // Mapper.cpp:242-272 — applied to the matches whose response is ~0
+    B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
+    B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    std::vector<b2s_match_result> keep(m->h_results, m->h_results + B);
+    std::vector<char> pending(B, 0);
+    bool any = false;
+    for (int b = 0; b < B; b++)
+      if (keep[b].status == B2S_OK && double_equal(keep[b].response, 0.0)) { pending[b] = 1; any = true; }
+    double new_off = m->p.coarse_search_angle_offset;
+    for (int it = 0; it < 3 && any; it++) {
+      new_off += 20 * 0.01745329251994329577;  // math::DegreesToRadians(20)
+      b2s_search ex = coarse;
+      ex.angle_offset = new_off;
+      B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_centers, m->d_sensor, sizeof(double) * 3 * B, cudaMemcpyDeviceToDevice, m->stream));
+      st = run_correlate(m, &ex, true);
+      if (st) return st;
+      B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
+      B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+      any = false;
+      for (int b = 0; b < B; b++) {
+        if (!pending[b]) continue;
+        keep[b] = m->h_results[b];
+        if (keep[b].status != B2S_OK || !double_equal(keep[b].response, 0.0)) pending[b] = 0;
+        else any = true;
+      }
+    }
+    for (int b = 0; b < B; b++) m->h_results[b] = keep[b];
+    B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_results, m->h_results, sizeof(b2s_match_result) * B, cudaMemcpyHostToDevice, m->stream));
+  }
+  if (do_refine) {  // Mapper.cpp:274-282
+    b2s_search fine;
+    fine.offset_x = coarse.res_x * 0.5;
+    fine.offset_y = coarse.res_y * 0.5;
+    fine.res_x = resolution;
+    fine.res_y = resolution;
+    fine.angle_offset = 0.5 * m->p.coarse_angle_resolution;
+    fine.angle_res = m->p.fine_search_angle_offset;
+    fine.do_penalize = do_penalize;
+    fine.fine = 1;
+    k_results_to_centers<<<ceil_div(B, 128), 128, 0, m->stream>>>(m->d_results, m->d_centers, B);
+    st = run_correlate(m, &fine, true);
+    if (st) return st;
+  }
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  std::memcpy(results, m->h_results, sizeof(b2s_match_result) * B);
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_match_scan_host(b2s_matcher *m, int batch, const double *ranges, const double *poses,
+                                       int n_base, const double *base_ranges, const double *base_poses,
+                                       int do_penalize, int do_refine, b2s_match_result *results) {
+  b2s_status st = b2s_matcher_set_scans(m, batch, ranges, poses);
+  if (st) return st;
+  st = b2s_matcher_add_scans(m, n_base, base_ranges, base_poses);
+  if (st) return st;
+  return b2s_matcher_match_scan(m, do_penalize, do_refine, results);
+}
+
+b2s_status b2s_matcher_get_response_sums(b2s_matcher *m, int b, int32_t *out, int32_t dims[3]) {
+  if (!m || !out || b < 0 || b >= m->batch) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad argument");
+  if (!m->have_sweep) B2S_FAIL(B2S_ERR_BAD_STATE, "no sweep has been run");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int nx = m->last.nx, ny = m->last.ny, na = m->last.na;
+  std::vector<int32_t> tmp((size_t)nx * ny * na);
+  B2S_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), m->d_sums + (size_t)b * nx * ny * na, sizeof(int32_t) * tmp.size(),
+                                 cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  // device layout [k][iy][ix] -> reference loop order [iy][ix][k]
+  for (int k = 0; k < na; k++)
+    for (int c = 0; c < nx * ny; c++) out[(size_t)c * na + k] = tmp[(size_t)k * nx * ny + c];
+  if (dims) { dims[0] = ny; dims[1] = nx; dims[2] = na; }
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_last_timing(b2s_matcher *m, double out[4]) {
+  if (!m || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  out[0] = m->last_ms[0]; out[1] = m->last_ms[1]; out[2] = m->last_ms[2]; out[3] = (double)m->last_path;
+  return B2S_OK;
+}
+
+}  // extern "C"
+
+namespace b2s {
+
+// One CorrelateScan over the batch with centres already in d_centers.  Results stay in d_results.
+static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*centers_on_device*/) {
+  if (s->angle_res == 0.0 || s->res_x == 0.0 || s->res_y == 0.0)
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "search resolutions must be non-zero");  // assert at Mapper.cpp:319
+  const int B = m->batch, n = m->n;
+  const int nx = n_steps(s->offset_x, s->res_x), ny = n_steps(s->offset_y, s->res_y);
+  const int na = n_steps(s->angle_offset, s->angle_res);
+  if (nx <= 0 || ny <= 0 || na <= 0 || (long long)nx * ny * na > (1ll << 28))
+    B2S_FAIL(B2S_ERR_TOO_LARGE, "search volume too large");
+  const double scale = 1.0 / m->p.resolution;
+  const int ncell = nx * ny;
+  b2s_status st;
+  if ((st = ensure_cap(&m->d_lut, &m->lut_cap, (size_t)B * na * std::max(n, 1)))) return st;
+  if ((st = ensure_cap(&m->d_sums, &m->sums_cap, (size_t)B * na * ncell))) return st;
+  if ((st = ensure_cap(&m->d_bases, &m->bases_cap, (size_t)B * ncell))) return st;
+
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev[0], m->stream));
+  k_offsets<<<B * na, 256, 0, m->stream>>>(m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, 3, 0.0, 0,
+                                           s->angle_offset, s->angle_res, na, n, m->g.width_step, scale, m->d_lut);
+  k_bases<<<B, 256, 0, m->stream>>>(m->d_centers, m->d_grid_off, *s, m->g, scale, nx, ny, m->d_bases, m->d_flags);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
+
+  // ---- response sweep ----
+  const int copy_bytes = (m->g.data_size + 15) & ~15;
+  const size_t win_smem = (size_t)copy_bytes + 2 * WIN_GUARD;
+  const bool stride1 = (s->res_x == 1.0 / (1.0 / m->p.resolution) || s->res_x == m->p.resolution) &&
+                       (s->res_y == 1.0 / (1.0 / m->p.resolution) || s->res_y == m->p.resolution);
+  bool use_window = stride1 && win_smem + 1024 <= (size_t)m->smem_optin && (m->g.width_step % 4) == 0 && n > 0;
+  if (m->force_kernel == 1) use_window = false;
+  if (m->force_kernel == 2 && !(win_smem + 1024 <= (size_t)m->smem_optin))
+    B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but the grid does not fit in shared memory");
+  if (m->force_kernel == 2) use_window = true;
+  const dim3 ggrid((unsigned)ceil_div(ncell, 8), (unsigned)B);
+  if (use_window) {
+    B2S_CUDA_CHECK(cudaMemsetAsync(m->d_work, 0, sizeof(int), m->stream));
+    B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
+    const int ctas = std::min(B, m->num_sms);
+    k_sweep_window<<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
+                                                               m->d_lut, m->d_bases, m->d_flags, B, n, na, nx, ny,
+                                                               m->g.width_step, m->d_sums, m->d_work);
+    // matches whose lattice is not the regular stride-1 raster (a centre exactly on a rounding tie) fall through
+    k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, m->d_lut, m->d_bases,
+                                                  m->d_flags, 1, n, na, ncell, m->d_sums);
+    m->last_path = 2;
+  } else {
+    k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, m->d_lut, m->d_bases,
+                                                  m->d_flags, 0, n, na, ncell, m->d_sums);
+    m->last_path = 1;
+  }
+  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev[2], m->stream));
+
+  // ---- fp64 tail ----
+  k_reduce<<<B, RED_THREADS, 0, m->stream>>>(m->d_sums, m->d_centers, m->d_flags, m->p, *s, m->g, scale, n, nx, ny, na,
+                                             m->d_probs, m->d_results);
+  if (s->fine) {
+    size_t sm = sizeof(double) * (size_t)na;
+    if (sm > 48 * 1024) B2S_FAIL(B2S_ERR_TOO_LARGE, "too many angles for the angular-covariance kernel");
+    k_angular_cov<<<B, 256, sm, m->stream>>>(m->d_grids, m->grid_pitch, m->g, m->d_grid_off, m->d_lut, m->d_centers, *s,
+                                             scale, n, na, m->d_results);
+  }
+  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev[3], m->stream));
+  m->last.nx = nx; m->last.ny = ny; m->last.na = na;
+  m->last_search = *s;
+  m->have_sweep = true;
+  return B2S_OK;
+}
+
+}  // namespace b2s
