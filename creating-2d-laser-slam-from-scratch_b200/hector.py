@@ -1,0 +1,105 @@
+"""ctypes harness over the C ABI — K2a (Hector log-odds map update) and K3 (Hector Gauss-Newton scan matching)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .matcher import check, lib
+
+_bound = False
+
+
+def _bind():
+    global _bound
+    L = lib()
+    if _bound:
+        return L
+    vp, fp = C.c_void_p, C.POINTER(C.c_float)
+    L.b2s_hector_map_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp, C.POINTER(vp)]
+    L.b2s_hector_map_destroy.argtypes = [vp]
+    L.b2s_hector_map_destroy.restype = None
+    L.b2s_hector_map_set_factors.argtypes = [vp, C.c_float, C.c_float]
+    L.b2s_hector_map_update_by_scan.argtypes = [vp, fp, C.c_int, fp, fp]
+    L.b2s_hector_map_match_data.argtypes = [vp, fp, C.c_int, fp, C.c_int, fp, fp]
+    L.b2s_hector_map_copy.argtypes = [vp, fp, C.POINTER(C.c_int32)]
+    L.b2s_hector_map_copy_ros.argtypes = [vp, C.POINTER(C.c_int8)]
+    L.b2s_hector_map_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    _bound = True
+    return L
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class HectorMap:
+    """Stand-in for hectorslam::GridMap (+ its OccGridMapUtil / ScanMatcher) on one pyramid level."""
+
+    def __init__(self, size_x, size_y, resolution, start_x=0.5, start_y=0.5, device=0, stream=None):
+        self.L = _bind()
+        self.sx, self.sy, self.resolution = size_x, size_y, resolution
+        self.h = C.c_void_p()
+        check(self.L.b2s_hector_map_create(size_x, size_y, resolution, start_x, start_y, device,
+                                           C.c_void_p(stream) if stream else None, C.byref(self.h)))
+
+    def set_factors(self, update_free, update_occupied):
+        check(self.L.b2s_hector_map_set_factors(self.h, update_free, update_occupied))
+
+    def update_by_scan(self, points, origo, world_pose):
+        p = f32(points).reshape(-1, 2)
+        check(self.L.b2s_hector_map_update_by_scan(self.h, _f(p), len(p), _f(f32(origo)), _f(f32(world_pose))))
+
+    def match_data(self, points, begin_world_pose, max_iterations):
+        p = f32(points).reshape(-1, 2)
+        pose, cov = np.zeros(3, np.float32), np.zeros(9, np.float32)
+        check(self.L.b2s_hector_map_match_data(self.h, _f(p), len(p), _f(f32(begin_world_pose)), max_iterations,
+                                               _f(pose), _f(cov)))
+        return pose, cov.reshape(3, 3)
+
+    def cells(self):
+        lo = np.zeros(self.sx * self.sy, np.float32)
+        ui = np.zeros(self.sx * self.sy, np.int32)
+        check(self.L.b2s_hector_map_copy(self.h, _f(lo), ui.ctypes.data_as(C.POINTER(C.c_int32))))
+        return lo.reshape(self.sy, self.sx), ui.reshape(self.sy, self.sx)
+
+    def ros_map(self):
+        out = np.zeros((self.sy, self.sx), np.int8)
+        check(self.L.b2s_hector_map_copy_ros(self.h, out.ctypes.data_as(C.POINTER(C.c_int8))))
+        return out
+
+    def last_timing(self):
+        out = np.zeros(2)
+        check(self.L.b2s_hector_map_last_timing(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return dict(update_ms=out[0], match_ms=out[1])
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.b2s_hector_map_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scan_to_data_container(ranges, laser, resolution, max_dist=20.0, min_dist=0.4):
+    """HectorMappingRos::rosPointCloudToDataContainer (hector_slam.cc:320-362) for a laser mounted at the base_link
+    origin: beam endpoints in the laser frame (float32), filtered by squared distance, scaled by 1/resolution."""
+    i = np.arange(laser.n_readings)
+    ang = (laser.min_angle + i * laser.angular_resolution).astype(np.float32)
+    r = np.asarray(ranges, dtype=np.float32)
+    ok = np.isfinite(r)
+    x = np.where(ok, r * np.cos(ang), 0).astype(np.float32)
+    y = np.where(ok, r * np.sin(ang), 0).astype(np.float32)
+    d2 = x * x + y * y
+    keep = ok & (d2 > np.float32(min_dist * min_dist)) & (d2 < np.float32(max_dist * max_dist))
+    keep &= ~((x < 0) & (d2 < 0.5))
+    scale = np.float32(1.0) / np.float32(resolution)
+    return np.stack([x[keep] * scale, y[keep] * scale], axis=1).astype(np.float32)

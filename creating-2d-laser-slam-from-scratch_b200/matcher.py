@@ -3,7 +3,7 @@
 Mirrors the reference's ScanMatcher call sequence (Mapper.cpp:126-523) for batches:
     m = ScanMatcher(params, laser, max_batch);  m.set_scans(ranges, poses);  m.add_scans(base_ranges, base_poses)
     results = m.correlate_scan(centers, search)   |   results = m.match_scan()
-This module never touches oracle/: if libb200slam.so or a CUDA device is missing it raises.
+There is no CPU path here: if libb200slam.so or a CUDA device is missing every call raises.
 """
 from __future__ import annotations
 

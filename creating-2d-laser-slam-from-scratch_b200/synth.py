@@ -2,7 +2,7 @@
 
 Workload generator shared by tests/, bench.py and the golden-fixture script.  It only
 produces INPUT data (range readings + poses); it never computes a result that is compared,
-so it is neither oracle nor product.  Everything is seeded (numpy PCG64) and double precision.
+so it is neither checker nor product.  Everything is seeded (numpy PCG64) and double precision.
 
 Sensor model = the reference's `LaserRangeFinder_Hokuyo_UTM_30LX` preset
 (/root/reference/lesson6/lib/open_karto/include/open_karto/Karto.h:4048-4065):

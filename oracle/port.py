@@ -157,3 +157,90 @@ def trace_line(w, h, x0, y0, x1, y1):
 
 def result_tuple(res):
     return res.response, np.array(res.pose[:]), np.array(res.cov[:]).reshape(3, 3)
+
+
+# ---------------------------------------------------------------- GMapping (gmapping_oracle.c)
+
+class PortGMap:
+    def __init__(self, xmin=-40.0, ymin=-40.0, xmax=40.0, ymax=40.0, delta=0.05):
+        self.L = lib()
+        self.bounds = (xmin, ymin, xmax, ymax, delta)
+        self.cx, self.cy = (xmin + xmax) / 2.0, (ymin + ymax) / 2.0
+        self.layout = np.zeros(4, np.int32)
+        self.L.orc_gmap_layout(C.c_double(self.cx), C.c_double(self.cy), C.c_double(xmin), C.c_double(ymin),
+                               C.c_double(xmax), C.c_double(ymax), C.c_double(delta), _p(self.layout, C.c_int32))
+        self.size_x, self.size_y = int(self.layout[0]), int(self.layout[1])
+        c = self.size_x * self.size_y
+        self.n, self.visits = np.zeros(c, np.int32), np.zeros(c, np.int32)
+        self.acc_x, self.acc_y = np.zeros(c, np.float32), np.zeros(c, np.float32)
+
+    def compute_map(self, ranges, angles, laser_xy=(0.0, 0.0), max_range=30 - 0.01, max_urange=25.0):
+        r, a = f64(ranges), f64(angles)
+        return self.L.orc_gmap_compute_map(C.c_double(self.cx), C.c_double(self.cy), C.c_double(self.bounds[4]),
+                                           _p(self.layout, C.c_int32), _d(r), _d(a), len(r), C.c_double(laser_xy[0]),
+                                           C.c_double(laser_xy[1]), C.c_double(max_range), C.c_double(max_urange),
+                                           _p(self.n, C.c_int32), _p(self.visits, C.c_int32), _p(self.acc_x, C.c_float),
+                                           _p(self.acc_y, C.c_float))
+
+    def cells(self):
+        sh = (self.size_y, self.size_x)
+        return self.n.reshape(sh), self.visits.reshape(sh), self.acc_x.reshape(sh), self.acc_y.reshape(sh)
+
+    def ros_map(self, occ_thresh=0.25):
+        xmin, ymin, xmax, ymax, delta = self.bounds
+        w, h = int((xmax - xmin) / delta), int((ymax - ymin) / delta)
+        out = np.zeros((h, w), np.int8)
+        self.L.orc_gmap_ros(_p(self.layout, C.c_int32), _p(self.n, C.c_int32), _p(self.visits, C.c_int32),
+                            C.c_double(occ_thresh), w, h, _p(out, C.c_int8))
+        return out
+
+
+def gmap_grid_line(x0, y0, x1, y1):
+    cap = abs(x1 - x0) + abs(y1 - y0) + 4
+    out = np.zeros((cap, 2), np.int32)
+    n = lib().orc_gmap_grid_line(x0, y0, x1, y1, _p(out, C.c_int32), cap)
+    return out[:n].copy()
+
+
+# ---------------------------------------------------------------- Hector (hector_oracle.c) — PARITY UNPINNED
+
+class PortHectorMap:
+    def __init__(self, size_x, size_y, resolution, start_x=0.5, start_y=0.5):
+        self.L = lib()
+        self.L.orc_hmap_create.restype = C.c_void_p
+        self.L.orc_hmap_update_by_scan.restype = C.c_long
+        self.sx, self.sy = size_x, size_y
+        self.h = C.c_void_p(self.L.orc_hmap_create(size_x, size_y, C.c_float(resolution), C.c_float(start_x),
+                                                   C.c_float(start_y)))
+
+    def set_factors(self, update_free, update_occupied):
+        self.L.orc_hmap_set_factors(self.h, C.c_float(update_free), C.c_float(update_occupied))
+
+    def update_by_scan(self, points, origo, world_pose):
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 2)
+        o, w = np.ascontiguousarray(origo, np.float32), np.ascontiguousarray(world_pose, np.float32)
+        return self.L.orc_hmap_update_by_scan(self.h, _p(p, C.c_float), len(p), _p(o, C.c_float), _p(w, C.c_float))
+
+    def match_data(self, points, begin_world_pose, max_iterations):
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 2)
+        b = np.ascontiguousarray(begin_world_pose, np.float32)
+        pose, cov = np.zeros(3, np.float32), np.zeros(9, np.float32)
+        self.L.orc_hmap_match_data(self.h, _p(p, C.c_float), len(p), _p(b, C.c_float), max_iterations,
+                                   _p(pose, C.c_float), _p(cov, C.c_float))
+        return pose, cov.reshape(3, 3)
+
+    def cells(self):
+        lo, ui = np.zeros(self.sx * self.sy, np.float32), np.zeros(self.sx * self.sy, np.int32)
+        self.L.orc_hmap_copy(self.h, _p(lo, C.c_float), _p(ui, C.c_int32))
+        return lo.reshape(self.sy, self.sx), ui.reshape(self.sy, self.sx)
+
+    def close(self):
+        if self.h:
+            self.L.orc_hmap_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

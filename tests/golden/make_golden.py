@@ -136,12 +136,38 @@ def trace_lines():
                         cells=np.concatenate(cells).astype(np.int16))
 
 
+def gmapping_case():
+    """lesson4 GMapping ComputeMap through the reference's real grid headers (oracle/ref_gmapping.cpp)."""
+    from oracle import ref_gmapping as rg
+    laser = synth.Laser()
+    out = {}
+    # the node computes beam angles in float32 (angle_min + i * angle_increment are float32 message fields)
+    ang = (np.float32(laser.min_angle) + np.arange(1081, dtype=np.float32) * np.float32(laser.angular_resolution))
+    out["angles"] = ang.astype(np.float64)
+    for k, (seed, bounds, lxy) in enumerate([(3, (-40.0, -40.0, 40.0, 40.0, 0.05), (0.0, 0.0)),
+                                             (4, (-20.0, -20.0, 30.1, 29.9, 0.05), (1.3, -0.7))]):
+        mc = synth.make_match_case(seed, dropout=0.02)
+        r = mc.ranges.astype(np.float32).astype(np.float64)  # LaserScan.ranges are float32
+        r[5], r[9], r[11] = 0.0, 28.0, 35.0
+        m = rg.RefGMap(*bounds)
+        assert m.compute_map(r, out["angles"], lxy) == 0
+        n, v, ax, ay, occ = m.cells()
+        ys, xs = np.nonzero(v)
+        out.update({f"c{k}_ranges": r, f"c{k}_bounds": np.array(bounds), f"c{k}_laser_xy": np.array(lxy),
+                    f"c{k}_size": np.array([m.size_x, m.size_y], np.int32),
+                    f"c{k}_cells_yx": np.stack([ys, xs], 1).astype(np.int16), f"c{k}_n": n[ys, xs], f"c{k}_visits": v[ys, xs],
+                    f"c{k}_acc_x": ax[ys, xs], f"c{k}_acc_y": ay[ys, xs]})
+        m.close()
+    np.savez_compressed(os.path.join(HERE, "gmapping.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref.available(), "run `make -C oracle ref` first"
     small_case()
     cfg1_case()
     multi_base_case()
     trace_lines()
+    gmapping_case()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,126 @@
+"""GPU parity tests for K2a (Hector log-odds update), K3 (Hector Gauss-Newton) and K2b (GMapping counters) through
+the C ABI.  Gates: traversed cells / update indices / integer counters bit-exact; log-odds floats bit-exact (same
+float32 operations in the reference's order); GN pose within 1e-4; GMapping acc floats within float rounding.
+The Hector oracle is 'parity unpinned' (Eigen unavailable): these tests pin the CUDA path to the restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def mods(pkg):
+    assert pkg.load("matcher").device_count() > 0
+    return pkg.load("hector"), pkg.load("gmapping")
+
+
+def test_hector_update_stream(pkg, mods):
+    """60-scan trajectory into a 1024^2 map (node settings: update factors 0.4 / 0.9), cell-for-cell identical
+    log-odds and update indices after every 10th scan, incl. the <50 clamp region after repeated hits."""
+    H, _ = mods
+    laser = pkg.synth.Laser()
+    world, poses, ranges = pkg.synth.make_trajectory(4, 60, laser, step_xy=0.1, step_th_deg=3)
+    g, c = H.HectorMap(1024, 1024, 0.05), port.PortHectorMap(1024, 1024, 0.05)
+    g.set_factors(0.4, 0.9)
+    c.set_factors(0.4, 0.9)
+    for i in range(60):
+        pts = H.scan_to_data_container(ranges[i], laser, 0.05)
+        wp = poses[i].astype(np.float32)
+        for _ in range(1 if i < 50 else 4):  # hammer the last poses to reach the clamp
+            g.update_by_scan(pts, (0.0, 0.0), wp)
+            c.update_by_scan(pts, (0.0, 0.0), wp)
+        if i % 10 == 9:
+            (glo, gui), (clo, cui) = g.cells(), c.cells()
+            assert np.array_equal(gui, cui)
+            assert np.array_equal(glo, clo)
+    assert glo.max() >= 50.0
+    ros = g.ros_map()
+    assert ((ros == 0) == (clo < 0)).all() and ((ros == 100) == (clo > 0)).all() and ((ros == -1) == (clo == 0)).all()
+    assert g.last_timing()["update_ms"] > 0
+
+
+def test_hector_origo_offset_and_out_of_map(pkg, mods):
+    H, _ = mods
+    laser = pkg.synth.Laser()
+    mc = pkg.synth.make_match_case(9)
+    pts = H.scan_to_data_container(mc.ranges, laser, 0.1)
+    for size, start in ((256, (0.5, 0.5)), (128, (0.3, 0.7)), (64, (0.5, 0.5))):  # small maps: many beams leave the map
+        g, c = H.HectorMap(size, size, 0.1, *start), port.PortHectorMap(size, size, 0.1, *start)
+        wp = np.array([0.7, -0.4, 2.1], np.float32)
+        g.update_by_scan(pts, (2.0, -1.5), wp)
+        c.update_by_scan(pts, (2.0, -1.5), wp)
+        assert np.array_equal(g.cells()[0], c.cells()[0]) and np.array_equal(g.cells()[1], c.cells()[1])
+
+
+def test_hector_match_data(pkg, mods):
+    """K3: three pyramid levels like MapRepMultiMap::matchData (3 / 3 / 5 extra iterations), level by level."""
+    H, _ = mods
+    laser = pkg.synth.Laser()
+    world, poses, ranges = pkg.synth.make_trajectory(6, 12, laser, step_xy=0.08, step_th_deg=2)
+    levels = [(1024, 0.05), (512, 0.1), (256, 0.2)]
+    gm = [H.HectorMap(s, s, r) for s, r in levels]
+    cm = [port.PortHectorMap(s, s, r) for s, r in levels]
+    for m in gm + cm:
+        m.set_factors(0.4, 0.9)
+    for i in range(11):
+        for (s, r), g, c in zip(levels, gm, cm):
+            pts = H.scan_to_data_container(ranges[i], laser, r)
+            g.update_by_scan(pts, (0, 0), poses[i].astype(np.float32))
+            c.update_by_scan(pts, (0, 0), poses[i].astype(np.float32))
+    est_g = est_c = (poses[10] + np.array([0.04, -0.03, 0.02])).astype(np.float32)
+    for lvl in (2, 1, 0):
+        pts = H.scan_to_data_container(ranges[11], laser, levels[lvl][1])
+        est_g, cov_g = gm[lvl].match_data(pts, est_g, 5 if lvl == 0 else 3)
+        est_c, cov_c = cm[lvl].match_data(pts, est_c, 5 if lvl == 0 else 3)
+        assert np.allclose(est_g, est_c, rtol=0, atol=1e-4), (lvl, est_g, est_c)
+        assert np.allclose(cov_g, cov_c, rtol=1e-3, atol=1e-2)
+    assert np.abs(est_g[:2] - poses[11][:2]).max() < 0.05
+    assert gm[0].last_timing()["match_ms"] > 0
+    e, _ = gm[0].match_data(np.zeros((0, 2), np.float32), est_g, 5)
+    assert np.array_equal(e, est_g)
+
+
+def test_gmapping_golden_and_oracle(pkg, mods):
+    _, GM = mods
+    g = np.load(os.path.join(G, "gmapping.npz"))
+    for k in range(2):
+        b = g[f"c{k}_bounds"]
+        m = GM.GMap(*b)
+        assert [m.size_x, m.size_y] == list(g[f"c{k}_size"])
+        m.compute_map(g[f"c{k}_ranges"], g["angles"], tuple(g[f"c{k}_laser_xy"]))
+        n, v, ax, ay = m.cells()
+        ys, xs = np.nonzero(v)
+        assert np.array_equal(np.stack([ys, xs], 1), g[f"c{k}_cells_yx"])
+        assert np.array_equal(n[ys, xs], g[f"c{k}_n"]) and np.array_equal(v[ys, xs], g[f"c{k}_visits"])
+        assert np.allclose(ax[ys, xs], g[f"c{k}_acc_x"], rtol=1e-6, atol=1e-5)
+        assert np.allclose(ay[ys, xs], g[f"c{k}_acc_y"], rtol=1e-6, atol=1e-5)
+        p = port.PortGMap(*b)
+        p.compute_map(g[f"c{k}_ranges"], g["angles"], tuple(g[f"c{k}_laser_xy"]))
+        assert np.array_equal(m.ros_map(), p.ros_map())
+        m.close()
+
+
+def test_gmapping_accumulate_and_errors(pkg, mods):
+    _, GM = mods
+    M = pkg.load("matcher")
+    laser = pkg.synth.Laser()
+    ang = (np.float32(laser.min_angle) + np.arange(1081, dtype=np.float32) * np.float32(laser.angular_resolution)).astype(np.float64)
+    m, p = GM.GMap(-25, -25, 25, 25, 0.1), port.PortGMap(-25, -25, 25, 25, 0.1)
+    for seed in range(6):
+        r = pkg.synth.make_match_case(60 + seed, dropout=0.01).ranges.astype(np.float32).astype(np.float64)
+        m.compute_map(r, ang, (0.3 * seed, -0.2 * seed))
+        assert p.compute_map(r, ang, (0.3 * seed, -0.2 * seed)) == 0
+    n, v, ax, ay = m.cells()
+    pn, pv, pax, pay = p.cells()
+    assert np.array_equal(n, pn) and np.array_equal(v, pv)
+    assert np.allclose(ax, pax, rtol=1e-6, atol=1e-4) and np.allclose(ay, pay, rtol=1e-6, atol=1e-4)
+    small = GM.GMap(-5, -5, 5, 5, 0.05)
+    with pytest.raises(M.B2SError) as e:
+        small.compute_map(np.full(1081, 20.0), ang)
+    assert e.value.status == pkg.abi.B2S_ERR_OUT_OF_RANGE
+    assert small.cells()[1].sum() == 0  # nothing was updated
