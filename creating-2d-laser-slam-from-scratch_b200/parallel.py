@@ -1,0 +1,59 @@
+"""Multi-GPU plumbing for the batched hot path: scan-matches are independent units, so a batch is
+partitioned by index over the ranks with NO data-path collective; only results are gathered.  One process per GPU,
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used for the gather and for barriers/timing."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_items: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced partition: the first (n_items % world) ranks get one extra item."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(array, world: int, rank: int):
+    lo, hi = shard_bounds(len(array), world, rank)
+    return array[lo:hi]
+
+
+def gather_results(local: np.ndarray, n_total: int, group=None) -> np.ndarray:
+    """All-gather per-match result rows ([n_local, k] float64) back into batch order on every rank.  Shards may have
+    different lengths (ragged): rows are padded to the largest shard for the collective and trimmed afterwards."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized():
+        assert len(local) == n_total
+        return np.asarray(local)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    k = local.shape[1] if local.ndim == 2 else 1
+    loc = np.asarray(local, dtype=np.float64).reshape(-1, k)
+    max_len = max(shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0] for r in range(world))
+    pad = np.zeros((max_len, k))
+    pad[:len(loc)] = loc
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.from_numpy(pad).to(dev)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    rows = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, world, r)
+        rows.append(outs[r][:hi - lo].cpu().numpy())
+    return np.concatenate(rows, axis=0) if rows else np.zeros((0, k))
+
+
+def max_over_ranks(value: float, group=None) -> float:
+    """Timing rule: report the MAX over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized():
+        return float(value)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
