@@ -134,6 +134,9 @@ struct b2s_matcher {
   size_t base_cap = 0;
   int32_t *d_lut = nullptr;
   size_t lut_cap = 0;
+  int32_t *d_lists = nullptr, *d_counts = nullptr;  // window kernel: per-(match, angle) sorted window origins
+  size_t lists_cap = 0, counts_cap = 0;
+  bool grid_high_bytes = false;  // set_grids saw a byte > 127: the packed-byte window kernel is not applicable
   int32_t *d_sums = nullptr;
   size_t sums_cap = 0;
   int32_t *d_bases = nullptr;  // [B][ny*nx] candidate base indices
@@ -283,6 +286,18 @@ __global__ void k_add_scans_seq(const double *__restrict__ base_pts, const doubl
   }
 }
 
+// GridIndexLookup::ComputeOffsets for one reading (Karto.h:6474-6499)
+__device__ __forceinline__ int32_t lut_value(double r, double lx, double ly, double cosine, double sine, double gox,
+                                             double goy, double scale, int width_step) {
+  if (isnan(r) || isinf(r)) return INVALID_SCAN;
+  double ox = __dsub_rn(__dmul_rn(cosine, lx), __dmul_rn(sine, ly));
+  double oy = __dadd_rn(__dmul_rn(sine, lx), __dmul_rn(cosine, ly));
+  // WorldToGrid(offset + rGridOffset): ((o + off) - off) * scale (Karto.h:6491, 4239-4251)
+  int32_t gx = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(ox, gox), gox), scale)));
+  int32_t gy = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(oy, goy), goy), scale)));
+  return (int32_t)((uint32_t)gx + (uint32_t)gy * (uint32_t)width_step);  // Grid<T>::GridIndex, no ROI
+}
+
 // ----------------------------------------------------------------------------------------------
 // k_offsets: GridIndexLookup::ComputeOffsets (Karto.h:6455-6501).  One block per (match, angle).
 // ----------------------------------------------------------------------------------------------
@@ -297,19 +312,8 @@ __global__ void k_offsets(const double *__restrict__ ranges, const double *__res
   const double cosine = cos(angle), sine = sin(angle);
   const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double r = ranges[(size_t)b * n + i];
-    int32_t v;
-    if (isnan(r) || isinf(r)) {
-      v = INVALID_SCAN;
-    } else {
-      double lx = local[((size_t)b * n + i) * 2], ly = local[((size_t)b * n + i) * 2 + 1];
-      double ox = __dsub_rn(__dmul_rn(cosine, lx), __dmul_rn(sine, ly));
-      double oy = __dadd_rn(__dmul_rn(sine, lx), __dmul_rn(cosine, ly));
-      // WorldToGrid(offset + rGridOffset): ((o + off) - off) * scale (Karto.h:6491, 4239-4251)
-      int32_t gx = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(ox, gox), gox), scale)));
-      int32_t gy = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(oy, goy), goy), scale)));
-      v = (int32_t)((uint32_t)gx + (uint32_t)gy * (uint32_t)width_step);  // Grid<T>::GridIndex, no ROI
-    }
+    const int32_t v = lut_value(ranges[(size_t)b * n + i], local[((size_t)b * n + i) * 2], local[((size_t)b * n + i) * 2 + 1],
+                                cosine, sine, gox, goy, scale, width_step);
     lut[((size_t)b * n_angles + k) * n + i] = v;
   }
 }
@@ -355,7 +359,12 @@ __global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict
                                                        int data_size, const int32_t *__restrict__ lut,
                                                        const int32_t *__restrict__ bases,
                                                        const int32_t *__restrict__ flags, int mode, int n, int na,
-                                                       int ncell, int32_t *__restrict__ sums) {
+                                                       int ncell, int32_t *__restrict__ sums,
+                                                       const double *__restrict__ ranges,
+                                                       const double *__restrict__ local,
+                                                       const double *__restrict__ grid_off,
+                                                       const double *__restrict__ centers, double angle_offset,
+                                                       double angle_res, int width_step, double scale) {
   const int b = blockIdx.y;
   const int f = flags[b];
   if (f & 2) return;
@@ -366,10 +375,18 @@ __global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict
   const uint8_t *grid = grids + (size_t)b * grid_pitch;
   const int32_t base = bases[(size_t)b * ncell + c];
   for (int k = 0; k < na; k++) {
-    const int32_t *offs = lut + ((size_t)b * na + k) * n;
+    const int32_t *offs = lut ? lut + ((size_t)b * na + k) * n : nullptr;
+    double cosine = 0, sine = 0, gox = 0, goy = 0;
+    if (!lut) {  // no materialised table (window mode fall-through): GridIndexLookup values on the fly
+      const double angle = (centers[(size_t)b * 3 + 2] - angle_offset) + (double)(uint32_t)k * angle_res;
+      cosine = cos(angle); sine = sin(angle);
+      gox = grid_off[2 * b]; goy = grid_off[2 * b + 1];
+    }
     int32_t sum = 0;
     for (int i = lane; i < n; i += 32) {
-      int32_t o = __ldg(offs + i);
+      int32_t o = lut ? __ldg(offs + i)
+                      : lut_value(ranges[(size_t)b * n + i], local[((size_t)b * n + i) * 2],
+                                  local[((size_t)b * n + i) * 2 + 1], cosine, sine, gox, goy, scale, width_step);
       if (o == INVALID_SCAN) continue;
       int32_t idx = (int32_t)((uint32_t)base + (uint32_t)o);
       if (idx >= 0 && idx < data_size) sum += __ldg(grid + idx);
@@ -384,65 +401,246 @@ __global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict
 // k_sweep_window — the hot kernel (stride-1 lattices, grid fits in shared memory).
 //
 // For a fixed angle k and beam i, the cells read by all (ix, iy) candidates form the nY x nX window of the
-// grid whose origin is  o = base00 + lut[k][i]  (flat index; rows are width_step apart).  So
-//     sums[k][iy][ix] = SUM_i grid[o_i + iy*width_step + ix].
+// grid whose origin is  a = base00 + lut[k][i]  (flat index; rows are width_step apart).  So
+//     sums[k][iy][ix] = SUM_i grid[a_i + iy*width_step + ix].
 // A persistent CTA stages one match's whole grid into shared memory with TMA bulk copies and its warps take
-// (angle, 32x32 window tile) work items.  Within a warp lane r owns candidate row r: per beam it loads the 9
-// aligned 32-bit words covering its 32 candidate bytes and, with two PRMTs per word, spreads them into packed
-// u16 accumulators (bytes 0,2 -> "lo", bytes 1,3 -> "hi"; the PRMT selector also absorbs the byte alignment of
-// o_i, which is identical for all rows because width_step % 8 == 0).  u16 lanes are flushed to 32-bit sums
-// every 512 beams (100 * 512 < 65536).  One shared-memory word therefore serves 4 candidates, and the only
-// other per-beam costs are one warp shuffle (offset broadcast) and a handful of integer ops.
+// (angle, 32x32 window tile) work items.  Within a warp lane r owns candidate row r.
+//
+// k_offsets_sorted prepares, per (match, angle), the window origins a_i grouped by byte alignment (a & 3) and
+// split into INTERIOR beams (every byte any lane will touch lies inside the staged image, no checks needed) and
+// EDGE beams (some row leaves [0, data_size): per-row redirect to a zero guard), with beams whose whole window is
+// outside dropped.  Integer sums commute, so the regrouping is free.
+//
+// Inner loop, per PAIR of same-alignment beams and per lane: 2 x 9 aligned 32-bit shared-memory loads (the 36
+// bytes covering the lane's 32 candidate cells), 9 packed-byte adds of the two beams' words (cell values <= 100,
+// so two fit a byte), then each summed word is split into two packed-u16 halves (bytes 0,2 / bytes 1,3) and added
+// to 18 packed-u16 accumulators kept in WORD-ALIGNED coordinates — the alignment (a compile-time constant of the
+// class) is only applied when the u16 lanes are flushed into the 32 per-candidate 32-bit sums.  One shared-memory
+// word therefore feeds 4 adjacent-x candidates and costs ~2.3 integer instructions per beam.
 //
 // Flat-index semantics of the reference are kept bit-exactly: rows wrap exactly as `base + offset` does, and
-// positions outside [0, data_size) read zeros (guard bands + redirect of fully-outside rows).
-// Lanes 16..31 fetch their 9 words rotated by one so that the two half-warps hit odd / even banks
-// (width_step/4 is even, so rows r and r+16 would otherwise always collide).
+// positions outside [0, data_size) read zeros (guard bands, zero padding of the HBM image, redirect of rows that
+// are entirely outside).  Lanes 16..31 fetch their 9 words rotated by one so that the two half-warps hit odd /
+// even banks (width_step/4 is even, so rows r and r+16 would otherwise always collide).
 // ----------------------------------------------------------------------------------------------
 constexpr int WIN_THREADS = 512;
-constexpr int WIN_WARPS = WIN_THREADS / 32;
-constexpr int WIN_GUARD = 128;       // zero bytes before and after the grid image in shared memory
-constexpr int WIN_FLUSH = 512;       // beams between u16 -> u32 flushes
+constexpr int WIN_GUARD = 128;          // zero bytes before and after the grid image in shared memory
+constexpr int WIN_FLUSH_BEAMS = 512;    // beams accumulated in u16 lanes between flushes (512 * 127 < 65536)
 constexpr int32_t WIN_SKIP = -(1 << 29);
+constexpr int LIST_PAD = 16;            // per-(match, angle) list capacity = n + LIST_PAD
 
-__device__ __forceinline__ void win_accumulate(const uint8_t *__restrict__ sgrid, int a, uint32_t sel_lo,
-                                               uint32_t sel_hi, int hi_half, uint32_t (&lo)[8], uint32_t (&hi)[8]) {
-  // a = byte address (within sgrid) of this lane's row start, already redirected if out of range
-  const uint32_t *wp = reinterpret_cast<const uint32_t *>(sgrid + (a & ~3)) + hi_half;
-  uint32_t v[9];
-#pragma unroll
-  for (int j = 0; j < 8; j++) v[j] = wp[j];
-  v[8] = wp[8 - 9 * hi_half];
-  // half 0: v[j] = word j.            pairs (v[j], v[j+1]) = x-word j, j = 0..7
-  // half 1: v[j] = word j+1 (j<8), v[8] = word 0.  pairs (v[j], v[j+1]) j=0..6 = x-word j+1; (v[8], v[0]) = x-word 0
-#pragma unroll
-  for (int j = 0; j < 7; j++) {
-    lo[j] += prmt(v[j], v[j + 1], sel_lo);
-    hi[j] += prmt(v[j], v[j + 1], sel_hi);
+// One block per (match, chunk of OFF_CHUNK angles): window origins grouped as [I0 I1 I2 I3 E0 E1 E2 E3] (I = interior,
+// E = edge, index = a & 3), every group a multiple of 4 long (an interior group donates its 0..3 surplus beams to its edge
+// group; edge groups are padded with far-negative sentinels of the same alignment).  counts[8] holds the group lengths.
+// The scan's readings and local points are staged in shared memory once per block and reused for every angle of
+// the chunk (8x less L2 traffic than one block per angle).
+constexpr int OFF_CHUNK = 8;
+__global__ void __launch_bounds__(256)
+    k_offsets_sorted(const double *__restrict__ ranges, const double *__restrict__ local,
+                     const double *__restrict__ grid_off, const double *__restrict__ centers,
+                     const int32_t *__restrict__ bases, const int32_t *__restrict__ flags, double angle_offset,
+                     double angle_res, int n_angles, int n, int ncell, int width_step, int data_size, double scale,
+                     int rows_total, int cols_total, int32_t *__restrict__ lists, int32_t *__restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  double *s_r = reinterpret_cast<double *>(s_raw);          // [n] readings
+  double *s_lx = s_r + n, *s_ly = s_lx + n;                  // [n] scan-local points
+  int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);   // [n] window origins
+  uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_vals + n);  // [n] group ids
+  __shared__ int cnt[8], fill[8], seg[8];
+  const int chunks = (n_angles + OFF_CHUNK - 1) / OFF_CHUNK;
+  const int b = blockIdx.x / chunks, k0 = (blockIdx.x % chunks) * OFF_CHUNK;
+  const int f = flags[b];
+  if ((f & 2) || !(f & 1)) return;  // error / irregular lattice: the generic kernel handles this match
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s_r[i] = ranges[(size_t)b * n + i];
+    s_lx[i] = local[((size_t)b * n + i) * 2];
+    s_ly[i] = local[((size_t)b * n + i) * 2 + 1];
   }
-  uint32_t pa = hi_half ? v[8] : v[7];
-  uint32_t pb = hi_half ? v[0] : v[8];
-  lo[7] += prmt(pa, pb, sel_lo);
-  hi[7] += prmt(pa, pb, sel_hi);
+  const double center = centers[(size_t)b * 3 + 2];
+  const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
+  const int32_t base00 = bases[(size_t)b * ncell];
+  const long long span = (long long)(rows_total - 1) * width_step + cols_total + 8;  // last byte any lane may touch
+  for (int k = k0; k < min(k0 + OFF_CHUNK, n_angles); k++) {
+    __syncthreads();  // staging done / previous angle's smem fully consumed
+    if (threadIdx.x < 8) { cnt[threadIdx.x] = 0; fill[threadIdx.x] = 0; }
+    __syncthreads();
+    const double angle = (center - angle_offset) + (double)(uint32_t)k * angle_res;
+    const double cosine = cos(angle), sine = sin(angle);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int32_t o = lut_value(s_r[i], s_lx[i], s_ly[i], cosine, sine, gox, goy, scale, width_step);
+      int cls = 8;  // dropped
+      int32_t a = 0;
+      if (o != INVALID_SCAN) {
+        a = (int32_t)((uint32_t)base00 + (uint32_t)o);
+        const long long lo = (long long)a - 8, hi = (long long)a + span;
+        if (hi < 0 || lo >= (long long)data_size) cls = 8;  // whole window outside: contributes 0
+        else if (lo >= -(WIN_GUARD - 16) && hi <= (long long)data_size + (WIN_GUARD - 16)) cls = a & 3;  // interior
+        else cls = 4 + (a & 3);                                                                           // edge
+      }
+      s_vals[i] = a;
+      s_cls[i] = (uint8_t)cls;
+      if (cls < 8) atomicAdd(&cnt[cls], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int pos = 0;
+      for (int c = 0; c < 4; c++) {
+        const int d = cnt[c] & 3;  // interior groups are multiples of 4: the last-placed 0..3 beams go to the edge group
+        cnt[c] -= d;
+        cnt[4 + c] += d;
+      }
+      for (int c = 0; c < 8; c++) {
+        seg[c] = pos;
+        pos += (cnt[c] + 3) & ~3;
+      }
+    }
+    __syncthreads();
+    int32_t *out = lists + ((size_t)b * n_angles + k) * (n + LIST_PAD);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int cls = s_cls[i];
+      if (cls >= 8) continue;
+      int slot = atomicAdd(&fill[cls], 1);
+      if (cls < 4 && slot >= cnt[cls]) {  // the donated one
+        cls += 4;
+        slot = atomicAdd(&fill[cls], 1);
+      }
+      out[seg[cls] + slot] = s_vals[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      const int c = 4 + threadIdx.x;
+      for (int q = cnt[c]; q < ((cnt[c] + 3) & ~3); q++)
+        out[seg[c] + q] = WIN_SKIP + threadIdx.x;  // pad: all-outside beams of the same alignment
+    }
+    if (threadIdx.x < 8) counts[((size_t)b * n_angles + k) * 8 + threadIdx.x] = (cnt[threadIdx.x] + 3) & ~3;
+  }
+}
+
+// flush the packed-u16 accumulators (word-aligned coordinates, alignment class SH) into the per-candidate sums.
+// slots 0..7 hold aligned word j (lanes 0..15) or aligned word (j+1)%8 (lanes 16..31); slot 8 holds aligned word 8;
+// byte q of word w is candidate x = 4*w + q - SH.
+template <int SH>
+__device__ __forceinline__ void win_flush(uint32_t (&lo)[9], uint32_t (&hi)[9], uint32_t (&acc)[32], int hi_half) {
+#define B2S_FLUSH_SLOT(J, W)                                                         \
+  {                                                                                  \
+    const int x0 = 4 * (W) - SH;                                                     \
+    if (x0 + 0 >= 0 && x0 + 0 < 32) acc[(x0 + 0) & 31] += lo[J] & 0xffffu;           \
+    if (x0 + 1 >= 0 && x0 + 1 < 32) acc[(x0 + 1) & 31] += hi[J] & 0xffffu;           \
+    if (x0 + 2 >= 0 && x0 + 2 < 32) acc[(x0 + 2) & 31] += lo[J] >> 16;               \
+    if (x0 + 3 >= 0 && x0 + 3 < 32) acc[(x0 + 3) & 31] += hi[J] >> 16;               \
+  }
+  if (!hi_half) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) B2S_FLUSH_SLOT(j, j)
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) B2S_FLUSH_SLOT(j, (j + 1) % 8)
+  }
+  B2S_FLUSH_SLOT(8, 8)
+#undef B2S_FLUSH_SLOT
+#pragma unroll
+  for (int j = 0; j < 9; j++) { lo[j] = 0; hi[j] = 0; }
+}
+
+// load the 8 (+1) words of one beam's row; `base` = byte address in sgrid of aligned word 0 of this lane's row.
+// Lanes 16..31 fetch words 1..7,0 so that every load instruction touches even banks in one half-warp and odd banks in
+// the other (rows r and r+16 are a multiple of 32 words apart).  Word 8 (only needed when the window's last
+// candidates spill past 32 bytes) cannot be de-conflicted and is loaded only when W9.
+template <bool W9>
+__device__ __forceinline__ void win_load(const uint8_t *__restrict__ sgrid, int base, int hi_half, uint32_t (&v)[9]) {
+  const uint32_t *w0 = reinterpret_cast<const uint32_t *>(sgrid + base);
+  const uint32_t *wp = w0 + hi_half;
+#pragma unroll
+  for (int j = 0; j < 7; j++) v[j] = wp[j];
+  v[7] = wp[7 - 8 * hi_half];
+  v[8] = W9 ? w0[8] : 0u;
+}
+
+template <bool W9>
+__device__ __forceinline__ void win_accumulate2(const uint32_t (&v1)[9], const uint32_t (&v2)[9], uint32_t (&lo)[9],
+                                                uint32_t (&hi)[9]) {
+#pragma unroll
+  for (int q = 0; q < (W9 ? 9 : 8); q++) {
+    const uint32_t w = v1[q] + v2[q];      // packed bytes, each <= 254
+    lo[q] += w & 0x00ff00ffu;              // bytes 0, 2 -> u16 lanes
+    hi[q] += __byte_perm(w, 0u, 0x4341);   // bytes 1, 3 -> u16 lanes
+  }
+}
+
+// all beams of one alignment class; count is a multiple of 4.  CHECK = per-row range test (edge beams).
+template <int SH, bool CHECK, bool W9>
+__device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, const int32_t *__restrict__ list,
+                                          int count, int lane, int hi_half, int lane_const, int row_delta,
+                                          int data_size, int32_t *__restrict__ s_off, uint32_t (&lo)[9],
+                                          uint32_t (&hi)[9], uint32_t (&acc)[32], int &pending) {
+  for (int ib = 0; ib < count; ib += 32) {
+    const int cnt = min(32, count - ib);
+    __syncwarp();
+    s_off[lane] = (lane < cnt) ? __ldg(list + ib + lane) : 0;  // this warp's staging row
+    __syncwarp();
+    if (pending + cnt > WIN_FLUSH_BEAMS) {
+      win_flush<SH>(lo, hi, acc, hi_half);
+      pending = 0;
+    }
+    pending += cnt;
+    for (int j = 0; j < cnt; j += 4) {
+      const int4 a = *reinterpret_cast<const int4 *>(s_off + j);  // one broadcast load: four window origins
+      int b0, b1, b2, b3;
+      if (CHECK) {
+        const int32_t i0 = a.x + row_delta, i1 = a.y + row_delta, i2 = a.z + row_delta, i3 = a.w + row_delta;
+        b0 = (((uint32_t)i0 + 35u) < ((uint32_t)data_size + 35u)) ? (i0 + (WIN_GUARD - SH)) : 0;
+        b1 = (((uint32_t)i1 + 35u) < ((uint32_t)data_size + 35u)) ? (i1 + (WIN_GUARD - SH)) : 0;
+        b2 = (((uint32_t)i2 + 35u) < ((uint32_t)data_size + 35u)) ? (i2 + (WIN_GUARD - SH)) : 0;
+        b3 = (((uint32_t)i3 + 35u) < ((uint32_t)data_size + 35u)) ? (i3 + (WIN_GUARD - SH)) : 0;
+      } else {
+        b0 = a.x + lane_const; b1 = a.y + lane_const; b2 = a.z + lane_const; b3 = a.w + lane_const;
+      }
+      uint32_t v1[9], v2[9];
+      win_load<W9>(sgrid, b0, hi_half, v1);
+      win_load<W9>(sgrid, b1, hi_half, v2);
+      win_accumulate2<W9>(v1, v2, lo, hi);
+      win_load<W9>(sgrid, b2, hi_half, v1);
+      win_load<W9>(sgrid, b3, hi_half, v2);
+      win_accumulate2<W9>(v1, v2, lo, hi);
+    }
+  }
+}
+
+template <int SH>
+__device__ __forceinline__ void win_class_pair(const uint8_t *__restrict__ sgrid, const int32_t *__restrict__ li,
+                                               int ci, const int32_t *__restrict__ le, int ce, int cols, int lane,
+                                               int hi_half, int row_delta, int data_size, int32_t *__restrict__ s_off,
+                                               uint32_t (&lo)[9], uint32_t (&hi)[9], uint32_t (&acc)[32]) {
+  int pending = 0;
+  if (SH + cols > 32) {  // the last candidates need aligned word 8
+    win_class<SH, false, true>(sgrid, li, ci, lane, hi_half, row_delta + WIN_GUARD - SH, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, true, true>(sgrid, le, ce, lane, hi_half, 0, row_delta, data_size, s_off, lo, hi, acc, pending);
+  } else {
+    win_class<SH, false, false>(sgrid, li, ci, lane, hi_half, row_delta + WIN_GUARD - SH, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, true, false>(sgrid, le, ce, lane, hi_half, 0, row_delta, data_size, s_off, lo, hi, acc, pending);
+  }
+  win_flush<SH>(lo, hi, acc, hi_half);
 }
 
 __global__ void __launch_bounds__(WIN_THREADS, 1)
     k_sweep_window(const uint8_t *__restrict__ grids, size_t grid_pitch, int data_size, int copy_bytes,
-                   const int32_t *__restrict__ lut, const int32_t *__restrict__ bases,
+                   const int32_t *__restrict__ lists, const int32_t *__restrict__ counts,
                    const int32_t *__restrict__ flags, int batch, int n, int na, int nx, int ny, int width_step,
                    int32_t *__restrict__ sums, int *__restrict__ work_counter) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint8_t *sgrid = smem;  // [WIN_GUARD zeros][grid image copy_bytes][WIN_GUARD zeros]
   __shared__ uint64_t bar;
   __shared__ int s_match, s_item;
+  __shared__ __align__(16) int32_t s_offsets[WIN_THREADS / 32][32];  // per-warp staging of 32 window origins
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  int32_t *s_off = s_offsets[threadIdx.x >> 5];
   const int tiles_x = (nx + 31) >> 5, tiles_y = (ny + 31) >> 5;
   const int items = na * tiles_x * tiles_y;
   const int hi_half = lane >> 4;
+  const int list_stride = n + LIST_PAD;
 
-  // zero the guard bands once
-  for (int i = threadIdx.x; i < WIN_GUARD / 4; i += blockDim.x) {
+  for (int i = threadIdx.x; i < WIN_GUARD / 4; i += blockDim.x) {  // zero the guard bands once
     reinterpret_cast<uint32_t *>(sgrid)[i] = 0;
     reinterpret_cast<uint32_t *>(sgrid + WIN_GUARD + copy_bytes)[i] = 0;
   }
@@ -479,10 +677,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
     mbar_wait(&bar, parity);
     parity ^= 1;
 
-    const int32_t base00 = bases[(size_t)b * nx * ny];
-    const int32_t *blut = lut + (size_t)b * na * n;
     int32_t *bsums = sums + (size_t)b * na * nx * ny;
-
     while (true) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&s_item, 1);
@@ -491,61 +686,33 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
       const int k = item / (tiles_x * tiles_y);
       const int t = item % (tiles_x * tiles_y);
       const int ty = t / tiles_x, tx = t % tiles_x;
-      const int32_t tile_org = base00 + ty * 32 * width_step + tx * 32;
-      const int row_off = lane * width_step;
+      const int row_delta = (ty * 32 + lane) * width_step + tx * 32;  // this lane's row start relative to a beam's origin
+      const int32_t *list = lists + ((size_t)b * na + k) * list_stride;
+      const int32_t *cn = counts + ((size_t)b * na + k) * 8;
 
       uint32_t acc[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) acc[j] = 0;
-      const int32_t *offs = blut + (size_t)k * n;
+      uint32_t lo[9], hi[9];
+#pragma unroll
+      for (int j = 0; j < 9; j++) { lo[j] = 0; hi[j] = 0; }
+      // list order: I0 I1 I2 I3 E0 E1 E2 E3 (interior / edge groups of each alignment class)
+      const int c0 = cn[0], c1 = cn[1], c2 = cn[2], c3 = cn[3], e0 = cn[4], e1 = cn[5], e2 = cn[6], e3 = cn[7];
+      const int p_i1 = c0, p_i2 = c0 + c1, p_i3 = c0 + c1 + c2;
+      const int p_e0 = p_i3 + c3, p_e1 = p_e0 + e0, p_e2 = p_e1 + e1, p_e3 = p_e2 + e2;
+      const int cols = min(32, nx - tx * 32);
+      win_class_pair<0>(sgrid, list, c0, list + p_e0, e0, cols, lane, hi_half, row_delta, data_size, s_off, lo, hi, acc);
+      win_class_pair<1>(sgrid, list + p_i1, c1, list + p_e1, e1, cols, lane, hi_half, row_delta, data_size, s_off, lo, hi, acc);
+      win_class_pair<2>(sgrid, list + p_i2, c2, list + p_e2, e2, cols, lane, hi_half, row_delta, data_size, s_off, lo, hi, acc);
+      win_class_pair<3>(sgrid, list + p_i3, c3, list + p_e3, e3, cols, lane, hi_half, row_delta, data_size, s_off, lo, hi, acc);
 
-      for (int i0 = 0; i0 < n; i0 += WIN_FLUSH) {
-        uint32_t lo[8], hi[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) { lo[j] = 0; hi[j] = 0; }
-        const int i1 = min(n, i0 + WIN_FLUSH);
-        for (int ib = i0; ib < i1; ib += 32) {
-          // lane j fetches beam ib+j's offset; INVALID_SCAN and exhausted lanes become a far-negative origin
-          int32_t my = WIN_SKIP;
-          if (ib + lane < i1) {
-            int32_t o = __ldg(offs + ib + lane);
-            if (o != INVALID_SCAN) my = (int32_t)((uint32_t)tile_org + (uint32_t)o);
-          }
-          const int cnt = min(32, i1 - ib);
-          for (int j = 0; j < cnt; j++) {
-            const int32_t o = __shfl_sync(0xffffffffu, my, j);
-            const int32_t idx = o + row_off;  // flat index of this lane's row start
-            // rows entirely outside [0, data_size) read the leading zero guard instead
-            const bool in = ((uint32_t)idx + 35u) < ((uint32_t)data_size + 35u);
-            const int a = in ? (WIN_GUARD + idx) : 0;
-            const uint32_t sh = (uint32_t)o & 3u;  // == idx & 3 (width_step % 4 == 0); uniform in the warp
-            const uint32_t sel_lo = 0x8280u + sh * 0x0101u;  // bytes sh, sh+2 -> u16 lanes
-            const uint32_t sel_hi = 0x8381u + sh * 0x0101u;  // bytes sh+1, sh+3
-            win_accumulate(sgrid, a, sel_lo, sel_hi, hi_half, lo, hi);
-          }
-        }
-        // flush packed u16 partial sums into 32-bit accumulators
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          acc[4 * j + 0] += lo[j] & 0xffffu;
-          acc[4 * j + 1] += hi[j] & 0xffffu;
-          acc[4 * j + 2] += lo[j] >> 16;
-          acc[4 * j + 3] += hi[j] >> 16;
-        }
-      }
-      // ---- write this lane's row.  Slot j holds x-word j (lanes 0..15) or x-word (j+1)%8 (lanes 16..31) ----
+      // ---- write this lane's row ----
       const int iy = ty * 32 + lane;
       if (iy < ny) {
         int32_t *dst = bsums + ((size_t)k * ny + iy) * nx + tx * 32;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int xw = hi_half ? ((j + 1) & 7) : j;
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int ix = xw * 4 + q;
-            if (tx * 32 + ix < nx) dst[ix] = (int32_t)acc[4 * j + q];
-          }
-        }
+        for (int x = 0; x < 32; x++)
+          if (tx * 32 + x < nx) dst[x] = (int32_t)acc[x];
       }
     }
     __syncthreads();  // everyone is done with sgrid before the next match's copy is issued
@@ -558,8 +725,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
 // (iy, ix, k) with linear index (iy*nx + ix)*na + k; ties are summed sequentially in that order when there are
 // at most RED_MAX_TIES of them (bit-identical to the reference), otherwise by a fixed-order tree.
 // ----------------------------------------------------------------------------------------------
-constexpr int RED_THREADS = 256;
+constexpr int RED_THREADS = 1024;
 constexpr int RED_MAX_TIES = 512;
+constexpr int RED_UNROLL = 8;
 
 __device__ __forceinline__ double candidate_response(int32_t isum, int n, bool do_penalize, double sq_xy,
                                                      double angle, double center_h, const b2s_matcher_params &p) {
@@ -574,6 +742,15 @@ __device__ __forceinline__ double candidate_response(int32_t isum, int n, bool d
     response *= (dpen * apen);
   }
   return response;
+}
+
+// float score of a candidate (see k_reduce): relative error < 3e-7 vs candidate_response
+__device__ __forceinline__ float red_fscore(int32_t isum, float apf_k, float dpf, float inv_d, bool do_penalize,
+                                            bool &ambiguous) {
+  const float u = (float)isum * inv_d;  // unpenalised response
+  ambiguous = (u > 0.5e-6f) && (u < 2.0e-6f);
+  if (!do_penalize || u <= 1.0e-6f) return u;
+  return (float)isum * apf_k * dpf;
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
@@ -594,27 +771,79 @@ __global__ void __launch_bounds__(RED_THREADS)
   const int pstep = (g.search_side + 7) & ~7;
   double *probs = probs_all + (size_t)b * pstep * g.search_side;
   const double pox = cx - s.offset_x, poy = cy - s.offset_y;  // Mapper.cpp:332-333
+  const bool pen = s.do_penalize != 0;
 
-  __shared__ double red[RED_THREADS];
+  __shared__ double red[8];
+  __shared__ double cov_terms[4][RED_THREADS];  // also the scratch of the block-wide max reduction
+  __shared__ float s_apf[1024];  // per-angle factor (anglePenalty / (N*100)) as float
   __shared__ int s_err, s_count;
   __shared__ int tie_idx[RED_MAX_TIES];
+  __shared__ int sorted[RED_MAX_TIES];
   __shared__ double s_best;
+  __shared__ double s_mean[3];
   if (tid == 0) { s_err = 0; s_count = 0; }
   if (!s.fine)
     for (int i = tid; i < pstep * g.search_side; i += RED_THREADS) probs[i] = 0.0;  // Clear (Mapper.cpp:329)
+
+  // Float pre-filter.  The exact fp64 response (reference operation order, candidate_response) is only needed for
+  // candidates that can be a maximum or a tie; a float score f = isum * w(c,k) with relative error < 3e-7 bounds it:
+  // a candidate whose f is more than 2e-6 (relative) below the largest f of its cell / below (best - 1e-6) cannot
+  // be the cell maximum / a tie.  Candidates whose unpenalised response is near the 1e-6 DoubleEqual threshold of
+  // the penalty test (Mapper.cpp:399) are always evaluated exactly.
+  const bool tab = na <= 1024;
+  const double D = (double)((uint32_t)n * (uint32_t)GRID_OCCUPIED);
+  const float inv_d = (float)(1.0 / D);
+  for (int k = tid; k < na && tab; k += RED_THREADS) {
+    double apen = 1.0;
+    if (pen) {
+      const double angle = start_a + (double)(uint32_t)k * s.angle_res;
+      apen = dmax(1.0 - (ANGLE_PENALTY_GAIN * ((angle - ch) * (angle - ch)) / p.angle_variance_penalty), p.minimum_angle_penalty);
+    }
+    s_apf[k] = (float)(apen / D);
+  }
   __syncthreads();
 
-  // ---- pass 1: best response + per-cell maxima (Mapper.cpp:430-451) ----
+  // ---- pass 1: best response + per-cell maxima (Mapper.cpp:430-451); one thread per (x,y) cell ----
   double best = -1.0;
   for (int c = tid; c < ncell; c += RED_THREADS) {
     const int iy = c / nx, ix = c % nx;
     const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
     const double sq = x * x + y * y;
     double cell_best = -1.0;
-    for (int k = 0; k < na; k++) {
-      const double angle = start_a + (double)(uint32_t)k * s.angle_res;
-      const double r = candidate_response(bs[(size_t)k * ncell + c], n, s.do_penalize, sq, angle, ch, p);
-      cell_best = dmax(cell_best, r);
+    if (tab) {
+      const float dpf = (float)dmax(1.0 - (DISTANCE_PENALTY_GAIN * sq / p.distance_variance_penalty), p.minimum_distance_penalty);
+      float fmax = -1.0f;
+      for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
+        int32_t v[RED_UNROLL];
+#pragma unroll
+        for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldg(bs + (size_t)(k0 + u) * ncell + c) : 0;
+#pragma unroll
+        for (int u = 0; u < RED_UNROLL; u++) {
+          bool amb;
+          if (k0 + u < na) fmax = fmaxf(fmax, red_fscore(v[u], s_apf[k0 + u], dpf, inv_d, pen, amb));
+        }
+      }
+      const float thr = fmax * (1.0f - 2.0e-6f) - 1.0e-30f;
+      for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
+        int32_t v[RED_UNROLL];
+#pragma unroll
+        for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldg(bs + (size_t)(k0 + u) * ncell + c) : 0;
+#pragma unroll
+        for (int u = 0; u < RED_UNROLL; u++) {
+          if (k0 + u >= na) continue;
+          bool amb;
+          const float f = red_fscore(v[u], s_apf[k0 + u], dpf, inv_d, pen, amb);
+          if (f >= thr || amb) {
+            const double angle = start_a + (double)(uint32_t)(k0 + u) * s.angle_res;
+            cell_best = dmax(cell_best, candidate_response(v[u], n, pen, sq, angle, ch, p));
+          }
+        }
+      }
+    } else {
+      for (int k = 0; k < na; k++) {
+        const double angle = start_a + (double)(uint32_t)k * s.angle_res;
+        cell_best = dmax(cell_best, candidate_response(bs[(size_t)k * ncell + c], n, pen, sq, angle, ch, p));
+      }
     }
     best = dmax(best, cell_best);
     if (!s.fine) {
@@ -628,13 +857,13 @@ __global__ void __launch_bounds__(RED_THREADS)
       }
     }
   }
-  red[tid] = best;
+  cov_terms[0][tid] = best;
   __syncthreads();
   for (int d = RED_THREADS / 2; d > 0; d >>= 1) {
-    if (tid < d) red[tid] = dmax(red[tid], red[tid + d]);
+    if (tid < d) cov_terms[0][tid] = dmax(cov_terms[0][tid], cov_terms[0][tid + d]);
     __syncthreads();
   }
-  if (tid == 0) s_best = red[0];
+  if (tid == 0) s_best = cov_terms[0][0];
   __syncthreads();
   best = s_best;
   if (s_err) {
@@ -644,33 +873,44 @@ __global__ void __launch_bounds__(RED_THREADS)
 
   // ---- pass 2: poses tied with the best (Mapper.cpp:455-487) ----
   double ax = 0, ay = 0, tx = 0, ty = 0;
-  int cnt = 0;
+  const float tie_thr = (float)((best - KT_TOLERANCE) * (1.0 - 1.0e-6)) - 1.0e-9f;
   for (int c = tid; c < ncell; c += RED_THREADS) {
     const int iy = c / nx, ix = c % nx;
     const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
     const double sq = x * x + y * y;
-    for (int k = 0; k < na; k++) {
-      const double angle = start_a + (double)(uint32_t)k * s.angle_res;
-      const double r = candidate_response(bs[(size_t)k * ncell + c], n, s.do_penalize, sq, angle, ch, p);
-      if (double_equal(r, best)) {
-        const double h = normalize_angle(angle);
-        ax += cx + x; ay += cy + y; tx += cos(h); ty += sin(h);
-        cnt++;
-        int slot = atomicAdd(&s_count, 1);
-        if (slot < RED_MAX_TIES) tie_idx[slot] = c * na + k;
+    const float dpf = (float)dmax(1.0 - (DISTANCE_PENALTY_GAIN * sq / p.distance_variance_penalty), p.minimum_distance_penalty);
+    for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
+      int32_t v[RED_UNROLL];
+#pragma unroll
+      for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldg(bs + (size_t)(k0 + u) * ncell + c) : 0;
+#pragma unroll
+      for (int u = 0; u < RED_UNROLL; u++) {
+        const int k = k0 + u;
+        if (k >= na) continue;
+        if (tab) {
+          bool amb;
+          const float f = red_fscore(v[u], s_apf[k], dpf, inv_d, pen, amb);
+          if (f < tie_thr && !amb) continue;
+        }
+        const double angle = start_a + (double)(uint32_t)k * s.angle_res;
+        const double r = candidate_response(v[u], n, pen, sq, angle, ch, p);
+        if (double_equal(r, best)) {
+          const double h = normalize_angle(angle);
+          ax += cx + x; ay += cy + y; tx += cos(h); ty += sin(h);
+          int slot = atomicAdd(&s_count, 1);
+          if (slot < RED_MAX_TIES) tie_idx[slot] = c * na + k;
+        }
       }
     }
   }
   __syncthreads();
   const int total = s_count;
-  double mean[3];
   if (total == 0) {
     if (tid == 0) res->status = B2S_ERR_NO_BEST_POSE;  // Mapper.cpp:484-487
     return;
   }
   if (total <= RED_MAX_TIES) {
     // rank-sort the tie list by reference linear index, then one thread sums in that exact order
-    __shared__ int sorted[RED_MAX_TIES];
     for (int i = tid; i < total; i += RED_THREADS) {
       int v = tie_idx[i], rank = 0;
       for (int j = 0; j < total; j++) rank += (tie_idx[j] < v);
@@ -692,49 +932,78 @@ __global__ void __launch_bounds__(RED_THREADS)
     __syncthreads();
   } else {
     // fixed-order tree reduction (deterministic; differs from the sequential sum only in the last bits)
-    __shared__ double r4[4][RED_THREADS];
-    r4[0][tid] = ax; r4[1][tid] = ay; r4[2][tid] = tx; r4[3][tid] = ty;
+    cov_terms[0][tid] = ax; cov_terms[1][tid] = ay; cov_terms[2][tid] = tx; cov_terms[3][tid] = ty;
     __syncthreads();
     for (int d = RED_THREADS / 2; d > 0; d >>= 1) {
       if (tid < d)
-        for (int q = 0; q < 4; q++) r4[q][tid] += r4[q][tid + d];
+        for (int q = 0; q < 4; q++) cov_terms[q][tid] += cov_terms[q][tid + d];
       __syncthreads();
     }
-    if (tid == 0) { red[0] = r4[0][0]; red[1] = r4[1][0]; red[2] = r4[2][0]; red[3] = r4[3][0]; }
+    if (tid == 0) { red[0] = cov_terms[0][0]; red[1] = cov_terms[1][0]; red[2] = cov_terms[2][0]; red[3] = cov_terms[3][0]; }
     __syncthreads();
   }
-  if (tid != 0) return;
-  {
+  if (tid == 0) {
     double sx = red[0], sy = red[1], cxs = red[2], sys = red[3];
     sx /= total; sy /= total; cxs /= total; sys /= total;
-    mean[0] = sx; mean[1] = sy; mean[2] = atan2(sys, cxs);
+    s_mean[0] = sx; s_mean[1] = sy; s_mean[2] = atan2(sys, cxs);
   }
+  __syncthreads();
+  const double mean0 = s_mean[0], mean1 = s_mean[1], mean2 = s_mean[2];
+
   // ---- covariance ----
   if (!s.fine) {
-    // ComputePositionalCovariance (Mapper.cpp:535-630), sequential in the reference's order
+    // ComputePositionalCovariance (Mapper.cpp:535-630).  The four running sums are accumulated in the reference's
+    // (y, x) order: the per-cell terms are produced in parallel (0.0 for cells the reference skips, which leaves a
+    // sum unchanged), then four threads add one series each sequentially.
     double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    int err = 0;
-    if (best < KT_TOLERANCE) {
+    const bool tiny = best < KT_TOLERANCE;
+    double axx = 0, axy = 0, ayy = 0, norm = 0;  // live in threads 0..3 (one series each)
+    const double dx = mean0 - cx, dy = mean1 - cy;
+    if (!tiny) {
+      for (int base = 0; base < ncell; base += RED_THREADS) {
+        const int c = base + tid;
+        double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        if (c < ncell) {
+          const int iy = c / nx, ix = c % nx;
+          const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
+          const int32_t px = world_to_grid_1(cx + x, pox, scale), py = world_to_grid_1(cy + y, poy, scale);
+          if (!(px >= 0 && px < g.search_side && py >= 0 && py < g.search_side)) {
+            s_err = 1;
+          } else {
+            const double response = probs[px + (size_t)py * pstep];
+            if (response >= (best - 0.1)) {
+              t0 = response;
+              t1 = ((x - dx) * (x - dx) * response);
+              t2 = ((x - dx) * (y - dy) * response);
+              t3 = ((y - dy) * (y - dy) * response);
+            }
+          }
+        }
+        cov_terms[0][tid] = t0; cov_terms[1][tid] = t1; cov_terms[2][tid] = t2; cov_terms[3][tid] = t3;
+        __syncthreads();
+        const int cnt = min(RED_THREADS, ncell - base);
+        if (tid < 4) {
+          double acc = tid == 0 ? norm : (tid == 1 ? axx : (tid == 2 ? axy : ayy));
+          for (int i = 0; i < cnt; i++) acc += cov_terms[tid][i];
+          if (tid == 0) norm = acc; else if (tid == 1) axx = acc; else if (tid == 2) axy = acc; else ayy = acc;
+        }
+        __syncthreads();
+      }
+      if (tid == 1) red[1] = axx;
+      if (tid == 2) red[2] = axy;
+      if (tid == 3) red[3] = ayy;
+      __syncthreads();
+    }
+    if (s_err) {
+      if (tid == 0) res->status = B2S_ERR_OUT_OF_RANGE;
+      return;
+    }
+    if (tid != 0) return;
+    if (tiny) {
       cov[0] = MAX_VARIANCE; cov[4] = MAX_VARIANCE;
       cov[8] = 4 * (s.angle_res * s.angle_res);
     } else {
-      double axx = 0, axy = 0, ayy = 0, norm = 0;
-      const double dx = mean[0] - cx, dy = mean[1] - cy;
-      for (int iy = 0; iy < ny && !err; iy++) {
-        const double y = start_y + (double)(uint32_t)iy * s.res_y;
-        for (int ix = 0; ix < nx; ix++) {
-          const double x = start_x + (double)(uint32_t)ix * s.res_x;
-          const int32_t px = world_to_grid_1(cx + x, pox, scale), py = world_to_grid_1(cy + y, poy, scale);
-          if (!(px >= 0 && px < g.search_side && py >= 0 && py < g.search_side)) { err = 1; break; }
-          const double response = probs[px + (size_t)py * pstep];
-          if (response >= (best - 0.1)) {
-            norm += response;
-            axx += ((x - dx) * (x - dx) * response);
-            axy += ((x - dx) * (y - dy) * response);
-            ayy += ((y - dy) * (y - dy) * response);
-          }
-        }
-      }
+      axx = red[1]; axy = red[2]; ayy = red[3];
       if (norm > KT_TOLERANCE) {
         double vxx = axx / norm, vxy = axy / norm, vyy = ayy / norm;
         const double vthth = 4 * (s.angle_res * s.angle_res);
@@ -746,10 +1015,10 @@ __global__ void __launch_bounds__(RED_THREADS)
       if (double_equal(cov[0], 0.0)) cov[0] = MAX_VARIANCE;
       if (double_equal(cov[4], 0.0)) cov[4] = MAX_VARIANCE;
     }
-    if (err) { res->status = B2S_ERR_OUT_OF_RANGE; return; }
     for (int i = 0; i < 9; i++) res->cov[i] = cov[i];
   }
-  res->pose[0] = mean[0]; res->pose[1] = mean[1]; res->pose[2] = mean[2];
+  if (tid != 0) return;
+  res->pose[0] = mean0; res->pose[1] = mean1; res->pose[2] = mean2;
   // un-clamped best goes through `response` for k_angular_cov; it clamps afterwards.  Coarse: clamp here.
   res->response = s.fine ? best : (best > 1.0 ? 1.0 : best);  // Mapper.cpp:514-517
   res->status = B2S_OK;
@@ -970,7 +1239,7 @@ void b2s_matcher_destroy(b2s_matcher *m) {
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
   void *ptrs[] = {m->d_kernel, m->d_ranges, m->d_poses, m->d_sensor, m->d_pts, m->d_local, m->d_grids,
-                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_sums, m->d_bases,
+                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_sums, m->d_bases,
                   m->d_flags, m->d_probs, m->d_centers, m->d_results, m->d_work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1059,6 +1328,7 @@ b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_
     B2S_CUDA_CHECK(cudaGetLastError());
   }
   m->grids_set = true;
+  m->grid_high_bytes = false;
   m->have_sweep = false;
   return B2S_OK;
 }
@@ -1068,6 +1338,9 @@ b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const dou
   if (!m->scans_set) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_set_scans must precede b2s_matcher_set_grids");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
   const int B = m->batch;
+  m->grid_high_bytes = false;  // the reference's grids hold 0..100; anything above 127 needs the generic kernel
+  for (size_t i = 0, e = (size_t)B * m->g.data_size; i < e; i++)
+    if (grids[i] > 127) { m->grid_high_bytes = true; break; }
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_grids, 0, (size_t)B * m->grid_pitch, m->stream));
   B2S_CUDA_CHECK(cudaMemcpy2DAsync(m->d_grids, m->grid_pitch, grids, (size_t)m->g.data_size, (size_t)m->g.data_size, B,
                                    cudaMemcpyHostToDevice, m->stream));
@@ -1276,42 +1549,65 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   const double scale = 1.0 / m->p.resolution;
   const int ncell = nx * ny;
   b2s_status st;
-  if ((st = ensure_cap(&m->d_lut, &m->lut_cap, (size_t)B * na * std::max(n, 1)))) return st;
   if ((st = ensure_cap(&m->d_sums, &m->sums_cap, (size_t)B * na * ncell))) return st;
   if ((st = ensure_cap(&m->d_bases, &m->bases_cap, (size_t)B * ncell))) return st;
 
-  B2S_CUDA_CHECK(cudaEventRecord(m->ev[0], m->stream));
-  k_offsets<<<B * na, 256, 0, m->stream>>>(m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, 3, 0.0, 0,
-                                           s->angle_offset, s->angle_res, na, n, m->g.width_step, scale, m->d_lut);
-  k_bases<<<B, 256, 0, m->stream>>>(m->d_centers, m->d_grid_off, *s, m->g, scale, nx, ny, m->d_bases, m->d_flags);
-  B2S_CUDA_CHECK(cudaGetLastError());
-  B2S_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
-
-  // ---- response sweep ----
+  // ---- which sweep kernel ----
   const int copy_bytes = (m->g.data_size + 15) & ~15;
   const size_t win_smem = (size_t)copy_bytes + 2 * WIN_GUARD;
   const bool stride1 = (s->res_x == 1.0 / (1.0 / m->p.resolution) || s->res_x == m->p.resolution) &&
                        (s->res_y == 1.0 / (1.0 / m->p.resolution) || s->res_y == m->p.resolution);
-  bool use_window = stride1 && win_smem + 1024 <= (size_t)m->smem_optin && (m->g.width_step % 4) == 0 && n > 0;
+  const bool win_fits = win_smem + 1024 <= (size_t)m->smem_optin && (m->g.width_step % 4) == 0 && n > 0 &&
+                        (size_t)n * 29 + 64 <= 200 * 1024 && !m->grid_high_bytes;
+  bool use_window = stride1 && win_fits;
   if (m->force_kernel == 1) use_window = false;
-  if (m->force_kernel == 2 && !(win_smem + 1024 <= (size_t)m->smem_optin))
+  if (m->force_kernel == 2 && !win_fits)
     B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but the grid does not fit in shared memory");
   if (m->force_kernel == 2) use_window = true;
+  const bool need_plain_lut = !use_window || s->fine;  // generic sweep and the angular covariance read the plain table
+  if (need_plain_lut && (st = ensure_cap(&m->d_lut, &m->lut_cap, (size_t)B * na * std::max(n, 1)))) return st;
+
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev[0], m->stream));
+  k_bases<<<B, 256, 0, m->stream>>>(m->d_centers, m->d_grid_off, *s, m->g, scale, nx, ny, m->d_bases, m->d_flags);
+  if (need_plain_lut)
+    k_offsets<<<B * na, 256, 0, m->stream>>>(m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, 3, 0.0, 0,
+                                             s->angle_offset, s->angle_res, na, n, m->g.width_step, scale, m->d_lut);
   const dim3 ggrid((unsigned)ceil_div(ncell, 8), (unsigned)B);
+  if (use_window) {
+    const int tiles_x = (nx + 31) / 32, tiles_y = (ny + 31) / 32;
+    if ((st = ensure_cap(&m->d_lists, &m->lists_cap, (size_t)B * na * (n + LIST_PAD)))) return st;
+    if ((st = ensure_cap(&m->d_counts, &m->counts_cap, (size_t)B * na * 8))) return st;
+    const size_t osm = (size_t)n * 29 + 64;
+    if (osm > 48 * 1024)
+      B2S_CUDA_CHECK(cudaFuncSetAttribute(k_offsets_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
+    k_offsets_sorted<<<B * ((na + OFF_CHUNK - 1) / OFF_CHUNK), 256, osm, m->stream>>>(m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases,
+                                                      m->d_flags, s->angle_offset, s->angle_res, na, n, ncell,
+                                                      m->g.width_step, m->g.data_size, scale, tiles_y * 32,
+                                                      tiles_x * 32, m->d_lists, m->d_counts);
+  }
+  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
+
+  // ---- response sweep ----
   if (use_window) {
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_work, 0, sizeof(int), m->stream));
     B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
     const int ctas = std::min(B, m->num_sms);
     k_sweep_window<<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
-                                                               m->d_lut, m->d_bases, m->d_flags, B, n, na, nx, ny,
+                                                               m->d_lists, m->d_counts, m->d_flags, B, n, na, nx, ny,
                                                                m->g.width_step, m->d_sums, m->d_work);
-    // matches whose lattice is not the regular stride-1 raster (a centre exactly on a rounding tie) fall through
-    k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, m->d_lut, m->d_bases,
-                                                  m->d_flags, 1, n, na, ncell, m->d_sums);
+    // matches whose lattice is not the regular stride-1 raster (a centre exactly on a rounding tie) fall through;
+    // they compute their lookup values on the fly (no table was materialised for them)
+    k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, nullptr, m->d_bases,
+                                                  m->d_flags, 1, n, na, ncell, m->d_sums, m->d_ranges, m->d_local,
+                                                  m->d_grid_off, m->d_centers, s->angle_offset, s->angle_res,
+                                                  m->g.width_step, scale);
     m->last_path = 2;
   } else {
     k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, m->d_lut, m->d_bases,
-                                                  m->d_flags, 0, n, na, ncell, m->d_sums);
+                                                  m->d_flags, 0, n, na, ncell, m->d_sums, m->d_ranges, m->d_local,
+                                                  m->d_grid_off, m->d_centers, s->angle_offset, s->angle_res,
+                                                  m->g.width_step, scale);
     m->last_path = 1;
   }
   B2S_CUDA_CHECK(cudaGetLastError());
