@@ -358,6 +358,7 @@ def main():
         t = m.last_timing()
         sweep_ms.append(t["sweep_ms"]); lut_ms.append(t["lut_ms"]); red_ms.append(t["reduce_ms"])
     e1.record(stream)
+    empty_frac = m.last_stats()["empty_window_frac"]
     barrier()
     ms = e0.elapsed_time(e1)
     t_ms = torch.tensor([ms], device="cuda")
@@ -432,6 +433,11 @@ def main():
                                          "frac_of_bank_ceiling": A1_BYTES * B / (sweep * 1e-3) / smem_ceiling,
                                          "lookups_per_clk_per_sm": A1_BYTES * B / (sweep * 1e-3) / (148 * sm_clk)}},
             "stage_ms": {"lut": float(np.mean(lut_ms)), "sweep": sweep, "reduce": float(np.mean(red_ms))},
+            "empty_windows_dropped": {"frac_of_beam_angle_pairs": empty_frac,
+                                      "note": "beams whose whole 31x31 window lies in empty 4x4 grid blocks add 0 to every "
+                                              "candidate and are dropped when the sorted lists are built; the response volume "
+                                              "is bit-identical (tests/test_gpu_matcher.py compares every candidate); "
+                                              "b2s_matcher_set_kernel(m, 3) sweeps every beam"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_k2:

@@ -31,6 +31,8 @@
 #include <new>
 #include <vector>
 
+#include <math_constants.h>
+
 #include "common.cuh"
 #include "scan_kernels.cuh"
 
@@ -136,6 +138,11 @@ struct b2s_matcher {
   size_t lut_cap = 0;
   int32_t *d_lists = nullptr, *d_counts = nullptr;  // window kernel: per-(match, angle) sorted window origins
   size_t lists_cap = 0, counts_cap = 0;
+  uint16_t *d_sat = nullptr;  // [B][(sby+1)(sbx+1)] block summed-area tables of the grids
+  int sbx = 0, sby = 0;
+  bool sat_valid = false;
+  unsigned long long *d_stats = nullptr;  // [0] beam-angle pairs dropped as empty windows in the last sweep
+  double last_empty_frac = 0.0;
   bool grid_high_bytes = false;  // set_grids saw a byte > 127: the packed-byte window kernel is not applicable
   int32_t *d_sums = nullptr;
   size_t sums_cap = 0;
@@ -429,33 +436,80 @@ constexpr int WIN_FLUSH_BEAMS = 512;    // beams accumulated in u16 lanes betwee
 constexpr int32_t WIN_SKIP = -(1 << 29);
 constexpr int LIST_PAD = 16;            // per-(match, angle) list capacity = n + LIST_PAD
 
+// ----------------------------------------------------------------------------------------------
+// k_grid_sat: per match, a summed-area table over 4x4-cell blocks of "block holds a non-zero cell".  A beam whose
+// whole nY x nX window covers only empty blocks adds 0 to every candidate, so k_offsets_sorted may drop it — the
+// response volume stays bit-identical.  sat[(by+1) x (bx+1)] u16, one block per match.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_grid_sat(const uint8_t *__restrict__ grids, size_t grid_pitch, int width_step, int height, int bx, int by,
+               uint16_t *__restrict__ sat_all) {
+  extern __shared__ uint32_t s_sat[];  // (by+1) x (bx+1)
+  const int b = blockIdx.x;
+  const uint8_t *grid = grids + (size_t)b * grid_pitch;
+  const int W = bx + 1;
+  for (int i = threadIdx.x; i < (by + 1) * W; i += blockDim.x) s_sat[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < bx * by; i += blockDim.x) {
+    const int cy = i / bx, cx = i % bx;
+    uint32_t any = 0;
+    for (int r = 0; r < 4; r++) {
+      const int y = cy * 4 + r;
+      if (y < height) any |= *reinterpret_cast<const uint32_t *>(grid + (size_t)y * width_step + cx * 4);  // width_step % 4 == 0
+    }
+    s_sat[(cy + 1) * W + (cx + 1)] = any ? 1u : 0u;
+  }
+  __syncthreads();
+  for (int y = threadIdx.x + 1; y <= by; y += blockDim.x) {  // row prefix sums
+    uint32_t acc = 0;
+    for (int x = 1; x <= bx; x++) { acc += s_sat[y * W + x]; s_sat[y * W + x] = acc; }
+  }
+  __syncthreads();
+  for (int x = threadIdx.x + 1; x <= bx; x += blockDim.x) {  // column prefix sums
+    uint32_t acc = 0;
+    for (int y = 1; y <= by; y++) { acc += s_sat[y * W + x]; s_sat[y * W + x] = acc; }
+  }
+  __syncthreads();
+  uint16_t *out = sat_all + (size_t)b * (by + 1) * W;
+  for (int i = threadIdx.x; i < (by + 1) * W; i += blockDim.x) out[i] = (uint16_t)s_sat[i];  // < 65536 blocks (checked by the host)
+}
+
 // One block per (match, chunk of OFF_CHUNK angles): window origins grouped as [I0 I1 I2 I3 E0 E1 E2 E3] (I = interior,
 // E = edge, index = a & 3), every group a multiple of 4 long (an interior group donates its 0..3 surplus beams to its edge
 // group; edge groups are padded with far-negative sentinels of the same alignment).  counts[8] holds the group lengths.
 // The scan's readings and local points are staged in shared memory once per block and reused for every angle of
-// the chunk (8x less L2 traffic than one block per angle).
-constexpr int OFF_CHUNK = 8;
+// the chunk (16x less L2 traffic than one block per angle).  A non-finite reading (INVALID_SCAN, Karto.h:6478) always
+// yields a non-finite local point (inf/NaN propagate through the inverse transform), so only the points are staged.
+constexpr int OFF_CHUNK = 16;
 __global__ void __launch_bounds__(256)
     k_offsets_sorted(const double *__restrict__ ranges, const double *__restrict__ local,
                      const double *__restrict__ grid_off, const double *__restrict__ centers,
                      const int32_t *__restrict__ bases, const int32_t *__restrict__ flags, double angle_offset,
                      double angle_res, int n_angles, int n, int ncell, int width_step, int data_size, double scale,
-                     int rows_total, int cols_total, int32_t *__restrict__ lists, int32_t *__restrict__ counts) {
+                     int rows_total, int cols_total, int32_t *__restrict__ lists, int32_t *__restrict__ counts,
+                     const uint16_t *__restrict__ sat_all, int sbx, int sby, int height, int nx, int ny,
+                     unsigned long long *__restrict__ stats) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  double *s_r = reinterpret_cast<double *>(s_raw);          // [n] readings
-  double *s_lx = s_r + n, *s_ly = s_lx + n;                  // [n] scan-local points
-  int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);   // [n] window origins
-  uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_vals + n);  // [n] group ids
+  double *s_lx = reinterpret_cast<double *>(s_raw), *s_ly = s_lx + n;  // [n] scan-local points
+  int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);             // [n] window origins
+  uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_vals + n);            // [n] group ids
+  uint16_t *s_sat = reinterpret_cast<uint16_t *>(s_raw + (((size_t)n * 21 + 15) & ~(size_t)15));  // [(sby+1)(sbx+1)] or unused
   __shared__ int cnt[8], fill[8], seg[8];
+  __shared__ int n_empty;
   const int chunks = (n_angles + OFF_CHUNK - 1) / OFF_CHUNK;
   const int b = blockIdx.x / chunks, k0 = (blockIdx.x % chunks) * OFF_CHUNK;
   const int f = flags[b];
   if ((f & 2) || !(f & 1)) return;  // error / irregular lattice: the generic kernel handles this match
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s_r[i] = ranges[(size_t)b * n + i];
     s_lx[i] = local[((size_t)b * n + i) * 2];
     s_ly[i] = local[((size_t)b * n + i) * 2 + 1];
   }
+  const int SW = sbx + 1;
+  if (sat_all) {
+    const uint16_t *src = sat_all + (size_t)b * (sby + 1) * SW;
+    for (int i = threadIdx.x; i < (sby + 1) * SW; i += blockDim.x) s_sat[i] = src[i];
+  }
+  if (threadIdx.x == 0) n_empty = 0;
   const double center = centers[(size_t)b * 3 + 2];
   const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
   const int32_t base00 = bases[(size_t)b * ncell];
@@ -466,8 +520,10 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     const double angle = (center - angle_offset) + (double)(uint32_t)k * angle_res;
     const double cosine = cos(angle), sine = sin(angle);
+    int empty_here = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int32_t o = lut_value(s_r[i], s_lx[i], s_ly[i], cosine, sine, gox, goy, scale, width_step);
+      const double plx = s_lx[i], ply = s_ly[i];
+      const int32_t o = lut_value((isfinite(plx) && isfinite(ply)) ? 0.0 : CUDART_NAN, plx, ply, cosine, sine, gox, goy, scale, width_step);
       int cls = 8;  // dropped
       int32_t a = 0;
       if (o != INVALID_SCAN) {
@@ -476,11 +532,22 @@ __global__ void __launch_bounds__(256)
         if (hi < 0 || lo >= (long long)data_size) cls = 8;  // whole window outside: contributes 0
         else if (lo >= -(WIN_GUARD - 16) && hi <= (long long)data_size + (WIN_GUARD - 16)) cls = a & 3;  // interior
         else cls = 4 + (a & 3);                                                                           // edge
+        if (sat_all && cls < 8 && a >= 0) {
+          // empty-window test on the 4x4-block summed-area table (only for windows that do not wrap a row end)
+          const int y = a / width_step, x = a - y * width_step;
+          if (x + nx <= width_step && y + ny <= height) {
+            const int bx0 = x >> 2, bx1 = (x + nx - 1) >> 2, by0 = y >> 2, by1 = (y + ny - 1) >> 2;
+            const uint32_t c = (uint32_t)s_sat[(by1 + 1) * SW + bx1 + 1] - (uint32_t)s_sat[by0 * SW + bx1 + 1] -
+                               (uint32_t)s_sat[(by1 + 1) * SW + bx0] + (uint32_t)s_sat[by0 * SW + bx0];
+            if (c == 0) { cls = 8; empty_here++; }
+          }
+        }
       }
       s_vals[i] = a;
       s_cls[i] = (uint8_t)cls;
       if (cls < 8) atomicAdd(&cnt[cls], 1);
     }
+    if (empty_here) atomicAdd(&n_empty, empty_here);
     __syncthreads();
     if (threadIdx.x == 0) {
       int pos = 0;
@@ -500,7 +567,7 @@ __global__ void __launch_bounds__(256)
       int cls = s_cls[i];
       if (cls >= 8) continue;
       int slot = atomicAdd(&fill[cls], 1);
-      if (cls < 4 && slot >= cnt[cls]) {  // the donated one
+      if (cls < 4 && slot >= cnt[cls]) {  // a donated one
         cls += 4;
         slot = atomicAdd(&fill[cls], 1);
       }
@@ -514,6 +581,8 @@ __global__ void __launch_bounds__(256)
     }
     if (threadIdx.x < 8) counts[((size_t)b * n_angles + k) * 8 + threadIdx.x] = (cnt[threadIdx.x] + 3) & ~3;
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && stats && n_empty) atomicAdd(stats, (unsigned long long)n_empty);
 }
 
 // flush the packed-u16 accumulators (word-aligned coordinates, alignment class SH) into the per-candidate sums.
@@ -1151,6 +1220,18 @@ static b2s_status ensure_cap(T **p, size_t *cap, size_t count) {
 
 static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool centers_on_device);
 
+// (re)build the per-match block summed-area tables after the grids changed
+static b2s_status build_sat(b2s_matcher *m) {
+  const size_t sm = sizeof(uint32_t) * (size_t)(m->sbx + 1) * (m->sby + 1);
+  m->sat_valid = false;
+  if (sm > 200 * 1024 || (m->g.width_step % 4) != 0 || (long long)m->sbx * m->sby >= 65535) return B2S_OK;  // no skipping
+  if (sm > 48 * 1024) B2S_CUDA_CHECK(cudaFuncSetAttribute(k_grid_sat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_grid_sat<<<m->batch, 256, sm, m->stream>>>(m->d_grids, m->grid_pitch, m->g.width_step, m->g.height, m->sbx, m->sby, m->d_sat);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  m->sat_valid = true;
+  return B2S_OK;
+}
+
 }  // namespace b2s
 
 // ================================================================================================
@@ -1226,6 +1307,10 @@ b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser 
   if ((st = dev_alloc(&m->d_centers, B * 3))) return st;
   if ((st = dev_alloc(&m->d_results, B))) return st;
   if ((st = dev_alloc(&m->d_work, 1))) return st;
+  m->sbx = (g.width_step + 3) / 4;
+  m->sby = (g.height + 3) / 4;
+  if ((st = dev_alloc(&m->d_sat, B * (size_t)(m->sbx + 1) * (m->sby + 1)))) return st;
+  if ((st = dev_alloc(&m->d_stats, 1))) return st;
   B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m->h_results), B * sizeof(b2s_match_result)));
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_grids, 0, B * m->grid_pitch, m->stream));
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_results, 0, B * sizeof(b2s_match_result), m->stream));
@@ -1239,7 +1324,7 @@ void b2s_matcher_destroy(b2s_matcher *m) {
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
   void *ptrs[] = {m->d_kernel, m->d_ranges, m->d_poses, m->d_sensor, m->d_pts, m->d_local, m->d_grids,
-                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_sums, m->d_bases,
+                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_sat, m->d_stats, m->d_sums, m->d_bases,
                   m->d_flags, m->d_probs, m->d_centers, m->d_results, m->d_work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1257,7 +1342,7 @@ b2s_status b2s_matcher_grid_info(const b2s_matcher *m, b2s_grid_info *out) {
 }
 
 b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which) {
-  if (!m || which < 0 || which > 2) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad kernel selector");
+  if (!m || which < 0 || which > 3) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad kernel selector");
   m->force_kernel = which;
   return B2S_OK;
 }
@@ -1330,7 +1415,7 @@ b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_
   m->grids_set = true;
   m->grid_high_bytes = false;
   m->have_sweep = false;
-  return B2S_OK;
+  return build_sat(m);
 }
 
 b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const double *offsets) {
@@ -1347,7 +1432,7 @@ b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const dou
   B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_grid_off, offsets, sizeof(double) * 2 * B, cudaMemcpyHostToDevice, m->stream));
   m->grids_set = true;
   m->have_sweep = false;
-  return B2S_OK;
+  return build_sat(m);
 }
 
 b2s_status b2s_matcher_get_grid(b2s_matcher *m, int b, uint8_t *out_bytes, double out_offset[2]) {
@@ -1410,6 +1495,13 @@ b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, con
   B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
   B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
   std::memcpy(results, m->h_results, sizeof(b2s_match_result) * B);
+  if (m->last_path == 2 && m->last.na > 0 && m->n > 0) {
+    unsigned long long dropped = 0;
+    B2S_CUDA_CHECK(cudaMemcpy(&dropped, m->d_stats, sizeof(dropped), cudaMemcpyDeviceToHost));
+    m->last_empty_frac = (double)dropped / ((double)B * m->last.na * m->n);
+  } else {
+    m->last_empty_frac = 0.0;
+  }
   for (int i = 1; i < 3; i++) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, m->ev[i - 1], m->ev[i]) == cudaSuccess) m->last_ms[i - 1] = ms;
@@ -1527,6 +1619,15 @@ b2s_status b2s_matcher_get_response_sums(b2s_matcher *m, int b, int32_t *out, in
   return B2S_OK;
 }
 
+b2s_status b2s_matcher_last_stats(b2s_matcher *m, double out[4]) {
+  if (!m || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  out[0] = m->last_empty_frac;
+  out[1] = (double)m->last_path;
+  out[2] = (double)m->last.na * m->last.nx * m->last.ny;
+  out[3] = (double)m->n;
+  return B2S_OK;
+}
+
 b2s_status b2s_matcher_last_timing(b2s_matcher *m, double out[4]) {
   if (!m || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   out[0] = m->last_ms[0]; out[1] = m->last_ms[1]; out[2] = m->last_ms[2]; out[3] = (double)m->last_path;
@@ -1558,12 +1659,12 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   const bool stride1 = (s->res_x == 1.0 / (1.0 / m->p.resolution) || s->res_x == m->p.resolution) &&
                        (s->res_y == 1.0 / (1.0 / m->p.resolution) || s->res_y == m->p.resolution);
   const bool win_fits = win_smem + 1024 <= (size_t)m->smem_optin && (m->g.width_step % 4) == 0 && n > 0 &&
-                        (size_t)n * 29 + 64 <= 200 * 1024 && !m->grid_high_bytes;
+                        (size_t)n * 21 + 64 <= 200 * 1024 && !m->grid_high_bytes;
   bool use_window = stride1 && win_fits;
   if (m->force_kernel == 1) use_window = false;
-  if (m->force_kernel == 2 && !win_fits)
+  if (m->force_kernel >= 2 && !win_fits)
     B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but the grid does not fit in shared memory");
-  if (m->force_kernel == 2) use_window = true;
+  if (m->force_kernel >= 2) use_window = true;
   const bool need_plain_lut = !use_window || s->fine;  // generic sweep and the angular covariance read the plain table
   if (need_plain_lut && (st = ensure_cap(&m->d_lut, &m->lut_cap, (size_t)B * na * std::max(n, 1)))) return st;
 
@@ -1577,13 +1678,19 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     const int tiles_x = (nx + 31) / 32, tiles_y = (ny + 31) / 32;
     if ((st = ensure_cap(&m->d_lists, &m->lists_cap, (size_t)B * na * (n + LIST_PAD)))) return st;
     if ((st = ensure_cap(&m->d_counts, &m->counts_cap, (size_t)B * na * 8))) return st;
-    const size_t osm = (size_t)n * 29 + 64;
+    bool skip_empty = m->sat_valid && m->force_kernel != 3;
+    if ((((size_t)n * 21 + 15) & ~(size_t)15) + sizeof(uint16_t) * (size_t)(m->sbx + 1) * (m->sby + 1) + 64 > 200 * 1024) skip_empty = false;
+    const size_t sat_bytes = skip_empty ? sizeof(uint16_t) * (size_t)(m->sbx + 1) * (m->sby + 1) : 0;
+    const size_t osm = (((size_t)n * 21 + 15) & ~(size_t)15) + sat_bytes + 64;
+    B2S_CUDA_CHECK(cudaMemsetAsync(m->d_stats, 0, sizeof(unsigned long long), m->stream));
     if (osm > 48 * 1024)
       B2S_CUDA_CHECK(cudaFuncSetAttribute(k_offsets_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
     k_offsets_sorted<<<B * ((na + OFF_CHUNK - 1) / OFF_CHUNK), 256, osm, m->stream>>>(m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases,
                                                       m->d_flags, s->angle_offset, s->angle_res, na, n, ncell,
                                                       m->g.width_step, m->g.data_size, scale, tiles_y * 32,
-                                                      tiles_x * 32, m->d_lists, m->d_counts);
+                                                      tiles_x * 32, m->d_lists, m->d_counts,
+                                                      skip_empty ? m->d_sat : nullptr, m->sbx, m->sby, m->g.height, nx, ny,
+                                                      m->d_stats);
   }
   B2S_CUDA_CHECK(cudaGetLastError());
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));

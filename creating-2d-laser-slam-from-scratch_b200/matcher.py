@@ -53,6 +53,7 @@ def lib():
     L.b2s_matcher_compute_offsets.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, ip, ip]
     L.b2s_matcher_get_response_sums.argtypes = [vp, C.c_int, ip, ip]
     L.b2s_matcher_last_timing.argtypes = [vp, dp]
+    L.b2s_matcher_last_stats.argtypes = [vp, dp]
     L.b2s_matcher_sync.argtypes = [vp]
     L.b2s_matcher_set_kernel.argtypes = [vp, C.c_int]
     _lib = L
@@ -192,6 +193,11 @@ class ScanMatcher:
         out = np.zeros(4)
         check(self.L.b2s_matcher_last_timing(self.h, _d(out)))
         return dict(lut_ms=out[0], sweep_ms=out[1], reduce_ms=out[2], path=int(out[3]))
+
+    def last_stats(self):
+        out = np.zeros(4)
+        check(self.L.b2s_matcher_last_stats(self.h, _d(out)))
+        return dict(empty_window_frac=out[0], path=int(out[1]), candidates=int(out[2]), beams=int(out[3]))
 
     def sync(self):
         check(self.L.b2s_matcher_sync(self.h))

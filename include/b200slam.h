@@ -163,8 +163,13 @@ b2s_status b2s_matcher_get_response_sums(b2s_matcher *m, int b, int32_t *out, in
  * out[0] = offsets/LUT, out[1] = response sweep, out[2] = reduce (max / tie-average / covariance),
  * out[3] = number of sweep kernel launches. */
 b2s_status b2s_matcher_last_timing(b2s_matcher *m, double out[4]);
+/* Statistics of the LAST correlate_scan call: out[0] = fraction of (beam, angle) windows the window kernel dropped
+ * because every cell of the nY x nX window lies in empty 4x4 blocks of the grid (they add 0 to every candidate, so
+ * results are unchanged); out[1] = sweep path (1 generic, 2 window); out[2] = candidates per match; out[3] = beams. */
+b2s_status b2s_matcher_last_stats(b2s_matcher *m, double out[4]);
 b2s_status b2s_matcher_sync(b2s_matcher *m);
-/* 0 = automatic, 1 = force the generic global-memory gather kernel, 2 = force the shared-memory window kernel */
+/* 0 = automatic, 1 = force the generic global-memory gather kernel, 2 = force the shared-memory window kernel,
+ * 3 = window kernel without dropping empty windows (every beam is swept) */
 b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which);
 
 /* ---------------------------------------------------------------- K2c: karto::OccupancyGrid */

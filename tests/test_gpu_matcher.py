@@ -50,7 +50,7 @@ def make_batch(synth, seeds, laser=None, **kw):
             np.stack([c.base_ranges for c in cases])[:, None, :], np.stack([c.base_pose for c in cases])[:, None, :])
 
 
-@pytest.mark.parametrize("kernel", [2, 1])  # 2 = shared-memory window kernel (hot path), 1 = generic gather kernel
+@pytest.mark.parametrize("kernel", [2, 3, 1])  # 2 = window kernel (hot path), 3 = same without empty-window dropping, 1 = generic
 def test_cfg1_correlate_parity(pkg, M, kernel):
     """BASELINE cfg 1/2 shape: 1081 beams, 31x31x181 window, 0.05 m grid; 6 matches incl. NaN/inf dropouts."""
     abi, synth = pkg.abi, pkg.synth
@@ -66,7 +66,9 @@ def test_cfg1_correlate_parity(pkg, M, kernel):
         se = abi.Search(0.75, 0.75, 0.05, 0.05, A, R, pen, 0)
         sensor = np.stack([port.PortMatcher(params, laser).sensor_pose(p) for p in poses])
         gpu = m.correlate_scan(sensor, se)
-        assert m.last_timing()["path"] == kernel
+        assert m.last_timing()["path"] == min(kernel, 2)
+        st = m.last_stats()
+        assert (st["empty_window_frac"] > 0.05) if kernel == 2 else (st["empty_window_frac"] == 0.0)
         for b in range(B):
             pm = port_case(abi, params, laser, ranges[b], poses[b], bran[b], bpos[b])
             if pen:
