@@ -66,6 +66,30 @@ class OccGridInfo(C.Structure):
                 ("offset", C.c_double * 2), ("resolution", C.c_double), ("cell_visits", C.c_uint64)]
 
 
+class IcpParams(C.Structure):
+    """b2s_icp_params; defaults = lesson3/src/plicp_odometry.cc:72-185."""
+    _fields_ = [("max_angular_correction_deg", C.c_double), ("max_linear_correction", C.c_double),
+                ("epsilon_xy", C.c_double), ("epsilon_theta", C.c_double), ("max_correspondence_dist", C.c_double),
+                ("outliers_maxPerc", C.c_double), ("outliers_adaptive_order", C.c_double),
+                ("outliers_adaptive_mult", C.c_double), ("max_iterations", C.c_int32),
+                ("use_point_to_line_distance", C.c_int32), ("outliers_remove_doubles", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def icp_params(**kw) -> IcpParams:
+    p = IcpParams(45.0, 1.0, 1e-6, 1e-6, 1.0, 0.90, 0.7, 2.0, 10, 1, 1, 0)
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("x", C.c_double * 3), ("error", C.c_double), ("valid", C.c_int32), ("iterations", C.c_int32),
+                ("nvalid", C.c_int32), ("reserved", C.c_int32)]
+
+
 def karto_round(v: float) -> float:
     """math::Round (Math.h:87-90)."""
     import math

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200slam.so")
-SOURCES = ["karto_matcher.cu", "karto_occgrid.cu", "hector_map.cu", "gmapping_map.cu"]
+SOURCES = ["karto_matcher.cu", "karto_occgrid.cu", "hector_map.cu", "gmapping_map.cu", "plicp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

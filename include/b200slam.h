@@ -242,6 +242,41 @@ b2s_status b2s_gmap_copy(b2s_gmap *g, int32_t *n, int32_t *visits, float *acc_x,
 /* the published map (gmapping.cc:141-159): -1 unknown, 100 if n/visits > 0.25 else 0 */
 b2s_status b2s_gmap_copy_ros(b2s_gmap *g, int8_t *out);
 
+/* ---------------------------------------------------------------- K3 (lesson3): PL-ICP fine alignment */
+
+/* The subset of CSM's sm_params the reference sets (lesson3/src/plicp_odometry.cc:72-185), defaults in comments. */
+typedef struct b2s_icp_params {
+  double max_angular_correction_deg; /* 45 */
+  double max_linear_correction;      /* 1.0 m (the node's yaml default; CSM's is 0.5) */
+  double epsilon_xy;                 /* 1e-6 */
+  double epsilon_theta;              /* 1e-6 */
+  double max_correspondence_dist;    /* 1.0 m */
+  double outliers_maxPerc;           /* 0.90 */
+  double outliers_adaptive_order;    /* 0.7 */
+  double outliers_adaptive_mult;     /* 2.0 */
+  int32_t max_iterations;            /* 10 */
+  int32_t use_point_to_line_distance;/* 1 */
+  int32_t outliers_remove_doubles;   /* 1 */
+  int32_t reserved;
+} b2s_icp_params;
+
+typedef struct b2s_icp_result {
+  double x[3];        /* sm_result.x: pose of the current scan in the reference scan's frame (plicp_odometry.cc:399-403) */
+  double error;       /* sum of point-to-segment distances of the kept correspondences */
+  int32_t valid;      /* sm_result.valid */
+  int32_t iterations;
+  int32_t nvalid;     /* correspondences kept in the last iteration */
+  int32_t reserved;
+} b2s_icp_result;
+
+/* sm_icp (plicp_odometry.cc:391) for `batch` independent scan pairs: ref_ranges / sens_ranges [batch][n] on the beam
+ * angles theta[n] (LaserScanToLDP, :285-322: a reading is valid iff range_min < r < range_max), first_guess [batch][3].
+ * PARITY UNPINNED: CSM is an external, un-versioned dependency absent from the reference tree; this follows the
+ * published algorithm (Censi, ICRA 2008) — see DESIGN.md §7. */
+b2s_status b2s_plicp_match(const b2s_icp_params *params, int batch, int n, const double *ref_ranges,
+                           const double *sens_ranges, const double *theta, double range_min, double range_max,
+                           const double *first_guess, int device, void *cuda_stream, b2s_icp_result *results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("karto_oracle.c", "gmapping_oracle.c", "hector_oracle.c",
+    srcs = [os.path.join(_HERE, f) for f in ("karto_oracle.c", "gmapping_oracle.c", "hector_oracle.c", "plicp_oracle.c",
                                              "oracle_common.h", "Makefile")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libslam_oracle.so"])
@@ -244,3 +244,13 @@ class PortHectorMap:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------- PL-ICP (plicp_oracle.c) — PARITY UNPINNED
+
+def plicp_match(params, ref_ranges, sens_ranges, theta, range_min, range_max, first_guess):
+    r, s_, t = f64(ref_ranges), f64(sens_ranges), f64(theta)
+    res = abi.IcpResult()
+    lib().orc_plicp_match(C.byref(params), len(t), _d(r), _d(s_), _d(t), C.c_double(range_min), C.c_double(range_max),
+                          _d(f64(first_guess)), C.byref(res))
+    return res
