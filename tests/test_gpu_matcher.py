@@ -326,3 +326,60 @@ def test_full_batch_1024_properties(pkg, M):
     err = np.abs(pose[:uniq, :2] - true[:, :2]).max()
     assert err < 0.1, err
     m.close()
+
+
+def test_randomised_configurations(pkg, M):
+    """Seeded fuzz over matcher geometry (resolution, smear, search size, beam count, sensor offset, window shape,
+    batch size): every integer volume bit-exact, every result within TOL, on whichever kernel the handle picks."""
+    abi, synth = pkg.abi, pkg.synth
+    rng = np.random.default_rng(2024)
+    kinds = {1: 0, 2: 0}
+    for trial in range(14):
+        res = float(rng.choice([0.03, 0.04, 0.05, 0.08, 0.1]))
+        side_cells = int(rng.choice([7, 11, 15, 21, 33, 41]))
+        search = (side_cells - 1) * res
+        smear = float(rng.uniform(0.6, 3.0)) * res
+        rt = float(rng.uniform(3.0, 7.0))
+        n_beams = int(rng.choice([181, 360, 721, 1081]))
+        span = float(rng.choice([180.0, 240.0, 270.0]))
+        laser_s = synth.Laser(type=0, n_readings=n_beams, min_angle=synth.deg2rad(-span / 2), max_angle=synth.deg2rad(span / 2),
+                              angular_resolution=synth.deg2rad(span / n_beams), min_range=0.05, max_range=25.0,
+                              range_threshold=rt, offset_pose=(float(rng.uniform(-0.2, 0.2)), float(rng.uniform(-0.2, 0.2)),
+                                                               float(rng.uniform(-0.3, 0.3))))
+        params = abi.matcher_params(search, res, smear, rt, use_response_expansion=int(rng.integers(0, 2)))
+        laser = abi.laser_from(laser_s)
+        B, nb = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        world, poses, ranges = synth.make_trajectory(1000 + trial, nb + B, laser_s, step_xy=0.1, step_th_deg=3)
+        if trial % 3 == 0:
+            ranges[:, ::17] = np.nan
+            ranges[:, 5::29] = np.inf
+        cur_r = ranges[nb:]
+        cur_p = poses[nb:] + rng.uniform(-0.05, 0.05, size=(B, 3))
+        bran = np.stack([ranges[:nb]] * B)
+        bpos = np.stack([poses[:nb]] * B)
+        m = M.ScanMatcher(params, laser, max_batch=B, max_base_scans=nb)
+        gpu = m.match_scan_host(cur_r, cur_p, bran, bpos, bool(trial % 2), True)
+        pms = []
+        for b in range(B):
+            pm = port.PortMatcher(params, laser)
+            rc, r0 = pm.match_scan(cur_r[b], cur_p[b], bran[b], bpos[b], bool(trial % 2), True)
+            assert rc == 0
+            assert np.array_equal(m.grid(b)[0], pm.grid), trial
+            assert_result(gpu, b, r0)
+            pm.set_scan(cur_r[b], cur_p[b])
+            pms.append(pm)
+        # a direct full-resolution sweep with an odd angle count
+        half = 0.5 * (m.g.search_side - 1) * res
+        na_off, na_res = float(rng.uniform(2, 12)) * D, float(rng.choice([0.5, 1.0, 1.5])) * D
+        se = abi.Search(half, half, res, res, na_off, na_res, int(rng.integers(0, 2)), 0)
+        centers = np.stack([pm.sp for pm in pms])
+        gpu = m.correlate_scan(centers, se)
+        kinds[m.last_timing()["path"]] += 1
+        na = abi.n_steps(na_off, na_res)
+        for b in range(B):
+            rc, r = pms[b].correlate_scan(pms[b].sp, se, want_sums=True)
+            assert rc == 0
+            assert np.array_equal(m.response_sums(b, (m.g.search_side, m.g.search_side, na)), pms[b].last_sums), trial
+            assert_result(gpu, b, r)
+        m.close()
+    assert kinds[2] >= 8  # most of these grids fit in shared memory and use the window kernel
