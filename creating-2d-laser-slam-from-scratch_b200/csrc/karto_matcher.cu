@@ -136,8 +136,8 @@ struct b2s_matcher {
   size_t base_cap = 0;
   int32_t *d_lut = nullptr;
   size_t lut_cap = 0;
-  int32_t *d_lists = nullptr, *d_counts = nullptr;  // window kernel: per-(match, angle) sorted window origins
-  size_t lists_cap = 0, counts_cap = 0;
+  int32_t *d_lists = nullptr, *d_counts = nullptr, *d_starts = nullptr;  // window kernel: per-(match, angle) grouped window origins
+  size_t lists_cap = 0, counts_cap = 0, starts_cap = 0;
   uint16_t *d_sat = nullptr;  // [B][(sby+1)(sbx+1)] block summed-area tables of the grids
   int sbx = 0, sby = 0;
   bool sat_valid = false;
@@ -434,7 +434,8 @@ constexpr int WIN_THREADS = 512;
 constexpr int WIN_GUARD = 128;          // zero bytes before and after the grid image in shared memory
 constexpr int WIN_FLUSH_BEAMS = 512;    // beams accumulated in u16 lanes between flushes (512 * 127 < 65536)
 constexpr int32_t WIN_SKIP = -(1 << 29);
-constexpr int LIST_PAD = 16;            // per-(match, angle) list capacity = n + LIST_PAD
+constexpr int WIN_MAX_BANDS = 16;      // row bands a grid larger than shared memory is swept in
+constexpr int LIST_PAD = 16;            // per-(match, angle) list capacity = n + LIST_PAD * nbands
 
 // ----------------------------------------------------------------------------------------------
 // k_grid_sat: per match, a summed-area table over 4x4-cell blocks of "block holds a non-zero cell".  A beam whose
@@ -488,14 +489,17 @@ __global__ void __launch_bounds__(256)
                      double angle_res, int n_angles, int n, int ncell, int width_step, int data_size, double scale,
                      int rows_total, int cols_total, int32_t *__restrict__ lists, int32_t *__restrict__ counts,
                      const uint16_t *__restrict__ sat_all, int sbx, int sby, int height, int nx, int ny,
-                     unsigned long long *__restrict__ stats) {
+                     unsigned long long *__restrict__ stats, int band_rows, int nbands,
+                     int32_t *__restrict__ starts) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   double *s_lx = reinterpret_cast<double *>(s_raw), *s_ly = s_lx + n;  // [n] scan-local points
   int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);             // [n] window origins
   uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_vals + n);            // [n] group ids
   uint16_t *s_sat = reinterpret_cast<uint16_t *>(s_raw + (((size_t)n * 21 + 15) & ~(size_t)15));  // [(sby+1)(sbx+1)] or unused
-  __shared__ int cnt[8], fill[8], seg[8];
+  __shared__ int cnt[8 * WIN_MAX_BANDS], fill[8 * WIN_MAX_BANDS], seg[8 * WIN_MAX_BANDS];  // [band][group]
   __shared__ int n_empty;
+  const int ngroups = 8 * nbands;
+  const int list_cap = n + LIST_PAD * nbands;
   const int chunks = (n_angles + OFF_CHUNK - 1) / OFF_CHUNK;
   const int b = blockIdx.x / chunks, k0 = (blockIdx.x % chunks) * OFF_CHUNK;
   const int f = flags[b];
@@ -514,9 +518,10 @@ __global__ void __launch_bounds__(256)
   const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
   const int32_t base00 = bases[(size_t)b * ncell];
   const long long span = (long long)(rows_total - 1) * width_step + cols_total + 8;  // last byte any lane may touch
+  const float inv_step = 1.0f / (float)width_step, inv_band = 1.0f / (float)band_rows;
   for (int k = k0; k < min(k0 + OFF_CHUNK, n_angles); k++) {
     __syncthreads();  // staging done / previous angle's smem fully consumed
-    if (threadIdx.x < 8) { cnt[threadIdx.x] = 0; fill[threadIdx.x] = 0; }
+    if (threadIdx.x < ngroups) { cnt[threadIdx.x] = 0; fill[threadIdx.x] = 0; }
     __syncthreads();
     const double angle = (center - angle_offset) + (double)(uint32_t)k * angle_res;
     const double cosine = cos(angle), sine = sin(angle);
@@ -524,62 +529,82 @@ __global__ void __launch_bounds__(256)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const double plx = s_lx[i], ply = s_ly[i];
       const int32_t o = lut_value((isfinite(plx) && isfinite(ply)) ? 0.0 : CUDART_NAN, plx, ply, cosine, sine, gox, goy, scale, width_step);
-      int cls = 8;  // dropped
+      int cls = 255;  // dropped
       int32_t a = 0;
       if (o != INVALID_SCAN) {
         a = (int32_t)((uint32_t)base00 + (uint32_t)o);
         const long long lo = (long long)a - 8, hi = (long long)a + span;
-        if (hi < 0 || lo >= (long long)data_size) cls = 8;  // whole window outside: contributes 0
+        if (hi < 0 || lo >= (long long)data_size) cls = 255;  // whole window outside: contributes 0
         else if (lo >= -(WIN_GUARD - 16) && hi <= (long long)data_size + (WIN_GUARD - 16)) cls = a & 3;  // interior
         else cls = 4 + (a & 3);                                                                           // edge
-        if (sat_all && cls < 8 && a >= 0) {
+        int y = 0, x = 0;
+        if ((sat_all || nbands > 1) && cls < 255 && a >= 0) {
+          // a / width_step by float reciprocal + fix-up (a < 2^24 is exact in float; larger values are corrected too)
+          if (data_size <= (1 << 24)) {
+            y = (int)((float)a * inv_step);
+            if (y * width_step > a) y--;
+            else if ((y + 1) * width_step <= a) y++;
+          } else {
+            y = a / width_step;
+          }
+          x = a - y * width_step;
+        }
+        if (nbands > 1 && cls < 8) {
+          int band = (int)((float)y * inv_band);
+          if (band * band_rows > y) band--;
+          else if ((band + 1) * band_rows <= y) band++;
+          cls += 8 * min(band, nbands - 1);  // the row band that holds the window origin
+        }
+        if (sat_all && cls < 255 && a >= 0) {
           // empty-window test on the 4x4-block summed-area table (only for windows that do not wrap a row end)
-          const int y = a / width_step, x = a - y * width_step;
           if (x + nx <= width_step && y + ny <= height) {
             const int bx0 = x >> 2, bx1 = (x + nx - 1) >> 2, by0 = y >> 2, by1 = (y + ny - 1) >> 2;
             const uint32_t c = (uint32_t)s_sat[(by1 + 1) * SW + bx1 + 1] - (uint32_t)s_sat[by0 * SW + bx1 + 1] -
                                (uint32_t)s_sat[(by1 + 1) * SW + bx0] + (uint32_t)s_sat[by0 * SW + bx0];
-            if (c == 0) { cls = 8; empty_here++; }
+            if (c == 0) { cls = 255; empty_here++; }
           }
         }
       }
       s_vals[i] = a;
       s_cls[i] = (uint8_t)cls;
-      if (cls < 8) atomicAdd(&cnt[cls], 1);
+      if (cls < 255) atomicAdd(&cnt[cls], 1);
     }
     if (empty_here) atomicAdd(&n_empty, empty_here);
     __syncthreads();
     if (threadIdx.x == 0) {
       int pos = 0;
-      for (int c = 0; c < 4; c++) {
-        const int d = cnt[c] & 3;  // interior groups are multiples of 4: the last-placed 0..3 beams go to the edge group
-        cnt[c] -= d;
-        cnt[4 + c] += d;
-      }
-      for (int c = 0; c < 8; c++) {
-        seg[c] = pos;
-        pos += (cnt[c] + 3) & ~3;
+      for (int g8 = 0; g8 < ngroups; g8 += 8) {
+        for (int c = 0; c < 4; c++) {
+          const int d = cnt[g8 + c] & 3;  // interior groups are multiples of 4: the last-placed 0..3 beams go to the edge group
+          cnt[g8 + c] -= d;
+          cnt[g8 + 4 + c] += d;
+        }
+        for (int c = 0; c < 8; c++) {
+          seg[g8 + c] = pos;
+          pos += (cnt[g8 + c] + 3) & ~3;
+        }
       }
     }
     __syncthreads();
-    int32_t *out = lists + ((size_t)b * n_angles + k) * (n + LIST_PAD);
+    int32_t *out = lists + ((size_t)b * n_angles + k) * list_cap;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       int cls = s_cls[i];
-      if (cls >= 8) continue;
+      if (cls == 255) continue;
       int slot = atomicAdd(&fill[cls], 1);
-      if (cls < 4 && slot >= cnt[cls]) {  // a donated one
+      if ((cls & 7) < 4 && slot >= cnt[cls]) {  // a donated one
         cls += 4;
         slot = atomicAdd(&fill[cls], 1);
       }
       out[seg[cls] + slot] = s_vals[i];
     }
     __syncthreads();
-    if (threadIdx.x < 4) {
-      const int c = 4 + threadIdx.x;
-      for (int q = cnt[c]; q < ((cnt[c] + 3) & ~3); q++)
-        out[seg[c] + q] = WIN_SKIP + threadIdx.x;  // pad: all-outside beams of the same alignment
+    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) {
+      if ((g & 7) >= 4)
+        for (int q = cnt[g]; q < ((cnt[g] + 3) & ~3); q++)
+          out[seg[g] + q] = WIN_SKIP + (g & 3);  // pad: all-outside beams of the same alignment
+      counts[((size_t)b * n_angles + k) * ngroups + g] = (cnt[g] + 3) & ~3;
+      starts[((size_t)b * n_angles + k) * ngroups + g] = seg[g];
     }
-    if (threadIdx.x < 8) counts[((size_t)b * n_angles + k) * 8 + threadIdx.x] = (cnt[threadIdx.x] + 3) & ~3;
   }
   __syncthreads();
   if (threadIdx.x == 0 && stats && n_empty) atomicAdd(stats, (unsigned long long)n_empty);
@@ -639,7 +664,7 @@ __device__ __forceinline__ void win_accumulate2(const uint32_t (&v1)[9], const u
 // all beams of one alignment class; count is a multiple of 4.  CHECK = per-row range test (edge beams).
 template <int SH, bool CHECK, bool W9>
 __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, const int32_t *__restrict__ list,
-                                          int count, int lane, int hi_half, int lane_const, int row_delta,
+                                          int count, int lane, int hi_half, int bias, int row_delta,
                                           int data_size, int32_t *__restrict__ s_off, uint32_t (&lo)[9],
                                           uint32_t (&hi)[9], uint32_t (&acc)[32], int &pending) {
   for (int ib = 0; ib < count; ib += 32) {
@@ -657,11 +682,12 @@ __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, con
       int b0, b1, b2, b3;
       if (CHECK) {
         const int32_t i0 = a.x + row_delta, i1 = a.y + row_delta, i2 = a.z + row_delta, i3 = a.w + row_delta;
-        b0 = (((uint32_t)i0 + 35u) < ((uint32_t)data_size + 35u)) ? (i0 + (WIN_GUARD - SH)) : 0;
-        b1 = (((uint32_t)i1 + 35u) < ((uint32_t)data_size + 35u)) ? (i1 + (WIN_GUARD - SH)) : 0;
-        b2 = (((uint32_t)i2 + 35u) < ((uint32_t)data_size + 35u)) ? (i2 + (WIN_GUARD - SH)) : 0;
-        b3 = (((uint32_t)i3 + 35u) < ((uint32_t)data_size + 35u)) ? (i3 + (WIN_GUARD - SH)) : 0;
+        b0 = (((uint32_t)i0 + 35u) < ((uint32_t)data_size + 35u)) ? (i0 + (bias - SH)) : 0;
+        b1 = (((uint32_t)i1 + 35u) < ((uint32_t)data_size + 35u)) ? (i1 + (bias - SH)) : 0;
+        b2 = (((uint32_t)i2 + 35u) < ((uint32_t)data_size + 35u)) ? (i2 + (bias - SH)) : 0;
+        b3 = (((uint32_t)i3 + 35u) < ((uint32_t)data_size + 35u)) ? (i3 + (bias - SH)) : 0;
       } else {
+        const int lane_const = row_delta + bias - SH;
         b0 = a.x + lane_const; b1 = a.y + lane_const; b2 = a.z + lane_const; b3 = a.w + lane_const;
       }
       uint32_t v1[9], v2[9];
@@ -678,15 +704,15 @@ __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, con
 template <int SH>
 __device__ __forceinline__ void win_class_pair(const uint8_t *__restrict__ sgrid, const int32_t *__restrict__ li,
                                                int ci, const int32_t *__restrict__ le, int ce, int cols, int lane,
-                                               int hi_half, int row_delta, int data_size, int32_t *__restrict__ s_off,
+                                               int hi_half, int row_delta, int bias, int data_size, int32_t *__restrict__ s_off,
                                                uint32_t (&lo)[9], uint32_t (&hi)[9], uint32_t (&acc)[32]) {
   int pending = 0;
   if (SH + cols > 32) {  // the last candidates need aligned word 8
-    win_class<SH, false, true>(sgrid, li, ci, lane, hi_half, row_delta + WIN_GUARD - SH, row_delta, data_size, s_off, lo, hi, acc, pending);
-    win_class<SH, true, true>(sgrid, le, ce, lane, hi_half, 0, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, false, true>(sgrid, li, ci, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, true, true>(sgrid, le, ce, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
   } else {
-    win_class<SH, false, false>(sgrid, li, ci, lane, hi_half, row_delta + WIN_GUARD - SH, row_delta, data_size, s_off, lo, hi, acc, pending);
-    win_class<SH, true, false>(sgrid, le, ce, lane, hi_half, 0, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, false, false>(sgrid, li, ci, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, true, false>(sgrid, le, ce, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
   }
   win_flush<SH>(lo, hi, acc, hi_half);
 }
@@ -694,12 +720,16 @@ __device__ __forceinline__ void win_class_pair(const uint8_t *__restrict__ sgrid
 __global__ void __launch_bounds__(WIN_THREADS, 1)
     k_sweep_window(const uint8_t *__restrict__ grids, size_t grid_pitch, int data_size, int copy_bytes,
                    const int32_t *__restrict__ lists, const int32_t *__restrict__ counts,
-                   const int32_t *__restrict__ flags, int batch, int n, int na, int nx, int ny, int width_step,
-                   int32_t *__restrict__ sums, int *__restrict__ work_counter) {
+                   const int32_t *__restrict__ starts, const int32_t *__restrict__ flags, int batch, int n, int na,
+                   int nx, int ny, int width_step, int32_t *__restrict__ sums, int *__restrict__ work_counter,
+                   int band_rows, int nbands, int band_bytes) {
+  // Grids larger than shared memory are swept in `nbands` row bands: a work unit is (match, band); the band image
+  // holds the rows a window whose ORIGIN lies in the band can touch (band_rows + window rows + 1), k_offsets_sorted
+  // grouped the beams by the band of their origin, and the partial sums of the bands are combined with RED.ADD.
   extern __shared__ __align__(128) unsigned char smem[];
-  uint8_t *sgrid = smem;  // [WIN_GUARD zeros][grid image copy_bytes][WIN_GUARD zeros]
+  uint8_t *sgrid = smem;  // [WIN_GUARD zeros][band image][WIN_GUARD zeros]
   __shared__ uint64_t bar;
-  __shared__ int s_match, s_item;
+  __shared__ int s_unit, s_item;
   __shared__ __align__(16) int32_t s_offsets[WIN_THREADS / 32][32];  // per-warp staging of 32 window origins
 
   const int lane = threadIdx.x & 31;
@@ -707,12 +737,10 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
   const int tiles_x = (nx + 31) >> 5, tiles_y = (ny + 31) >> 5;
   const int items = na * tiles_x * tiles_y;
   const int hi_half = lane >> 4;
-  const int list_stride = n + LIST_PAD;
+  const int list_cap = n + LIST_PAD * nbands;
+  const int ngroups = 8 * nbands;
 
-  for (int i = threadIdx.x; i < WIN_GUARD / 4; i += blockDim.x) {  // zero the guard bands once
-    reinterpret_cast<uint32_t *>(sgrid)[i] = 0;
-    reinterpret_cast<uint32_t *>(sgrid + WIN_GUARD + copy_bytes)[i] = 0;
-  }
+  for (int i = threadIdx.x; i < WIN_GUARD / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sgrid)[i] = 0;  // leading guard
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -722,29 +750,35 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
 
   while (true) {
     if (threadIdx.x == 0) {
-      s_match = atomicAdd(work_counter, 1);
+      s_unit = atomicAdd(work_counter, 1);
       s_item = 0;
     }
     __syncthreads();
-    const int b = s_match;
-    if (b >= batch) break;
+    const int unit = s_unit;
+    if (unit >= batch * nbands) break;
+    const int b = unit / nbands, band = unit % nbands;
     const int f = flags[b];
     if ((f & 2) || !(f & 1)) {  // out-of-range lattice (error) or irregular lattice (generic kernel takes it)
       __syncthreads();
       continue;
     }
-    // ---- stage this match's grid: TMA bulk copies, 32 KB each, one mbarrier phase ----
+    // ---- stage this unit's band image: TMA bulk copies, 32 KB each, one mbarrier phase ----
+    const int band_lo = band * band_rows * width_step;  // flat index of the first staged byte (multiple of 16)
+    const int bytes = min(band_bytes, copy_bytes - band_lo);
     if (threadIdx.x == 0) {
       fence_proxy_async();  // earlier generic-proxy reads of sgrid are ordered before the async-proxy writes
-      mbar_expect_tx(&bar, (uint32_t)copy_bytes);
-      const uint8_t *src = grids + (size_t)b * grid_pitch;
-      for (int off = 0; off < copy_bytes; off += 32768) {
-        int len = min(32768, copy_bytes - off);
+      mbar_expect_tx(&bar, (uint32_t)bytes);
+      const uint8_t *src = grids + (size_t)b * grid_pitch + band_lo;
+      for (int off = 0; off < bytes; off += 32768) {
+        int len = min(32768, bytes - off);
         bulk_g2s(sgrid + WIN_GUARD + off, src + off, (uint32_t)len, &bar);
       }
     }
+    if (threadIdx.x < WIN_GUARD / 4) reinterpret_cast<uint32_t *>(sgrid + WIN_GUARD + bytes)[threadIdx.x] = 0;  // trailing guard
     mbar_wait(&bar, parity);
     parity ^= 1;
+    __syncthreads();
+    const int bias = WIN_GUARD - band_lo;
 
     int32_t *bsums = sums + (size_t)b * na * nx * ny;
     while (true) {
@@ -756,8 +790,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
       const int t = item % (tiles_x * tiles_y);
       const int ty = t / tiles_x, tx = t % tiles_x;
       const int row_delta = (ty * 32 + lane) * width_step + tx * 32;  // this lane's row start relative to a beam's origin
-      const int32_t *list = lists + ((size_t)b * na + k) * list_stride;
-      const int32_t *cn = counts + ((size_t)b * na + k) * 8;
+      const int32_t *list = lists + ((size_t)b * na + k) * list_cap;
+      const int32_t *cn = counts + ((size_t)b * na + k) * ngroups + band * 8;
+      const int32_t *sg = starts + ((size_t)b * na + k) * ngroups + band * 8;
 
       uint32_t acc[32];
 #pragma unroll
@@ -765,26 +800,29 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
       uint32_t lo[9], hi[9];
 #pragma unroll
       for (int j = 0; j < 9; j++) { lo[j] = 0; hi[j] = 0; }
-      // list order: I0 I1 I2 I3 E0 E1 E2 E3 (interior / edge groups of each alignment class)
-      const int c0 = cn[0], c1 = cn[1], c2 = cn[2], c3 = cn[3], e0 = cn[4], e1 = cn[5], e2 = cn[6], e3 = cn[7];
-      const int p_i1 = c0, p_i2 = c0 + c1, p_i3 = c0 + c1 + c2;
-      const int p_e0 = p_i3 + c3, p_e1 = p_e0 + e0, p_e2 = p_e1 + e1, p_e3 = p_e2 + e2;
+      // groups of this band: I0 I1 I2 I3 E0 E1 E2 E3 (interior / edge beams of each alignment class)
       const int cols = min(32, nx - tx * 32);
-      win_class_pair<0>(sgrid, list, c0, list + p_e0, e0, cols, lane, hi_half, row_delta, data_size, s_off, lo, hi, acc);
-      win_class_pair<1>(sgrid, list + p_i1, c1, list + p_e1, e1, cols, lane, hi_half, row_delta, data_size, s_off, lo, hi, acc);
-      win_class_pair<2>(sgrid, list + p_i2, c2, list + p_e2, e2, cols, lane, hi_half, row_delta, data_size, s_off, lo, hi, acc);
-      win_class_pair<3>(sgrid, list + p_i3, c3, list + p_e3, e3, cols, lane, hi_half, row_delta, data_size, s_off, lo, hi, acc);
+      win_class_pair<0>(sgrid, list + sg[0], cn[0], list + sg[4], cn[4], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<1>(sgrid, list + sg[1], cn[1], list + sg[5], cn[5], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<2>(sgrid, list + sg[2], cn[2], list + sg[6], cn[6], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<3>(sgrid, list + sg[3], cn[3], list + sg[7], cn[7], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
 
-      // ---- write this lane's row ----
+      // ---- write / accumulate this lane's row ----
       const int iy = ty * 32 + lane;
       if (iy < ny) {
         int32_t *dst = bsums + ((size_t)k * ny + iy) * nx + tx * 32;
+        if (nbands == 1) {
 #pragma unroll
-        for (int x = 0; x < 32; x++)
-          if (tx * 32 + x < nx) dst[x] = (int32_t)acc[x];
+          for (int x = 0; x < 32; x++)
+            if (tx * 32 + x < nx) dst[x] = (int32_t)acc[x];
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; x++)
+            if (tx * 32 + x < nx && acc[x]) atomicAdd(dst + x, (int32_t)acc[x]);
+        }
       }
     }
-    __syncthreads();  // everyone is done with sgrid before the next match's copy is issued
+    __syncthreads();  // everyone is done with sgrid before the next unit's copy is issued
   }
 }
 
@@ -1324,7 +1362,7 @@ void b2s_matcher_destroy(b2s_matcher *m) {
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
   void *ptrs[] = {m->d_kernel, m->d_ranges, m->d_poses, m->d_sensor, m->d_pts, m->d_local, m->d_grids,
-                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_sat, m->d_stats, m->d_sums, m->d_bases,
+                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_starts, m->d_sat, m->d_stats, m->d_sums, m->d_bases,
                   m->d_flags, m->d_probs, m->d_centers, m->d_results, m->d_work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1654,16 +1692,34 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   if ((st = ensure_cap(&m->d_bases, &m->bases_cap, (size_t)B * ncell))) return st;
 
   // ---- which sweep kernel ----
+  // The window kernel needs a stride-1 lattice and a band of the grid in shared memory: the whole grid when it fits
+  // (nbands = 1), otherwise nbands row bands of band_rows origin rows + (window rows + 1) halo rows each.
   const int copy_bytes = (m->g.data_size + 15) & ~15;
-  const size_t win_smem = (size_t)copy_bytes + 2 * WIN_GUARD;
+  const int tiles_x_w = (nx + 31) / 32, tiles_y_w = (ny + 31) / 32;
+  const int rows_total = tiles_y_w * 32;
+  const long long smem_limit = (long long)m->smem_optin - 4096;  // static shared memory of the kernel + margin
+  int band_rows = std::max(m->g.height, 1), nbands = 1, band_bytes = copy_bytes;
+  bool bands_ok = true;
+  if ((long long)copy_bytes + 2 * WIN_GUARD > smem_limit) {
+    const long long rows_fit = (smem_limit - 2 * WIN_GUARD) / m->g.width_step;
+    band_rows = (int)((rows_fit - rows_total - 1) & ~1LL);  // even: band starts stay 16-byte aligned (width_step % 8 == 0)
+    if (band_rows < 8) {
+      bands_ok = false;
+    } else {
+      nbands = (m->g.height + band_rows - 1) / band_rows;
+      band_bytes = (int)((((long long)(band_rows + rows_total + 1) * m->g.width_step) + 15) & ~15LL);
+      if (nbands > WIN_MAX_BANDS) bands_ok = false;
+    }
+  }
+  const size_t win_smem = (size_t)band_bytes + 2 * WIN_GUARD;
   const bool stride1 = (s->res_x == 1.0 / (1.0 / m->p.resolution) || s->res_x == m->p.resolution) &&
                        (s->res_y == 1.0 / (1.0 / m->p.resolution) || s->res_y == m->p.resolution);
-  const bool win_fits = win_smem + 1024 <= (size_t)m->smem_optin && (m->g.width_step % 4) == 0 && n > 0 &&
-                        (size_t)n * 21 + 64 <= 200 * 1024 && !m->grid_high_bytes;
+  const bool win_fits = bands_ok && (m->g.width_step % 8) == 0 && n > 0 && (size_t)n * 21 + 64 <= 200 * 1024 &&
+                        !m->grid_high_bytes;
   bool use_window = stride1 && win_fits;
   if (m->force_kernel == 1) use_window = false;
   if (m->force_kernel >= 2 && !win_fits)
-    B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but the grid does not fit in shared memory");
+    B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but not applicable to this grid / beam count");
   if (m->force_kernel >= 2) use_window = true;
   const bool need_plain_lut = !use_window || s->fine;  // generic sweep and the angular covariance read the plain table
   if (need_plain_lut && (st = ensure_cap(&m->d_lut, &m->lut_cap, (size_t)B * na * std::max(n, 1)))) return st;
@@ -1675,9 +1731,9 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
                                              s->angle_offset, s->angle_res, na, n, m->g.width_step, scale, m->d_lut);
   const dim3 ggrid((unsigned)ceil_div(ncell, 8), (unsigned)B);
   if (use_window) {
-    const int tiles_x = (nx + 31) / 32, tiles_y = (ny + 31) / 32;
-    if ((st = ensure_cap(&m->d_lists, &m->lists_cap, (size_t)B * na * (n + LIST_PAD)))) return st;
-    if ((st = ensure_cap(&m->d_counts, &m->counts_cap, (size_t)B * na * 8))) return st;
+    if ((st = ensure_cap(&m->d_lists, &m->lists_cap, (size_t)B * na * (n + LIST_PAD * nbands)))) return st;
+    if ((st = ensure_cap(&m->d_counts, &m->counts_cap, (size_t)B * na * 8 * nbands))) return st;
+    if ((st = ensure_cap(&m->d_starts, &m->starts_cap, (size_t)B * na * 8 * nbands))) return st;
     bool skip_empty = m->sat_valid && m->force_kernel != 3;
     if ((((size_t)n * 21 + 15) & ~(size_t)15) + sizeof(uint16_t) * (size_t)(m->sbx + 1) * (m->sby + 1) + 64 > 200 * 1024) skip_empty = false;
     const size_t sat_bytes = skip_empty ? sizeof(uint16_t) * (size_t)(m->sbx + 1) * (m->sby + 1) : 0;
@@ -1685,12 +1741,10 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_stats, 0, sizeof(unsigned long long), m->stream));
     if (osm > 48 * 1024)
       B2S_CUDA_CHECK(cudaFuncSetAttribute(k_offsets_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
-    k_offsets_sorted<<<B * ((na + OFF_CHUNK - 1) / OFF_CHUNK), 256, osm, m->stream>>>(m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases,
-                                                      m->d_flags, s->angle_offset, s->angle_res, na, n, ncell,
-                                                      m->g.width_step, m->g.data_size, scale, tiles_y * 32,
-                                                      tiles_x * 32, m->d_lists, m->d_counts,
-                                                      skip_empty ? m->d_sat : nullptr, m->sbx, m->sby, m->g.height, nx, ny,
-                                                      m->d_stats);
+    k_offsets_sorted<<<B * ((na + OFF_CHUNK - 1) / OFF_CHUNK), 256, osm, m->stream>>>(
+        m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases, m->d_flags, s->angle_offset, s->angle_res, na, n,
+        ncell, m->g.width_step, m->g.data_size, scale, rows_total, tiles_x_w * 32, m->d_lists, m->d_counts,
+        skip_empty ? m->d_sat : nullptr, m->sbx, m->sby, m->g.height, nx, ny, m->d_stats, band_rows, nbands, m->d_starts);
   }
   B2S_CUDA_CHECK(cudaGetLastError());
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
@@ -1698,11 +1752,14 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   // ---- response sweep ----
   if (use_window) {
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_work, 0, sizeof(int), m->stream));
+    if (nbands > 1)  // bands accumulate with RED.ADD
+      B2S_CUDA_CHECK(cudaMemsetAsync(m->d_sums, 0, sizeof(int32_t) * (size_t)B * na * ncell, m->stream));
     B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
-    const int ctas = std::min(B, m->num_sms);
+    const int ctas = (int)std::min<long long>((long long)B * nbands, m->num_sms);
     k_sweep_window<<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
-                                                               m->d_lists, m->d_counts, m->d_flags, B, n, na, nx, ny,
-                                                               m->g.width_step, m->d_sums, m->d_work);
+                                                               m->d_lists, m->d_counts, m->d_starts, m->d_flags, B, n, na,
+                                                               nx, ny, m->g.width_step, m->d_sums, m->d_work, band_rows,
+                                                               nbands, band_bytes);
     // matches whose lattice is not the regular stride-1 raster (a centre exactly on a rounding tie) fall through;
     // they compute their lookup values on the fly (no table was materialised for them)
     k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, nullptr, m->d_bases,

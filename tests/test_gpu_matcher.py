@@ -160,7 +160,7 @@ def test_multibase_custom_laser_golden(pkg, M):
 @pytest.mark.parametrize("res,smear,search,rt", [(0.025, 0.03, 0.5, 6.0), (0.1, 0.3, 1.0, 6.0), (0.05, 0.1, 0.4, 6.0),
                                                  (0.025, 0.03, 1.5, 9.25)])
 def test_other_geometries(pkg, M, res, smear, search, rt):
-    """cfg-4 style 0.025 m grids (the last one is 652 KB: too large for shared memory -> generic kernel), the
+    """cfg-4 style 0.025 m grids (the last one is 652 KB: swept by the window kernel in row bands), the
     outdoor yaml's 0.1 m / smear 0.3 (13x13 smear kernel), and a mid case; MatchScan + a direct full-window
     CorrelateScan with the integer volume compared bit-exactly."""
     abi, synth = pkg.abi, pkg.synth
@@ -383,3 +383,37 @@ def test_randomised_configurations(pkg, M):
             assert_result(gpu, b, r)
         m.close()
     assert kinds[2] >= 8  # most of these grids fit in shared memory and use the window kernel
+
+
+@pytest.mark.parametrize("res,search,rt,na_deg", [(0.05, 1.5, 12.0, 10), (0.025, 1.5, 9.25, 5), (0.025, 0.75, 9.25, 8)])
+def test_banded_window_kernel_large_grids(pkg, M, res, search, rt, na_deg):
+    """Grids larger than shared memory (266 KB for a 12 m range threshold @0.05 m; 652 KB for cfg 4's 0.025 m grid,
+    with a 61x61 or 31x31 window) are swept by the window kernel in row bands whose partial sums are combined with
+    RED.ADD: bit-exact vs the restatement and vs the generic kernel, empty-window dropping on and off."""
+    abi, synth = pkg.abi, pkg.synth
+    laser_s = synth.Laser(range_threshold=rt)
+    params, laser = abi.matcher_params(search, res, 0.03, rt), abi.laser_from(laser_s)
+    cases, ranges, poses, bran, bpos = make_batch(synth, range(600, 603), laser_s, max_xy=0.2, max_th_deg=5)
+    B = len(cases)
+    m = M.ScanMatcher(params, laser, max_batch=B, max_base_scans=1)
+    assert m.g.data_size > 230_000
+    m.set_scans(ranges, poses)
+    m.add_scans(bran, bpos)
+    side = m.g.search_side
+    half = 0.5 * (side - 1) * res
+    se = abi.Search(half, half, res, res, na_deg * D, 1 * D, 1, 0)
+    na = abi.n_steps(na_deg * D, 1 * D)
+    vols = {}
+    for kernel in (2, 3, 1):
+        m.set_kernel(kernel)
+        gpu = m.correlate_scan(poses, se)
+        assert m.last_timing()["path"] == min(kernel, 2)
+        vols[kernel] = [m.response_sums(b, (side, side, na)) for b in range(B)]
+    for b in range(B):
+        pm = port_case(abi, params, laser, ranges[b], poses[b], bran[b], bpos[b])
+        rc, r = pm.correlate_scan(pm.sp, se, want_sums=True)
+        assert rc == 0
+        for kernel in (2, 3, 1):
+            assert np.array_equal(vols[kernel][b], pm.last_sums), (kernel, b)
+        assert_result(gpu, b, r)
+    m.close()
