@@ -303,6 +303,52 @@ def bench_k2(pkg, local, quick=False):
                                     "map built from the previous scans, then all 3 levels are updated"}
     for m in maps:
         m.close()
+    # --- K1 beyond the headline shape: the default two-stage MatchScan, and cfg-4 windows on a 0.025 m grid (banded kernel)
+    M = pkg.load("matcher")
+    try:
+        Bm = 256 if quick else 1024
+        cases = [synth.make_match_case(3_000_000 + i) for i in range(Bm)]
+        mr, mp = np.stack([c.ranges for c in cases]), np.stack([c.odom_pose for c in cases])
+        mbr, mbp = np.stack([c.base_ranges for c in cases])[:, None, :], np.stack([c.base_pose for c in cases])[:, None, :]
+        mm = M.ScanMatcher(abi.matcher_params(1.5, 0.05, 0.03, 9.25), al, max_batch=Bm, max_base_scans=1, device=local)
+        mm.match_scan_host(mr, mp, mbr, mbp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            r_ms = mm.match_scan_host(mr, mp, mbr, mbp)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        truth = np.stack([c.true_pose for c in cases])
+        out["match_scan_two_stage"] = {"batch": Bm, "shape": "coarse 16x16x21 (stride 2) + fine 3x3x11, 1.5 m / 0.05 m, 1 base scan",
+                                       "matches_per_s_e2e": Bm / dt, "ms": dt * 1e3,
+                                       "median_xy_err_m": float(np.median(np.abs(r_ms[1][:, :2] - truth[:, :2]).max(axis=1)))}
+        mm.close()
+        B4 = 64 if quick else 256
+        l4 = synth.Laser(range_threshold=9.25)
+        cases = [synth.make_match_case(4_000_000 + i, l4) for i in range(B4)]
+        mr, mp = np.stack([c.ranges for c in cases]), np.stack([c.odom_pose for c in cases])
+        mbr, mbp = np.stack([c.base_ranges for c in cases])[:, None, :], np.stack([c.base_pose for c in cases])[:, None, :]
+        m4 = M.ScanMatcher(abi.matcher_params(1.5, 0.025, 0.03, 9.25), abi.laser_from(l4), max_batch=B4, max_base_scans=1, device=local)
+        m4.set_scans(mr, mp)
+        m4.add_scans(mbr, mbp)
+        rows = []
+        for W, nth in ((11, 61), (31, 181), (61, 361)):
+            half = 0.5 * (W - 1) * 0.025
+            se4 = abi.Search(half, half, 0.025, 0.025, 0.5 * (nth - 1) * 0.25 * D, 0.25 * D, 1, 0)
+            m4.correlate_scan(mp, se4)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r4 = m4.correlate_scan(mp, se4)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tm = m4.last_timing()
+            rows.append({"window": [W, W, nth], "matches_per_s": B4 / dt, "sweep_ms": tm["sweep_ms"],
+                         "lookups_per_s_kernel": B4 * W * W * nth * 1081 / (tm["sweep_ms"] * 1e-3), "path": tm["path"],
+                         "ok": int((r4[3] == 0).sum())})
+        out["cfg4_window_sweep"] = {"batch": B4, "grid": "0.025 m, 807x807 (652 KB, 4 row bands)", "rows": rows}
+        m4.close()
+    except Exception as e:
+        out["k1_extras_error"] = repr(e)
     # --- K3 (lesson3): batched PL-ICP, 1024 independent scan pairs with odometry-like motion
     P = pkg.load("plicp")
     nb = 256 if quick else 1024
