@@ -327,12 +327,12 @@ __global__ void k_offsets(const double *__restrict__ ranges, const double *__res
 
 // ----------------------------------------------------------------------------------------------
 // k_bases: candidate lattice of CorrelateScan (Mapper.cpp:338-358, 373-386) -> flat base index per (iy, ix).
-// flags[b]: bit0 = lattice is the regular stride-1 raster base00 + ix + iy*width_step;
+// flags[b]: bit0 = lattice is the regular raster base00 + stride*(ix + iy*width_step), stride = 1 or 2 cells;
 //           bit1 = some candidate fell outside the grid (reference throws karto::Exception, Karto.h:4490-4499)
 // ----------------------------------------------------------------------------------------------
 __global__ void k_bases(const double *__restrict__ centers, const double *__restrict__ grid_off, b2s_search s,
                         b2s_grid_info g, double scale, int nx, int ny, int32_t *__restrict__ bases,
-                        int32_t *__restrict__ flags) {
+                        int32_t *__restrict__ flags, int stride) {
   const int b = blockIdx.x;
   __shared__ int irregular, oob;
   if (threadIdx.x == 0) { irregular = 0; oob = 0; }
@@ -349,7 +349,7 @@ __global__ void k_bases(const double *__restrict__ centers, const double *__rest
     int32_t gx = world_to_grid_1(cx + x, gox, scale) + g.roi_x;  // CorrelationGrid::GridIndex (Mapper.h:941-947)
     int32_t gy = world_to_grid_1(cy + y, goy, scale) + g.roi_y;
     if (!(gx >= 0 && gx < g.width && gy >= 0 && gy < g.height)) oob = 1;
-    if (gx != gx0 + ix || gy != gy0 + iy) irregular = 1;
+    if (gx != gx0 + stride * ix || gy != gy0 + stride * iy) irregular = 1;
     bases[(size_t)b * nx * ny + c] = gx + gy * g.width_step;
   }
   __syncthreads();
@@ -390,13 +390,30 @@ __global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict
       gox = grid_off[2 * b]; goy = grid_off[2 * b + 1];
     }
     int32_t sum = 0;
-    for (int i = lane; i < n; i += 32) {
-      int32_t o = lut ? __ldg(offs + i)
-                      : lut_value(ranges[(size_t)b * n + i], local[((size_t)b * n + i) * 2],
-                                  local[((size_t)b * n + i) * 2 + 1], cosine, sine, gox, goy, scale, width_step);
-      if (o == INVALID_SCAN) continue;
-      int32_t idx = (int32_t)((uint32_t)base + (uint32_t)o);
-      if (idx >= 0 && idx < data_size) sum += __ldg(grid + idx);
+    if (lut) {
+      // 8 independent (offset, cell) load chains in flight per lane: the gather is latency bound
+      constexpr int U = 8;
+      for (int i0 = lane; i0 < n; i0 += 32 * U) {
+        int32_t o[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) o[u] = (i0 + 32 * u < n) ? __ldg(offs + i0 + 32 * u) : INVALID_SCAN;
+        uint32_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int32_t idx = (int32_t)((uint32_t)base + (uint32_t)o[u]);
+          v[u] = (o[u] != INVALID_SCAN && idx >= 0 && idx < data_size) ? (uint32_t)__ldg(grid + idx) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) sum += (int32_t)v[u];
+      }
+    } else {
+      for (int i = lane; i < n; i += 32) {
+        const int32_t o = lut_value(ranges[(size_t)b * n + i], local[((size_t)b * n + i) * 2],
+                                    local[((size_t)b * n + i) * 2 + 1], cosine, sine, gox, goy, scale, width_step);
+        if (o == INVALID_SCAN) continue;
+        const int32_t idx = (int32_t)((uint32_t)base + (uint32_t)o);
+        if (idx >= 0 && idx < data_size) sum += __ldg(grid + idx);
+      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
@@ -490,7 +507,7 @@ __global__ void __launch_bounds__(256)
                      int rows_total, int cols_total, int32_t *__restrict__ lists, int32_t *__restrict__ counts,
                      const uint16_t *__restrict__ sat_all, int sbx, int sby, int height, int nx, int ny,
                      unsigned long long *__restrict__ stats, int band_rows, int nbands,
-                     int32_t *__restrict__ starts) {
+                     int32_t *__restrict__ starts, int stride) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   double *s_lx = reinterpret_cast<double *>(s_raw), *s_ly = s_lx + n;  // [n] scan-local points
   int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);             // [n] window origins
@@ -517,7 +534,8 @@ __global__ void __launch_bounds__(256)
   const double center = centers[(size_t)b * 3 + 2];
   const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
   const int32_t base00 = bases[(size_t)b * ncell];
-  const long long span = (long long)(rows_total - 1) * width_step + cols_total + 8;  // last byte any lane may touch
+  const long long span = (long long)stride * (rows_total - 1) * width_step + cols_total + 8;  // last byte any lane may touch
+  const int fx = stride * (nx - 1) + 1, fy = stride * (ny - 1) + 1;  // footprint of the candidate lattice in cells
   const float inv_step = 1.0f / (float)width_step, inv_band = 1.0f / (float)band_rows;
   for (int k = k0; k < min(k0 + OFF_CHUNK, n_angles); k++) {
     __syncthreads();  // staging done / previous angle's smem fully consumed
@@ -557,8 +575,8 @@ __global__ void __launch_bounds__(256)
         }
         if (sat_all && cls < 255 && a >= 0) {
           // empty-window test on the 4x4-block summed-area table (only for windows that do not wrap a row end)
-          if (x + nx <= width_step && y + ny <= height) {
-            const int bx0 = x >> 2, bx1 = (x + nx - 1) >> 2, by0 = y >> 2, by1 = (y + ny - 1) >> 2;
+          if (x + fx <= width_step && y + fy <= height) {
+            const int bx0 = x >> 2, bx1 = (x + fx - 1) >> 2, by0 = y >> 2, by1 = (y + fy - 1) >> 2;
             const uint32_t c = (uint32_t)s_sat[(by1 + 1) * SW + bx1 + 1] - (uint32_t)s_sat[by0 * SW + bx1 + 1] -
                                (uint32_t)s_sat[(by1 + 1) * SW + bx0] + (uint32_t)s_sat[by0 * SW + bx0];
             if (c == 0) { cls = 255; empty_here++; }
@@ -613,15 +631,19 @@ __global__ void __launch_bounds__(256)
 // flush the packed-u16 accumulators (word-aligned coordinates, alignment class SH) into the per-candidate sums.
 // slots 0..7 hold aligned word j (lanes 0..15) or aligned word (j+1)%8 (lanes 16..31); slot 8 holds aligned word 8;
 // byte q of word w is candidate x = 4*w + q - SH.
-template <int SH>
+// With STRIDE = 2 (candidates every other cell) only the bytes at even distance from the origin are candidates:
+// byte position p = 4*w + q - SH is candidate x = p / 2 when p is even; a tile then holds 16 candidates in 32 bytes.
+template <int SH, int STRIDE>
 __device__ __forceinline__ void win_flush(uint32_t (&lo)[9], uint32_t (&hi)[9], uint32_t (&acc)[32], int hi_half) {
+#define B2S_FLUSH_ONE(P, VAL)                                                        \
+  if ((P) >= 0 && ((P) % STRIDE) == 0 && (P) / STRIDE < 32 / STRIDE) acc[((P) / STRIDE) & 31] += (VAL);
 #define B2S_FLUSH_SLOT(J, W)                                                         \
   {                                                                                  \
     const int x0 = 4 * (W) - SH;                                                     \
-    if (x0 + 0 >= 0 && x0 + 0 < 32) acc[(x0 + 0) & 31] += lo[J] & 0xffffu;           \
-    if (x0 + 1 >= 0 && x0 + 1 < 32) acc[(x0 + 1) & 31] += hi[J] & 0xffffu;           \
-    if (x0 + 2 >= 0 && x0 + 2 < 32) acc[(x0 + 2) & 31] += lo[J] >> 16;               \
-    if (x0 + 3 >= 0 && x0 + 3 < 32) acc[(x0 + 3) & 31] += hi[J] >> 16;               \
+    B2S_FLUSH_ONE(x0 + 0, lo[J] & 0xffffu)                                           \
+    B2S_FLUSH_ONE(x0 + 1, hi[J] & 0xffffu)                                           \
+    B2S_FLUSH_ONE(x0 + 2, lo[J] >> 16)                                               \
+    B2S_FLUSH_ONE(x0 + 3, hi[J] >> 16)                                               \
   }
   if (!hi_half) {
 #pragma unroll
@@ -632,6 +654,7 @@ __device__ __forceinline__ void win_flush(uint32_t (&lo)[9], uint32_t (&hi)[9], 
   }
   B2S_FLUSH_SLOT(8, 8)
 #undef B2S_FLUSH_SLOT
+#undef B2S_FLUSH_ONE
 #pragma unroll
   for (int j = 0; j < 9; j++) { lo[j] = 0; hi[j] = 0; }
 }
@@ -662,7 +685,7 @@ __device__ __forceinline__ void win_accumulate2(const uint32_t (&v1)[9], const u
 }
 
 // all beams of one alignment class; count is a multiple of 4.  CHECK = per-row range test (edge beams).
-template <int SH, bool CHECK, bool W9>
+template <int SH, int STRIDE, bool CHECK, bool W9>
 __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, const int32_t *__restrict__ list,
                                           int count, int lane, int hi_half, int bias, int row_delta,
                                           int data_size, int32_t *__restrict__ s_off, uint32_t (&lo)[9],
@@ -673,7 +696,7 @@ __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, con
     s_off[lane] = (lane < cnt) ? __ldg(list + ib + lane) : 0;  // this warp's staging row
     __syncwarp();
     if (pending + cnt > WIN_FLUSH_BEAMS) {
-      win_flush<SH>(lo, hi, acc, hi_half);
+      win_flush<SH, STRIDE>(lo, hi, acc, hi_half);
       pending = 0;
     }
     pending += cnt;
@@ -701,22 +724,23 @@ __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, con
   }
 }
 
-template <int SH>
+template <int SH, int STRIDE>
 __device__ __forceinline__ void win_class_pair(const uint8_t *__restrict__ sgrid, const int32_t *__restrict__ li,
                                                int ci, const int32_t *__restrict__ le, int ce, int cols, int lane,
                                                int hi_half, int row_delta, int bias, int data_size, int32_t *__restrict__ s_off,
                                                uint32_t (&lo)[9], uint32_t (&hi)[9], uint32_t (&acc)[32]) {
   int pending = 0;
-  if (SH + cols > 32) {  // the last candidates need aligned word 8
-    win_class<SH, false, true>(sgrid, li, ci, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
-    win_class<SH, true, true>(sgrid, le, ce, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+  if (SH + STRIDE * (cols - 1) + 1 > 32) {  // the last candidates need aligned word 8
+    win_class<SH, STRIDE, false, true>(sgrid, li, ci, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, STRIDE, true, true>(sgrid, le, ce, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
   } else {
-    win_class<SH, false, false>(sgrid, li, ci, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
-    win_class<SH, true, false>(sgrid, le, ce, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, STRIDE, false, false>(sgrid, li, ci, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, STRIDE, true, false>(sgrid, le, ce, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
   }
-  win_flush<SH>(lo, hi, acc, hi_half);
+  win_flush<SH, STRIDE>(lo, hi, acc, hi_half);
 }
 
+template <int STRIDE>
 __global__ void __launch_bounds__(WIN_THREADS, 1)
     k_sweep_window(const uint8_t *__restrict__ grids, size_t grid_pitch, int data_size, int copy_bytes,
                    const int32_t *__restrict__ lists, const int32_t *__restrict__ counts,
@@ -734,7 +758,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
 
   const int lane = threadIdx.x & 31;
   int32_t *s_off = s_offsets[threadIdx.x >> 5];
-  const int tiles_x = (nx + 31) >> 5, tiles_y = (ny + 31) >> 5;
+  constexpr int CPT = 32 / STRIDE;  // candidates per tile row (a tile row is always 32 bytes)
+  const int tiles_x = (nx + CPT - 1) / CPT, tiles_y = (ny + 31) >> 5;
   const int items = na * tiles_x * tiles_y;
   const int hi_half = lane >> 4;
   const int list_cap = n + LIST_PAD * nbands;
@@ -789,7 +814,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
       const int k = item / (tiles_x * tiles_y);
       const int t = item % (tiles_x * tiles_y);
       const int ty = t / tiles_x, tx = t % tiles_x;
-      const int row_delta = (ty * 32 + lane) * width_step + tx * 32;  // this lane's row start relative to a beam's origin
+      const int row_delta = STRIDE * (ty * 32 + lane) * width_step + tx * 32;  // this lane's row start relative to a beam's origin
       const int32_t *list = lists + ((size_t)b * na + k) * list_cap;
       const int32_t *cn = counts + ((size_t)b * na + k) * ngroups + band * 8;
       const int32_t *sg = starts + ((size_t)b * na + k) * ngroups + band * 8;
@@ -801,24 +826,24 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
 #pragma unroll
       for (int j = 0; j < 9; j++) { lo[j] = 0; hi[j] = 0; }
       // groups of this band: I0 I1 I2 I3 E0 E1 E2 E3 (interior / edge beams of each alignment class)
-      const int cols = min(32, nx - tx * 32);
-      win_class_pair<0>(sgrid, list + sg[0], cn[0], list + sg[4], cn[4], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
-      win_class_pair<1>(sgrid, list + sg[1], cn[1], list + sg[5], cn[5], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
-      win_class_pair<2>(sgrid, list + sg[2], cn[2], list + sg[6], cn[6], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
-      win_class_pair<3>(sgrid, list + sg[3], cn[3], list + sg[7], cn[7], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
+      const int cols = min(CPT, nx - tx * CPT);
+      win_class_pair<0, STRIDE>(sgrid, list + sg[0], cn[0], list + sg[4], cn[4], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<1, STRIDE>(sgrid, list + sg[1], cn[1], list + sg[5], cn[5], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<2, STRIDE>(sgrid, list + sg[2], cn[2], list + sg[6], cn[6], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<3, STRIDE>(sgrid, list + sg[3], cn[3], list + sg[7], cn[7], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
 
       // ---- write / accumulate this lane's row ----
       const int iy = ty * 32 + lane;
       if (iy < ny) {
-        int32_t *dst = bsums + ((size_t)k * ny + iy) * nx + tx * 32;
+        int32_t *dst = bsums + ((size_t)k * ny + iy) * nx + tx * CPT;
         if (nbands == 1) {
 #pragma unroll
-          for (int x = 0; x < 32; x++)
-            if (tx * 32 + x < nx) dst[x] = (int32_t)acc[x];
+          for (int x = 0; x < CPT; x++)
+            if (tx * CPT + x < nx) dst[x] = (int32_t)acc[x];
         } else {
 #pragma unroll
-          for (int x = 0; x < 32; x++)
-            if (tx * 32 + x < nx && acc[x]) atomicAdd(dst + x, (int32_t)acc[x]);
+          for (int x = 0; x < CPT; x++)
+            if (tx * CPT + x < nx && acc[x]) atomicAdd(dst + x, (int32_t)acc[x]);
         }
       }
     }
@@ -1695,37 +1720,43 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   // The window kernel needs a stride-1 lattice and a band of the grid in shared memory: the whole grid when it fits
   // (nbands = 1), otherwise nbands row bands of band_rows origin rows + (window rows + 1) halo rows each.
   const int copy_bytes = (m->g.data_size + 15) & ~15;
-  const int tiles_x_w = (nx + 31) / 32, tiles_y_w = (ny + 31) / 32;
+  // candidate stride in grid cells: 1 (search resolution == grid resolution) or 2 (the coarse stage of MatchScan,
+  // Mapper.cpp:233-234); anything else goes to the generic kernel
+  const double gres = 1.0 / (1.0 / m->p.resolution);
+  auto stride_of = [&](double r) { return (r == gres || r == m->p.resolution) ? 1 : ((r == 2 * gres || r == 2 * m->p.resolution) ? 2 : 0); };
+  const int stride = (stride_of(s->res_x) == stride_of(s->res_y)) ? stride_of(s->res_x) : 0;
+  const int cpt = stride == 2 ? 16 : 32;  // candidates per 32-byte tile row
+  const int tiles_x_w = (nx + cpt - 1) / cpt, tiles_y_w = (ny + 31) / 32;
   const int rows_total = tiles_y_w * 32;
+  const int halo_rows = std::max(stride, 1) * rows_total + 1;  // rows below a window origin that a lane may touch
   const long long smem_limit = (long long)m->smem_optin - 4096;  // static shared memory of the kernel + margin
   int band_rows = std::max(m->g.height, 1), nbands = 1, band_bytes = copy_bytes;
   bool bands_ok = true;
   if ((long long)copy_bytes + 2 * WIN_GUARD > smem_limit) {
     const long long rows_fit = (smem_limit - 2 * WIN_GUARD) / m->g.width_step;
-    band_rows = (int)((rows_fit - rows_total - 1) & ~1LL);  // even: band starts stay 16-byte aligned (width_step % 8 == 0)
+    band_rows = (int)((rows_fit - halo_rows) & ~1LL);  // even: band starts stay 16-byte aligned (width_step % 8 == 0)
     if (band_rows < 8) {
       bands_ok = false;
     } else {
       nbands = (m->g.height + band_rows - 1) / band_rows;
-      band_bytes = (int)((((long long)(band_rows + rows_total + 1) * m->g.width_step) + 15) & ~15LL);
+      band_bytes = (int)((((long long)(band_rows + halo_rows) * m->g.width_step) + 15) & ~15LL);
       if (nbands > WIN_MAX_BANDS) bands_ok = false;
     }
   }
   const size_t win_smem = (size_t)band_bytes + 2 * WIN_GUARD;
-  const bool stride1 = (s->res_x == 1.0 / (1.0 / m->p.resolution) || s->res_x == m->p.resolution) &&
-                       (s->res_y == 1.0 / (1.0 / m->p.resolution) || s->res_y == m->p.resolution);
-  const bool win_fits = bands_ok && (m->g.width_step % 8) == 0 && n > 0 && (size_t)n * 21 + 64 <= 200 * 1024 &&
-                        !m->grid_high_bytes;
-  bool use_window = stride1 && win_fits;
+  const bool win_fits = bands_ok && stride != 0 && (m->g.width_step % 8) == 0 && n > 0 &&
+                        (size_t)n * 21 + 64 <= 200 * 1024 && !m->grid_high_bytes;
+  bool use_window = win_fits;
   if (m->force_kernel == 1) use_window = false;
   if (m->force_kernel >= 2 && !win_fits)
-    B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but not applicable to this grid / beam count");
+    B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but not applicable to this lattice / grid / beam count");
   if (m->force_kernel >= 2) use_window = true;
   const bool need_plain_lut = !use_window || s->fine;  // generic sweep and the angular covariance read the plain table
   if (need_plain_lut && (st = ensure_cap(&m->d_lut, &m->lut_cap, (size_t)B * na * std::max(n, 1)))) return st;
 
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[0], m->stream));
-  k_bases<<<B, 256, 0, m->stream>>>(m->d_centers, m->d_grid_off, *s, m->g, scale, nx, ny, m->d_bases, m->d_flags);
+  k_bases<<<B, 256, 0, m->stream>>>(m->d_centers, m->d_grid_off, *s, m->g, scale, nx, ny, m->d_bases, m->d_flags,
+                                    std::max(stride, 1));
   if (need_plain_lut)
     k_offsets<<<B * na, 256, 0, m->stream>>>(m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, 3, 0.0, 0,
                                              s->angle_offset, s->angle_res, na, n, m->g.width_step, scale, m->d_lut);
@@ -1744,7 +1775,8 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     k_offsets_sorted<<<B * ((na + OFF_CHUNK - 1) / OFF_CHUNK), 256, osm, m->stream>>>(
         m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases, m->d_flags, s->angle_offset, s->angle_res, na, n,
         ncell, m->g.width_step, m->g.data_size, scale, rows_total, tiles_x_w * 32, m->d_lists, m->d_counts,
-        skip_empty ? m->d_sat : nullptr, m->sbx, m->sby, m->g.height, nx, ny, m->d_stats, band_rows, nbands, m->d_starts);
+        skip_empty ? m->d_sat : nullptr, m->sbx, m->sby, m->g.height, nx, ny, m->d_stats, band_rows, nbands, m->d_starts,
+        stride);
   }
   B2S_CUDA_CHECK(cudaGetLastError());
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
@@ -1754,13 +1786,21 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_work, 0, sizeof(int), m->stream));
     if (nbands > 1)  // bands accumulate with RED.ADD
       B2S_CUDA_CHECK(cudaMemsetAsync(m->d_sums, 0, sizeof(int32_t) * (size_t)B * na * ncell, m->stream));
-    B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
     const int ctas = (int)std::min<long long>((long long)B * nbands, m->num_sms);
-    k_sweep_window<<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
-                                                               m->d_lists, m->d_counts, m->d_starts, m->d_flags, B, n, na,
-                                                               nx, ny, m->g.width_step, m->d_sums, m->d_work, band_rows,
-                                                               nbands, band_bytes);
-    // matches whose lattice is not the regular stride-1 raster (a centre exactly on a rounding tie) fall through;
+    if (stride == 2) {
+      B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
+      k_sweep_window<2><<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
+                                                                    m->d_lists, m->d_counts, m->d_starts, m->d_flags, B, n,
+                                                                    na, nx, ny, m->g.width_step, m->d_sums, m->d_work,
+                                                                    band_rows, nbands, band_bytes);
+    } else {
+      B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
+      k_sweep_window<1><<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
+                                                                    m->d_lists, m->d_counts, m->d_starts, m->d_flags, B, n,
+                                                                    na, nx, ny, m->g.width_step, m->d_sums, m->d_work,
+                                                                    band_rows, nbands, band_bytes);
+    }
+    // matches whose lattice is not the regular raster (a centre exactly on a rounding tie) fall through;
     // they compute their lookup values on the fly (no table was materialised for them)
     k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, nullptr, m->d_bases,
                                                   m->d_flags, 1, n, na, ncell, m->d_sums, m->d_ranges, m->d_local,

@@ -417,3 +417,38 @@ def test_banded_window_kernel_large_grids(pkg, M, res, search, rt, na_deg):
             assert np.array_equal(vols[kernel][b], pm.last_sums), (kernel, b)
         assert_result(gpu, b, r)
     m.close()
+
+
+@pytest.mark.parametrize("res,search,rt", [(0.05, 1.5, 9.25), (0.05, 3.7, 6.0), (0.1, 15.0, 5.0)])
+def test_stride2_coarse_lattice(pkg, M, res, search, rt):
+    """The coarse stage of MatchScan searches every other cell (Mapper.cpp:233-234).  The window kernel handles that
+    lattice with 16 candidates per 32-byte tile row: 16x16 (one tile), 38x38 (3x2 tiles) and the outdoor yaml's
+    76x76 loop-closure window (151-cell side @0.1 m, smear 0.3; banded 1.36 MB-class grid is emulated with rt = 5 m).
+    Integer volumes bit-exact vs the restatement on every kernel."""
+    abi, synth = pkg.abi, pkg.synth
+    laser_s = synth.Laser(range_threshold=rt)
+    smear = 0.3 if res == 0.1 else 0.03
+    params, laser = abi.matcher_params(search, res, smear, rt), abi.laser_from(laser_s)
+    cases, ranges, poses, bran, bpos = make_batch(synth, range(700, 702), laser_s, max_xy=0.2, max_th_deg=5)
+    B = len(cases)
+    m = M.ScanMatcher(params, laser, max_batch=B, max_base_scans=1)
+    m.set_scans(ranges, poses)
+    m.add_scans(bran, bpos)
+    side = m.g.search_side
+    half = 0.5 * (side - 1) * res
+    se = abi.Search(half, half, 2 * res, 2 * res, 20 * D, 2 * D, 1, 0)
+    nxy, na = abi.n_steps(half, 2 * res), abi.n_steps(20 * D, 2 * D)
+    vols = {}
+    for kernel in (2, 3, 1):
+        m.set_kernel(kernel)
+        gpu = m.correlate_scan(poses, se)
+        assert m.last_timing()["path"] == min(kernel, 2)
+        vols[kernel] = [m.response_sums(b, (nxy, nxy, na)) for b in range(B)]
+    for b in range(B):
+        pm = port_case(abi, params, laser, ranges[b], poses[b], bran[b], bpos[b])
+        rc, r = pm.correlate_scan(pm.sp, se, want_sums=True)
+        assert rc == 0
+        for kernel in (2, 3, 1):
+            assert np.array_equal(vols[kernel][b], pm.last_sums), (kernel, b)
+        assert_result(gpu, b, r)
+    m.close()
