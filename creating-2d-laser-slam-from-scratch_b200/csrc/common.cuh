@@ -46,7 +46,14 @@ constexpr double DISTANCE_PENALTY_GAIN = 0.2;      // Mapper.cpp:37
 constexpr double ANGLE_PENALTY_GAIN = 0.2;         // Mapper.cpp:38
 
 // math::Round (Math.h:87-90): half away from zero
-__host__ __device__ __forceinline__ double kround(double v) { return v >= 0.0 ? floor(v + 0.5) : ceil(v - 0.5); }
+__host__ __device__ __forceinline__ double kround(double v) {
+#ifdef __CUDA_ARCH__
+  // identical values: ceil(v - 0.5) == -floor(-v + 0.5) for v < 0 (negation is exact); one rounding op instead of two
+  return copysign(floor(fabs(v) + 0.5), v);
+#else
+  return v >= 0.0 ? floor(v + 0.5) : ceil(v - 0.5);
+#endif
+}
 
 // static_cast<kt_int32s>(double) as the reference's x86-64 build performs it (cvttsd2si: out-of-range and NaN
 // give INT_MIN); CUDA's own conversion saturates instead.

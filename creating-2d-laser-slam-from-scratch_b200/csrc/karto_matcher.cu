@@ -532,29 +532,42 @@ __global__ void __launch_bounds__(256)
   }
   if (threadIdx.x == 0) n_empty = 0;
   const double center = centers[(size_t)b * 3 + 2];
+  __shared__ double s_cos[OFF_CHUNK], s_sin[OFF_CHUNK];
+  if (threadIdx.x < OFF_CHUNK && k0 + threadIdx.x < n_angles) {  // one sincos per angle, not per thread
+    const double ang = (center - angle_offset) + (double)(uint32_t)(k0 + threadIdx.x) * angle_res;
+    s_cos[threadIdx.x] = cos(ang);
+    s_sin[threadIdx.x] = sin(ang);
+  }
   const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
   const int32_t base00 = bases[(size_t)b * ncell];
   const long long span = (long long)stride * (rows_total - 1) * width_step + cols_total + 8;  // last byte any lane may touch
+  const int32_t span32 = (int32_t)min(span, (long long)(1 << 29));
   const int fx = stride * (nx - 1) + 1, fy = stride * (ny - 1) + 1;  // footprint of the candidate lattice in cells
   const float inv_step = 1.0f / (float)width_step, inv_band = 1.0f / (float)band_rows;
   for (int k = k0; k < min(k0 + OFF_CHUNK, n_angles); k++) {
     __syncthreads();  // staging done / previous angle's smem fully consumed
     if (threadIdx.x < ngroups) { cnt[threadIdx.x] = 0; fill[threadIdx.x] = 0; }
     __syncthreads();
-    const double angle = (center - angle_offset) + (double)(uint32_t)k * angle_res;
-    const double cosine = cos(angle), sine = sin(angle);
+    const double cosine = s_cos[k - k0], sine = s_sin[k - k0];
     int empty_here = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const double plx = s_lx[i], ply = s_ly[i];
-      const int32_t o = lut_value((isfinite(plx) && isfinite(ply)) ? 0.0 : CUDART_NAN, plx, ply, cosine, sine, gox, goy, scale, width_step);
+      // lut_value() inlined: a non-finite local point (INVALID_SCAN reading) makes ox/oy non-finite
+      const double ox = __dsub_rn(__dmul_rn(cosine, plx), __dmul_rn(sine, ply));
+      const double oy = __dadd_rn(__dmul_rn(sine, plx), __dmul_rn(cosine, ply));
       int cls = 255;  // dropped
       int32_t a = 0;
-      if (o != INVALID_SCAN) {
+      if (isfinite(ox) && isfinite(oy)) {
+        const int32_t gx = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(ox, gox), gox), scale)));
+        const int32_t gy = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(oy, goy), goy), scale)));
+        const int32_t o = (int32_t)((uint32_t)gx + (uint32_t)gy * (uint32_t)width_step);
         a = (int32_t)((uint32_t)base00 + (uint32_t)o);
-        const long long lo = (long long)a - 8, hi = (long long)a + span;
-        if (hi < 0 || lo >= (long long)data_size) cls = 255;  // whole window outside: contributes 0
-        else if (lo >= -(WIN_GUARD - 16) && hi <= (long long)data_size + (WIN_GUARD - 16)) cls = a & 3;  // interior
-        else cls = 4 + (a & 3);                                                                           // edge
+        // window [a - 8, a + span] against [0, data_size): 32-bit arithmetic after clamping far-away origins
+        const int32_t ac = max(min(a, (int32_t)(1 << 29)), -(int32_t)(1 << 29));
+        const int32_t lo = ac - 8, hi = ac + span32;
+        if (hi < 0 || lo >= data_size) cls = 255;  // whole window outside: contributes 0
+        else if (lo >= -(WIN_GUARD - 16) && hi <= data_size + (WIN_GUARD - 16)) cls = a & 3;  // interior
+        else cls = 4 + (a & 3);                                                                // edge
         int y = 0, x = 0;
         if ((sat_all || nbands > 1) && cls < 255 && a >= 0) {
           // a / width_step by float reciprocal + fix-up (a < 2^24 is exact in float; larger values are corrected too)
