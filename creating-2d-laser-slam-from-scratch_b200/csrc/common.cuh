@@ -29,6 +29,19 @@ std::string &last_error_ref();
     }                                                                                                 \
   } while (0)
 
+// same, running `cleanup` (e.g. destroying a half-built handle) before returning
+#define B2S_CUDA_CHECK_CLEAN(cleanup, expr)                                                            \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      const std::string _why = std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +      \
+                               __FILE__ + ":" + std::to_string(__LINE__) + ")";                       \
+      cleanup;                                                                                        \
+      ::b2s::set_last_error(_why);                                                                    \
+      return B2S_ERR_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+
 #define B2S_FAIL(code, msg)        \
   do {                             \
     ::b2s::set_last_error(msg);    \

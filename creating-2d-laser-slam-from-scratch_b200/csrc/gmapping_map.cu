@@ -125,6 +125,7 @@ __global__ void k_gm_ros(const int32_t *__restrict__ n, const int32_t *__restric
 
 }  // namespace b2s
 
+extern "C" void b2s_gmap_destroy(b2s_gmap *g);
 extern "C" {
 
 b2s_status b2s_gmap_create(double center_x, double center_y, double xmin, double ymin, double xmax, double ymax,
@@ -143,22 +144,25 @@ b2s_status b2s_gmap_create(double center_x, double center_y, double xmin, double
   g->msy = (ys >> 5) << 5;
   g->sx2 = (int)round((center_x - xmin) / delta);  // map.h:139-140
   g->sy2 = (int)round((center_y - ymin) / delta);
-  if (g->msx <= 0 || g->msy <= 0) B2S_FAIL(B2S_ERR_BAD_PARAMS, "map smaller than one 32-cell patch");
+  if (g->msx <= 0 || g->msy <= 0) {
+    delete g;
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "map smaller than one 32-cell patch");
+  }
   if (cuda_stream) {
     g->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   } else {
-    B2S_CUDA_CHECK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    B2S_CUDA_CHECK_CLEAN(b2s_gmap_destroy(g), cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     g->own_stream = true;
   }
   const size_t cells = (size_t)g->msx * g->msy;
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_n), cells * 4));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_visits), cells * 4));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_accx), cells * 4));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_accy), cells * 4));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_flag), sizeof(int)));
+  B2S_CUDA_CHECK_CLEAN(b2s_gmap_destroy(g), cudaMalloc(reinterpret_cast<void **>(&g->d_n), cells * 4));
+  B2S_CUDA_CHECK_CLEAN(b2s_gmap_destroy(g), cudaMalloc(reinterpret_cast<void **>(&g->d_visits), cells * 4));
+  B2S_CUDA_CHECK_CLEAN(b2s_gmap_destroy(g), cudaMalloc(reinterpret_cast<void **>(&g->d_accx), cells * 4));
+  B2S_CUDA_CHECK_CLEAN(b2s_gmap_destroy(g), cudaMalloc(reinterpret_cast<void **>(&g->d_accy), cells * 4));
+  B2S_CUDA_CHECK_CLEAN(b2s_gmap_destroy(g), cudaMalloc(reinterpret_cast<void **>(&g->d_flag), sizeof(int)));
   for (void *p : {(void *)g->d_n, (void *)g->d_visits, (void *)g->d_accx, (void *)g->d_accy})
-    B2S_CUDA_CHECK(cudaMemsetAsync(p, 0, cells * 4, g->stream));
-  B2S_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    B2S_CUDA_CHECK_CLEAN(b2s_gmap_destroy(g), cudaMemsetAsync(p, 0, cells * 4, g->stream));
+  B2S_CUDA_CHECK_CLEAN(b2s_gmap_destroy(g), cudaStreamSynchronize(g->stream));
   *out = g;
   return B2S_OK;
 }
@@ -166,10 +170,10 @@ b2s_status b2s_gmap_create(double center_x, double center_y, double xmin, double
 void b2s_gmap_destroy(b2s_gmap *g) {
   if (!g) return;
   cudaSetDevice(g->device);
-  cudaStreamSynchronize(g->stream);
+  if (g->stream) cudaStreamSynchronize(g->stream);
   for (void *p : {(void *)g->d_n, (void *)g->d_visits, (void *)g->d_accx, (void *)g->d_accy, (void *)g->d_flag})
     if (p) cudaFree(p);
-  if (g->own_stream) cudaStreamDestroy(g->stream);
+  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
 

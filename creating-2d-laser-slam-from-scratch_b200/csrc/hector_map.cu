@@ -281,6 +281,7 @@ __global__ void k_hc_ros(const float *__restrict__ lo, int n, int8_t *__restrict
 
 }  // namespace b2s
 
+extern "C" void b2s_hector_map_destroy(b2s_hector_map *m);
 extern "C" {
 
 b2s_status b2s_hector_map_create(int size_x, int size_y, float resolution, float start_x, float start_y, int device,
@@ -313,22 +314,22 @@ b2s_status b2s_hector_map_create(int size_x, int size_y, float resolution, float
   if (cuda_stream) {
     m->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   } else {
-    B2S_CUDA_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     m->own_stream = true;
   }
-  for (auto &e : m->ev) B2S_CUDA_CHECK(cudaEventCreate(&e));
+  for (auto &e : m->ev) B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaEventCreate(&e));
   const size_t cells = (size_t)size_x * size_y;
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&m->d_lo), cells * 4));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&m->d_ui), cells * 4));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&m->d_free), cells * 8));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&m->d_occ), cells * 8));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&m->d_out), 12 * sizeof(float)));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&m->d_visits), sizeof(unsigned long long)));
-  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_lo, 0, cells * 4, m->stream));     // resetGridCell: logOdds 0
-  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_ui, 0xff, cells * 4, m->stream));  // updateIndex -1
-  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_free, 0, cells * 8, m->stream));
-  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_occ, 0, cells * 8, m->stream));
-  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMalloc(reinterpret_cast<void **>(&m->d_lo), cells * 4));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMalloc(reinterpret_cast<void **>(&m->d_ui), cells * 4));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMalloc(reinterpret_cast<void **>(&m->d_free), cells * 8));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMalloc(reinterpret_cast<void **>(&m->d_occ), cells * 8));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMalloc(reinterpret_cast<void **>(&m->d_out), 12 * sizeof(float)));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMalloc(reinterpret_cast<void **>(&m->d_visits), sizeof(unsigned long long)));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMemsetAsync(m->d_lo, 0, cells * 4, m->stream));     // resetGridCell: logOdds 0
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMemsetAsync(m->d_ui, 0xff, cells * 4, m->stream));  // updateIndex -1
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMemsetAsync(m->d_free, 0, cells * 8, m->stream));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaMemsetAsync(m->d_occ, 0, cells * 8, m->stream));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_map_destroy(m), cudaStreamSynchronize(m->stream));
   m->epoch = 0;
   *out = m;
   return B2S_OK;
@@ -337,13 +338,13 @@ b2s_status b2s_hector_map_create(int size_x, int size_y, float resolution, float
 void b2s_hector_map_destroy(b2s_hector_map *m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaStreamSynchronize(m->stream);
+  if (m->stream) cudaStreamSynchronize(m->stream);
   for (void *p : {(void *)m->d_lo, (void *)m->d_ui, (void *)m->d_free, (void *)m->d_occ, (void *)m->d_pts, (void *)m->d_out,
                   (void *)m->d_visits})
     if (p) cudaFree(p);
   for (auto &e : m->ev)
     if (e) cudaEventDestroy(e);
-  if (m->own_stream) cudaStreamDestroy(m->stream);
+  if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
 

@@ -1326,18 +1326,10 @@ int b2s_device_count(void) {
   return n;
 }
 
-b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser *laser, int device, int max_batch,
-                              int max_base_scans, void *cuda_stream, b2s_matcher **out) {
-  if (!params || !laser || !out || max_batch <= 0 || laser->n_readings < 0 || max_base_scans < 0)
-    B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_matcher_create: null/negative argument");
-  *out = nullptr;
-  b2s_grid_info g;
-  b2s_status st = layout_from_params(params, &g);
-  if (st) return st;
-  if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
-  B2S_CUDA_CHECK(cudaSetDevice(device));
-  b2s_matcher *m = new (std::nothrow) b2s_matcher();
-  if (!m) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
+void b2s_matcher_destroy(b2s_matcher *m);
+static b2s_status matcher_create_impl(const b2s_matcher_params *params, const b2s_laser *laser, int device, int max_batch,
+                                      int max_base_scans, void *cuda_stream, b2s_matcher *m, const b2s_grid_info &g) {
+  b2s_status st;
   m->p = *params; m->l = *laser; m->g = g; m->device = device;
   m->max_batch = max_batch; m->max_base = max_base_scans; m->n = laser->n_readings;
   cudaDeviceProp prop;
@@ -1364,8 +1356,7 @@ b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser 
         K[(i + half) + ks * (j + half)] = (uint8_t)kv;
         if ((i != 0 || j != 0) && kv >= (uint32_t)GRID_OCCUPIED) m->smear_degenerate = true;
       }
-    st = dev_alloc(&m->d_kernel, K.size());
-    if (st) return st;
+    if ((st = dev_alloc(&m->d_kernel, K.size()))) return st;
     B2S_CUDA_CHECK(cudaMemcpy(m->d_kernel, K.data(), K.size(), cudaMemcpyHostToDevice));
   }
   const size_t B = (size_t)max_batch, N = (size_t)std::max(m->n, 1);
@@ -1391,6 +1382,28 @@ b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser 
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_grids, 0, B * m->grid_pitch, m->stream));
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_results, 0, B * sizeof(b2s_match_result), m->stream));
   B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser *laser, int device, int max_batch,
+                              int max_base_scans, void *cuda_stream, b2s_matcher **out) {
+  if (!params || !laser || !out || max_batch <= 0 || laser->n_readings < 0 || max_base_scans < 0)
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_matcher_create: null/negative argument");
+  *out = nullptr;
+  b2s_grid_info g;
+  b2s_status st = layout_from_params(params, &g);
+  if (st) return st;
+  if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
+  B2S_CUDA_CHECK(cudaSetDevice(device));
+  b2s_matcher *m = new (std::nothrow) b2s_matcher();
+  if (!m) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
+  st = matcher_create_impl(params, laser, device, max_batch, max_base_scans, cuda_stream, m, g);
+  if (st) {  // release whatever was allocated before the failure
+    const std::string why = b2s::last_error_ref();
+    b2s_matcher_destroy(m);
+    b2s::set_last_error(why);
+    return st;
+  }
   *out = m;
   return B2S_OK;
 }
@@ -1398,7 +1411,7 @@ b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser 
 void b2s_matcher_destroy(b2s_matcher *m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaStreamSynchronize(m->stream);
+  if (m->stream) cudaStreamSynchronize(m->stream);
   void *ptrs[] = {m->d_kernel, m->d_ranges, m->d_poses, m->d_sensor, m->d_pts, m->d_local, m->d_grids,
                   m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_starts, m->d_sat, m->d_stats, m->d_sums, m->d_bases,
                   m->d_flags, m->d_probs, m->d_centers, m->d_results, m->d_work};
@@ -1407,7 +1420,7 @@ void b2s_matcher_destroy(b2s_matcher *m) {
   if (m->h_results) cudaFreeHost(m->h_results);
   for (auto &e : m->ev)
     if (e) cudaEventDestroy(e);
-  if (m->own_stream) cudaStreamDestroy(m->stream);
+  if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
 

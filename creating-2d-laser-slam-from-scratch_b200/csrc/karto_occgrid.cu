@@ -180,6 +180,7 @@ __global__ void k_occ_ros(const uint8_t *__restrict__ cells, int w, int h, int s
 
 }  // namespace b2s
 
+extern "C" void b2s_occ_grid_destroy(b2s_occ_grid *g);
 extern "C" {
 
 b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, const double *ranges,
@@ -198,7 +199,7 @@ b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, c
   if (cuda_stream) {
     g->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   } else {
-    B2S_CUDA_CHECK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     g->own_stream = true;
   }
   cudaStream_t st = g->stream;
@@ -206,30 +207,32 @@ b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, c
   double *d_ranges = nullptr, *d_poses = nullptr, *d_sensor = nullptr, *d_pts = nullptr, *d_bbox = nullptr;
   unsigned long long *d_visits = nullptr;
   cudaEvent_t ev[3];
-  for (auto &e : ev) B2S_CUDA_CHECK(cudaEventCreate(&e));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_ranges), sizeof(double) * std::max<size_t>(M * n, 1), st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_poses), sizeof(double) * M * 3, st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_sensor), sizeof(double) * M * 3, st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_pts), sizeof(double) * std::max<size_t>(M * n * 2, 1), st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_bbox), sizeof(double) * (M + 1) * 4, st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_visits), sizeof(unsigned long long), st));
-  if (n) B2S_CUDA_CHECK(cudaMemcpyAsync(d_ranges, ranges, sizeof(double) * M * n, cudaMemcpyHostToDevice, st));
-  B2S_CUDA_CHECK(cudaMemcpyAsync(d_poses, poses, sizeof(double) * M * 3, cudaMemcpyHostToDevice, st));
-  B2S_CUDA_CHECK(cudaMemsetAsync(d_visits, 0, sizeof(unsigned long long), st));
+  for (auto &e : ev) B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaEventCreate(&e));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_ranges), sizeof(double) * std::max<size_t>(M * n, 1), st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_poses), sizeof(double) * M * 3, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_sensor), sizeof(double) * M * 3, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_pts), sizeof(double) * std::max<size_t>(M * n * 2, 1), st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_bbox), sizeof(double) * (M + 1) * 4, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_visits), sizeof(unsigned long long), st));
+  if (n) B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(d_ranges, ranges, sizeof(double) * M * n, cudaMemcpyHostToDevice, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(d_poses, poses, sizeof(double) * M * 3, cudaMemcpyHostToDevice, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemsetAsync(d_visits, 0, sizeof(unsigned long long), st));
   k_scan_points<<<(unsigned)M, 256, 0, st>>>(d_ranges, d_poses, *laser, d_sensor, d_pts, nullptr);
   k_scan_bbox<<<(unsigned)M, 256, 0, st>>>(d_ranges, d_sensor, d_pts, *laser, d_bbox);
   k_bbox_union<<<1, 256, 0, st>>>(d_bbox, n_scans, d_bbox + 4 * M);
-  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaGetLastError());
   double bb[4];
-  B2S_CUDA_CHECK(cudaMemcpyAsync(bb, d_bbox + 4 * M, sizeof(bb), cudaMemcpyDeviceToHost, st));
-  B2S_CUDA_CHECK(cudaStreamSynchronize(st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(bb, d_bbox + 4 * M, sizeof(bb), cudaMemcpyDeviceToHost, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaStreamSynchronize(st));
   // OccupancyGrid::ComputeDimensions (Karto.h:5816-5821)
   const double scale = 1.0 / resolution;
   b2s_occ_grid_info &I = g->info;
   I.width = cast_i32(kround((bb[2] - bb[0]) * scale));
   I.height = cast_i32(kround((bb[3] - bb[1]) * scale));
-  if (I.width < 0 || I.height < 0 || (long long)I.width * I.height > (1ll << 31))
+  if (I.width < 0 || I.height < 0 || (long long)I.width * I.height > (1ll << 31)) {
+    b2s_occ_grid_destroy(g);
     B2S_FAIL(B2S_ERR_TOO_LARGE, "occupancy grid dimensions out of range");
+  }
   I.width_step = (I.width + 7) & ~7;
   I.data_size = I.width_step * I.height;
   I.offset[0] = bb[0];
@@ -237,12 +240,12 @@ b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, c
   I.resolution = resolution;
   I.cell_visits = 0;
   const size_t cells = (size_t)std::max(I.data_size, 1);
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_pass), sizeof(uint32_t) * cells));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_hit), sizeof(uint32_t) * cells));
-  B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_cells), cells));
-  B2S_CUDA_CHECK(cudaMemsetAsync(g->d_pass, 0, sizeof(uint32_t) * cells, st));
-  B2S_CUDA_CHECK(cudaMemsetAsync(g->d_hit, 0, sizeof(uint32_t) * cells, st));
-  B2S_CUDA_CHECK(cudaEventRecord(ev[0], st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMalloc(reinterpret_cast<void **>(&g->d_pass), sizeof(uint32_t) * cells));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMalloc(reinterpret_cast<void **>(&g->d_hit), sizeof(uint32_t) * cells));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMalloc(reinterpret_cast<void **>(&g->d_cells), cells));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemsetAsync(g->d_pass, 0, sizeof(uint32_t) * cells, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemsetAsync(g->d_hit, 0, sizeof(uint32_t) * cells, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaEventRecord(ev[0], st));
   if (n && I.data_size > 0) {
     const long long n_beams = (long long)M * (long long)n;
     int sms = 148;
@@ -251,15 +254,15 @@ b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, c
     k_raytrace<<<blocks, 256, 0, st>>>(d_ranges, d_sensor, d_pts, *laser, n_beams, I.width, I.height, I.width_step,
                                        I.offset[0], I.offset[1], scale, g->d_pass, g->d_hit, d_visits);
   }
-  B2S_CUDA_CHECK(cudaEventRecord(ev[1], st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaEventRecord(ev[1], st));
   if (I.data_size > 0) k_occ_threshold<<<ceil_div(I.data_size, 256), 256, 0, st>>>(g->d_pass, g->d_hit, I.data_size, g->d_cells);
-  B2S_CUDA_CHECK(cudaEventRecord(ev[2], st));
-  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaEventRecord(ev[2], st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaGetLastError());
   unsigned long long visits = 0;
-  B2S_CUDA_CHECK(cudaMemcpyAsync(&visits, d_visits, sizeof(visits), cudaMemcpyDeviceToHost, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(&visits, d_visits, sizeof(visits), cudaMemcpyDeviceToHost, st));
   for (void *p : {(void *)d_ranges, (void *)d_poses, (void *)d_sensor, (void *)d_pts, (void *)d_bbox, (void *)d_visits})
-    B2S_CUDA_CHECK(cudaFreeAsync(p, st));
-  B2S_CUDA_CHECK(cudaStreamSynchronize(st));
+    B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaFreeAsync(p, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaStreamSynchronize(st));
   I.cell_visits = visits;
   float ms = 0;
   if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) g->last_ms[0] = ms;
@@ -311,11 +314,11 @@ b2s_status b2s_occ_grid_last_timing(b2s_occ_grid *g, double out[2]) {
 void b2s_occ_grid_destroy(b2s_occ_grid *g) {
   if (!g) return;
   cudaSetDevice(g->device);
-  cudaStreamSynchronize(g->stream);
+  if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->d_pass) cudaFree(g->d_pass);
   if (g->d_hit) cudaFree(g->d_hit);
   if (g->d_cells) cudaFree(g->d_cells);
-  if (g->own_stream) cudaStreamDestroy(g->stream);
+  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
 
