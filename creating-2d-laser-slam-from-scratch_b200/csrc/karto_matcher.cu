@@ -138,6 +138,8 @@ struct b2s_matcher {
   size_t lut_cap = 0;
   int32_t *d_lists = nullptr, *d_counts = nullptr, *d_starts = nullptr;  // window kernel: per-(match, angle) grouped window origins
   size_t lists_cap = 0, counts_cap = 0, starts_cap = 0;
+  double *d_part_best = nullptr, *d_glob_best = nullptr, *d_tie = nullptr;  // split-sweep phases: [B], [B], [B][5]
+  int last_k_first = 0;
   uint16_t *d_sat = nullptr;  // [B][(sby+1)(sbx+1)] block summed-area tables of the grids
   int sbx = 0, sby = 0;
   bool sat_valid = false;
@@ -311,11 +313,11 @@ __device__ __forceinline__ int32_t lut_value(double r, double lx, double ly, dou
 __global__ void k_offsets(const double *__restrict__ ranges, const double *__restrict__ local,
                           const double *__restrict__ grid_off, const double *__restrict__ centers, int center_stride,
                           double angle_center_override, int use_override, double angle_offset, double angle_res,
-                          int n_angles, int n, int width_step, double scale, int32_t *__restrict__ lut) {
+                          int n_angles, int n, int width_step, double scale, int32_t *__restrict__ lut, int k_first) {
   const int b = blockIdx.x / n_angles, k = blockIdx.x % n_angles;
   const double center = use_override ? angle_center_override : centers[(size_t)b * center_stride + 2];
   const double start = center - angle_offset;
-  const double angle = start + (double)(uint32_t)k * angle_res;
+  const double angle = start + (double)(uint32_t)(k_first + k) * angle_res;  // k_first: angle subset of a split sweep
   const double cosine = cos(angle), sine = sin(angle);
   const double gox = grid_off[2 * b], goy = grid_off[2 * b + 1];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict
                                                        const double *__restrict__ local,
                                                        const double *__restrict__ grid_off,
                                                        const double *__restrict__ centers, double angle_offset,
-                                                       double angle_res, int width_step, double scale) {
+                                                       double angle_res, int width_step, double scale, int k_first) {
   const int b = blockIdx.y;
   const int f = flags[b];
   if (f & 2) return;
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict
     const int32_t *offs = lut ? lut + ((size_t)b * na + k) * n : nullptr;
     double cosine = 0, sine = 0, gox = 0, goy = 0;
     if (!lut) {  // no materialised table (window mode fall-through): GridIndexLookup values on the fly
-      const double angle = (centers[(size_t)b * 3 + 2] - angle_offset) + (double)(uint32_t)k * angle_res;
+      const double angle = (centers[(size_t)b * 3 + 2] - angle_offset) + (double)(uint32_t)(k_first + k) * angle_res;
       cosine = cos(angle); sine = sin(angle);
       gox = grid_off[2 * b]; goy = grid_off[2 * b + 1];
     }
@@ -507,7 +509,7 @@ __global__ void __launch_bounds__(256)
                      int rows_total, int cols_total, int32_t *__restrict__ lists, int32_t *__restrict__ counts,
                      const uint16_t *__restrict__ sat_all, int sbx, int sby, int height, int nx, int ny,
                      unsigned long long *__restrict__ stats, int band_rows, int nbands,
-                     int32_t *__restrict__ starts, int stride) {
+                     int32_t *__restrict__ starts, int stride, int k_first) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   double *s_lx = reinterpret_cast<double *>(s_raw), *s_ly = s_lx + n;  // [n] scan-local points
   int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);             // [n] window origins
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(256)
   const double center = centers[(size_t)b * 3 + 2];
   __shared__ double s_cos[OFF_CHUNK], s_sin[OFF_CHUNK];
   if (threadIdx.x < OFF_CHUNK && k0 + threadIdx.x < n_angles) {  // one sincos per angle, not per thread
-    const double ang = (center - angle_offset) + (double)(uint32_t)(k0 + threadIdx.x) * angle_res;
+    const double ang = (center - angle_offset) + (double)(uint32_t)(k_first + k0 + threadIdx.x) * angle_res;
     s_cos[threadIdx.x] = cos(ang);
     s_sin[threadIdx.x] = sin(ang);
   }
@@ -901,7 +903,12 @@ __device__ __forceinline__ float red_fscore(int32_t isum, float apf_k, float dpf
 __global__ void __launch_bounds__(RED_THREADS)
     k_reduce(const int32_t *__restrict__ sums, const double *__restrict__ centers, const int32_t *__restrict__ flags,
              b2s_matcher_params p, b2s_search s, b2s_grid_info g, double scale, int n, int nx, int ny, int na,
-             double *__restrict__ probs_all, b2s_match_result *__restrict__ results) {
+             double *__restrict__ probs_all, b2s_match_result *__restrict__ results, int k_first, int mode,
+             double *__restrict__ part_best, const double *__restrict__ glob_best, double *__restrict__ tie_out,
+             const double *__restrict__ tie_in) {
+  // mode 0: the whole tail.  Modes 1-3 are the phases of a sweep whose ANGLES are split over several GPUs
+  // (SURVEY.md §8(e)(ii)); between them the host all-reduces: 1 = best + per-cell maxima of this angle subset;
+  // 2 = tie sums of this subset against the global best; 3 = mean pose + covariance from the global sums / plane.
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int ncell = nx * ny;
@@ -927,7 +934,7 @@ __global__ void __launch_bounds__(RED_THREADS)
   __shared__ double s_best;
   __shared__ double s_mean[3];
   if (tid == 0) { s_err = 0; s_count = 0; }
-  if (!s.fine)
+  if (!s.fine && mode <= 1)
     for (int i = tid; i < pstep * g.search_side; i += RED_THREADS) probs[i] = 0.0;  // Clear (Mapper.cpp:329)
 
   // Float pre-filter.  The exact fp64 response (reference operation order, candidate_response) is only needed for
@@ -941,7 +948,7 @@ __global__ void __launch_bounds__(RED_THREADS)
   for (int k = tid; k < na && tab; k += RED_THREADS) {
     double apen = 1.0;
     if (pen) {
-      const double angle = start_a + (double)(uint32_t)k * s.angle_res;
+      const double angle = start_a + (double)(uint32_t)(k_first + k) * s.angle_res;
       apen = dmax(1.0 - (ANGLE_PENALTY_GAIN * ((angle - ch) * (angle - ch)) / p.angle_variance_penalty), p.minimum_angle_penalty);
     }
     s_apf[k] = (float)(apen / D);
@@ -950,7 +957,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 
   // ---- pass 1: best response + per-cell maxima (Mapper.cpp:430-451); one thread per (x,y) cell ----
   double best = -1.0;
-  for (int c = tid; c < ncell; c += RED_THREADS) {
+  for (int c = tid; c < ncell && mode <= 1; c += RED_THREADS) {
     const int iy = c / nx, ix = c % nx;
     const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
     const double sq = x * x + y * y;
@@ -979,14 +986,14 @@ __global__ void __launch_bounds__(RED_THREADS)
           bool amb;
           const float f = red_fscore(v[u], s_apf[k0 + u], dpf, inv_d, pen, amb);
           if (f >= thr || amb) {
-            const double angle = start_a + (double)(uint32_t)(k0 + u) * s.angle_res;
+            const double angle = start_a + (double)(uint32_t)(k_first + k0 + u) * s.angle_res;
             cell_best = dmax(cell_best, candidate_response(v[u], n, pen, sq, angle, ch, p));
           }
         }
       }
     } else {
       for (int k = 0; k < na; k++) {
-        const double angle = start_a + (double)(uint32_t)k * s.angle_res;
+        const double angle = start_a + (double)(uint32_t)(k_first + k) * s.angle_res;
         cell_best = dmax(cell_best, candidate_response(bs[(size_t)k * ncell + c], n, pen, sq, angle, ch, p));
       }
     }
@@ -1008,18 +1015,22 @@ __global__ void __launch_bounds__(RED_THREADS)
     if (tid < d) cov_terms[0][tid] = dmax(cov_terms[0][tid], cov_terms[0][tid + d]);
     __syncthreads();
   }
-  if (tid == 0) s_best = cov_terms[0][0];
+  if (tid == 0) s_best = mode <= 1 ? cov_terms[0][0] : glob_best[b];
   __syncthreads();
   best = s_best;
   if (s_err) {
     if (tid == 0) res->status = B2S_ERR_OUT_OF_RANGE;
     return;
   }
+  if (mode == 1) {  // split sweep, phase 1: this angle subset's best (the per-cell maxima are in `probs`)
+    if (tid == 0) { part_best[b] = best; res->status = B2S_OK; }
+    return;
+  }
 
   // ---- pass 2: poses tied with the best (Mapper.cpp:455-487) ----
   double ax = 0, ay = 0, tx = 0, ty = 0;
   const float tie_thr = (float)((best - KT_TOLERANCE) * (1.0 - 1.0e-6)) - 1.0e-9f;
-  for (int c = tid; c < ncell; c += RED_THREADS) {
+  for (int c = tid; c < ncell && mode != 3; c += RED_THREADS) {
     const int iy = c / nx, ix = c % nx;
     const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
     const double sq = x * x + y * y;
@@ -1037,7 +1048,7 @@ __global__ void __launch_bounds__(RED_THREADS)
           const float f = red_fscore(v[u], s_apf[k], dpf, inv_d, pen, amb);
           if (f < tie_thr && !amb) continue;
         }
-        const double angle = start_a + (double)(uint32_t)k * s.angle_res;
+        const double angle = start_a + (double)(uint32_t)(k_first + k) * s.angle_res;
         const double r = candidate_response(v[u], n, pen, sq, angle, ch, p);
         if (double_equal(r, best)) {
           const double h = normalize_angle(angle);
@@ -1049,12 +1060,17 @@ __global__ void __launch_bounds__(RED_THREADS)
     }
   }
   __syncthreads();
+  if (mode == 3 && tid == 0) s_count = (int)tie_in[5 * b + 4];
+  __syncthreads();
   const int total = s_count;
-  if (total == 0) {
+  if (total == 0 && mode != 2) {
     if (tid == 0) res->status = B2S_ERR_NO_BEST_POSE;  // Mapper.cpp:484-487
     return;
   }
-  if (total <= RED_MAX_TIES) {
+  if (mode == 3) {
+    if (tid == 0) { red[0] = tie_in[5 * b]; red[1] = tie_in[5 * b + 1]; red[2] = tie_in[5 * b + 2]; red[3] = tie_in[5 * b + 3]; }
+    __syncthreads();
+  } else if (total <= RED_MAX_TIES && mode == 0) {
     // rank-sort the tie list by reference linear index, then one thread sums in that exact order
     for (int i = tid; i < total; i += RED_THREADS) {
       int v = tie_idx[i], rank = 0;
@@ -1069,7 +1085,7 @@ __global__ void __launch_bounds__(RED_THREADS)
         int c = v / na, k = v % na;
         int iy = c / nx, ix = c % nx;
         double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
-        double h = normalize_angle(start_a + (double)(uint32_t)k * s.angle_res);
+        double h = normalize_angle(start_a + (double)(uint32_t)(k_first + k) * s.angle_res);
         sx += cx + x; sy += cy + y; cxs += cos(h); sys += sin(h);
       }
       red[0] = sx; red[1] = sy; red[2] = cxs; red[3] = sys;
@@ -1086,6 +1102,13 @@ __global__ void __launch_bounds__(RED_THREADS)
     }
     if (tid == 0) { red[0] = cov_terms[0][0]; red[1] = cov_terms[1][0]; red[2] = cov_terms[2][0]; red[3] = cov_terms[3][0]; }
     __syncthreads();
+  }
+  if (mode == 2) {  // split sweep, phase 2: this subset's tie sums {x, y, cos, sin, count}
+    if (tid == 0) {
+      tie_out[5 * b] = red[0]; tie_out[5 * b + 1] = red[1]; tie_out[5 * b + 2] = red[2]; tie_out[5 * b + 3] = red[3];
+      tie_out[5 * b + 4] = (double)total;
+    }
+    return;
   }
   if (tid == 0) {
     double sx = red[0], sy = red[1], cxs = red[2], sys = red[3];
@@ -1294,7 +1317,8 @@ static b2s_status ensure_cap(T **p, size_t *cap, size_t count) {
   return B2S_OK;
 }
 
-static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool centers_on_device);
+static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool centers_on_device, int k_first = 0,
+                                int na_override = -1, int mode = 0);
 
 // (re)build the per-match block summed-area tables after the grids changed
 static b2s_status build_sat(b2s_matcher *m) {
@@ -1378,6 +1402,9 @@ static b2s_status matcher_create_impl(const b2s_matcher_params *params, const b2
   m->sby = (g.height + 3) / 4;
   if ((st = dev_alloc(&m->d_sat, B * (size_t)(m->sbx + 1) * (m->sby + 1)))) return st;
   if ((st = dev_alloc(&m->d_stats, 1))) return st;
+  if ((st = dev_alloc(&m->d_part_best, B))) return st;
+  if ((st = dev_alloc(&m->d_glob_best, B))) return st;
+  if ((st = dev_alloc(&m->d_tie, B * 5))) return st;
   B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m->h_results), B * sizeof(b2s_match_result)));
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_grids, 0, B * m->grid_pitch, m->stream));
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_results, 0, B * sizeof(b2s_match_result), m->stream));
@@ -1413,7 +1440,7 @@ void b2s_matcher_destroy(b2s_matcher *m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   void *ptrs[] = {m->d_kernel, m->d_ranges, m->d_poses, m->d_sensor, m->d_pts, m->d_local, m->d_grids,
-                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_starts, m->d_sat, m->d_stats, m->d_sums, m->d_bases,
+                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_starts, m->d_sat, m->d_stats, m->d_part_best, m->d_glob_best, m->d_tie, m->d_sums, m->d_bases,
                   m->d_flags, m->d_probs, m->d_centers, m->d_results, m->d_work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1558,7 +1585,7 @@ b2s_status b2s_matcher_compute_offsets(b2s_matcher *m, int b, double angle_cente
   // one-match launch on the slices of match b
   k_offsets<<<na, 256, 0, m->stream>>>(m->d_ranges + (size_t)b * n, m->d_local + (size_t)b * n * 2,
                                        m->d_grid_off + 2 * b, nullptr, 0, angle_center, 1, angle_offset, angle_res, na,
-                                       (int)n, m->g.width_step, 1.0 / m->p.resolution, tmp);
+                                       (int)n, m->g.width_step, 1.0 / m->p.resolution, tmp, 0);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, sizeof(int32_t) * na * n, cudaMemcpyDeviceToHost, m->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
@@ -1692,6 +1719,72 @@ b2s_status b2s_matcher_match_scan_host(b2s_matcher *m, int batch, const double *
   return b2s_matcher_match_scan(m, do_penalize, do_refine, results);
 }
 
+/* ---- a CorrelateScan whose ANGLES are split over several GPUs ----
+ * Every rank holds the same scans + grids and sweeps angle indices [k_first, k_first + k_count) of the search.
+ * Between the three phases the caller all-reduces small host arrays (torch.distributed / NCCL):
+ *   begin : out best[B] (MAX), per-cell maxima plane probs[B][probs_len] (MAX), status[B] (MAX)
+ *   ties  : in global best; out tie sums {x, y, cos, sin, count}[B][5] (SUM)
+ *   finish: in global best / tie sums / plane; out the same results as b2s_matcher_correlate_scan (coarse stage). */
+b2s_status b2s_matcher_correlate_split_begin(b2s_matcher *m, const double *centers, const b2s_search *search, int k_first,
+                                             int k_count, double *best, double *probs, int32_t *status) {
+  if (!m || !centers || !search || !best || !probs || !status || k_count < 0) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (search->fine) B2S_FAIL(B2S_ERR_BAD_PARAMS, "only the coarse stage (doingFineMatch = false) can be split");
+  if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int B = m->batch;
+  const size_t plen = (size_t)((m->g.search_side + 7) & ~7) * m->g.search_side;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_centers, centers, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, m->stream));
+  b2s_status st = run_correlate(m, search, true, k_first, k_count, 1);
+  if (st) return st;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(best, m->d_part_best, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(probs, m->d_probs, sizeof(double) * plen * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  for (int b = 0; b < B; b++) status[b] = m->h_results[b].status;
+  return B2S_OK;
+}
+
+static b2s_status split_phase(b2s_matcher *m, int mode) {
+  const b2s_search &s = m->last_search;
+  k_reduce<<<m->batch, RED_THREADS, 0, m->stream>>>(m->d_sums, m->d_centers, m->d_flags, m->p, s, m->g, 1.0 / m->p.resolution,
+                                                    m->n, m->last.nx, m->last.ny, m->last.na, m->d_probs, m->d_results,
+                                                    m->last_k_first, mode, m->d_part_best, m->d_glob_best, m->d_tie, m->d_tie);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_correlate_split_ties(b2s_matcher *m, const double *global_best, double *tie_sums) {
+  if (!m || !global_best || !tie_sums) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (!m->have_sweep) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_correlate_split_begin must come first");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int B = m->batch;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_glob_best, global_best, sizeof(double) * B, cudaMemcpyHostToDevice, m->stream));
+  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_tie, 0, sizeof(double) * 5 * B, m->stream));
+  b2s_status st = split_phase(m, 2);
+  if (st) return st;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(tie_sums, m->d_tie, sizeof(double) * 5 * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_correlate_split_finish(b2s_matcher *m, const double *global_best, const double *tie_sums,
+                                              const double *probs, b2s_match_result *results) {
+  if (!m || !global_best || !tie_sums || !probs || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (!m->have_sweep) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_correlate_split_begin must come first");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int B = m->batch;
+  const size_t plen = (size_t)((m->g.search_side + 7) & ~7) * m->g.search_side;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_glob_best, global_best, sizeof(double) * B, cudaMemcpyHostToDevice, m->stream));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_tie, tie_sums, sizeof(double) * 5 * B, cudaMemcpyHostToDevice, m->stream));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_probs, probs, sizeof(double) * plen * B, cudaMemcpyHostToDevice, m->stream));
+  b2s_status st = split_phase(m, 3);
+  if (st) return st;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  std::memcpy(results, m->h_results, sizeof(b2s_match_result) * B);
+  return B2S_OK;
+}
+
 b2s_status b2s_matcher_get_response_sums(b2s_matcher *m, int b, int32_t *out, int32_t dims[3]) {
   if (!m || !out || b < 0 || b >= m->batch) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad argument");
   if (!m->have_sweep) B2S_FAIL(B2S_ERR_BAD_STATE, "no sweep has been run");
@@ -1728,13 +1821,16 @@ b2s_status b2s_matcher_last_timing(b2s_matcher *m, double out[4]) {
 namespace b2s {
 
 // One CorrelateScan over the batch with centres already in d_centers.  Results stay in d_results.
-static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*centers_on_device*/) {
+static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*centers_on_device*/, int k_first, int na_override,
+                                int mode) {
   if (s->angle_res == 0.0 || s->res_x == 0.0 || s->res_y == 0.0)
     B2S_FAIL(B2S_ERR_BAD_PARAMS, "search resolutions must be non-zero");  // assert at Mapper.cpp:319
   const int B = m->batch, n = m->n;
   const int nx = n_steps(s->offset_x, s->res_x), ny = n_steps(s->offset_y, s->res_y);
-  const int na = n_steps(s->angle_offset, s->angle_res);
-  if (nx <= 0 || ny <= 0 || na <= 0 || (long long)nx * ny * na > (1ll << 28))
+  const int na_full = n_steps(s->angle_offset, s->angle_res);
+  const int na = na_override >= 0 ? na_override : na_full;  // angles swept by THIS call (a subset when the sweep is split)
+  if (k_first < 0 || k_first + na > na_full) B2S_FAIL(B2S_ERR_BAD_PARAMS, "angle subset outside the search");
+  if (nx <= 0 || ny <= 0 || na_full <= 0 || (long long)nx * ny * std::max(na, 1) > (1ll << 28))
     B2S_FAIL(B2S_ERR_TOO_LARGE, "search volume too large");
   const double scale = 1.0 / m->p.resolution;
   const int ncell = nx * ny;
@@ -1783,11 +1879,11 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[0], m->stream));
   k_bases<<<B, 256, 0, m->stream>>>(m->d_centers, m->d_grid_off, *s, m->g, scale, nx, ny, m->d_bases, m->d_flags,
                                     std::max(stride, 1));
-  if (need_plain_lut)
+  if (need_plain_lut && na > 0)
     k_offsets<<<B * na, 256, 0, m->stream>>>(m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, 3, 0.0, 0,
-                                             s->angle_offset, s->angle_res, na, n, m->g.width_step, scale, m->d_lut);
+                                             s->angle_offset, s->angle_res, na, n, m->g.width_step, scale, m->d_lut, k_first);
   const dim3 ggrid((unsigned)ceil_div(ncell, 8), (unsigned)B);
-  if (use_window) {
+  if (use_window && na > 0) {
     if ((st = ensure_cap(&m->d_lists, &m->lists_cap, (size_t)B * na * (n + LIST_PAD * nbands)))) return st;
     if ((st = ensure_cap(&m->d_counts, &m->counts_cap, (size_t)B * na * 8 * nbands))) return st;
     if ((st = ensure_cap(&m->d_starts, &m->starts_cap, (size_t)B * na * 8 * nbands))) return st;
@@ -1802,13 +1898,15 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
         m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases, m->d_flags, s->angle_offset, s->angle_res, na, n,
         ncell, m->g.width_step, m->g.data_size, scale, rows_total, tiles_x_w * 32, m->d_lists, m->d_counts,
         skip_empty ? m->d_sat : nullptr, m->sbx, m->sby, m->g.height, nx, ny, m->d_stats, band_rows, nbands, m->d_starts,
-        stride);
+        stride, k_first);
   }
   B2S_CUDA_CHECK(cudaGetLastError());
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
 
   // ---- response sweep ----
-  if (use_window) {
+  if (na == 0) {
+    m->last_path = use_window ? 2 : 1;  // empty angle subset of a split sweep: nothing to sweep
+  } else if (use_window) {
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_work, 0, sizeof(int), m->stream));
     if (nbands > 1)  // bands accumulate with RED.ADD
       B2S_CUDA_CHECK(cudaMemsetAsync(m->d_sums, 0, sizeof(int32_t) * (size_t)B * na * ncell, m->stream));
@@ -1831,13 +1929,13 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, nullptr, m->d_bases,
                                                   m->d_flags, 1, n, na, ncell, m->d_sums, m->d_ranges, m->d_local,
                                                   m->d_grid_off, m->d_centers, s->angle_offset, s->angle_res,
-                                                  m->g.width_step, scale);
+                                                  m->g.width_step, scale, k_first);
     m->last_path = 2;
   } else {
     k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, m->d_lut, m->d_bases,
                                                   m->d_flags, 0, n, na, ncell, m->d_sums, m->d_ranges, m->d_local,
                                                   m->d_grid_off, m->d_centers, s->angle_offset, s->angle_res,
-                                                  m->g.width_step, scale);
+                                                  m->g.width_step, scale, k_first);
     m->last_path = 1;
   }
   B2S_CUDA_CHECK(cudaGetLastError());
@@ -1845,7 +1943,8 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
 
   // ---- fp64 tail ----
   k_reduce<<<B, RED_THREADS, 0, m->stream>>>(m->d_sums, m->d_centers, m->d_flags, m->p, *s, m->g, scale, n, nx, ny, na,
-                                             m->d_probs, m->d_results);
+                                             m->d_probs, m->d_results, k_first, mode, m->d_part_best, m->d_glob_best,
+                                             m->d_tie, m->d_tie);
   if (s->fine) {
     size_t sm = sizeof(double) * (size_t)na;
     if (sm > 48 * 1024) B2S_FAIL(B2S_ERR_TOO_LARGE, "too many angles for the angular-covariance kernel");
@@ -1856,6 +1955,7 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[3], m->stream));
   m->last.nx = nx; m->last.ny = ny; m->last.na = na;
   m->last_search = *s;
+  m->last_k_first = k_first;
   m->have_sweep = true;
   return B2S_OK;
 }

@@ -45,6 +45,10 @@ def lib():
     L.b2s_matcher_add_scans.argtypes = [vp, C.c_int, dp, dp]
     L.b2s_matcher_set_grids.argtypes = [vp, u8p, dp]
     L.b2s_matcher_correlate_scan.argtypes = [vp, dp, C.POINTER(abi.Search), C.POINTER(abi.MatchResult)]
+    i32p = C.POINTER(C.c_int32)
+    L.b2s_matcher_correlate_split_begin.argtypes = [vp, dp, C.POINTER(abi.Search), C.c_int, C.c_int, dp, dp, i32p]
+    L.b2s_matcher_correlate_split_ties.argtypes = [vp, dp, dp]
+    L.b2s_matcher_correlate_split_finish.argtypes = [vp, dp, dp, dp, C.POINTER(abi.MatchResult)]
     L.b2s_matcher_match_scan.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.MatchResult)]
     L.b2s_matcher_match_scan_host.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, dp, C.c_int, C.c_int,
                                               C.POINTER(abi.MatchResult)]
@@ -141,6 +145,33 @@ class ScanMatcher:
                 for i in range(9):
                     res[b].cov[i] = ci[b, i]
         check(self.L.b2s_matcher_correlate_scan(self.h, _d(c), C.byref(search), res))
+        return results_to_arrays(res, self.batch)
+
+    # ---- a coarse sweep whose ANGLES are split over ranks (three phases, see include/b200slam.h) ----
+    def probs_len(self) -> int:
+        return ((self.g.search_side + 7) & ~7) * self.g.search_side
+
+    def split_begin(self, centers, search: abi.Search, k_first: int, k_count: int):
+        """-> (best[B], probs[B, probs_len], status[B]) of angle indices [k_first, k_first + k_count)"""
+        c = f64(centers).reshape(self.batch, 3)
+        best = np.empty(self.batch)
+        probs = np.empty((self.batch, self.probs_len()))
+        status = np.empty(self.batch, dtype=np.int32)
+        check(self.L.b2s_matcher_correlate_split_begin(self.h, _d(c), C.byref(search), k_first, k_count, _d(best),
+                                                       _d(probs), status.ctypes.data_as(C.POINTER(C.c_int32))))
+        return best, probs, status
+
+    def split_ties(self, global_best):
+        gb = f64(global_best).reshape(self.batch)
+        ties = np.empty((self.batch, 5))
+        check(self.L.b2s_matcher_correlate_split_ties(self.h, _d(gb), _d(ties)))
+        return ties
+
+    def split_finish(self, global_best, tie_sums, probs):
+        gb, ts = f64(global_best).reshape(self.batch), f64(tie_sums).reshape(self.batch, 5)
+        pr = f64(probs).reshape(self.batch, self.probs_len())
+        res = (abi.MatchResult * self.batch)()
+        check(self.L.b2s_matcher_correlate_split_finish(self.h, _d(gb), _d(ts), _d(pr), res))
         return results_to_arrays(res, self.batch)
 
     def match_scan(self, do_penalize=True, do_refine=True):

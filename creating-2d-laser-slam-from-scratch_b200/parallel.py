@@ -57,3 +57,36 @@ def max_over_ranks(value: float, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+
+def _all_reduce(arr: np.ndarray, op: str, group=None) -> np.ndarray:
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized():
+        return arr
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def correlate_scan_angle_split(matcher, centers, search, n_angles: int, group=None):
+    """One coarse CorrelateScan (Mapper.cpp:315-523) whose ANGLES are split over the ranks: every
+    rank holds the same scans + grids, sweeps its contiguous share of the `n_angles` angle steps, and three small
+    all-reduces (MAX on best response / per-cell maxima / status, SUM on the tie sums) stand where the reference's
+    single-threaded max + tie average run.  Returns the same tuple as ScanMatcher.correlate_scan on every rank."""
+    import torch.distributed as dist
+
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_available() and dist.is_initialized() else (1, 0)
+    lo, hi = shard_bounds(n_angles, world, rank)
+    best, probs, status = matcher.split_begin(centers, search, lo, hi - lo)
+    best = _all_reduce(best, "max", group)
+    probs = _all_reduce(probs, "max", group)
+    status = _all_reduce(status.astype(np.float64), "max", group).astype(np.int32)
+    ties = _all_reduce(matcher.split_ties(best), "sum", group)
+    out = matcher.split_finish(best, ties, probs)
+    if (status != 0).any():  # a rank saw an out-of-range candidate: the reference throws for the whole sweep
+        out[3][status != 0] = status[status != 0]
+    return out

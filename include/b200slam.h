@@ -149,6 +149,19 @@ b2s_status b2s_matcher_match_scan_host(b2s_matcher *m, int batch, const double *
                                        int n_base, const double *base_ranges, const double *base_poses,
                                        int do_penalize, int do_refine, b2s_match_result *results);
 
+/* A coarse CorrelateScan whose ANGLES are split over several GPUs: every rank holds the same
+ * scans + grids and sweeps angle indices [k_first, k_first + k_count).  Between the three phases the caller
+ * all-reduces the small host arrays (NCCL via torch.distributed in creating-..._b200/parallel.py):
+ *   begin : best[batch] (MAX), probs[batch][probs_len] per-cell maxima plane (MAX), status[batch] (MAX);
+ *           probs_len = AlignValue(search_side, 8) * search_side
+ *   ties  : global best in; tie_sums[batch][5] = {sum x, sum y, sum cos, sum sin, count} out (SUM)
+ *   finish: global best / tie sums / plane in; results as b2s_matcher_correlate_scan (positional covariance incl.) */
+b2s_status b2s_matcher_correlate_split_begin(b2s_matcher *m, const double *centers, const b2s_search *search, int k_first,
+                                             int k_count, double *best, double *probs, int32_t *status);
+b2s_status b2s_matcher_correlate_split_ties(b2s_matcher *m, const double *global_best, double *tie_sums);
+b2s_status b2s_matcher_correlate_split_finish(b2s_matcher *m, const double *global_best, const double *tie_sums,
+                                              const double *probs, b2s_match_result *results);
+
 /* Inspection (parity tests; also ScanMatcher::GetCorrelationGrid, Mapper.h:1192). */
 b2s_status b2s_matcher_get_grid(b2s_matcher *m, int b, uint8_t *out_bytes, double out_offset[2]);
 b2s_status b2s_matcher_get_point_readings(b2s_matcher *m, int b, double *out_xy /* [n_readings][2] */);

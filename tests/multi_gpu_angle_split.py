@@ -1,0 +1,70 @@
+"""Real multi-GPU check of the angle-split sweep; not collected by pytest.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_angle_split.py
+
+Every rank holds the same scans + grids, sweeps its share of the angle steps, and the best response / per-cell maxima /
+tie sums are all-reduced over NCCL.  Rank 0 also runs the whole sweep alone and prints one JSON line with the largest
+difference and device timings (max over ranks)."""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("creating-2d-laser-slam-from-scratch_b200")
+D = 0.01745329251994329577
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    abi, synth, M, par = pkg.abi, pkg.synth, pkg.load("matcher"), pkg.load("parallel")
+    B = int(os.environ.get("B2S_SPLIT_BATCH", 16))
+    params, laser = abi.matcher_params(1.5, 0.05, 0.03, 9.25), abi.laser_from(synth.Laser())
+    cases = [synth.make_match_case(700 + s, synth.Laser()) for s in range(min(B, 8))]
+    pick = [cases[i % len(cases)] for i in range(B)]
+    ranges, poses = np.stack([c.ranges for c in pick]), np.stack([c.odom_pose for c in pick])
+    bran, bpos = np.stack([c.base_ranges for c in pick])[:, None, :], np.stack([c.base_pose for c in pick])[:, None, :]
+    m = M.ScanMatcher(params, laser, max_batch=B, max_base_scans=1, device=local)
+    m.set_scans(ranges, poses)
+    m.add_scans(bran, bpos)
+    A, R = 22.5 * D, 0.25 * D
+    se = abi.Search(0.75, 0.75, 0.05, 0.05, A, R, 1, 0)
+    na = abi.n_steps(A, R)
+    centers = poses.copy()
+    worst, t_split, t_whole = 0.0, [], []
+    for it in range(4):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = par.correlate_scan_angle_split(m, centers, se, na)
+        torch.cuda.synchronize()
+        t_split.append(par.max_over_ranks(time.perf_counter() - t0))
+        t0 = time.perf_counter()
+        whole = m.correlate_scan(centers, se)
+        t_whole.append(par.max_over_ranks(time.perf_counter() - t0))
+        for a, b in zip(got, whole):
+            worst = max(worst, float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)))))
+        assert (whole[3] == 0).all()
+    worst = par.max_over_ranks(worst)
+    if rank == 0:
+        print(json.dumps({"check": "angle_split_vs_whole_sweep", "n_gpus": world, "batch": B, "angles": na,
+                          "max_abs_diff": worst, "ok": bool(worst <= 1e-9),
+                          "host_ms_split_incl_allreduce": round(1e3 * min(t_split[1:]), 3),
+                          "host_ms_whole_one_gpu": round(1e3 * min(t_whole[1:]), 3)}))
+    dist.barrier()
+    dist.destroy_process_group()
+    if worst > 1e-9:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -452,3 +452,62 @@ def test_stride2_coarse_lattice(pkg, M, res, search, rt):
             assert np.array_equal(vols[kernel][b], pm.last_sums), (kernel, b)
         assert_result(gpu, b, r)
     m.close()
+
+
+@pytest.mark.parametrize("world,kernel", [(2, 2), (3, 2), (2, 1), (5, 2)])
+def test_angle_split_sweep_matches_whole_sweep(pkg, M, world, kernel):
+    """the angle range of ONE sweep split over `world` ranks, emulated on one handle (each rank's
+    begin/ties phases run in turn; numpy max/sum stand for the all-reduces).  Result must equal the whole sweep and
+    the CPU restatement; empty-grid ties (every candidate ties) exercise the SUM path."""
+    abi, synth, par = pkg.abi, pkg.synth, pkg.load("parallel")
+    params, laser = abi.matcher_params(1.5, 0.05, 0.03, 9.25), abi.laser_from(synth.Laser())
+    cases, ranges, poses, bran, bpos = make_batch(synth, range(300, 304))
+    B = len(cases)
+    m = M.ScanMatcher(params, laser, max_batch=B, max_base_scans=1)
+    m.set_kernel(kernel)
+    m.set_scans(ranges, poses)
+    m.add_scans(bran, bpos)
+    A, R = 22.5 * D, 0.25 * D
+    na = abi.n_steps(A, R)
+    sensor = np.stack([port.PortMatcher(params, laser).sensor_pose(p) for p in poses])
+    for pen in (1, 0):
+        se = abi.Search(0.75, 0.75, 0.05, 0.05, A, R, pen, 0)
+        whole = m.correlate_scan(sensor, se)
+        bounds = [par.shard_bounds(na, world, r) for r in range(world)]
+        parts = [m.split_begin(sensor, se, lo, hi - lo) for lo, hi in bounds]
+        best = np.max([p[0] for p in parts], axis=0)
+        probs = np.max([p[1] for p in parts], axis=0)
+        assert all((p[2] == 0).all() for p in parts)
+        ties = np.zeros((B, 5))
+        for lo, hi in bounds:
+            m.split_begin(sensor, se, lo, hi - lo)  # this "rank"'s sweep volume is resident again
+            ties += m.split_ties(best)
+        got = m.split_finish(best, ties, probs)
+        for a, b_ in zip(got, whole):
+            assert np.allclose(a, b_, rtol=0, atol=TOL), (world, pen)
+        for b in range(B):
+            pm = port_case(abi, params, laser, ranges[b], poses[b], bran[b], bpos[b])
+            rc, res = pm.correlate_scan(pm.sp, se)
+            assert rc == 0
+            assert_result(got, b, res)
+    # world > number of angles: some ranks sweep nothing
+    se = abi.Search(0.75, 0.75, 0.05, 0.05, 1.0 * D, 1.0 * D, 1, 0)
+    na = abi.n_steps(1.0 * D, 1.0 * D)
+    assert na == 3
+    whole = m.correlate_scan(sensor, se)
+    bounds = [par.shard_bounds(na, 5, r) for r in range(5)]
+    parts = [m.split_begin(sensor, se, lo, hi - lo) for lo, hi in bounds]
+    best = np.max([p[0] for p in parts], axis=0)
+    probs = np.max([p[1] for p in parts], axis=0)
+    ties = np.zeros((B, 5))
+    for lo, hi in bounds:
+        m.split_begin(sensor, se, lo, hi - lo)
+        ties += m.split_ties(best)
+    got = m.split_finish(best, ties, probs)
+    for a, b_ in zip(got, whole):
+        assert np.allclose(a, b_, rtol=0, atol=TOL)
+    # the single-process form of the orchestration helper (world 1, no process group)
+    got1 = par.correlate_scan_angle_split(m, sensor, se, na)
+    for a, b_ in zip(got1, whole):
+        assert np.allclose(a, b_, rtol=0, atol=TOL)
+    m.close()

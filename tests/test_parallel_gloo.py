@@ -65,3 +65,65 @@ def test_shard_bounds_cover_exactly(pkg):
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+class StandInMatcher:
+    """CPU stand-in with the three split-sweep phases of ScanMatcher (matcher.py) over a seeded response volume
+    R[B, na, cells]; only the collective plumbing of correlate_scan_angle_split is under test here."""
+
+    def __init__(self, B, na, cells, seed=5):
+        rng = np.random.default_rng(seed)
+        self.R = rng.integers(0, 6, size=(B, na, cells)).astype(np.float64)  # small range => many exact ties
+        self.batch = B
+
+    def split_begin(self, centers, search, k_first, k_count):
+        self.sub = self.R[:, k_first:k_first + k_count]
+        self.k_first = k_first
+        if k_count == 0:
+            return np.full(self.batch, -1.0), np.zeros((self.batch, self.R.shape[2])), np.zeros(self.batch, np.int32)
+        return self.sub.max(axis=(1, 2)), self.sub.max(axis=1), np.zeros(self.batch, np.int32)
+
+    def split_ties(self, best):
+        out = np.zeros((self.batch, 5))
+        for b in range(self.batch):
+            k, c = np.nonzero(self.sub[b] == best[b])
+            out[b] = [c.sum(), (c * c).sum(), (k + self.k_first).sum(), 0.0, len(k)]
+        return out
+
+    def split_finish(self, best, ties, probs):
+        return best.copy(), ties[:, :3] / ties[:, 4:5], probs.sum(axis=1), np.zeros(self.batch, np.int32), ties[:, 4].astype(np.int32)
+
+
+def split_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import importlib
+    import torch.distributed as dist
+    par = importlib.import_module("creating-2d-laser-slam-from-scratch_b200.parallel")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = StandInMatcher(4, 7, 25)
+    out = par.correlate_scan_angle_split(m, None, None, 7)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_angle_split_collectives(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=split_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = StandInMatcher(4, 7, 25)
+    best, probs, _ = m.split_begin(None, None, 0, 7)
+    expect = m.split_finish(best, m.split_ties(best), probs)
+    for rank, out in outs:
+        for a, b in zip(out, expect):
+            assert np.array_equal(a, b)
