@@ -62,6 +62,7 @@ static float prob_to_log_odds(float prob) {  // GridMapLogOdds.h:153-157
 
 struct HcTransform {
   float c, s, mx, my;  // poseTransform = Translation2f(mx, my) * Rotation2Df(theta)
+  int just_once;       // updateByScanJustOnce: end = begin + (int)round(p / 0.05) (OccGridMapBase.h:202-203)
 };
 
 __device__ __forceinline__ void hc_apply(const HcTransform &t, float px, float py, float &ox, float &oy) {
@@ -85,6 +86,10 @@ __device__ __forceinline__ HcLine hc_line(const HcTransform &t, int bx, int by, 
   ey = __fadd_rn(ey, 0.5f);
   L.x0 = bx; L.y0 = by;
   L.x1 = (int)ex; L.y1 = (int)ey;  // Vector2f::cast<int>(): truncation
+  if (t.just_once) {  // points in metres; float / double literal -> double, ::round, (int)
+    L.x1 = bx + cast_i32(round((double)px / 0.05));
+    L.y1 = by + cast_i32(round((double)py / 0.05));
+  }
   L.ok = !(L.x0 == L.x1 && L.y0 == L.y1);
   if ((L.x0 < 0) || (L.x0 >= sx) || (L.y0 < 0) || (L.y0 >= sy)) L.ok = false;
   if ((L.x1 < 0) || (L.x1 >= sx) || (L.y1 < 0) || (L.y1 >= sy)) L.ok = false;
@@ -366,17 +371,20 @@ static b2s_status hc_upload_points(b2s_hector_map *m, const float *points, int n
   return B2S_OK;
 }
 
-b2s_status b2s_hector_map_update_by_scan(b2s_hector_map *m, const float *points, int n_points, const float origo[2],
-                                         const float world_pose[3]) {
+static b2s_status hc_update(b2s_hector_map *m, const float *points, int n_points, const float origo[2],
+                            const float world_pose[3], bool just_once) {
   if (!m || !origo || !world_pose || n_points < 0 || (n_points > 0 && !points)) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
   const int mark_free = m->curr_update_index + 1, mark_occ = m->curr_update_index + 2;  // OccGridMapBase.h:120-121
   // getMapCoordsPose (GridMapBase.h:238-242)
-  const float mx = (m->tw_lin * world_pose[0] + 0.0f * world_pose[1]) + m->tw_tx;
-  const float my = (0.0f * world_pose[0] + m->tw_lin * world_pose[1]) + m->tw_ty;
+  float mx = (m->tw_lin * world_pose[0] + 0.0f * world_pose[1]) + m->tw_tx;
+  float my = (0.0f * world_pose[0] + m->tw_lin * world_pose[1]) + m->tw_ty;
+  float heading = world_pose[2];
+  if (just_once) { mx = 800.0f; my = 800.0f; heading = 0.0f; }  // Eigen::Vector3f mapPose(800, 800, 0) (OccGridMapBase.h:182)
   HcTransform t;
-  t.c = cosf(world_pose[2]);  // Rotation2Df: std::cos / std::sin on float, taken on the host (glibc)
-  t.s = sinf(world_pose[2]);
+  t.c = cosf(heading);  // Rotation2Df: std::cos / std::sin on float, taken on the host (glibc)
+  t.s = sinf(heading);
+  t.just_once = just_once ? 1 : 0;
   t.mx = mx; t.my = my;
   const float bxf = (t.c * origo[0] + (-t.s) * origo[1]) + mx, byf = (t.s * origo[0] + t.c * origo[1]) + my;
   const int bx = (int)(bxf + 0.5f), by = (int)(byf + 0.5f);  // Vector2i(float, float): truncation
@@ -396,6 +404,17 @@ b2s_status b2s_hector_map_update_by_scan(b2s_hector_map *m, const float *points,
   }
   m->curr_update_index += 3;  // OccGridMapBase.h:167
   return B2S_OK;
+}
+
+b2s_status b2s_hector_map_update_by_scan(b2s_hector_map *m, const float *points, int n_points, const float origo[2],
+                                         const float world_pose[3]) {
+  return hc_update(m, points, n_points, origo, world_pose, false);
+}
+
+b2s_status b2s_hector_map_update_by_scan_just_once(b2s_hector_map *m, const float *points, int n_points,
+                                                   const float origo[2]) {
+  const float unused_pose[3] = {0.0f, 0.0f, 0.0f};
+  return hc_update(m, points, n_points, origo, unused_pose, true);
 }
 
 b2s_status b2s_hector_map_match_data(b2s_hector_map *m, const float *points, int n_points,

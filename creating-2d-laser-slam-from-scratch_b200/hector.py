@@ -21,6 +21,7 @@ def _bind():
     L.b2s_hector_map_destroy.restype = None
     L.b2s_hector_map_set_factors.argtypes = [vp, C.c_float, C.c_float]
     L.b2s_hector_map_update_by_scan.argtypes = [vp, fp, C.c_int, fp, fp]
+    L.b2s_hector_map_update_by_scan_just_once.argtypes = [vp, fp, C.c_int, fp]
     L.b2s_hector_map_match_data.argtypes = [vp, fp, C.c_int, fp, C.c_int, fp, fp]
     L.b2s_hector_map_copy.argtypes = [vp, fp, C.POINTER(C.c_int32)]
     L.b2s_hector_map_copy_ros.argtypes = [vp, C.POINTER(C.c_int8)]
@@ -53,6 +54,11 @@ class HectorMap:
     def update_by_scan(self, points, origo, world_pose):
         p = f32(points).reshape(-1, 2)
         check(self.L.b2s_hector_map_update_by_scan(self.h, _f(p), len(p), _f(f32(origo)), _f(f32(world_pose))))
+
+    def update_by_scan_just_once(self, points_m, origo):
+        """OccGridMapBase::updateByScanJustOnce (OccGridMapBase.h:175-217): points in metres, map pose (800, 800, 0)"""
+        p = f32(points_m).reshape(-1, 2)
+        check(self.L.b2s_hector_map_update_by_scan_just_once(self.h, _f(p), len(p), _f(f32(origo))))
 
     def match_data(self, points, begin_world_pose, max_iterations):
         p = f32(points).reshape(-1, 2)

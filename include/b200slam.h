@@ -226,6 +226,11 @@ b2s_status b2s_hector_map_set_factors(b2s_hector_map *m, float update_free, floa
  * same frame, pose = robot pose in WORLD coordinates (x, y, heading). */
 b2s_status b2s_hector_map_update_by_scan(b2s_hector_map *m, const float *points, int n_points,
                                          const float origo[2], const float world_pose[3]);
+/* OccGridMapBase::updateByScanJustOnce (OccGridMapBase.h:175-217), the make-map demo variant of lesson4
+ * (hector_mapping/src/hector_mapping/...: map pose fixed at cell (800, 800), heading 0; points in METRES, the end cell is
+ * begin + (int)round(p / 0.05)). */
+b2s_status b2s_hector_map_update_by_scan_just_once(b2s_hector_map *m, const float *points, int n_points,
+                                                   const float origo[2]);
 /* ScanMatcher::matchData (ScanMatcher.h:60-98) on ONE grid level: Gauss-Newton scan-to-map alignment.
  * begin_world_pose in, new world pose + 3x3 Hessian ("covariance") out. */
 b2s_status b2s_hector_map_match_data(b2s_hector_map *m, const float *points, int n_points,

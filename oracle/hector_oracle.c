@@ -168,6 +168,25 @@ long orc_hmap_update_by_scan(orc_hmap *m, const float *points, int n, const floa
 }
 
 /* getGridProbability (GridMapLogOdds.h:136-140) */
+/* OccGridMapBase::updateByScanJustOnce (OccGridMapBase.h:175-217), the lesson4 make-map demo variant: fixed map
+ * pose (800, 800, 0); points are in METRES and the end cell is begin + (int)round(p / 0.05) in double. */
+long orc_hmap_update_by_scan_just_once(orc_hmap *m, const float *points, int n, const float origo[2]) {
+  int mark_free = m->curr_update_index + 1, mark_occ = m->curr_update_index + 2;
+  float mp[3] = {800.0f, 800.0f, 0.0f};
+  float c = cosf(mp[2]), s = sinf(mp[2]);
+  float bx = (c * origo[0] + (-s) * origo[1]) + mp[0];
+  float by = (s * origo[0] + c * origo[1]) + mp[1];
+  int bxi = (int)(bx + 0.5f), byi = (int)(by + 0.5f);
+  long visits = 0;
+  for (int i = 0; i < n; i++) {
+    int exi = bxi + (int)round(points[2 * i] / 0.05);
+    int eyi = byi + (int)round(points[2 * i + 1] / 0.05);
+    if (bxi != exi || byi != eyi) visits += update_line(m, bxi, byi, exi, eyi, mark_free, mark_occ);
+  }
+  m->curr_update_index += 3;
+  return visits;
+}
+
 static float grid_prob(const orc_hmap *m, int index) {
   float odds = expf(m->log_odds[index]);
   return odds / (odds + 1.0f);

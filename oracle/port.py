@@ -221,6 +221,12 @@ class PortHectorMap:
         o, w = np.ascontiguousarray(origo, np.float32), np.ascontiguousarray(world_pose, np.float32)
         return self.L.orc_hmap_update_by_scan(self.h, _p(p, C.c_float), len(p), _p(o, C.c_float), _p(w, C.c_float))
 
+    def update_by_scan_just_once(self, points_m, origo):
+        p = np.ascontiguousarray(points_m, np.float32).reshape(-1, 2)
+        o = np.ascontiguousarray(origo, np.float32)
+        self.L.orc_hmap_update_by_scan_just_once.restype = C.c_long
+        return self.L.orc_hmap_update_by_scan_just_once(self.h, _p(p, C.c_float), len(p), _p(o, C.c_float))
+
     def match_data(self, points, begin_world_pose, max_iterations):
         p = np.ascontiguousarray(points, np.float32).reshape(-1, 2)
         b = np.ascontiguousarray(begin_world_pose, np.float32)

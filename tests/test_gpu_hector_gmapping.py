@@ -57,6 +57,27 @@ def test_hector_origo_offset_and_out_of_map(pkg, mods):
         assert np.array_equal(g.cells()[0], c.cells()[0]) and np.array_equal(g.cells()[1], c.cells()[1])
 
 
+def test_hector_update_by_scan_just_once(pkg, mods):
+    """The lesson4 make-map demo variant (OccGridMapBase.h:175-217): 1600^2 map (the fixed map pose is cell 800, 800),
+    points in metres with half-cell values (round half away from zero), repeated scans, origo offset."""
+    H, _ = mods
+    laser = pkg.synth.Laser()
+    g, c = H.HectorMap(1601, 1601, 0.05), port.PortHectorMap(1601, 1601, 0.05)
+    for seed, origo in ((11, (0.0, 0.0)), (12, (0.0, 0.0)), (13, (3.2, -1.7)), (11, (0.0, 0.0))):
+        mc = pkg.synth.make_match_case(seed)
+        th = laser.min_angle + laser.angular_resolution * np.arange(laser.n_readings)
+        r = np.where(np.isfinite(mc.ranges), mc.ranges, 0.0)
+        pts = np.stack([r * np.cos(th), r * np.sin(th)], axis=1).astype(np.float32)
+        pts[::7] = np.round(pts[::7] / 0.05) * 0.05 + 0.025  # exact .5 cells: ::round semantics
+        pts[5] = (1000.0, 3.0)  # leaves the map: skipped
+        g.update_by_scan_just_once(pts, origo)
+        c.update_by_scan_just_once(pts, origo)
+        (glo, gui), (clo, cui) = g.cells(), c.cells()
+        assert np.array_equal(gui, cui)
+        assert np.array_equal(glo, clo)
+    assert (gui >= 0).sum() > 10000
+
+
 def test_hector_match_data(pkg, mods):
     """K3: three pyramid levels like MapRepMultiMap::matchData (3 / 3 / 5 extra iterations), level by level."""
     H, _ = mods

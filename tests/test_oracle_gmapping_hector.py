@@ -97,3 +97,16 @@ def test_hector_gn_recovers_pose(pkg):
     assert np.allclose(cov, cov.T) and cov[0, 0] > 0 and cov[1, 1] > 0
     est0, _ = m.match_data(pts[:0], start, 5)
     assert np.array_equal(est0, start)
+
+
+def test_hector_just_once_semantics(pkg):
+    """updateByScanJustOnce (OccGridMapBase.h:175-217): begin = cell (800, 800) whatever the pose; end = begin +
+    round(p / 0.05); one beam along +x frees cells 800..end-1 and occupies the end cell."""
+    m = port.PortHectorMap(1601, 1601, 0.05)
+    visits = m.update_by_scan_just_once(np.array([[1.0, 0.0], [0.0, -0.524]], np.float32), (0.0, 0.0))
+    lo, ui = m.cells()
+    assert visits == (20 + 1) + (10 + 1)           # round(0.524 / 0.05) = round(10.48) = 10
+    assert (ui[800, 800:820] == 1).all() and ui[800, 820] == 2
+    assert (lo[800, 800:820] < 0).all() and lo[800, 820] > 0
+    assert ui[790, 800] == 2 and (ui[791:800, 800] == 1).all()
+    m.close()
