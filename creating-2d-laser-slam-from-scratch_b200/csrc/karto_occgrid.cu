@@ -183,13 +183,21 @@ __global__ void k_occ_ros(const uint8_t *__restrict__ cells, int w, int h, int s
 extern "C" void b2s_occ_grid_destroy(b2s_occ_grid *g);
 extern "C" {
 
-b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, const double *ranges,
-                                          const double *poses, double resolution, int device, void *cuda_stream,
-                                          b2s_occ_grid **out) {
-  if (!laser || !out || n_scans < 0 || (n_scans > 0 && (!ranges || !poses)))
-    B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_occ_grid_create_from_scans: null/negative argument");
-  *out = nullptr;
-  if (n_scans == 0) return B2S_OK;  // CreateFromScans returns NULL for an empty scan list (Karto.h:5661-5664)
+// given_bbox == nullptr: CreateFromScans (the box is the union over these scans).  given_bbox != nullptr: the scans
+// are one SHARD of a scan list whose global box the caller has reduced over all shards; the
+// counters then hold this shard's contribution only.  bbox_out != nullptr: compute the shard's box and stop.
+static b2s_status occ_create_impl(const b2s_laser *laser, int n_scans, const double *ranges, const double *poses,
+                                  double resolution, const double *given_bbox, double *bbox_out, int device,
+                                  void *cuda_stream, b2s_occ_grid **out) {
+  if (!laser || n_scans < 0 || (n_scans > 0 && (!ranges || !poses)) || (!out && !bbox_out))
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_occ_grid: null/negative argument");
+  if (out) *out = nullptr;
+  if (n_scans == 0 && !given_bbox && !bbox_out) return B2S_OK;  // CreateFromScans returns NULL for an empty scan list (Karto.h:5661-5664)
+  if (bbox_out && n_scans == 0) {  // BoundingBox2 of nothing (Karto.h:2765-2770)
+    const double big = 999999999999999999.99999;
+    bbox_out[0] = big; bbox_out[1] = big; bbox_out[2] = -big; bbox_out[3] = -big;
+    return B2S_OK;
+  }
   if (double_equal(resolution, 0.0)) B2S_FAIL(B2S_ERR_BAD_PARAMS, "Resolution cannot be 0");  // Karto.h:5627-5630
   if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
   B2S_CUDA_CHECK(cudaSetDevice(device));
@@ -209,21 +217,33 @@ b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, c
   cudaEvent_t ev[3];
   for (auto &e : ev) B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaEventCreate(&e));
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_ranges), sizeof(double) * std::max<size_t>(M * n, 1), st));
-  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_poses), sizeof(double) * M * 3, st));
-  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_sensor), sizeof(double) * M * 3, st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_poses), sizeof(double) * std::max<size_t>(M * 3, 1), st));
+  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_sensor), sizeof(double) * std::max<size_t>(M * 3, 1), st));
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_pts), sizeof(double) * std::max<size_t>(M * n * 2, 1), st));
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_bbox), sizeof(double) * (M + 1) * 4, st));
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMallocAsync(reinterpret_cast<void **>(&d_visits), sizeof(unsigned long long), st));
-  if (n) B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(d_ranges, ranges, sizeof(double) * M * n, cudaMemcpyHostToDevice, st));
-  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(d_poses, poses, sizeof(double) * M * 3, cudaMemcpyHostToDevice, st));
+  if (n && M) B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(d_ranges, ranges, sizeof(double) * M * n, cudaMemcpyHostToDevice, st));
+  if (M) B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(d_poses, poses, sizeof(double) * M * 3, cudaMemcpyHostToDevice, st));
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemsetAsync(d_visits, 0, sizeof(unsigned long long), st));
-  k_scan_points<<<(unsigned)M, 256, 0, st>>>(d_ranges, d_poses, *laser, d_sensor, d_pts, nullptr);
-  k_scan_bbox<<<(unsigned)M, 256, 0, st>>>(d_ranges, d_sensor, d_pts, *laser, d_bbox);
-  k_bbox_union<<<1, 256, 0, st>>>(d_bbox, n_scans, d_bbox + 4 * M);
-  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaGetLastError());
   double bb[4];
-  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(bb, d_bbox + 4 * M, sizeof(bb), cudaMemcpyDeviceToHost, st));
-  B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaStreamSynchronize(st));
+  if (M) k_scan_points<<<(unsigned)M, 256, 0, st>>>(d_ranges, d_poses, *laser, d_sensor, d_pts, nullptr);
+  if (given_bbox) {
+    for (int i = 0; i < 4; i++) bb[i] = given_bbox[i];
+  } else {
+    k_scan_bbox<<<(unsigned)M, 256, 0, st>>>(d_ranges, d_sensor, d_pts, *laser, d_bbox);
+    k_bbox_union<<<1, 256, 0, st>>>(d_bbox, n_scans, d_bbox + 4 * M);
+    B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaGetLastError());
+    B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(bb, d_bbox + 4 * M, sizeof(bb), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaStreamSynchronize(st));
+  }
+  if (bbox_out) {
+    for (int i = 0; i < 4; i++) bbox_out[i] = bb[i];
+    for (void *p : {(void *)d_ranges, (void *)d_poses, (void *)d_sensor, (void *)d_pts, (void *)d_bbox, (void *)d_visits})
+      cudaFreeAsync(p, st);
+    for (auto &e : ev) cudaEventDestroy(e);
+    b2s_occ_grid_destroy(g);
+    return B2S_OK;
+  }
   // OccupancyGrid::ComputeDimensions (Karto.h:5816-5821)
   const double scale = 1.0 / resolution;
   b2s_occ_grid_info &I = g->info;
@@ -246,7 +266,7 @@ b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, c
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemsetAsync(g->d_pass, 0, sizeof(uint32_t) * cells, st));
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemsetAsync(g->d_hit, 0, sizeof(uint32_t) * cells, st));
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaEventRecord(ev[0], st));
-  if (n && I.data_size > 0) {
+  if (n && M && I.data_size > 0) {
     const long long n_beams = (long long)M * (long long)n;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -269,6 +289,57 @@ b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, c
   if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) g->last_ms[1] = ms;
   for (auto &e : ev) cudaEventDestroy(e);
   *out = g;
+  return B2S_OK;
+}
+
+b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, const double *ranges,
+                                          const double *poses, double resolution, int device, void *cuda_stream,
+                                          b2s_occ_grid **out) {
+  if (!out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_occ_grid_create_from_scans: null argument");
+  return occ_create_impl(laser, n_scans, ranges, poses, resolution, nullptr, nullptr, device, cuda_stream, out);
+}
+
+b2s_status b2s_occ_grid_scans_bbox(const b2s_laser *laser, int n_scans, const double *ranges, const double *poses,
+                                   int device, void *cuda_stream, double bbox[4]) {
+  if (!bbox) B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_occ_grid_scans_bbox: null argument");
+  return occ_create_impl(laser, n_scans, ranges, poses, 1.0, nullptr, bbox, device, cuda_stream, nullptr);
+}
+
+b2s_status b2s_occ_grid_create_shard(const b2s_laser *laser, int n_scans, const double *ranges, const double *poses,
+                                     double resolution, const double bbox[4], int device, void *cuda_stream,
+                                     b2s_occ_grid **out) {
+  if (!out || !bbox) B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_occ_grid_create_shard: null argument");
+  return occ_create_impl(laser, n_scans, ranges, poses, resolution, bbox, nullptr, device, cuda_stream, out);
+}
+
+b2s_status b2s_occ_grid_device_counters(b2s_occ_grid *g, uint32_t **d_pass, uint32_t **d_hit) {
+  if (!g || !d_pass || !d_hit) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  B2S_CUDA_CHECK(cudaSetDevice(g->device));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(g->stream));  // the caller's collective runs on its own stream
+  *d_pass = g->d_pass;
+  *d_hit = g->d_hit;
+  return B2S_OK;
+}
+
+b2s_status b2s_occ_grid_set_counters(b2s_occ_grid *g, const uint32_t *pass, const uint32_t *hit) {
+  if (!g || !pass || !hit) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  B2S_CUDA_CHECK(cudaSetDevice(g->device));
+  const size_t n = (size_t)g->info.data_size;
+  if (n) {
+    B2S_CUDA_CHECK(cudaMemcpyAsync(g->d_pass, pass, n * sizeof(uint32_t), cudaMemcpyHostToDevice, g->stream));
+    B2S_CUDA_CHECK(cudaMemcpyAsync(g->d_hit, hit, n * sizeof(uint32_t), cudaMemcpyHostToDevice, g->stream));
+    B2S_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  }
+  return B2S_OK;
+}
+
+b2s_status b2s_occ_grid_update(b2s_occ_grid *g) {  // OccupancyGrid::Update (Karto.h:5953-5968)
+  if (!g) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null handle");
+  B2S_CUDA_CHECK(cudaSetDevice(g->device));
+  const int n = g->info.data_size;
+  if (n > 0) k_occ_threshold<<<ceil_div(n, 256), 256, 0, g->stream>>>(g->d_pass, g->d_hit, n, g->d_cells);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK(cudaStreamSynchronize(g->stream));
   return B2S_OK;
 }
 

@@ -90,3 +90,33 @@ def correlate_scan_angle_split(matcher, centers, search, n_angles: int, group=No
     if (status != 0).any():  # a rank saw an out-of-range candidate: the reference throws for the whole sweep
         out[3][status != 0] = status[status != 0]
     return out
+
+
+def occupancy_grid_sharded(occgrid_mod, laser, ranges_shard, poses_shard, resolution: float, device: int = 0, group=None):
+    """karto::OccupancyGrid::CreateFromScans (Karto.h:5659-5673) over a scan list SHARDED across the ranks
+    (SURVEY.md §8(e)(iii)): bounding boxes are reduced (MIN/MAX), each rank ray-traces its shard into the globally
+    dimensioned grid, the uint32 pass/hit counters are summed with one all-reduce each (in place on the device with
+    NCCL; through host arrays with gloo), then every rank thresholds the same cells."""
+    import torch
+    import torch.distributed as dist
+
+    live = dist.is_available() and dist.is_initialized()
+    bbox = occgrid_mod.scans_bbox(laser, ranges_shard, poses_shard, device=device)
+    if live:
+        lo = _all_reduce(-bbox[:2], "max", group)  # MIN via MAX of the negation
+        hi = _all_reduce(bbox[2:], "max", group)
+        bbox = np.concatenate([-lo, hi])
+    g = occgrid_mod.OccupancyGrid(laser, ranges_shard, poses_shard, resolution, device=device, bbox=bbox)
+    if live and g.info.data_size > 0:
+        if dist.get_backend(group) == "nccl":
+            for arr in g.device_counters():
+                t = torch.as_tensor(arr, device=torch.device("cuda", device))
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            torch.cuda.synchronize(device)
+        else:
+            a = g.arrays()
+            pa = _all_reduce(a["passes"].astype(np.int64), "sum", group)
+            hi_ = _all_reduce(a["hits"].astype(np.int64), "sum", group)
+            g.set_counters(pa, hi_)
+    g.update()
+    return g

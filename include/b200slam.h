@@ -201,6 +201,23 @@ typedef struct b2s_occ_grid b2s_occ_grid; /* opaque: replaces karto::OccupancyGr
 b2s_status b2s_occ_grid_create_from_scans(const b2s_laser *laser, int n_scans, const double *ranges,
                                           const double *poses, double resolution, int device,
                                           void *cuda_stream, b2s_occ_grid **out);
+/* The same map built from a scan list SHARDED over several GPUs: pass/hit counters are
+ * commutative, so each rank ray-traces its shard into a grid sized by the GLOBAL bounding box and the counters are
+ * summed (NCCL all-reduce, in place on the device pointers) before OccupancyGrid::Update thresholds them.
+ *   1. b2s_occ_grid_scans_bbox  -> this shard's BoundingBox2 {min x, min y, max x, max y} (Karto.h:5810-5814);
+ *                                  the caller reduces MIN on [0..1], MAX on [2..3] over the ranks
+ *   2. b2s_occ_grid_create_shard -> grid dimensioned by the global box (ComputeDimensions, Karto.h:5816-5821),
+ *                                  counters = this shard's rays; n_scans may be 0
+ *   3. b2s_occ_grid_device_counters (all-reduce SUM on both) or b2s_occ_grid_set_counters (host arrays)
+ *   4. b2s_occ_grid_update       -> cells from the summed counters (OccupancyGrid::Update, Karto.h:5953-5968) */
+b2s_status b2s_occ_grid_scans_bbox(const b2s_laser *laser, int n_scans, const double *ranges, const double *poses,
+                                   int device, void *cuda_stream, double bbox[4]);
+b2s_status b2s_occ_grid_create_shard(const b2s_laser *laser, int n_scans, const double *ranges, const double *poses,
+                                     double resolution, const double bbox[4], int device, void *cuda_stream,
+                                     b2s_occ_grid **out);
+b2s_status b2s_occ_grid_device_counters(b2s_occ_grid *g, uint32_t **d_pass, uint32_t **d_hit);
+b2s_status b2s_occ_grid_set_counters(b2s_occ_grid *g, const uint32_t *pass, const uint32_t *hit);
+b2s_status b2s_occ_grid_update(b2s_occ_grid *g);
 b2s_status b2s_occ_grid_info_get(const b2s_occ_grid *g, b2s_occ_grid_info *out);
 /* cells: uint8 {0 unknown, 100 occupied, 255 free}; pass/hit: uint32 counters; any pointer may be NULL */
 b2s_status b2s_occ_grid_copy(b2s_occ_grid *g, uint8_t *cells, uint32_t *pass, uint32_t *hit);

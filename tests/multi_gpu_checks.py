@@ -1,7 +1,7 @@
 """Real multi-GPU check of the angle-split sweep; not collected by pytest.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/multi_gpu_angle_split.py
+        tests/multi_gpu_checks.py
 
 Every rank holds the same scans + grids, sweeps its share of the angle steps, and the best response / per-cell maxima /
 tie sums are all-reduced over NCCL.  Rank 0 also runs the whole sweep alone and prints one JSON line with the largest
@@ -60,8 +60,34 @@ def main():
                           "max_abs_diff": worst, "ok": bool(worst <= 1e-9),
                           "host_ms_split_incl_allreduce": round(1e3 * min(t_split[1:]), 3),
                           "host_ms_whole_one_gpu": round(1e3 * min(t_whole[1:]), 3)}))
+    # ---- K2c: the scan list sharded over the ranks, counters all-reduced in place over NCCL ----
+    O = pkg.load("occgrid")
+    n_scans = int(os.environ.get("B2S_SPLIT_SCANS", 400))
+    _, tposes, tranges = synth.make_trajectory(21, n_scans, synth.Laser(), step_xy=0.2, step_th_deg=5)
+    lo, hi = par.shard_bounds(n_scans, world, rank)
+    t_sh, t_wh = [], []
+    for it in range(3):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gs = par.occupancy_grid_sharded(O, laser, tranges[lo:hi], tposes[lo:hi], 0.05, device=local)
+        t_sh.append(par.max_over_ranks(time.perf_counter() - t0))
+        t0 = time.perf_counter()
+        gw = O.OccupancyGrid(laser, tranges, tposes, 0.05, device=local)
+        t_wh.append(par.max_over_ranks(time.perf_counter() - t0))
+        a, b = gs.arrays(), gw.arrays()
+        same = all(np.array_equal(a[k], b[k]) for k in ("passes", "hits", "cells", "offset")) and \
+            (a["width"], a["height"]) == (b["width"], b["height"])
+        gs.close(); gw.close()
+    same_all = par.max_over_ranks(0.0 if same else 1.0) == 0.0
+    if rank == 0:
+        print(json.dumps({"check": "occupancy_grid_sharded_vs_whole", "n_gpus": world, "scans": n_scans,
+                          "bit_identical_on_all_ranks": bool(same_all),
+                          "host_ms_sharded_incl_allreduce": round(1e3 * min(t_sh[1:]), 3),
+                          "host_ms_whole_one_gpu": round(1e3 * min(t_wh[1:]), 3)}))
     dist.barrier()
     dist.destroy_process_group()
+    if not same_all:
+        sys.exit(2)
     if worst > 1e-9:
         sys.exit(1)
 

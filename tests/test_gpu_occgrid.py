@@ -103,3 +103,43 @@ def test_large_map_properties(pkg, O):
     t = g.last_timing()
     assert t["raytrace_ms"] > 0
     g.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_sharded_scan_list_equals_whole(pkg, O, world):
+    """the scan list sharded over `world` ranks (emulated on one GPU): per-shard boxes reduced by
+    min/max, per-shard counters summed, thresholded once — identical to CreateFromScans over the whole list, incl.
+    an EMPTY shard (world 5 > 4 scans in the second case) and the device-pointer alias used for the NCCL all-reduce."""
+    import torch
+    abi, synth, par = pkg.abi, pkg.synth, pkg.load("parallel")
+    laser = synth.Laser()
+    al = abi.laser_from(laser)
+    for n_scans in (31, 4):
+        _, poses, ranges = synth.make_trajectory(8, n_scans, laser, step_xy=0.3, step_th_deg=8)
+        whole = O.OccupancyGrid(al, ranges, poses, 0.05)
+        bounds = [par.shard_bounds(n_scans, world, r) for r in range(world)]
+        boxes = np.stack([O.scans_bbox(al, ranges[lo:hi], poses[lo:hi]) for lo, hi in bounds])
+        bbox = np.concatenate([boxes[:, :2].min(axis=0), boxes[:, 2:].max(axis=0)])
+        shards = [O.OccupancyGrid(al, ranges[lo:hi], poses[lo:hi], 0.05, bbox=bbox) for lo, hi in bounds]
+        arrs = [s.arrays() for s in shards]
+        # device alias: torch sees the library's counters without a copy
+        dpass, dhit = shards[0].device_counters()
+        tp = torch.as_tensor(dpass, device="cuda")
+        assert np.array_equal(tp.cpu().numpy().view(np.uint32), arrs[0]["passes"].reshape(-1))
+        tp += torch.as_tensor(np.sum([a["passes"] for a in arrs[1:]], axis=0).reshape(-1).astype(np.int32), device="cuda")
+        th = torch.as_tensor(dhit, device="cuda")
+        th += torch.as_tensor(np.sum([a["hits"] for a in arrs[1:]], axis=0).reshape(-1).astype(np.int32), device="cuda")
+        torch.cuda.synchronize()
+        shards[0].update()
+        same(shards[0].arrays(), whole.arrays())
+        # host path (what the gloo tests use)
+        shards[1].set_counters(np.sum([a["passes"] for a in arrs], axis=0), np.sum([a["hits"] for a in arrs], axis=0))
+        shards[1].update()
+        same(shards[1].arrays(), whole.arrays())
+        assert sum(a["cell_visits"] for a in arrs) == whole.arrays()["cell_visits"]
+        for s in shards:
+            s.close()
+        whole.close()
+    # single-process form of the orchestration helper
+    g1 = par.occupancy_grid_sharded(O, al, ranges, poses, 0.05)
+    same(g1.arrays(), O.OccupancyGrid(al, ranges, poses, 0.05).arrays())

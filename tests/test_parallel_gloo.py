@@ -127,3 +127,76 @@ def test_angle_split_collectives(world):
     for rank, out in outs:
         for a, b in zip(out, expect):
             assert np.array_equal(a, b)
+
+
+class _StandInGrid:
+    """numpy stand-in for occgrid.OccupancyGrid (shard form): every scan adds 3 passes + 1 hit at its pose's cell."""
+
+    class _Info:
+        data_size = 0
+
+    def __init__(self, laser, ranges, poses, resolution, device=0, bbox=None):
+        w = int(round((bbox[2] - bbox[0]) / resolution)) + 1
+        h = int(round((bbox[3] - bbox[1]) / resolution)) + 1
+        self.p, self.h = np.zeros((h, w), np.uint32), np.zeros((h, w), np.uint32)
+        for x, y, _ in np.asarray(poses).reshape(-1, 3):
+            cx, cy = int(round((x - bbox[0]) / resolution)), int(round((y - bbox[1]) / resolution))
+            self.p[cy, cx] += 3
+            self.h[cy, cx] += 1
+        self.info = self._Info()
+        self.info.data_size = w * h
+        self.cells = None
+
+    def arrays(self):
+        return dict(passes=self.p, hits=self.h, cells=self.cells)
+
+    def set_counters(self, p, h):
+        self.p, self.h = np.asarray(p, np.uint32).reshape(self.p.shape), np.asarray(h, np.uint32).reshape(self.h.shape)
+
+    def update(self):
+        self.cells = np.where(self.p > 2, 100, 0).astype(np.uint8)
+
+
+class _StandInOccMod:
+    OccupancyGrid = _StandInGrid
+
+    @staticmethod
+    def scans_bbox(laser, ranges, poses, device=0):
+        p = np.asarray(poses).reshape(-1, 3)
+        big = 999999999999999999.99999
+        return np.array([p[:, 0].min(), p[:, 1].min(), p[:, 0].max(), p[:, 1].max()]) if len(p) else np.array([big, big, -big, -big])
+
+
+def occ_worker(rank, world, port, n_scans, q):
+    sys.path.insert(0, ROOT)
+    import importlib
+    import torch.distributed as dist
+    par = importlib.import_module("creating-2d-laser-slam-from-scratch_b200.parallel")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    poses = np.random.default_rng(3).uniform(-5, 5, size=(n_scans, 3))
+    lo, hi = par.shard_bounds(n_scans, world, rank)
+    g = par.occupancy_grid_sharded(_StandInOccMod, None, None, poses[lo:hi], 0.5)
+    q.put((rank, g.p, g.h, g.cells))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_scans", [(2, 40), (3, 2)])  # (3, 2): one rank has an empty shard
+def test_sharded_occupancy_grid_collectives(world, n_scans):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=occ_worker, args=(r, world, port, n_scans, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    poses = np.random.default_rng(3).uniform(-5, 5, size=(n_scans, 3))
+    whole = _StandInGrid(None, None, poses, 0.5, bbox=_StandInOccMod.scans_bbox(None, None, poses))
+    whole.update()
+    for rank, p, h, cells in outs:
+        assert np.array_equal(p, whole.p) and np.array_equal(h, whole.h) and np.array_equal(cells, whole.cells)
