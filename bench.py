@@ -347,6 +347,36 @@ def bench_k2(pkg, local, quick=False):
                          "ok": int((r4[3] == 0).sum())})
         out["cfg4_window_sweep"] = {"batch": B4, "grid": "0.025 m, 807x807 (652 KB, 4 row bands)", "rows": rows}
         m4.close()
+        # cfg 5 (mapper_params_outdoor.yaml): the loop-closure matcher's coarse sweep, 151-cell side @0.1 m, smear 0.3,
+        # 1165 x 1168-byte grid (1.36 MB), 76x76x21 candidates every other cell; 4 base scans per candidate chain
+        B5 = 32 if quick else 128
+        l5 = synth.Laser(range_threshold=50.0)
+        cases = [synth.make_match_case(5_000_000 + i, l5, max_xy=3.0, max_th_deg=15) for i in range(min(B5, 32))]
+        pick = [cases[i % len(cases)] for i in range(B5)]
+        mr, mp = np.stack([c.ranges for c in pick]), np.stack([c.odom_pose for c in pick])
+        mbr, mbp = np.stack([c.base_ranges for c in pick])[:, None, :], np.stack([c.base_pose for c in pick])[:, None, :]
+        m5 = M.ScanMatcher(abi.matcher_params(15.0, 0.1, 0.3, 50.0), abi.laser_from(l5), max_batch=B5, max_base_scans=1, device=local)
+        m5.set_scans(mr, mp)
+        m5.add_scans(mbr, mbp)
+        se5 = abi.Search(7.5, 7.5, 0.2, 0.2, 20 * D, 2 * D, 1, 0)
+        rows5 = {}
+        for name, kern in (("window", 0), ("generic", 1)):
+            m5.set_kernel(kern)
+            m5.correlate_scan(mp, se5)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r5 = m5.correlate_scan(mp, se5)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tm = m5.last_timing()
+            rows5[name] = {"matches_per_s": B5 / dt, "sweep_ms": tm["sweep_ms"], "lut_ms": tm["lut_ms"], "path": tm["path"],
+                           "lookups_per_s_kernel": B5 * 76 * 76 * 21 * 1081 / (tm["sweep_ms"] * 1e-3),
+                           "ok": int((r5[3] == 0).sum())}
+        truth = np.stack([c.true_pose for c in pick])
+        rows5["median_xy_err_m"] = float(np.median(np.abs(r5[1][:, :2] - truth[:, :2]).max(axis=1)))
+        out["cfg5_loop_closure_coarse"] = {"batch": B5, "grid": "0.1 m, 1165x1168 B (1.36 MB; row bands x row tiles)",
+                                           "window": [76, 76, 21], **rows5}
+        m5.close()
     except Exception as e:
         out["k1_extras_error"] = repr(e)
     # --- K3 (lesson3): batched PL-ICP, 1024 independent scan pairs with odometry-like motion

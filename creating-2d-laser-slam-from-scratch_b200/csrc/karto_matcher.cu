@@ -453,7 +453,7 @@ constexpr int WIN_THREADS = 512;
 constexpr int WIN_GUARD = 128;          // zero bytes before and after the grid image in shared memory
 constexpr int WIN_FLUSH_BEAMS = 512;    // beams accumulated in u16 lanes between flushes (512 * 127 < 65536)
 constexpr int32_t WIN_SKIP = -(1 << 29);
-constexpr int WIN_MAX_BANDS = 16;      // row bands a grid larger than shared memory is swept in
+constexpr int WIN_MAX_BANDS = 32;      // row bands a grid larger than shared memory is swept in
 constexpr int LIST_PAD = 16;            // per-(match, angle) list capacity = n + LIST_PAD * nbands
 
 // ----------------------------------------------------------------------------------------------
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(256)
                      int rows_total, int cols_total, int32_t *__restrict__ lists, int32_t *__restrict__ counts,
                      const uint16_t *__restrict__ sat_all, int sbx, int sby, int height, int nx, int ny,
                      unsigned long long *__restrict__ stats, int band_rows, int nbands,
-                     int32_t *__restrict__ starts, int stride, int k_first) {
+                     int32_t *__restrict__ starts, int stride, int k_first, int neg_bands) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   double *s_lx = reinterpret_cast<double *>(s_raw), *s_ly = s_lx + n;  // [n] scan-local points
   int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);             // [n] window origins
@@ -571,14 +571,16 @@ __global__ void __launch_bounds__(256)
         else if (lo >= -(WIN_GUARD - 16) && hi <= data_size + (WIN_GUARD - 16)) cls = a & 3;  // interior
         else cls = 4 + (a & 3);                                                                // edge
         int y = 0, x = 0;
-        if ((sat_all || nbands > 1) && cls < 255 && a >= 0) {
-          // a / width_step by float reciprocal + fix-up (a < 2^24 is exact in float; larger values are corrected too)
-          if (data_size <= (1 << 24)) {
+        if ((sat_all || nbands > 1) && cls < 255 && (a >= 0 || neg_bands > 0)) {
+          // floor(a / width_step) by float reciprocal + fix-up (|a| < 2^24 is exact in float; larger values are
+          // corrected too); a < 0 only matters when origins below the grid get row bands of their own (neg_bands)
+          if (data_size <= (1 << 24) && ac == a) {
             y = (int)((float)a * inv_step);
             if (y * width_step > a) y--;
             else if ((y + 1) * width_step <= a) y++;
           } else {
             y = a / width_step;
+            if (y * width_step > a) y--;
           }
           x = a - y * width_step;
         }
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(256)
           int band = (int)((float)y * inv_band);
           if (band * band_rows > y) band--;
           else if ((band + 1) * band_rows <= y) band++;
-          cls += 8 * min(band, nbands - 1);  // the row band that holds the window origin
+          cls += 8 * max(min(band + neg_bands, nbands - 1), 0);  // the row band that holds the window origin
         }
         if (sat_all && cls < 255 && a >= 0) {
           // empty-window test on the 4x4-block summed-area table (only for windows that do not wrap a row end)
@@ -761,10 +763,11 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
                    const int32_t *__restrict__ lists, const int32_t *__restrict__ counts,
                    const int32_t *__restrict__ starts, const int32_t *__restrict__ flags, int batch, int n, int na,
                    int nx, int ny, int width_step, int32_t *__restrict__ sums, int *__restrict__ work_counter,
-                   int band_rows, int nbands, int band_bytes) {
-  // Grids larger than shared memory are swept in `nbands` row bands: a work unit is (match, band); the band image
-  // holds the rows a window whose ORIGIN lies in the band can touch (band_rows + window rows + 1), k_offsets_sorted
-  // grouped the beams by the band of their origin, and the partial sums of the bands are combined with RED.ADD.
+                   int band_rows, int nbands, int band_bytes, int neg_bands) {
+  // Grids larger than shared memory are swept in `nbands` row bands: a work unit is (match, band, 32-row candidate
+  // tile); the image holds the rows that tile of a window whose ORIGIN lies in the band can touch (band_rows +
+  // STRIDE * 31 + 2), k_offsets_sorted grouped the beams by the band of their origin (bands [0, neg_bands) hold origins
+  // BELOW the grid, whose upper tiles still reach it), and the partial sums of the bands are combined with RED.ADD.
   extern __shared__ __align__(128) unsigned char smem[];
   uint8_t *sgrid = smem;  // [WIN_GUARD zeros][band image][WIN_GUARD zeros]
   __shared__ uint64_t bar;
@@ -775,7 +778,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
   int32_t *s_off = s_offsets[threadIdx.x >> 5];
   constexpr int CPT = 32 / STRIDE;  // candidates per tile row (a tile row is always 32 bytes)
   const int tiles_x = (nx + CPT - 1) / CPT, tiles_y = (ny + 31) >> 5;
-  const int items = na * tiles_x * tiles_y;
+  const int unit_tiles_y = nbands > 1 ? tiles_y : 1;        // banded: one row tile per unit
+  const int items = na * tiles_x * (nbands > 1 ? 1 : tiles_y);
   const int hi_half = lane >> 4;
   const int list_cap = n + LIST_PAD * nbands;
   const int ngroups = 8 * nbands;
@@ -795,16 +799,26 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
     }
     __syncthreads();
     const int unit = s_unit;
-    if (unit >= batch * nbands) break;
-    const int b = unit / nbands, band = unit % nbands;
+    if (unit >= batch * nbands * unit_tiles_y) break;
+    const int b = unit / (nbands * unit_tiles_y), band = (unit / unit_tiles_y) % nbands, unit_ty = unit % unit_tiles_y;
     const int f = flags[b];
     if ((f & 2) || !(f & 1)) {  // out-of-range lattice (error) or irregular lattice (generic kernel takes it)
       __syncthreads();
       continue;
     }
+    // first / one-past-last grid row of this unit's image (the whole grid when nbands == 1)
+    const int row0 = (band - neg_bands) * band_rows + STRIDE * unit_ty * 32;
+    const int lo_row = max(row0, 0);
+    const int band_lo = lo_row * width_step;  // flat index of the first staged byte (multiple of 16)
+    int bytes = nbands > 1 ? min((((row0 - lo_row) * width_step + band_bytes) + 15) & ~15, copy_bytes - band_lo) : copy_bytes;
+    if (nbands > 1) {
+      // nothing to do when the image misses the grid or no beam of any angle has its origin in this band
+      int any = 0;
+      if (bytes > 0)
+        for (int i = threadIdx.x; i < na * 8; i += blockDim.x) any |= counts[((size_t)b * na + (i >> 3)) * ngroups + band * 8 + (i & 7)];
+      if (!__syncthreads_or(any)) continue;
+    }
     // ---- stage this unit's band image: TMA bulk copies, 32 KB each, one mbarrier phase ----
-    const int band_lo = band * band_rows * width_step;  // flat index of the first staged byte (multiple of 16)
-    const int bytes = min(band_bytes, copy_bytes - band_lo);
     if (threadIdx.x == 0) {
       fence_proxy_async();  // earlier generic-proxy reads of sgrid are ordered before the async-proxy writes
       mbar_expect_tx(&bar, (uint32_t)bytes);
@@ -826,9 +840,14 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
       if (lane == 0) item = atomicAdd(&s_item, 1);
       item = __shfl_sync(0xffffffffu, item, 0);
       if (item >= items) break;
-      const int k = item / (tiles_x * tiles_y);
-      const int t = item % (tiles_x * tiles_y);
-      const int ty = t / tiles_x, tx = t % tiles_x;
+      int k, ty, tx;
+      if (nbands > 1) {
+        k = item / tiles_x; tx = item % tiles_x; ty = unit_ty;
+      } else {
+        k = item / (tiles_x * tiles_y);
+        const int t = item % (tiles_x * tiles_y);
+        ty = t / tiles_x; tx = t % tiles_x;
+      }
       const int row_delta = STRIDE * (ty * 32 + lane) * width_step + tx * 32;  // this lane's row start relative to a beam's origin
       const int32_t *list = lists + ((size_t)b * na + k) * list_cap;
       const int32_t *cn = counts + ((size_t)b * na + k) * ngroups + band * 8;
@@ -1850,9 +1869,9 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   const int cpt = stride == 2 ? 16 : 32;  // candidates per 32-byte tile row
   const int tiles_x_w = (nx + cpt - 1) / cpt, tiles_y_w = (ny + 31) / 32;
   const int rows_total = tiles_y_w * 32;
-  const int halo_rows = std::max(stride, 1) * rows_total + 1;  // rows below a window origin that a lane may touch
+  const int halo_rows = std::max(stride, 1) * 31 + 2;  // rows below the first row of a 32-row candidate tile that a lane may touch
   const long long smem_limit = (long long)m->smem_optin - 4096;  // static shared memory of the kernel + margin
-  int band_rows = std::max(m->g.height, 1), nbands = 1, band_bytes = copy_bytes;
+  int band_rows = std::max(m->g.height, 1), nbands = 1, band_bytes = copy_bytes, neg_bands = 0;
   bool bands_ok = true;
   if ((long long)copy_bytes + 2 * WIN_GUARD > smem_limit) {
     const long long rows_fit = (smem_limit - 2 * WIN_GUARD) / m->g.width_step;
@@ -1860,12 +1879,14 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     if (band_rows < 8) {
       bands_ok = false;
     } else {
-      nbands = (m->g.height + band_rows - 1) / band_rows;
-      band_bytes = (int)((((long long)(band_rows + halo_rows) * m->g.width_step) + 15) & ~15LL);
+      // origins up to (window rows) below the grid still reach it from their upper row tiles: bands of their own
+      neg_bands = tiles_y_w > 1 ? (std::max(stride, 1) * (rows_total - 1) + 1 + band_rows - 1) / band_rows : 0;
+      nbands = (m->g.height + band_rows - 1) / band_rows + neg_bands;
+      band_bytes = (int)((long long)(band_rows + halo_rows) * m->g.width_step);
       if (nbands > WIN_MAX_BANDS) bands_ok = false;
     }
   }
-  const size_t win_smem = (size_t)band_bytes + 2 * WIN_GUARD;
+  const size_t win_smem = (size_t)((band_bytes + 15) & ~15) + 2 * WIN_GUARD;
   const bool win_fits = bands_ok && stride != 0 && (m->g.width_step % 8) == 0 && n > 0 &&
                         (size_t)n * 21 + 64 <= 200 * 1024 && !m->grid_high_bytes;
   bool use_window = win_fits;
@@ -1898,7 +1919,7 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
         m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases, m->d_flags, s->angle_offset, s->angle_res, na, n,
         ncell, m->g.width_step, m->g.data_size, scale, rows_total, tiles_x_w * 32, m->d_lists, m->d_counts,
         skip_empty ? m->d_sat : nullptr, m->sbx, m->sby, m->g.height, nx, ny, m->d_stats, band_rows, nbands, m->d_starts,
-        stride, k_first);
+        stride, k_first, neg_bands);
   }
   B2S_CUDA_CHECK(cudaGetLastError());
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
@@ -1910,19 +1931,19 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_work, 0, sizeof(int), m->stream));
     if (nbands > 1)  // bands accumulate with RED.ADD
       B2S_CUDA_CHECK(cudaMemsetAsync(m->d_sums, 0, sizeof(int32_t) * (size_t)B * na * ncell, m->stream));
-    const int ctas = (int)std::min<long long>((long long)B * nbands, m->num_sms);
+    const int ctas = (int)std::min<long long>((long long)B * nbands * (nbands > 1 ? tiles_y_w : 1), m->num_sms);
     if (stride == 2) {
       B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
       k_sweep_window<2><<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
                                                                     m->d_lists, m->d_counts, m->d_starts, m->d_flags, B, n,
                                                                     na, nx, ny, m->g.width_step, m->d_sums, m->d_work,
-                                                                    band_rows, nbands, band_bytes);
+                                                                    band_rows, nbands, band_bytes, neg_bands);
     } else {
       B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
       k_sweep_window<1><<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
                                                                     m->d_lists, m->d_counts, m->d_starts, m->d_flags, B, n,
                                                                     na, nx, ny, m->g.width_step, m->d_sums, m->d_work,
-                                                                    band_rows, nbands, band_bytes);
+                                                                    band_rows, nbands, band_bytes, neg_bands);
     }
     // matches whose lattice is not the regular raster (a centre exactly on a rounding tie) fall through;
     // they compute their lookup values on the fly (no table was materialised for them)

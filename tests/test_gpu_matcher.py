@@ -385,8 +385,9 @@ def test_randomised_configurations(pkg, M):
     assert kinds[2] >= 8  # most of these grids fit in shared memory and use the window kernel
 
 
-@pytest.mark.parametrize("res,search,rt,na_deg", [(0.05, 1.5, 12.0, 10), (0.025, 1.5, 9.25, 5), (0.025, 0.75, 9.25, 8)])
-def test_banded_window_kernel_large_grids(pkg, M, res, search, rt, na_deg):
+@pytest.mark.parametrize("res,search,rt,na_deg,far", [(0.05, 1.5, 12.0, 10, 0), (0.025, 1.5, 9.25, 5, 0), (0.025, 0.75, 9.25, 8, 0),
+                                                      (0.025, 1.5, 9.25, 4, 1), (0.05, 3.1, 12.0, 4, 1)])
+def test_banded_window_kernel_large_grids(pkg, M, res, search, rt, na_deg, far):
     """Grids larger than shared memory (266 KB for a 12 m range threshold @0.05 m; 652 KB for cfg 4's 0.025 m grid,
     with a 61x61 or 31x31 window) are swept by the window kernel in row bands whose partial sums are combined with
     RED.ADD: bit-exact vs the restatement and vs the generic kernel, empty-window dropping on and off."""
@@ -394,6 +395,13 @@ def test_banded_window_kernel_large_grids(pkg, M, res, search, rt, na_deg):
     laser_s = synth.Laser(range_threshold=rt)
     params, laser = abi.matcher_params(search, res, 0.03, rt), abi.laser_from(laser_s)
     cases, ranges, poses, bran, bpos = make_batch(synth, range(600, 603), laser_s, max_xy=0.2, max_th_deg=5)
+    if far:
+        # readings far beyond the range threshold: their window origins lie outside the grid on every side (flat index
+        # below 0 / above the data, row-wrapped), some close enough that the upper row tiles still reach the grid
+        ranges = ranges.copy()
+        n = ranges.shape[1]
+        ranges[:, ::5] = rt + 0.02 * (np.arange(0, n, 5) % 97)
+        ranges[:, 3::11] = 14.0 + (np.arange(3, n, 11) % 13)
     B = len(cases)
     m = M.ScanMatcher(params, laser, max_batch=B, max_base_scans=1)
     assert m.g.data_size > 230_000
@@ -419,11 +427,12 @@ def test_banded_window_kernel_large_grids(pkg, M, res, search, rt, na_deg):
     m.close()
 
 
-@pytest.mark.parametrize("res,search,rt", [(0.05, 1.5, 9.25), (0.05, 3.7, 6.0), (0.1, 15.0, 5.0)])
+@pytest.mark.parametrize("res,search,rt", [(0.05, 1.5, 9.25), (0.05, 3.7, 6.0), (0.1, 15.0, 5.0), (0.1, 15.0, 50.0)])
 def test_stride2_coarse_lattice(pkg, M, res, search, rt):
     """The coarse stage of MatchScan searches every other cell (Mapper.cpp:233-234).  The window kernel handles that
     lattice with 16 candidates per 32-byte tile row: 16x16 (one tile), 38x38 (3x2 tiles) and the outdoor yaml's
-    76x76 loop-closure window (151-cell side @0.1 m, smear 0.3; banded 1.36 MB-class grid is emulated with rt = 5 m).
+    76x76 loop-closure window (151-cell side @0.1 m, smear 0.3) on a small grid (rt = 5 m) and on cfg 5's real 1.36 MB
+    grid (rt = 50 m: 1165 x 1168 bytes, swept as (row band, row tile) units).
     Integer volumes bit-exact vs the restatement on every kernel."""
     abi, synth = pkg.abi, pkg.synth
     laser_s = synth.Laser(range_threshold=rt)
