@@ -650,8 +650,8 @@ __global__ void __launch_bounds__(256)
 // byte q of word w is candidate x = 4*w + q - SH.
 // With STRIDE = 2 (candidates every other cell) only the bytes at even distance from the origin are candidates:
 // byte position p = 4*w + q - SH is candidate x = p / 2 when p is even; a tile then holds 16 candidates in 32 bytes.
-template <int SH, int STRIDE>
-__device__ __forceinline__ void win_flush(uint32_t (&lo)[9], uint32_t (&hi)[9], uint32_t (&acc)[32], int hi_half) {
+template <int SH, int STRIDE, int ROT>
+__device__ __forceinline__ void win_flush_rot(const uint32_t (&lo)[9], const uint32_t (&hi)[9], uint32_t (&acc)[32]) {
 #define B2S_FLUSH_ONE(P, VAL)                                                        \
   if ((P) >= 0 && ((P) % STRIDE) == 0 && (P) / STRIDE < 32 / STRIDE) acc[((P) / STRIDE) & 31] += (VAL);
 #define B2S_FLUSH_SLOT(J, W)                                                         \
@@ -662,32 +662,60 @@ __device__ __forceinline__ void win_flush(uint32_t (&lo)[9], uint32_t (&hi)[9], 
     B2S_FLUSH_ONE(x0 + 2, lo[J] >> 16)                                               \
     B2S_FLUSH_ONE(x0 + 3, hi[J] >> 16)                                               \
   }
-  if (!hi_half) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) B2S_FLUSH_SLOT(j, j)
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; j++) B2S_FLUSH_SLOT(j, (j + 1) % 8)
-  }
+  for (int j = 0; j < 8; j++) B2S_FLUSH_SLOT(j, (j + ROT) % 8)
   B2S_FLUSH_SLOT(8, 8)
 #undef B2S_FLUSH_SLOT
 #undef B2S_FLUSH_ONE
+}
+
+// `rot` = this lane's word rotation: slot j holds aligned word (j + rot) % 8 (see win_load).  GEN = false: rot is 0 for
+// lanes 0..15 and 1 for lanes 16..31; GEN = true: any of 0..7.
+template <int SH, int STRIDE, bool GEN>
+__device__ __forceinline__ void win_flush(uint32_t (&lo)[9], uint32_t (&hi)[9], uint32_t (&acc)[32], int rot) {
+  if (!GEN) {
+    if (!rot) win_flush_rot<SH, STRIDE, 0>(lo, hi, acc);
+    else win_flush_rot<SH, STRIDE, 1>(lo, hi, acc);
+  } else {
+    switch (rot) {
+      case 0: win_flush_rot<SH, STRIDE, 0>(lo, hi, acc); break;
+      case 1: win_flush_rot<SH, STRIDE, 1>(lo, hi, acc); break;
+      case 2: win_flush_rot<SH, STRIDE, 2>(lo, hi, acc); break;
+      case 3: win_flush_rot<SH, STRIDE, 3>(lo, hi, acc); break;
+      case 4: win_flush_rot<SH, STRIDE, 4>(lo, hi, acc); break;
+      case 5: win_flush_rot<SH, STRIDE, 5>(lo, hi, acc); break;
+      case 6: win_flush_rot<SH, STRIDE, 6>(lo, hi, acc); break;
+      default: win_flush_rot<SH, STRIDE, 7>(lo, hi, acc); break;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 9; j++) { lo[j] = 0; hi[j] = 0; }
 }
 
 // load the 8 (+1) words of one beam's row; `base` = byte address in sgrid of aligned word 0 of this lane's row.
-// Lanes 16..31 fetch words 1..7,0 so that every load instruction touches even banks in one half-warp and odd banks in
-// the other (rows r and r+16 are a multiple of 32 words apart).  Word 8 (only needed when the window's last
+// Bank conflicts: lane L's row starts (L * STRIDE * width_step / 4) mod 32 banks after lane 0's; with width_step a
+// multiple of 8 that step is even, so m = gcd(step, 32) >= 2 lanes share every row-start bank.  Rotating the order in
+// which a lane fetches its 8 words by rot = L / (32 / m) gives each of those m lanes a different bank at every load
+// instruction, and the m-lane groups tile the 32 banks when m <= 8: conflict-free.  The common case m = 2 (cfg 1/2's
+// 408-byte step: 102 words) is the GEN = false path, lanes 16..31 fetch words 1..7,0 with immediate offsets; GEN =
+// true takes any rotation through per-lane byte offsets `loff`.  Word 8 (only needed when the window's last
 // candidates spill past 32 bytes) cannot be de-conflicted and is loaded only when W9.
-template <bool W9>
-__device__ __forceinline__ void win_load(const uint8_t *__restrict__ sgrid, int base, int hi_half, uint32_t (&v)[9]) {
-  const uint32_t *w0 = reinterpret_cast<const uint32_t *>(sgrid + base);
-  const uint32_t *wp = w0 + hi_half;
+template <bool W9, bool GEN>
+__device__ __forceinline__ void win_load(const uint8_t *__restrict__ sgrid, int base, int rot, const int (&loff)[8],
+                                         uint32_t (&v)[9]) {
+  if (!GEN) {
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(sgrid + base);
+    const uint32_t *wp = w0 + rot;
 #pragma unroll
-  for (int j = 0; j < 7; j++) v[j] = wp[j];
-  v[7] = wp[7 - 8 * hi_half];
-  v[8] = W9 ? w0[8] : 0u;
+    for (int j = 0; j < 7; j++) v[j] = wp[j];
+    v[7] = wp[7 - 8 * rot];
+    v[8] = W9 ? w0[8] : 0u;
+  } else {
+    const uint8_t *p = sgrid + base;
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = *reinterpret_cast<const uint32_t *>(p + loff[j]);
+    v[8] = W9 ? *reinterpret_cast<const uint32_t *>(p + 32) : 0u;
+  }
 }
 
 template <bool W9>
@@ -702,9 +730,9 @@ __device__ __forceinline__ void win_accumulate2(const uint32_t (&v1)[9], const u
 }
 
 // all beams of one alignment class; count is a multiple of 4.  CHECK = per-row range test (edge beams).
-template <int SH, int STRIDE, bool CHECK, bool W9>
+template <int SH, int STRIDE, bool CHECK, bool W9, bool GEN>
 __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, const int32_t *__restrict__ list,
-                                          int count, int lane, int hi_half, int bias, int row_delta,
+                                          int count, int lane, int hi_half, const int (&loff)[8], int bias, int row_delta,
                                           int data_size, int32_t *__restrict__ s_off, uint32_t (&lo)[9],
                                           uint32_t (&hi)[9], uint32_t (&acc)[32], int &pending) {
   for (int ib = 0; ib < count; ib += 32) {
@@ -713,7 +741,7 @@ __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, con
     s_off[lane] = (lane < cnt) ? __ldg(list + ib + lane) : 0;  // this warp's staging row
     __syncwarp();
     if (pending + cnt > WIN_FLUSH_BEAMS) {
-      win_flush<SH, STRIDE>(lo, hi, acc, hi_half);
+      win_flush<SH, STRIDE, GEN>(lo, hi, acc, hi_half);
       pending = 0;
     }
     pending += cnt;
@@ -731,33 +759,33 @@ __device__ __forceinline__ void win_class(const uint8_t *__restrict__ sgrid, con
         b0 = a.x + lane_const; b1 = a.y + lane_const; b2 = a.z + lane_const; b3 = a.w + lane_const;
       }
       uint32_t v1[9], v2[9];
-      win_load<W9>(sgrid, b0, hi_half, v1);
-      win_load<W9>(sgrid, b1, hi_half, v2);
+      win_load<W9, GEN>(sgrid, b0, hi_half, loff, v1);
+      win_load<W9, GEN>(sgrid, b1, hi_half, loff, v2);
       win_accumulate2<W9>(v1, v2, lo, hi);
-      win_load<W9>(sgrid, b2, hi_half, v1);
-      win_load<W9>(sgrid, b3, hi_half, v2);
+      win_load<W9, GEN>(sgrid, b2, hi_half, loff, v1);
+      win_load<W9, GEN>(sgrid, b3, hi_half, loff, v2);
       win_accumulate2<W9>(v1, v2, lo, hi);
     }
   }
 }
 
-template <int SH, int STRIDE>
+template <int SH, int STRIDE, bool GEN>
 __device__ __forceinline__ void win_class_pair(const uint8_t *__restrict__ sgrid, const int32_t *__restrict__ li,
                                                int ci, const int32_t *__restrict__ le, int ce, int cols, int lane,
-                                               int hi_half, int row_delta, int bias, int data_size, int32_t *__restrict__ s_off,
+                                               int hi_half, const int (&loff)[8], int row_delta, int bias, int data_size, int32_t *__restrict__ s_off,
                                                uint32_t (&lo)[9], uint32_t (&hi)[9], uint32_t (&acc)[32]) {
   int pending = 0;
   if (SH + STRIDE * (cols - 1) + 1 > 32) {  // the last candidates need aligned word 8
-    win_class<SH, STRIDE, false, true>(sgrid, li, ci, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
-    win_class<SH, STRIDE, true, true>(sgrid, le, ce, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, STRIDE, false, true, GEN>(sgrid, li, ci, lane, hi_half, loff, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, STRIDE, true, true, GEN>(sgrid, le, ce, lane, hi_half, loff, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
   } else {
-    win_class<SH, STRIDE, false, false>(sgrid, li, ci, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
-    win_class<SH, STRIDE, true, false>(sgrid, le, ce, lane, hi_half, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, STRIDE, false, false, GEN>(sgrid, li, ci, lane, hi_half, loff, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
+    win_class<SH, STRIDE, true, false, GEN>(sgrid, le, ce, lane, hi_half, loff, bias, row_delta, data_size, s_off, lo, hi, acc, pending);
   }
-  win_flush<SH, STRIDE>(lo, hi, acc, hi_half);
+  win_flush<SH, STRIDE, GEN>(lo, hi, acc, hi_half);
 }
 
-template <int STRIDE>
+template <int STRIDE, bool GEN>
 __global__ void __launch_bounds__(WIN_THREADS, 1)
     k_sweep_window(const uint8_t *__restrict__ grids, size_t grid_pitch, int data_size, int copy_bytes,
                    const int32_t *__restrict__ lists, const int32_t *__restrict__ counts,
@@ -780,7 +808,16 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
   const int tiles_x = (nx + CPT - 1) / CPT, tiles_y = (ny + 31) >> 5;
   const int unit_tiles_y = nbands > 1 ? tiles_y : 1;        // banded: one row tile per unit
   const int items = na * tiles_x * (nbands > 1 ? 1 : tiles_y);
-  const int hi_half = lane >> 4;
+  // word rotation of this lane (see win_load): lanes whose rows start in the same bank get different rotations
+  int hi_half = lane >> 4;
+  int loff[8];
+  if (GEN) {
+    const int step = ((width_step >> 2) * STRIDE) & 31;
+    const int m = step ? (step & -step) : 32;  // gcd(step, 32): lanes L and L + 32/m share a row-start bank
+    hi_half = ((lane * m) >> 5) & 7;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) loff[j] = 4 * ((j + hi_half) & 7);
   const int list_cap = n + LIST_PAD * nbands;
   const int ngroups = 8 * nbands;
 
@@ -861,10 +898,10 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
       for (int j = 0; j < 9; j++) { lo[j] = 0; hi[j] = 0; }
       // groups of this band: I0 I1 I2 I3 E0 E1 E2 E3 (interior / edge beams of each alignment class)
       const int cols = min(CPT, nx - tx * CPT);
-      win_class_pair<0, STRIDE>(sgrid, list + sg[0], cn[0], list + sg[4], cn[4], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
-      win_class_pair<1, STRIDE>(sgrid, list + sg[1], cn[1], list + sg[5], cn[5], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
-      win_class_pair<2, STRIDE>(sgrid, list + sg[2], cn[2], list + sg[6], cn[6], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
-      win_class_pair<3, STRIDE>(sgrid, list + sg[3], cn[3], list + sg[7], cn[7], cols, lane, hi_half, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<0, STRIDE, GEN>(sgrid, list + sg[0], cn[0], list + sg[4], cn[4], cols, lane, hi_half, loff, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<1, STRIDE, GEN>(sgrid, list + sg[1], cn[1], list + sg[5], cn[5], cols, lane, hi_half, loff, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<2, STRIDE, GEN>(sgrid, list + sg[2], cn[2], list + sg[6], cn[6], cols, lane, hi_half, loff, row_delta, bias, data_size, s_off, lo, hi, acc);
+      win_class_pair<3, STRIDE, GEN>(sgrid, list + sg[3], cn[3], list + sg[7], cn[7], cols, lane, hi_half, loff, row_delta, bias, data_size, s_off, lo, hi, acc);
 
       // ---- write / accumulate this lane's row ----
       const int iy = ty * 32 + lane;
@@ -1932,19 +1969,20 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     if (nbands > 1)  // bands accumulate with RED.ADD
       B2S_CUDA_CHECK(cudaMemsetAsync(m->d_sums, 0, sizeof(int32_t) * (size_t)B * na * ncell, m->stream));
     const int ctas = (int)std::min<long long>((long long)B * nbands * (nbands > 1 ? tiles_y_w : 1), m->num_sms);
-    if (stride == 2) {
-      B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
-      k_sweep_window<2><<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
-                                                                    m->d_lists, m->d_counts, m->d_starts, m->d_flags, B, n,
-                                                                    na, nx, ny, m->g.width_step, m->d_sums, m->d_work,
-                                                                    band_rows, nbands, band_bytes, neg_bands);
-    } else {
-      B2S_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_window<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
-      k_sweep_window<1><<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes,
-                                                                    m->d_lists, m->d_counts, m->d_starts, m->d_flags, B, n,
-                                                                    na, nx, ny, m->g.width_step, m->d_sums, m->d_work,
-                                                                    band_rows, nbands, band_bytes, neg_bands);
-    }
+    // the GEN = false instantiation assumes exactly two lanes per row-start bank (see win_load)
+    const int bank_step = ((m->g.width_step >> 2) * std::max(stride, 1)) & 31;
+    const bool gen = (bank_step & 3) != 2;
+    auto launch = [&](auto kern) -> b2s_status {
+      B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
+      kern<<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes, m->d_lists,
+                                                       m->d_counts, m->d_starts, m->d_flags, B, n, na, nx, ny,
+                                                       m->g.width_step, m->d_sums, m->d_work, band_rows, nbands,
+                                                       band_bytes, neg_bands);
+      return B2S_OK;
+    };
+    if (stride == 2) st = gen ? launch(k_sweep_window<2, true>) : launch(k_sweep_window<2, false>);
+    else st = gen ? launch(k_sweep_window<1, true>) : launch(k_sweep_window<1, false>);
+    if (st) return st;
     // matches whose lattice is not the regular raster (a centre exactly on a rounding tie) fall through;
     // they compute their lookup values on the fly (no table was materialised for them)
     k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, nullptr, m->d_bases,
