@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(256)
     for (int y = 1; y <= by; y++) { acc += s_sat[y * W + x]; s_sat[y * W + x] = acc; }
   }
   __syncthreads();
-  uint16_t *out = sat_all + (size_t)b * (by + 1) * W;
+  uint16_t *out = sat_all + (size_t)b * (size_t)(((by + 1) * W + 7) & ~7);  // padded stride: k_offsets_sorted copies 16 bytes at a time
   for (int i = threadIdx.x; i < (by + 1) * W; i += blockDim.x) out[i] = (uint16_t)s_sat[i];  // < 65536 blocks (checked by the host)
 }
 
@@ -501,6 +501,9 @@ __global__ void __launch_bounds__(256)
 // the chunk (16x less L2 traffic than one block per angle).  A non-finite reading (INVALID_SCAN, Karto.h:6478) always
 // yields a non-finite local point (inf/NaN propagate through the inverse transform), so only the points are staged.
 constexpr int OFF_CHUNK = 16;
+constexpr int OFF_Q = 2;                              // angles classified per pass
+constexpr int OFF_GS = 8 * WIN_MAX_BANDS;             // group slots per angle
+constexpr int OFF_SMEM_PER_BEAM = 16 + 5 * OFF_Q;     // two doubles + OFF_Q x (origin int32 + class byte)
 __global__ void __launch_bounds__(256)
     k_offsets_sorted(const double *__restrict__ ranges, const double *__restrict__ local,
                      const double *__restrict__ grid_off, const double *__restrict__ centers,
@@ -512,10 +515,10 @@ __global__ void __launch_bounds__(256)
                      int32_t *__restrict__ starts, int stride, int k_first, int neg_bands) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   double *s_lx = reinterpret_cast<double *>(s_raw), *s_ly = s_lx + n;  // [n] scan-local points
-  int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);             // [n] window origins
-  uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_vals + n);            // [n] group ids
-  uint16_t *s_sat = reinterpret_cast<uint16_t *>(s_raw + (((size_t)n * 21 + 15) & ~(size_t)15));  // [(sby+1)(sbx+1)] or unused
-  __shared__ int cnt[8 * WIN_MAX_BANDS], fill[8 * WIN_MAX_BANDS], seg[8 * WIN_MAX_BANDS];  // [band][group]
+  int32_t *s_vals = reinterpret_cast<int32_t *>(s_ly + n);             // [OFF_Q][n] window origins
+  uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_vals + OFF_Q * n);    // [OFF_Q][n] group ids
+  uint16_t *s_sat = reinterpret_cast<uint16_t *>(s_raw + (((size_t)n * OFF_SMEM_PER_BEAM + 15) & ~(size_t)15));  // [(sby+1)(sbx+1)] or unused
+  __shared__ int cnt[OFF_Q * OFF_GS], fill[OFF_Q * OFF_GS], seg[OFF_Q * OFF_GS];  // [angle][band][group]
   __shared__ int n_empty;
   const int ngroups = 8 * nbands;
   const int list_cap = n + LIST_PAD * nbands;
@@ -528,9 +531,11 @@ __global__ void __launch_bounds__(256)
     s_ly[i] = local[((size_t)b * n + i) * 2 + 1];
   }
   const int SW = sbx + 1;
-  if (sat_all) {
-    const uint16_t *src = sat_all + (size_t)b * (sby + 1) * SW;
-    for (int i = threadIdx.x; i < (sby + 1) * SW; i += blockDim.x) s_sat[i] = src[i];
+  if (sat_all) {  // per-match tables are padded to a multiple of 8 entries: 16-byte copies
+    const int sat_stride = ((sby + 1) * SW + 7) & ~7;
+    const uint4 *src = reinterpret_cast<const uint4 *>(sat_all + (size_t)b * sat_stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_sat);
+    for (int i = threadIdx.x; i < sat_stride / 8; i += blockDim.x) dst[i] = src[i];
   }
   if (threadIdx.x == 0) n_empty = 0;
   const double center = centers[(size_t)b * 3 + 2];
@@ -546,99 +551,112 @@ __global__ void __launch_bounds__(256)
   const int32_t span32 = (int32_t)min(span, (long long)(1 << 29));
   const int fx = stride * (nx - 1) + 1, fy = stride * (ny - 1) + 1;  // footprint of the candidate lattice in cells
   const float inv_step = 1.0f / (float)width_step, inv_band = 1.0f / (float)band_rows;
-  for (int k = k0; k < min(k0 + OFF_CHUNK, n_angles); k++) {
-    __syncthreads();  // staging done / previous angle's smem fully consumed
-    if (threadIdx.x < ngroups) { cnt[threadIdx.x] = 0; fill[threadIdx.x] = 0; }
+  const int kend = min(k0 + OFF_CHUNK, n_angles);
+  for (int kq = k0; kq < kend; kq += OFF_Q) {  // OFF_Q angles per pass: half the barriers, one read of the points
+    const int nq = min(OFF_Q, kend - kq);
+    __syncthreads();  // staging done / previous angles' smem fully consumed
+    for (int t = threadIdx.x; t < OFF_Q * OFF_GS; t += blockDim.x) { cnt[t] = 0; fill[t] = 0; }
     __syncthreads();
-    const double cosine = s_cos[k - k0], sine = s_sin[k - k0];
     int empty_here = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const double plx = s_lx[i], ply = s_ly[i];
-      // lut_value() inlined: a non-finite local point (INVALID_SCAN reading) makes ox/oy non-finite
-      const double ox = __dsub_rn(__dmul_rn(cosine, plx), __dmul_rn(sine, ply));
-      const double oy = __dadd_rn(__dmul_rn(sine, plx), __dmul_rn(cosine, ply));
-      int cls = 255;  // dropped
-      int32_t a = 0;
-      if (isfinite(ox) && isfinite(oy)) {
-        const int32_t gx = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(ox, gox), gox), scale)));
-        const int32_t gy = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(oy, goy), goy), scale)));
-        const int32_t o = (int32_t)((uint32_t)gx + (uint32_t)gy * (uint32_t)width_step);
-        a = (int32_t)((uint32_t)base00 + (uint32_t)o);
-        // window [a - 8, a + span] against [0, data_size): 32-bit arithmetic after clamping far-away origins
-        const int32_t ac = max(min(a, (int32_t)(1 << 29)), -(int32_t)(1 << 29));
-        const int32_t lo = ac - 8, hi = ac + span32;
-        if (hi < 0 || lo >= data_size) cls = 255;  // whole window outside: contributes 0
-        else if (lo >= -(WIN_GUARD - 16) && hi <= data_size + (WIN_GUARD - 16)) cls = a & 3;  // interior
-        else cls = 4 + (a & 3);                                                                // edge
-        int y = 0, x = 0;
-        if ((sat_all || nbands > 1) && cls < 255 && (a >= 0 || neg_bands > 0)) {
-          // floor(a / width_step) by float reciprocal + fix-up (|a| < 2^24 is exact in float; larger values are
-          // corrected too); a < 0 only matters when origins below the grid get row bands of their own (neg_bands)
-          if (data_size <= (1 << 24) && ac == a) {
-            y = (int)((float)a * inv_step);
-            if (y * width_step > a) y--;
-            else if ((y + 1) * width_step <= a) y++;
-          } else {
-            y = a / width_step;
-            if (y * width_step > a) y--;
+#pragma unroll
+      for (int q = 0; q < OFF_Q; q++) {
+        if (q >= nq) break;
+        const double cosine = s_cos[kq - k0 + q], sine = s_sin[kq - k0 + q];
+        // lut_value() inlined: a non-finite local point (INVALID_SCAN reading) makes ox/oy non-finite
+        const double ox = __dsub_rn(__dmul_rn(cosine, plx), __dmul_rn(sine, ply));
+        const double oy = __dadd_rn(__dmul_rn(sine, plx), __dmul_rn(cosine, ply));
+        int cls = 255;  // dropped
+        int32_t a = 0;
+        if (isfinite(ox) && isfinite(oy)) {
+          const int32_t gx = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(ox, gox), gox), scale)));
+          const int32_t gy = cast_i32(kround(__dmul_rn(__dsub_rn(__dadd_rn(oy, goy), goy), scale)));
+          const int32_t o = (int32_t)((uint32_t)gx + (uint32_t)gy * (uint32_t)width_step);
+          a = (int32_t)((uint32_t)base00 + (uint32_t)o);
+          // window [a - 8, a + span] against [0, data_size): 32-bit arithmetic after clamping far-away origins
+          const int32_t ac = max(min(a, (int32_t)(1 << 29)), -(int32_t)(1 << 29));
+          const int32_t lo = ac - 8, hi = ac + span32;
+          if (hi < 0 || lo >= data_size) cls = 255;  // whole window outside: contributes 0
+          else if (lo >= -(WIN_GUARD - 16) && hi <= data_size + (WIN_GUARD - 16)) cls = a & 3;  // interior
+          else cls = 4 + (a & 3);                                                                // edge
+          int y = 0, x = 0;
+          if ((sat_all || nbands > 1) && cls < 255 && (a >= 0 || neg_bands > 0)) {
+            // floor(a / width_step) by float reciprocal + fix-up (|a| < 2^24 is exact in float; larger values are
+            // corrected too); a < 0 only matters when origins below the grid get row bands of their own (neg_bands)
+            if (data_size <= (1 << 24) && ac == a) {
+              y = (int)((float)a * inv_step);
+              if (y * width_step > a) y--;
+              else if ((y + 1) * width_step <= a) y++;
+            } else {
+              y = a / width_step;
+              if (y * width_step > a) y--;
+            }
+            x = a - y * width_step;
           }
-          x = a - y * width_step;
-        }
-        if (nbands > 1 && cls < 8) {
-          int band = (int)((float)y * inv_band);
-          if (band * band_rows > y) band--;
-          else if ((band + 1) * band_rows <= y) band++;
-          cls += 8 * max(min(band + neg_bands, nbands - 1), 0);  // the row band that holds the window origin
-        }
-        if (sat_all && cls < 255 && a >= 0) {
-          // empty-window test on the 4x4-block summed-area table (only for windows that do not wrap a row end)
-          if (x + fx <= width_step && y + fy <= height) {
-            const int bx0 = x >> 2, bx1 = (x + fx - 1) >> 2, by0 = y >> 2, by1 = (y + fy - 1) >> 2;
-            const uint32_t c = (uint32_t)s_sat[(by1 + 1) * SW + bx1 + 1] - (uint32_t)s_sat[by0 * SW + bx1 + 1] -
-                               (uint32_t)s_sat[(by1 + 1) * SW + bx0] + (uint32_t)s_sat[by0 * SW + bx0];
-            if (c == 0) { cls = 255; empty_here++; }
+          if (nbands > 1 && cls < 8) {
+            int band = (int)((float)y * inv_band);
+            if (band * band_rows > y) band--;
+            else if ((band + 1) * band_rows <= y) band++;
+            cls += 8 * max(min(band + neg_bands, nbands - 1), 0);  // the row band that holds the window origin
+          }
+          if (sat_all && cls < 255 && a >= 0) {
+            // empty-window test on the 4x4-block summed-area table (only for windows that do not wrap a row end)
+            if (x + fx <= width_step && y + fy <= height) {
+              const int bx0 = x >> 2, bx1 = (x + fx - 1) >> 2, by0 = y >> 2, by1 = (y + fy - 1) >> 2;
+              const uint32_t c = (uint32_t)s_sat[(by1 + 1) * SW + bx1 + 1] - (uint32_t)s_sat[by0 * SW + bx1 + 1] -
+                                 (uint32_t)s_sat[(by1 + 1) * SW + bx0] + (uint32_t)s_sat[by0 * SW + bx0];
+              if (c == 0) { cls = 255; empty_here++; }
+            }
           }
         }
+        s_vals[q * n + i] = a;
+        s_cls[q * n + i] = (uint8_t)cls;
+        if (cls < 255) atomicAdd(&cnt[q * OFF_GS + cls], 1);
       }
-      s_vals[i] = a;
-      s_cls[i] = (uint8_t)cls;
-      if (cls < 255) atomicAdd(&cnt[cls], 1);
     }
     if (empty_here) atomicAdd(&n_empty, empty_here);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < nq) {  // one thread (of its own warp) per angle
+      int *c_ = cnt + (threadIdx.x >> 5) * OFF_GS, *seg_ = seg + (threadIdx.x >> 5) * OFF_GS;
       int pos = 0;
       for (int g8 = 0; g8 < ngroups; g8 += 8) {
         for (int c = 0; c < 4; c++) {
-          const int d = cnt[g8 + c] & 3;  // interior groups are multiples of 4: the last-placed 0..3 beams go to the edge group
-          cnt[g8 + c] -= d;
-          cnt[g8 + 4 + c] += d;
+          const int d = c_[g8 + c] & 3;  // interior groups are multiples of 4: the last-placed 0..3 beams go to the edge group
+          c_[g8 + c] -= d;
+          c_[g8 + 4 + c] += d;
         }
         for (int c = 0; c < 8; c++) {
-          seg[g8 + c] = pos;
-          pos += (cnt[g8 + c] + 3) & ~3;
+          seg_[g8 + c] = pos;
+          pos += (c_[g8 + c] + 3) & ~3;
         }
       }
     }
     __syncthreads();
-    int32_t *out = lists + ((size_t)b * n_angles + k) * list_cap;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      int cls = s_cls[i];
-      if (cls == 255) continue;
-      int slot = atomicAdd(&fill[cls], 1);
-      if ((cls & 7) < 4 && slot >= cnt[cls]) {  // a donated one
-        cls += 4;
-        slot = atomicAdd(&fill[cls], 1);
+#pragma unroll
+      for (int q = 0; q < OFF_Q; q++) {
+        if (q >= nq) break;
+        int cls = s_cls[q * n + i];
+        if (cls == 255) continue;
+        int slot = atomicAdd(&fill[q * OFF_GS + cls], 1);
+        if ((cls & 7) < 4 && slot >= cnt[q * OFF_GS + cls]) {  // a donated one
+          cls += 4;
+          slot = atomicAdd(&fill[q * OFF_GS + cls], 1);
+        }
+        lists[((size_t)b * n_angles + kq + q) * list_cap + seg[q * OFF_GS + cls] + slot] = s_vals[q * n + i];
       }
-      out[seg[cls] + slot] = s_vals[i];
     }
     __syncthreads();
-    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) {
+    for (int t = threadIdx.x; t < nq * ngroups; t += blockDim.x) {
+      const int q = t / ngroups, g = t % ngroups;
+      const int cg = cnt[q * OFF_GS + g], sg_ = seg[q * OFF_GS + g];
+      int32_t *out = lists + ((size_t)b * n_angles + kq + q) * list_cap;
       if ((g & 7) >= 4)
-        for (int q = cnt[g]; q < ((cnt[g] + 3) & ~3); q++)
-          out[seg[g] + q] = WIN_SKIP + (g & 3);  // pad: all-outside beams of the same alignment
-      counts[((size_t)b * n_angles + k) * ngroups + g] = (cnt[g] + 3) & ~3;
-      starts[((size_t)b * n_angles + k) * ngroups + g] = seg[g];
+        for (int r = cg; r < ((cg + 3) & ~3); r++)
+          out[sg_ + r] = WIN_SKIP + (g & 3);  // pad: all-outside beams of the same alignment
+      counts[((size_t)b * n_angles + kq + q) * ngroups + g] = (cg + 3) & ~3;
+      starts[((size_t)b * n_angles + kq + q) * ngroups + g] = sg_;
     }
   }
   __syncthreads();
@@ -1012,7 +1030,13 @@ __global__ void __launch_bounds__(RED_THREADS)
   __syncthreads();
 
   // ---- pass 1: best response + per-cell maxima (Mapper.cpp:430-451); one thread per (x,y) cell ----
+  // One read of the cell's nA sums: the running float maximum remembers its angle and whether any OTHER candidate
+  // came within the filter margin of it; if none did, the exact maximum is at that angle and needs one fp64
+  // evaluation, otherwise (near-ties, e.g. equal sums under the clamped penalty) the row is re-read and every
+  // candidate inside the margin is evaluated exactly.
   double best = -1.0;
+  float first_fmax = 0.0f;      // float maximum of this thread's first cell, kept for pass 2
+  bool first_known = false;
   for (int c = tid; c < ncell && mode <= 1; c += RED_THREADS) {
     const int iy = c / nx, ix = c % nx;
     const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
@@ -1021,17 +1045,9 @@ __global__ void __launch_bounds__(RED_THREADS)
     if (tab) {
       const float dpf = (float)dmax(1.0 - (DISTANCE_PENALTY_GAIN * sq / p.distance_variance_penalty), p.minimum_distance_penalty);
       float fmax = -1.0f;
-      for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
-        int32_t v[RED_UNROLL];
-#pragma unroll
-        for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldg(bs + (size_t)(k0 + u) * ncell + c) : 0;
-#pragma unroll
-        for (int u = 0; u < RED_UNROLL; u++) {
-          bool amb;
-          if (k0 + u < na) fmax = fmaxf(fmax, red_fscore(v[u], s_apf[k0 + u], dpf, inv_d, pen, amb));
-        }
-      }
-      const float thr = fmax * (1.0f - 2.0e-6f) - 1.0e-30f;
+      int kmax = 0;
+      int32_t vmax = 0;
+      bool near = false, any_amb = false;
       for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
         int32_t v[RED_UNROLL];
 #pragma unroll
@@ -1041,9 +1057,36 @@ __global__ void __launch_bounds__(RED_THREADS)
           if (k0 + u >= na) continue;
           bool amb;
           const float f = red_fscore(v[u], s_apf[k0 + u], dpf, inv_d, pen, amb);
-          if (f >= thr || amb) {
-            const double angle = start_a + (double)(uint32_t)(k_first + k0 + u) * s.angle_res;
-            cell_best = dmax(cell_best, candidate_response(v[u], n, pen, sq, angle, ch, p));
+          any_amb |= amb;
+          if (f > fmax) {
+            near = fmax >= f * (1.0f - 2.0e-6f) - 1.0e-30f;  // the old maximum (and only it or its own near ones) may still be near
+            fmax = f; kmax = k0 + u; vmax = v[u];
+          } else if (f >= fmax * (1.0f - 2.0e-6f) - 1.0e-30f) {
+            near = true;
+          }
+        }
+      }
+      if (c == tid) { first_fmax = fmax; first_known = !any_amb; }
+      if (!near && !any_amb) {
+        const double angle = start_a + (double)(uint32_t)(k_first + kmax) * s.angle_res;
+        cell_best = candidate_response(vmax, n, pen, sq, angle, ch, p);
+      } else if (fmax == 0.0f && !any_amb) {
+        cell_best = 0.0;  // every sum is 0: response 0 / D, never penalised (Mapper.cpp:399)
+      } else {
+        const float thr = fmax * (1.0f - 2.0e-6f) - 1.0e-30f;
+        for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
+          int32_t v[RED_UNROLL];
+#pragma unroll
+          for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldg(bs + (size_t)(k0 + u) * ncell + c) : 0;
+#pragma unroll
+          for (int u = 0; u < RED_UNROLL; u++) {
+            if (k0 + u >= na) continue;
+            bool amb;
+            const float f = red_fscore(v[u], s_apf[k0 + u], dpf, inv_d, pen, amb);
+            if (f >= thr || amb) {
+              const double angle = start_a + (double)(uint32_t)(k_first + k0 + u) * s.angle_res;
+              cell_best = dmax(cell_best, candidate_response(v[u], n, pen, sq, angle, ch, p));
+            }
           }
         }
       }
@@ -1087,6 +1130,7 @@ __global__ void __launch_bounds__(RED_THREADS)
   double ax = 0, ay = 0, tx = 0, ty = 0;
   const float tie_thr = (float)((best - KT_TOLERANCE) * (1.0 - 1.0e-6)) - 1.0e-9f;
   for (int c = tid; c < ncell && mode != 3; c += RED_THREADS) {
+    if (c == tid && first_known && first_fmax < tie_thr) continue;  // no candidate of this cell can tie (pass 1's maximum)
     const int iy = c / nx, ix = c % nx;
     const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
     const double sq = x * x + y * y;
@@ -1456,7 +1500,7 @@ static b2s_status matcher_create_impl(const b2s_matcher_params *params, const b2
   if ((st = dev_alloc(&m->d_work, 1))) return st;
   m->sbx = (g.width_step + 3) / 4;
   m->sby = (g.height + 3) / 4;
-  if ((st = dev_alloc(&m->d_sat, B * (size_t)(m->sbx + 1) * (m->sby + 1)))) return st;
+  if ((st = dev_alloc(&m->d_sat, B * (size_t)((((m->sbx + 1) * (m->sby + 1)) + 7) & ~7)))) return st;  // per-match stride padded to 16 bytes
   if ((st = dev_alloc(&m->d_stats, 1))) return st;
   if ((st = dev_alloc(&m->d_part_best, B))) return st;
   if ((st = dev_alloc(&m->d_glob_best, B))) return st;
@@ -1925,7 +1969,7 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   }
   const size_t win_smem = (size_t)((band_bytes + 15) & ~15) + 2 * WIN_GUARD;
   const bool win_fits = bands_ok && stride != 0 && (m->g.width_step % 8) == 0 && n > 0 &&
-                        (size_t)n * 21 + 64 <= 200 * 1024 && !m->grid_high_bytes;
+                        (size_t)n * OFF_SMEM_PER_BEAM + 64 <= 200 * 1024 && !m->grid_high_bytes;
   bool use_window = win_fits;
   if (m->force_kernel == 1) use_window = false;
   if (m->force_kernel >= 2 && !win_fits)
@@ -1946,9 +1990,9 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     if ((st = ensure_cap(&m->d_counts, &m->counts_cap, (size_t)B * na * 8 * nbands))) return st;
     if ((st = ensure_cap(&m->d_starts, &m->starts_cap, (size_t)B * na * 8 * nbands))) return st;
     bool skip_empty = m->sat_valid && m->force_kernel != 3;
-    if ((((size_t)n * 21 + 15) & ~(size_t)15) + sizeof(uint16_t) * (size_t)(m->sbx + 1) * (m->sby + 1) + 64 > 200 * 1024) skip_empty = false;
-    const size_t sat_bytes = skip_empty ? sizeof(uint16_t) * (size_t)(m->sbx + 1) * (m->sby + 1) : 0;
-    const size_t osm = (((size_t)n * 21 + 15) & ~(size_t)15) + sat_bytes + 64;
+    if ((((size_t)n * OFF_SMEM_PER_BEAM + 15) & ~(size_t)15) + sizeof(uint16_t) * (size_t)((((m->sbx + 1) * (m->sby + 1)) + 7) & ~7) + 64 > 200 * 1024) skip_empty = false;
+    const size_t sat_bytes = skip_empty ? sizeof(uint16_t) * (size_t)((((m->sbx + 1) * (m->sby + 1)) + 7) & ~7) : 0;
+    const size_t osm = (((size_t)n * OFF_SMEM_PER_BEAM + 15) & ~(size_t)15) + sat_bytes + 64;
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_stats, 0, sizeof(unsigned long long), m->stream));
     if (osm > 48 * 1024)
       B2S_CUDA_CHECK(cudaFuncSetAttribute(k_offsets_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
