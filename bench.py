@@ -510,6 +510,13 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         sweep = float(np.mean(sweep_ms))
+        # DRAM bytes of one k_sweep_window launch from the committed `ncu --set full` capture (same batch only)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "k1_sweep_dram_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath))
+            if int(t.get("batch", -1)) == B:
+                traffic, traffic_src = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), t["source"]
         achieved = A1_BYTES * B / (sweep * 1e-3) / 1e9
         clocks = sampler.summary()
         sm_clk = (clocks["sm_mhz"] or 1965.0) * 1e6
@@ -527,7 +534,7 @@ def main():
                     "includes": "set_scans + add_scans (rasterise) + correlate_scan from pinned host buffers"},
             "gpu_launches": args.steps * KERNELS_PER_STEP,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_sweep_window", "kernel_ms": sweep, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_sweep_window", "kernel_ms": sweep, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": A1_BYTES * B,
                          "note": "K1 is not DRAM-bound: the algorithmic bytes are served from shared memory "
                                  "(effective bandwidth); see smem_gather",

@@ -191,7 +191,7 @@ __device__ __forceinline__ void hc_interp(const float *__restrict__ lo, int sx, 
 
 __device__ inline void hc_inv3_mul(const float m[9], const float v[3], float out[3]) {  // Matrix3f::inverse() * v
   const float c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
-  const float det = c00 * m[0] + c10 * m[1] + c20 * m[2];
+  const float det = c00 * m[0] + (c10 * m[1] + c20 * m[2]);  /* Eigen's unrolled 3-term redux: a0 + (a1 + a2) */
   const float invdet = 1.0f / det;
   float inv[9];
   inv[0] = c00 * invdet; inv[3] = c10 * invdet; inv[6] = c20 * invdet;
@@ -201,7 +201,7 @@ __device__ inline void hc_inv3_mul(const float m[9], const float v[3], float out
   inv[2] = (m[1] * m[5] - m[2] * m[4]) * invdet;
   inv[5] = (m[2] * m[3] - m[0] * m[5]) * invdet;
   inv[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
-  for (int r = 0; r < 3; r++) out[r] = inv[3 * r] * v[0] + inv[3 * r + 1] * v[1] + inv[3 * r + 2] * v[2];
+  for (int r = 0; r < 3; r++) out[r] = inv[3 * r] * v[0] + (inv[3 * r + 1] * v[1] + inv[3 * r + 2] * v[2]);
 }
 
 constexpr int GN_THREADS = 512;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(GN_THREADS)
     // util::normalize_angle (UtilFunctions.h:36-48): double fmod, float result
     const double two_pi = 2.0f * 3.14159265358979323846;
     float a = (float)fmod(fmod((double)est[2], two_pi) + two_pi, two_pi);
-    if (a > 3.14159265358979323846) a -= (float)two_pi;
+    if (a > 3.14159265358979323846) a = (float)((double)a - two_pi);  // `a -= 2.0f*M_PI` promotes to double
     // getWorldCoordsPose (GridMapBase.h:229-233)
     out[0] = (wt_lin * est[0] + (-0.0f) * est[1]) + wt_tx;
     out[1] = ((-0.0f) * est[0] + wt_lin * est[1]) + wt_ty;

@@ -10,12 +10,16 @@
  *   ScanMatcher::matchData / estimateTransformationLogLh                             matcher/ScanMatcher.h:60-141
  *   util::sign, util::normalize_angle                                               util/UtilFunctions.h:36-58
  *
- * PARITY UNPINNED: every one of those headers includes <Eigen/...>, Eigen is not installed in this image and cannot
- * be fetched, so the reference code itself could not be executed.  This file follows the sources line by line and
- * mirrors Eigen's documented fixed-size semantics: Translation*Rotation2D -> x' = (c*x + (-s)*y) + tx
- * in float32 without FMA; AlignedScaling*Translation -> linear diag(s,s), translation s*off; float -> int casts
- * truncate; Affine / Matrix3f inverse are the cofactor/determinant forms.  It is checked only for self-consistency
- * (tests/test_oracle_hector.py) — re-verify against a real Eigen build when one is available.
+ * PINNED (was "unpinned" until a way to execute the reference was found): Eigen is not installed in this image, so the
+ * reference headers are compiled UNMODIFIED against a minimal stand-in for the fixed-size Eigen types they use
+ * (oracle/shim/Eigen/mini_eigen.h; oracle/ref_hector.cpp -> oracle/_ref/libhector_ref.so).  This file agrees with that
+ * build bit for bit — update indices, float32 log-odds, Gauss-Newton poses and Hessians, whole HectorSlamProcessor
+ * streams (tests/test_oracle_hector_reference.py) — and with the golden vectors it produced (tests/golden/hector.npz).
+ * What remains an assumption is only the stand-in's reading of Eigen's fixed-size primitives (listed in its header:
+ * Translation*Rotation2D -> x' = (c*x + (-s)*y) + tx in float32 without FMA; AlignedScaling*Translation -> linear
+ * diag(s,s), translation s*off; float -> int casts truncate; Affine / Matrix3f inverse in cofactor/determinant form;
+ * 3-term sums as a0 + (a1 + a2)).  The live comparison found and fixed one slip of the restatement
+ * (normalize_angle's `a -= 2.0f*M_PI` is evaluated in double).
  */
 #include <math.h>
 #include <stdint.h>
@@ -236,14 +240,14 @@ static void hessian_derivs(const orc_hmap *m, const float pose[3], const float *
 
 static float hnormalize_angle(float angle) { /* UtilFunctions.h:36-48 (double fmod, float return) */
   float a = (float)fmod(fmod((double)angle, 2.0f * M_PI) + 2.0f * M_PI, 2.0f * M_PI);
-  if (a > M_PI) a -= (float)(2.0f * M_PI);
+  if (a > M_PI) a = (float)((double)a - 2.0f * M_PI); /* `a -= 2.0f*M_PI` is evaluated in double */
   return a;
 }
 
 /* Matrix3f::inverse() * v, cofactor / determinant form (Eigen compute_inverse_size3) */
 static void inv3_mul(const float m[9], const float v[3], float out[3]) {
   float c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
-  float det = c00 * m[0] + c10 * m[1] + c20 * m[2];
+  float det = c00 * m[0] + (c10 * m[1] + c20 * m[2]);  /* Eigen's unrolled 3-term redux: a0 + (a1 + a2) */
   float invdet = 1.0f / det;
   float inv[9];
   inv[0] = c00 * invdet; inv[3] = c10 * invdet; inv[6] = c20 * invdet;
@@ -253,7 +257,7 @@ static void inv3_mul(const float m[9], const float v[3], float out[3]) {
   inv[2] = (m[1] * m[5] - m[2] * m[4]) * invdet;
   inv[5] = (m[2] * m[3] - m[0] * m[5]) * invdet;
   inv[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
-  for (int r = 0; r < 3; r++) out[r] = inv[3 * r] * v[0] + inv[3 * r + 1] * v[1] + inv[3 * r + 2] * v[2];
+  for (int r = 0; r < 3; r++) out[r] = inv[3 * r] * v[0] + (inv[3 * r + 1] * v[1] + inv[3 * r + 2] * v[2]);
 }
 
 /* ScanMatcher::matchData (ScanMatcher.h:60-98): 1 + max_iterations Gauss-Newton steps on one grid level */
@@ -278,4 +282,122 @@ void orc_hmap_match_data(const orc_hmap *m, const float *pts, int n, const float
   est[2] = hnormalize_angle(est[2]);
   memcpy(out_cov, H, 9 * sizeof(float));
   world_coords_pose(m, est, out_world);
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HectorSlamProcessor (slam_main/HectorSlamProcessor.h:53-125) over MapRepMultiMap (slam_main/MapRepMultiMap.h:56-191):
+ * the lesson4 front end.  PINNED against the reference headers compiled with the Eigen stand-in
+ * (oracle/ref_hector.cpp, tests/test_oracle_hector_reference.py).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define ORC_HPROC_MAX_LEVELS 8
+typedef struct {
+  int levels;
+  orc_hmap *map[ORC_HPROC_MAX_LEVELS];
+  float *pts[ORC_HPROC_MAX_LEVELS];   /* dataContainers[level-1]: the last MATCHED scan scaled by 1/2^level */
+  int n_pts[ORC_HPROC_MAX_LEVELS];
+  float origo[ORC_HPROC_MAX_LEVELS][2];
+  float last_map_update_pose[3], last_scan_match_pose[3], last_cov[9];
+  float min_dist, min_angle;
+} orc_hproc;
+
+orc_hproc *orc_hproc_create(float resolution, int size_x, int size_y, float start_x, float start_y, int levels) {
+  if (levels < 1 || levels > ORC_HPROC_MAX_LEVELS) return NULL;
+  orc_hproc *p = (orc_hproc *)calloc(1, sizeof(orc_hproc));
+  p->levels = levels;
+  /* MapRepMultiMap.h:61-86: ONE offset (level-0 size * resolution * startCoords) for every level; dims halve by
+   * integer division, the cell length doubles */
+  float total_x = resolution * (float)size_x, total_y = resolution * (float)size_y;
+  float off_x = total_x * start_x, off_y = total_y * start_y;
+  for (int l = 0; l < levels; l++) {
+    orc_hmap *m = orc_hmap_create(size_x, size_y, resolution, 0.0f, 0.0f);
+    m->off_x = off_x; m->off_y = off_y;
+    m->tw_tx = m->scale_to_map * off_x; m->tw_ty = m->scale_to_map * off_y;
+    float det = m->tw_lin * m->tw_lin - 0.0f * 0.0f, invdet = 1.0f / det, i01 = -0.0f * invdet;
+    m->wt_tx = -(m->wt_lin * m->tw_tx + i01 * m->tw_ty);
+    m->wt_ty = -(i01 * m->tw_tx + m->wt_lin * m->tw_ty);
+    p->map[l] = m;
+    size_x /= 2; size_y /= 2;
+    resolution *= 2.0f;
+  }
+  /* reset() (HectorSlamProcessor.h:111-116); ctor thresholds (:63-64) */
+  p->last_map_update_pose[0] = p->last_map_update_pose[1] = p->last_map_update_pose[2] = 3.402823466e+38F;
+  p->min_dist = 0.4f * 1.0f;
+  p->min_angle = 0.13f * 1.0f;
+  return p;
+}
+
+void orc_hproc_destroy(orc_hproc *p) {
+  if (!p) return;
+  for (int l = 0; l < p->levels; l++) { orc_hmap_destroy(p->map[l]); free(p->pts[l]); }
+  free(p);
+}
+
+void orc_hproc_set_params(orc_hproc *p, float update_free, float update_occ, float min_dist, float min_angle) {
+  for (int l = 0; l < p->levels; l++) orc_hmap_set_factors(p->map[l], update_free, update_occ);
+  p->min_dist = min_dist;
+  p->min_angle = min_angle;
+}
+
+/* util::poseDifferenceLargerThan (UtilFunctions.h:72-90).  The header includes only <cmath>, so the unqualified
+ * `abs(angleDiff)` resolves to `int abs(int)`: the angle difference is TRUNCATED to an integer before the compare
+ * (verified on the reference build: a 0.5 rad turn with angleDiffThresh 0.13 returns false). */
+static int pose_difference_larger_than(const float a[3], const float b[3], float dist_thresh, float angle_thresh) {
+  float dx = a[0] - b[0], dy = a[1] - b[1];
+  if (sqrtf(dx * dx + dy * dy) > dist_thresh) return 1;
+  float d = a[2] - b[2];
+  if (d > M_PI) d = (float)((double)d - M_PI * 2.0f);
+  else if (d < -M_PI) d = (float)((double)d + M_PI * 2.0f);
+  return (float)abs((int)d) > angle_thresh;
+}
+
+/* DataPointContainer::setFrom (DataPointContainer.h:46-59) */
+static void set_from(orc_hproc *p, int l, const float *points, int n, const float origo[2], float factor) {
+  p->pts[l] = (float *)realloc(p->pts[l], (size_t)(n > 0 ? n : 1) * 2 * sizeof(float));
+  p->n_pts[l] = n;
+  p->origo[l][0] = origo[0] * factor; p->origo[l][1] = origo[1] * factor;
+  for (int i = 0; i < 2 * n; i++) p->pts[l][i] = points[i] * factor;
+}
+
+/* HectorSlamProcessor::update (:81-108).  points/origo in level-0 map-cell units; pose hint in world metres. */
+void orc_hproc_update(orc_hproc *p, const float *points, int n, const float origo[2], const float pose_hint[3],
+                      int map_without_matching, float out_pose[3], float out_cov[9]) {
+  float est[3];
+  if (!map_without_matching) { /* MapRepMultiMap::matchData (:144-166): coarsest level first */
+    float tmp[3] = {pose_hint[0], pose_hint[1], pose_hint[2]};
+    for (int l = p->levels - 1; l >= 0; l--) {
+      float next[3];
+      if (l == 0) {
+        orc_hmap_match_data(p->map[0], points, n, tmp, 5, next, p->last_cov);
+      } else {
+        set_from(p, l, points, n, origo, (float)(1.0 / pow(2.0, (double)l)));
+        orc_hmap_match_data(p->map[l], p->pts[l], n, tmp, 3, next, p->last_cov);
+      }
+      memcpy(tmp, next, sizeof(tmp));
+    }
+    memcpy(est, tmp, sizeof(est));
+  } else {
+    memcpy(est, pose_hint, sizeof(est));
+  }
+  memcpy(p->last_scan_match_pose, est, sizeof(est));
+  if (pose_difference_larger_than(est, p->last_map_update_pose, p->min_dist, p->min_angle) || map_without_matching) {
+    /* MapRepMultiMap::updateByScan (:174-191): the coarse levels use dataContainers filled by the LAST matchData —
+     * with map_without_matching they are stale (empty before the first match); reproduced as is */
+    for (int l = 0; l < p->levels; l++) {
+      if (l == 0) orc_hmap_update_by_scan(p->map[0], points, n, origo, est);
+      else orc_hmap_update_by_scan(p->map[l], p->pts[l], p->n_pts[l], p->origo[l], est);
+    }
+    memcpy(p->last_map_update_pose, est, sizeof(est));
+  }
+  memcpy(out_pose, est, sizeof(est));
+  if (out_cov && !map_without_matching) memcpy(out_cov, p->last_cov, sizeof(p->last_cov));
+}
+
+int orc_hproc_level_dims(const orc_hproc *p, int level, int dims[2]) {
+  if (level < 0 || level >= p->levels) return -1;
+  dims[0] = p->map[level]->size_x; dims[1] = p->map[level]->size_y;
+  return 0;
+}
+
+void orc_hproc_copy_level(const orc_hproc *p, int level, float *log_odds, int32_t *update_index) {
+  orc_hmap_copy(p->map[level], log_odds, update_index);
 }

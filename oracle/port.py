@@ -202,7 +202,8 @@ def gmap_grid_line(x0, y0, x1, y1):
     return out[:n].copy()
 
 
-# ---------------------------------------------------------------- Hector (hector_oracle.c) — PARITY UNPINNED
+# ---------------------------------------------------------------- Hector (hector_oracle.c) — pinned against
+# oracle/ref_hector.cpp (the reference headers compiled with the Eigen stand-in) by tests/test_oracle_hector_reference.py
 
 class PortHectorMap:
     def __init__(self, size_x, size_y, resolution, start_x=0.5, start_y=0.5):
@@ -243,6 +244,47 @@ class PortHectorMap:
     def close(self):
         if self.h:
             self.L.orc_hmap_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PortHectorProcessor:
+    """orc_hproc_* — HectorSlamProcessor / MapRepMultiMap restatement; interface of oracle.ref_hector.RefHectorProcessor."""
+
+    def __init__(self, resolution=0.05, size_x=1024, size_y=1024, start=(0.5, 0.5), levels=3,
+                 update_free=0.4, update_occupied=0.9, min_dist=0.4, min_angle=0.13):
+        self.L = lib()
+        self.L.orc_hproc_create.restype = C.c_void_p
+        self.levels = levels
+        self.h = C.c_void_p(self.L.orc_hproc_create(C.c_float(resolution), size_x, size_y, C.c_float(start[0]),
+                                                    C.c_float(start[1]), levels))
+        self.L.orc_hproc_set_params(self.h, C.c_float(update_free), C.c_float(update_occupied), C.c_float(min_dist),
+                                    C.c_float(min_angle))
+
+    def update(self, points, origo, pose_hint, map_without_matching=False):
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 2)
+        o, w = np.ascontiguousarray(origo, np.float32), np.ascontiguousarray(pose_hint, np.float32)
+        pose, cov = np.zeros(3, np.float32), np.zeros(9, np.float32)
+        self.L.orc_hproc_update(self.h, _p(p, C.c_float), len(p), _p(o, C.c_float), _p(w, C.c_float),
+                                int(map_without_matching), _p(pose, C.c_float), _p(cov, C.c_float))
+        return pose, cov.reshape(3, 3)
+
+    def level(self, i):
+        dims = (C.c_int * 2)()
+        assert self.L.orc_hproc_level_dims(self.h, i, dims) == 0
+        sx, sy = dims[0], dims[1]
+        lo, ui = np.zeros(sx * sy, np.float32), np.zeros(sx * sy, np.int32)
+        self.L.orc_hproc_copy_level(self.h, i, _p(lo, C.c_float), _p(ui, C.c_int32))
+        return lo.reshape(sy, sx), ui.reshape(sy, sx)
+
+    def close(self):
+        if self.h:
+            self.L.orc_hproc_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -161,13 +161,54 @@ def gmapping_case():
     np.savez_compressed(os.path.join(HERE, "gmapping.npz"), **out)
 
 
+def hector_case():
+    """lesson4 HectorSlamProcessor (3-level MapRepMultiMap: GN match + log-odds update) and updateByScanJustOnce through
+    the reference's real headers (oracle/ref_hector.cpp; Eigen stand-in oracle/shim/Eigen/mini_eigen.h)."""
+    from oracle import ref_hector as rh
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_hector_reference import data_container
+    laser = synth.Laser(n_readings=541, angular_resolution=synth.deg2rad(0.5))  # every other beam keeps the file small
+    n = 14
+    _, poses, ranges = synth.make_trajectory(41, n, laser, step_xy=0.15, step_th_deg=3.0)
+    kw = dict(resolution=0.05, size_x=640, size_y=640, start=(0.5, 0.5), levels=3, min_dist=0.12, min_angle=0.05)
+    p = rh.RefHectorProcessor(**kw)
+    out = {"resolution": np.float32(0.05), "size": np.int32(640), "min_dist": np.float32(0.12), "min_angle": np.float32(0.05),
+           "n_scans": np.int32(n), "start_pose": poses[0].astype(np.float32),
+           "without_matching": np.array([1] + [0] * (n - 1), np.int8)}
+    est, trace = poses[0].astype(np.float32), []
+    for i in range(n):
+        pts = data_container(laser, ranges[i]).astype(np.float32)
+        out[f"pts{i}"] = pts
+        est, cov = p.update(pts, (0, 0), est, i == 0)
+        trace.append(np.concatenate([est, cov.ravel()]))
+    out["trace"] = np.array(trace, np.float32)
+    for lvl in range(3):
+        lo, ui = p.level(lvl)
+        idx = np.flatnonzero(ui.ravel() >= 0)
+        out[f"l{lvl}_idx"], out[f"l{lvl}_ui"], out[f"l{lvl}_lo"] = idx, ui.ravel()[idx], lo.ravel()[idx]
+    assert (out["l0_ui"].max() + 1) // 3 >= 4
+    rng = np.random.default_rng(77)
+    jo = rng.uniform(-12, 12, (300, 2)).astype(np.float32)
+    m = rh.RefHectorMap(1601, 1601, 0.05)
+    m.update_by_scan_just_once(jo, (0, 0))
+    lo, ui = m.cells()
+    idx = np.flatnonzero(ui.ravel() >= 0)
+    out.update({"jo_size": np.int32(1601), "jo_pts": jo, "jo_idx": idx, "jo_ui": ui.ravel()[idx], "jo_lo": lo.ravel()[idx]})
+    np.savez_compressed(os.path.join(HERE, "hector.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref.available(), "run `make -C oracle ref` first"
+    if sys.argv[1:] == ["hector"]:
+        hector_case()
+        print("hector.npz", os.path.getsize(os.path.join(HERE, "hector.npz")))
+        sys.exit(0)
     small_case()
     cfg1_case()
     multi_base_case()
     trace_lines()
     gmapping_case()
+    hector_case()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

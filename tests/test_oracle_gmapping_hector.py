@@ -1,5 +1,6 @@
 """CPU tests of the GMapping restatement (pinned to the reference's real headers + golden vectors) and of the
-Hector restatement (PARITY UNPINNED — Eigen is unavailable, so only self-consistency can be checked)."""
+Hector restatement (semantic self-checks here; bit-exact pinning to the reference headers is in
+test_oracle_hector_reference.py)."""
 import os
 
 import numpy as np
