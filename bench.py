@@ -273,36 +273,62 @@ def bench_k2(pkg, local, quick=False):
                 "ms": float(np.median(secs)) * 1e3}
     except Exception as e:
         out["karto_occupancy_grid"]["cpu_reference"] = {"error": repr(e)}
-    # --- K2a + K3: Hector stream (cfg 3 shape): per scan 3-level GN match then 3-level map update, 1000^2 @0.05 map
-    n_stream = 100 if quick else 400
+    # --- K2a + K3: Hector stream (cfg 3 shape): HectorSlamProcessor::update per scan = 3-level GN match + gated
+    #     3-level log-odds update on a 1000^2 @0.05 m map (50 m x 50 m), node defaults (0.4/0.9 factors, 0.4 m / 0.9 rad gate)
+    n_stream = 300 if quick else 10000  # cfg 3: a 10 000-scan stream
     world, poses, ranges = synth.make_trajectory(22, n_stream, laser, step_xy=0.05, step_th_deg=1.0)
-    levels = [(1000, 0.05), (500, 0.1), (250, 0.2)]
-    maps = [H.HectorMap(s, s, r, device=local) for s, r in levels]
-    for m in maps:
-        m.set_factors(0.4, 0.9)
-    pts = [[H.scan_to_data_container(ranges[i], laser, r) for _, r in levels] for i in range(n_stream)]
+    pts = [H.scan_to_data_container(ranges[i], laser, 0.05, max_dist=30.0, min_dist=0.2) for i in range(n_stream)]
+    kw = dict(resolution=0.05, size_x=1000, size_y=1000, start=(0.5, 0.5), levels=3, update_free=0.4, update_occupied=0.9,
+              min_dist=0.4, min_angle=0.9)
+    hs = H.HectorSlam(device=local, **kw)
     est = poses[0].astype(np.float32)
-    for lvl, m in enumerate(maps):
-        m.update_by_scan(pts[0][lvl], (0, 0), est)
+    est, _ = hs.update(pts[0], (0, 0), est)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(1, n_stream):
-        for lvl in (2, 1, 0):
-            est, cov = maps[lvl].match_data(pts[i][lvl], est, 5 if lvl == 0 else 3)
-        for lvl, m in enumerate(maps):
-            m.update_by_scan(pts[i][lvl], (0, 0), est)
-    maps[0].cells()
-    torch.cuda.synchronize()
+        est, cov = hs.update(pts[i], (0, 0), est)
+    st = hs.stats()
     dt = time.perf_counter() - t0
     err = float(np.abs(est[:2] - poses[-1][:2]).max())
-    upd = maps[0].last_timing()
     out["hector_stream"] = {"scans": n_stream - 1, "levels": 3, "scans_per_s": (n_stream - 1) / dt,
                             "ms_per_scan": 1e3 * dt / (n_stream - 1), "final_xy_err_m": err,
-                            "level0_update_ms": upd["update_ms"], "level0_match_ms": upd["match_ms"],
-                            "note": "sequential stream: each scan is matched (3 levels, 4+4+6 GN iterations) against the "
-                                    "map built from the previous scans, then all 3 levels are updated"}
-    for m in maps:
-        m.close()
+                            "map_updates": st["updated"], "cell_visits": st["cell_visits"],
+                            "cells_per_s": st["cell_visits"] / dt, "last_match_ms": st["match_ms"],
+                            "last_update_ms": st["update_ms"],
+                            "note": "sequential SLAM stream through b2s_hector_slam_update (hint = previous estimate): per scan "
+                                    "one H2D of the scan, one launch for the 3-level Gauss-Newton match (4+4+6 iterations), "
+                                    "a 13-float D2H, the map-update gate on the host, two launches for the 3-level update"}
+    hs.close()
+    # every-scan mapping (gate off): the K2a update rate itself
+    hs = H.HectorSlam(device=local, **dict(kw, min_dist=0.0, min_angle=0.0))
+    n_map = min(n_stream, 1000)
+    hs.update(pts[0], (0, 0), poses[0].astype(np.float32), True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(1, n_map):
+        hs.update(pts[i], (0, 0), poses[i].astype(np.float32), True)
+    st = hs.stats()
+    dt = time.perf_counter() - t0
+    out["hector_mapping_only"] = {"scans": n_map - 1, "scans_per_s": (n_map - 1) / dt, "cell_visits": st["cell_visits"],
+                                  "cells_per_s": st["cell_visits"] / dt,
+                                  "achieved_GBps": 2 * 8 * st["cell_visits"] / dt / 1e9,
+                                  "note": "updateByScan with given poses (map_without_matching), level 0 only receives data"}
+    hs.close()
+    try:  # the reference's own HectorSlamProcessor (unmodified headers + Eigen stand-in), 1 thread, same stream sample
+        from oracle import ref_hector as rh
+        if rh.available():
+            n_ref = min(n_stream, 300)
+            rp = rh.RefHectorProcessor(**kw)
+            e = poses[0].astype(np.float32)
+            t0 = time.perf_counter()
+            for i in range(n_ref):
+                e, _ = rp.update(pts[i], (0, 0), e)
+            dt = time.perf_counter() - t0
+            rp.close()
+            out["hector_stream"]["cpu_reference"] = {"scans_per_s": n_ref / dt, "sample": f"first {n_ref} scans of the same stream, "
+                                                     "HectorSlamProcessor::update, g++ -O2, 1 thread"}
+    except Exception as e:
+        out["hector_stream"]["cpu_reference"] = {"error": repr(e)}
     # --- K1 beyond the headline shape: the default two-stage MatchScan, and cfg-4 windows on a 0.025 m grid (banded kernel)
     M = pkg.load("matcher")
     try:

@@ -26,6 +26,17 @@ def _bind():
     L.b2s_hector_map_copy.argtypes = [vp, fp, C.POINTER(C.c_int32)]
     L.b2s_hector_map_copy_ros.argtypes = [vp, C.POINTER(C.c_int8)]
     L.b2s_hector_map_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    L.b2s_hector_slam_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.b2s_hector_slam_destroy.argtypes = [vp]
+    L.b2s_hector_slam_destroy.restype = None
+    L.b2s_hector_slam_set_update_factors.argtypes = [vp, C.c_float, C.c_float]
+    L.b2s_hector_slam_set_map_update_min_diff.argtypes = [vp, C.c_float, C.c_float]
+    L.b2s_hector_slam_reset.argtypes = [vp]
+    L.b2s_hector_slam_update.argtypes = [vp, fp, C.c_int, fp, fp, C.c_int, fp, fp, C.POINTER(C.c_int)]
+    L.b2s_hector_slam_level_dims.argtypes = [vp, C.c_int, C.POINTER(C.c_int), fp]
+    L.b2s_hector_slam_copy_level.argtypes = [vp, C.c_int, fp, C.POINTER(C.c_int32)]
+    L.b2s_hector_slam_copy_level_ros.argtypes = [vp, C.c_int, C.POINTER(C.c_int8)]
+    L.b2s_hector_slam_stats.argtypes = [vp, C.POINTER(C.c_double)]
     _bound = True
     return L
 
@@ -86,6 +97,66 @@ class HectorMap:
     def close(self):
         if getattr(self, "h", None) and self.h.value:
             self.L.b2s_hector_map_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HectorSlam:
+    """Stand-in for hectorslam::HectorSlamProcessor (slam_main/HectorSlamProcessor.h): same constructor arguments,
+    update() = multi-level matchData + gated updateByScan, one call per LaserScan."""
+
+    def __init__(self, resolution=0.05, size_x=1024, size_y=1024, start=(0.5, 0.5), levels=3,
+                 update_free=0.4, update_occupied=0.9, min_dist=0.4, min_angle=0.13, device=0, stream=None):
+        self.L = _bind()
+        self.levels = levels
+        self.h = C.c_void_p()
+        check(self.L.b2s_hector_slam_create(resolution, size_x, size_y, start[0], start[1], levels, device,
+                                            C.c_void_p(stream) if stream else None, C.byref(self.h)))
+        check(self.L.b2s_hector_slam_set_update_factors(self.h, update_free, update_occupied))
+        check(self.L.b2s_hector_slam_set_map_update_min_diff(self.h, min_dist, min_angle))
+        self.map_updated = False
+
+    def update(self, points, origo, pose_hint, map_without_matching=False):
+        p = f32(points).reshape(-1, 2)
+        pose, cov, upd = np.zeros(3, np.float32), np.zeros(9, np.float32), C.c_int(0)
+        check(self.L.b2s_hector_slam_update(self.h, _f(p), len(p), _f(f32(origo)), _f(f32(pose_hint)),
+                                            int(map_without_matching), _f(pose), _f(cov), C.byref(upd)))
+        self.map_updated = bool(upd.value)
+        return pose, cov.reshape(3, 3)
+
+    def reset(self):
+        check(self.L.b2s_hector_slam_reset(self.h))
+
+    def level_dims(self, i):
+        dims, cl = (C.c_int * 2)(), C.c_float(0)
+        check(self.L.b2s_hector_slam_level_dims(self.h, i, dims, C.byref(cl)))
+        return dims[0], dims[1], cl.value
+
+    def level(self, i):
+        sx, sy, _ = self.level_dims(i)
+        lo, ui = np.zeros(sx * sy, np.float32), np.zeros(sx * sy, np.int32)
+        check(self.L.b2s_hector_slam_copy_level(self.h, i, _f(lo), ui.ctypes.data_as(C.POINTER(C.c_int32))))
+        return lo.reshape(sy, sx), ui.reshape(sy, sx)
+
+    def ros_map(self, i=0):
+        sx, sy, _ = self.level_dims(i)
+        out = np.zeros((sy, sx), np.int8)
+        check(self.L.b2s_hector_slam_copy_level_ros(self.h, i, out.ctypes.data_as(C.POINTER(C.c_int8))))
+        return out
+
+    def stats(self):
+        out = np.zeros(5)
+        check(self.L.b2s_hector_slam_stats(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return dict(matched=int(out[0]), updated=int(out[1]), cell_visits=int(out[2]), match_ms=out[3], update_ms=out[4])
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.b2s_hector_slam_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

@@ -259,6 +259,47 @@ b2s_status b2s_hector_map_copy(b2s_hector_map *m, float *log_odds, int32_t *upda
 b2s_status b2s_hector_map_copy_ros(b2s_hector_map *m, int8_t *out);
 b2s_status b2s_hector_map_last_timing(b2s_hector_map *m, double out[2]);
 
+/* ---------------------------------------------------------------- lesson4 front end: HectorSlamProcessor
+ * One call per LaserScan = MapRepMultiMap::matchData (coarse-to-fine Gauss-Newton over all pyramid levels, one kernel
+ * launch) + the map-update gate + MapRepMultiMap::updateByScan (all levels, two kernel launches).  The maps, the
+ * per-level scaled copies of the scan and the running stamps stay resident on the device between calls. */
+
+typedef struct b2s_hector_slam b2s_hector_slam; /* opaque: replaces hectorslam::HectorSlamProcessor
+                                                   (slam_main/HectorSlamProcessor.h:50-150) */
+
+#define B2S_HECTOR_MAX_LEVELS 8
+
+/* HectorSlamProcessor(mapResolution, mapSizeX, mapSizeY, startCoords, multi_res_size) (HectorSlamProcessor.h:56-65):
+ * level l has cell length resolution * 2^l and size >> l cells; every level shares the level-0 offset
+ * (MapRepMultiMap.h:56-89).  Defaults as the constructor sets them: update factors 0.4 / 0.6
+ * (GridMapLogOdds.h:98-102), map-update gate 0.4 m / 0.13 rad. */
+b2s_status b2s_hector_slam_create(float map_resolution, int map_size_x, int map_size_y, float start_x, float start_y,
+                                  int levels, int device, void *cuda_stream, b2s_hector_slam **out);
+void b2s_hector_slam_destroy(b2s_hector_slam *p);
+/* setUpdateFactorFree / setUpdateFactorOccupied (HectorSlamProcessor.h:128-129) */
+b2s_status b2s_hector_slam_set_update_factors(b2s_hector_slam *p, float update_free, float update_occupied);
+/* setMapUpdateMinDistDiff / setMapUpdateMinAngleDiff (HectorSlamProcessor.h:130-131).  The gate is
+ * util::poseDifferenceLargerThan (UtilFunctions.h:72-90), including its integer-truncating abs() on the angle. */
+b2s_status b2s_hector_slam_set_map_update_min_diff(b2s_hector_slam *p, float min_dist, float min_angle);
+/* reset() (HectorSlamProcessor.h:111-116): clears every level and the last poses */
+b2s_status b2s_hector_slam_reset(b2s_hector_slam *p);
+/* update(dataContainer, poseHintWorld, map_without_matching) (HectorSlamProcessor.h:81-108).  points = the
+ * DataContainer in LEVEL-0 map-cell units ([n][2] float, as hector_slam.cc:320-362 fills it), origo likewise, pose
+ * hint in world coordinates.  out_pose = getLastScanMatchPose(); out_cov (may be NULL) = getLastScanMatchCovariance()
+ * (the level-0 Hessian; untouched when map_without_matching).  out_map_updated (may be NULL) tells whether the gate
+ * let this scan into the maps. */
+b2s_status b2s_hector_slam_update(b2s_hector_slam *p, const float *points, int n_points, const float origo[2],
+                                  const float pose_hint_world[3], int map_without_matching, float out_pose[3],
+                                  float out_cov[9], int *out_map_updated);
+/* getMapLevels / getGridMap(level) (HectorSlamProcessor.h:124-125) */
+b2s_status b2s_hector_slam_level_dims(b2s_hector_slam *p, int level, int dims[2], float *cell_length);
+b2s_status b2s_hector_slam_copy_level(b2s_hector_slam *p, int level, float *log_odds, int32_t *update_index);
+/* nav_msgs/OccupancyGrid payload of one level as HectorMappingRos::publishMap fills it (hector_slam.cc:254-317) */
+b2s_status b2s_hector_slam_copy_level_ros(b2s_hector_slam *p, int level, int8_t *out);
+/* out[0] = scans matched, out[1] = scans let into the maps, out[2] = Bresenham cell visits so far (all levels),
+ * out[3] / out[4] = ms of the last match / update kernels */
+b2s_status b2s_hector_slam_stats(b2s_hector_slam *p, double out[5]);
+
 /* ---------------------------------------------------------------- K2b: GMapping hit/visit map */
 
 typedef struct b2s_gmap b2s_gmap; /* opaque: replaces GMapping::ScanMatcherMap (gmapping.cc:135) */
