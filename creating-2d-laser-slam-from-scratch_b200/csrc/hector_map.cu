@@ -307,108 +307,124 @@ struct HsUpdate {  // per-level update parameters of one scan (host: getMapCoord
   int mark_free[B2S_HECTOR_MAX_LEVELS], mark_occ[B2S_HECTOR_MAX_LEVELS];
 };
 
-// DataPointContainer::setFrom (DataPointContainer.h:46-59): dataPoints[i] *= factor, one float multiply per coordinate
-__global__ void k_hs_scale(const float *__restrict__ src, int n2, HsLevels L) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n2) return;
-  const float v = src[i];
-  float factor = 1.0f;
-  for (int l = 1; l < L.count; l++) {
-    factor *= 0.5f;  // static_cast<float>(1.0 / pow(2.0, l)) is exactly 2^-l
-    const_cast<float *>(L.l[l].pts)[i] = __fmul_rn(v, factor);
-  }
-}
-
 // MapRepMultiMap::matchData (:144-166) -> ScanMatcher::matchData (ScanMatcher.h:60-98) on every level, coarsest first,
-// in ONE launch of one CTA.  Per iteration every thread evaluates its points (bilinear map value + gradient, 4 cell
-// reads + 4 expf) and the 9 sums of getCompleteHessianDerivs are reduced by warp shuffles in a fixed tree (the result
-// is deterministic run to run; it differs from the reference's point-order float sums in the last bits, far inside
-// the 1e-4 contract — device cosf/sinf/expf differ from glibc's in the last ulp anyway).
-constexpr int HS_THREADS = 512;
+// in ONE launch of one CTA (the problem is a latency chain of 14 dependent Gauss-Newton iterations over ~1000 points,
+// not a throughput problem).  The scan is staged in shared memory once; level l reads it scaled by 2^-l on the fly
+// (DataPointContainer::setFrom, DataPointContainer.h:46-59: one float multiply per coordinate, exact) and also
+// writes that scaled copy to the level's device container for the update kernels.  Per iteration every thread
+// evaluates its points (bilinear map value + gradient: 4 cell reads + 4 expf, all loads issued up front), the 9 sums
+// of getCompleteHessianDerivs are reduced through shared memory in a fixed order (deterministic run to run; they
+// differ from the reference's point-order float sums in the last bits, far inside the 1e-4 contract — device
+// cosf/sinf/expf differ from glibc's in the last ulp anyway), and every thread solves the 3x3 system redundantly so
+// the new estimate needs no broadcast.
+constexpr int HS_THREADS = 1024;
+constexpr int HS_PPT = 2;                        // points per thread held in registers
+constexpr int HS_SMEM_PTS = HS_THREADS * HS_PPT; // scans up to 2048 points take the staged path
+constexpr int HS_SMEM_BYTES = (int)sizeof(float2) * HS_SMEM_PTS + 9 * HS_THREADS * (int)sizeof(float);
+
+__device__ __forceinline__ void hs_point_terms(const float *__restrict__ lo, int sx, int sy, float2 p, float c, float s,
+                                               float e0, float e1, float a[9]) {
+  const float tx = (c * p.x + (-s) * p.y) + e0, ty = (s * p.x + c * p.y) + e1;
+  float t[3];
+  hc_interp(lo, sx, sy, tx, ty, t);
+  const float rot = ((-s * p.x - c * p.y) * t[1] + (c * p.x - s * p.y) * t[2]);
+  const float fun = 1.0f - t[0];
+  a[0] += t[1] * fun; a[1] += t[2] * fun; a[2] += rot * fun;    // dTr
+  a[3] += t[1] * t[1]; a[4] += t[2] * t[2]; a[5] += rot * rot;  // H00 H11 H22
+  a[6] += t[1] * t[2]; a[7] += t[1] * rot; a[8] += t[2] * rot;  // H01 H02 H12
+}
 
 __global__ void __launch_bounds__(HS_THREADS)
     k_hs_match(HsLevels L, float w0, float w1, float w2, float *__restrict__ out) {
-  __shared__ float red[HS_THREADS / 32][9];
-  __shared__ float est[3];
-  __shared__ float world[3];
-  __shared__ float Hs[9];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { world[0] = w0; world[1] = w1; world[2] = w2; }
+  extern __shared__ __align__(16) unsigned char hs_smem[];  // HS_SMEM_BYTES, opt-in (> 48 KB)
+  float2 *spts = reinterpret_cast<float2 *>(hs_smem);                                                   // [HS_SMEM_PTS]
+  float(*part)[HS_THREADS] = reinterpret_cast<float(*)[HS_THREADS]>(hs_smem + sizeof(float2) * HS_SMEM_PTS);  // [9][HS_THREADS]
+  __shared__ float tot[9];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = L.l[0].n;
+  const bool staged = n <= HS_SMEM_PTS;
+  const float2 *gp = reinterpret_cast<const float2 *>(L.l[0].pts);
+  if (staged)
+    for (int i = tid; i < n; i += HS_THREADS) spts[i] = gp[i];
+  float world0 = w0, world1 = w1, world2 = w2;  // every thread carries the same estimate
+  float H[9];
+  bool any = false;
+#pragma unroll
+  for (int q = 0; q < 9; q++) H[q] = 0.0f;
   __syncthreads();
-  for (int lv = L.count - 1; lv >= 0; lv--) {
-    const HsLevel &m = L.l[lv];
-    if (m.n == 0) continue;  // ScanMatcher.h:66,97: no data -> the begin estimate is returned unchanged
-    if (threadIdx.x == 0) {  // getMapCoordsPose (GridMapBase.h:238-242)
-      est[0] = (m.tw_lin * world[0] + 0.0f * world[1]) + m.tw_tx;
-      est[1] = (0.0f * world[0] + m.tw_lin * world[1]) + m.tw_ty;
-      est[2] = world[2];
+  float factor = 1.0f;
+  for (int l = 1; l < L.count; l++) factor *= 0.5f;  // static_cast<float>(1.0 / pow(2.0, l)) is exactly 2^-l
+  for (int lv = L.count - 1; lv >= 0; lv--, factor *= 2.0f) {
+    const HsLevel m = L.l[lv];
+    if (n == 0) break;  // ScanMatcher.h:66,97: no data -> the begin estimate is returned unchanged
+    float2 p[HS_PPT];
+#pragma unroll
+    for (int j = 0; j < HS_PPT; j++) {
+      const int i = tid + j * HS_THREADS;
+      p[j] = make_float2(0.0f, 0.0f);
+      if (staged && i < n) {
+        p[j] = make_float2(__fmul_rn(spts[i].x, factor), __fmul_rn(spts[i].y, factor));
+        if (lv > 0) reinterpret_cast<float2 *>(const_cast<float *>(m.pts))[i] = p[j];
+      }
     }
-    __syncthreads();
+    if (!staged && lv > 0)
+      for (int i = tid; i < n; i += HS_THREADS)
+        reinterpret_cast<float2 *>(const_cast<float *>(m.pts))[i] = make_float2(__fmul_rn(gp[i].x, factor), __fmul_rn(gp[i].y, factor));
+    // getMapCoordsPose (GridMapBase.h:238-242)
+    float e0 = (m.tw_lin * world0 + 0.0f * world1) + m.tw_tx;
+    float e1 = (0.0f * world0 + m.tw_lin * world1) + m.tw_ty;
+    float e2 = world2;
     for (int it = 0; it < m.iterations; it++) {
-      const float e0 = est[0], e1 = est[1], e2 = est[2];
       const float c = cosf(e2), s = sinf(e2);
       float a[9];
 #pragma unroll
       for (int q = 0; q < 9; q++) a[q] = 0.0f;
-      for (int i = threadIdx.x; i < m.n; i += HS_THREADS) {
-        const float2 p = reinterpret_cast<const float2 *>(m.pts)[i];
-        const float tx = (c * p.x + (-s) * p.y) + e0, ty = (s * p.x + c * p.y) + e1;
-        float t[3];
-        hc_interp(m.lo, m.sx, m.sy, tx, ty, t);
-        const float rot = ((-s * p.x - c * p.y) * t[1] + (c * p.x - s * p.y) * t[2]);
-        const float fun = 1.0f - t[0];
-        a[0] += t[1] * fun; a[1] += t[2] * fun; a[2] += rot * fun;            // dTr
-        a[3] += t[1] * t[1]; a[4] += t[2] * t[2]; a[5] += rot * rot;          // H00 H11 H22
-        a[6] += t[1] * t[2]; a[7] += t[1] * rot; a[8] += t[2] * rot;          // H01 H02 H12
+      if (staged) {
+#pragma unroll
+        for (int j = 0; j < HS_PPT; j++)
+          if (tid + j * HS_THREADS < n) hs_point_terms(m.lo, m.sx, m.sy, p[j], c, s, e0, e1, a);
+      } else {
+        for (int i = tid; i < n; i += HS_THREADS)
+          hs_point_terms(m.lo, m.sx, m.sy, make_float2(__fmul_rn(gp[i].x, factor), __fmul_rn(gp[i].y, factor)), c, s, e0, e1, a);
       }
 #pragma unroll
-      for (int q = 0; q < 9; q++) {
+      for (int q = 0; q < 9; q++) part[q][tid] = a[q];
+      __syncthreads();
+      if (warp < 9) {  // warp q sums quantity q: 32 conflict-free reads per lane, then 5 shuffles
+        float v = 0.0f;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], d);
-      }
-      if (lane == 0) {
+        for (int j = 0; j < HS_THREADS / 32; j++) v += part[warp][lane + 32 * j];
 #pragma unroll
-        for (int q = 0; q < 9; q++) red[warp][q] = a[q];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) tot[warp] = v;
       }
       __syncthreads();
-      if (warp == 0) {
-        float v[9];
-#pragma unroll
-        for (int q = 0; q < 9; q++) {
-          v[q] = lane < HS_THREADS / 32 ? red[lane][q] : 0.0f;
-#pragma unroll
-          for (int d = 8; d > 0; d >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], d);
-        }
-        if (lane == 0) {
-          float H[9], dTr[3] = {v[0], v[1], v[2]};
-          H[0] = v[3]; H[4] = v[4]; H[8] = v[5];
-          H[1] = H[3] = v[6]; H[2] = H[6] = v[7]; H[5] = H[7] = v[8];
-          if (H[0] != 0.0f && H[4] != 0.0f) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
-            float dir[3];
-            hc_inv3_mul(H, dTr, dir);
-            if (dir[2] > 0.2f) dir[2] = 0.2f;
-            else if (dir[2] < -0.2f) dir[2] = -0.2f;
-            est[0] += dir[0]; est[1] += dir[1]; est[2] += dir[2];
-          }
-#pragma unroll
-          for (int q = 0; q < 9; q++) Hs[q] = H[q];
-        }
+      const float dTr[3] = {tot[0], tot[1], tot[2]};
+      H[0] = tot[3]; H[4] = tot[4]; H[8] = tot[5];
+      H[1] = H[3] = tot[6]; H[2] = H[6] = tot[7]; H[5] = H[7] = tot[8];
+      if (H[0] != 0.0f && H[4] != 0.0f) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
+        float dir[3];
+        hc_inv3_mul(H, dTr, dir);
+        if (dir[2] > 0.2f) dir[2] = 0.2f;
+        else if (dir[2] < -0.2f) dir[2] = -0.2f;
+        e0 += dir[0]; e1 += dir[1]; e2 += dir[2];
       }
-      __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    {
       const double two_pi = 2.0f * 3.14159265358979323846;  // util::normalize_angle (UtilFunctions.h:36-48)
-      float a = (float)fmod(fmod((double)est[2], two_pi) + two_pi, two_pi);
+      float a = (float)fmod(fmod((double)e2, two_pi) + two_pi, two_pi);
       if (a > 3.14159265358979323846) a = (float)((double)a - two_pi);
-      world[0] = (m.wt_lin * est[0] + (-0.0f) * est[1]) + m.wt_tx;  // getWorldCoordsPose (GridMapBase.h:229-233)
-      world[1] = ((-0.0f) * est[0] + m.wt_lin * est[1]) + m.wt_ty;
-      world[2] = a;
-      out[12] = 1.0f;  // some level ran: covMatrix = H of the LAST level matched (level 0 unless it had no points)
-      for (int q = 0; q < 9; q++) out[3 + q] = Hs[q];
+      world0 = (m.wt_lin * e0 + (-0.0f) * e1) + m.wt_tx;  // getWorldCoordsPose (GridMapBase.h:229-233)
+      world1 = ((-0.0f) * e0 + m.wt_lin * e1) + m.wt_ty;
+      world2 = a;
+      any = true;
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) { out[0] = world[0]; out[1] = world[1]; out[2] = world[2]; }
+  if (tid == 0) {
+    out[0] = world0; out[1] = world1; out[2] = world2;
+    for (int q = 0; q < 9; q++) out[3 + q] = H[q];  // covMatrix = H of the last level matched (level 0)
+    out[12] = any ? 1.0f : 0.0f;
+  }
 }
 
 // MapRepMultiMap::updateByScan (:174-191): mark / apply passes of every level in one launch each (blockIdx.y = level)
@@ -778,6 +794,8 @@ b2s_status b2s_hector_slam_create(float map_resolution, int map_size_x, int map_
   hs_reset_poses(p);
   std::memset(p->last_cov, 0, sizeof(p->last_cov));
   for (auto &e : p->ev) B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaEventCreate(&e));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p),
+                       cudaFuncSetAttribute(k_hs_match, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM_BYTES));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaMalloc(reinterpret_cast<void **>(&p->d_out), 16 * sizeof(float)));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaMallocHost(reinterpret_cast<void **>(&p->h_out), 16 * sizeof(float)));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaMalloc(reinterpret_cast<void **>(&p->d_visits), sizeof(unsigned long long)));
@@ -876,10 +894,8 @@ b2s_status b2s_hector_slam_update(b2s_hector_slam *p, const float *points, int n
     }
     const HsLevels L = hs_levels(p);
     if (n_points > 0) {
-      if (p->levels > 1) k_hs_scale<<<ceil_div(2 * n_points, 256), 256, 0, p->stream>>>(p->d_pts[0], 2 * n_points, L);
-      B2S_CUDA_CHECK(cudaMemsetAsync(p->d_out + 12, 0, sizeof(float), p->stream));
       B2S_CUDA_CHECK(cudaEventRecord(p->ev[0], p->stream));
-      k_hs_match<<<1, HS_THREADS, 0, p->stream>>>(L, est[0], est[1], est[2], p->d_out);
+      k_hs_match<<<1, HS_THREADS, HS_SMEM_BYTES, p->stream>>>(L, est[0], est[1], est[2], p->d_out);
       B2S_CUDA_CHECK(cudaEventRecord(p->ev[1], p->stream));
       p->ev_match = true;
       B2S_CUDA_CHECK(cudaGetLastError());
