@@ -1,16 +1,20 @@
-"""Build libb200slam.so (CUDA, sm_100a) in-tree with nvcc.  nvcc cross-compiles without a GPU."""
+"""Build libb200slam.so (CUDA, sm_100a) in-tree with nvcc.  nvcc cross-compiles without a GPU.
+Each source is compiled to an object under csrc/build/ (only when stale, in parallel), then linked."""
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libb200slam.so")
-SOURCES = ["karto_matcher.cu", "karto_occgrid.cu", "hector_map.cu", "gmapping_map.cu", "plicp.cu"]
+SOURCES = ["karto_matcher.cu", "karto_occgrid.cu", "hector_map.cu", "gmapping_map.cu", "plicp.cu", "karto_mapper.cu", "pose_graph.cu"]
+HEADERS = ["common.cuh", "scan_kernels.cuh", os.path.join("..", "..", "include", "b200slam.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC"]
 
 
 def nvcc() -> str:
@@ -20,20 +24,35 @@ def nvcc() -> str:
     return "nvcc"
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b200slam.h")]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def needs_build() -> bool:
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return _stale(LIB, deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB]
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    jobs = []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s.replace(".cu", ".o"))
+        if force or _stale(obj, [src] + hdrs):
+            jobs.append([nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        for rc in ex.map(lambda cmd: subprocess.run(cmd).returncode, jobs):
+            if rc != 0:
+                raise RuntimeError("nvcc failed")
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
+                           "-Xcompiler", "-fPIC"] + objs + ["-o", LIB])
     return LIB
 
 

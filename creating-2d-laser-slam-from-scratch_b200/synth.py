@@ -146,3 +146,32 @@ def make_trajectory(seed: int, n_poses: int, laser: Laser = Laser(), half_w: flo
         q[2] = (q[2] + np.pi) % (2 * np.pi) - np.pi
         p = q
     return world, poses, ranges
+
+
+def make_loop_trajectory(seed: int, n_poses: int, laser: Laser = Laser(), radius: float = 2.0, step: float = 0.25,
+                         drift=(0.004, 0.003, 0.0015), half_w: float = 8.0, half_h: float = 6.0, n_boxes: int = 6):
+    """A robot circling the box-free middle of the room (heading tangent to the circle), lap after lap, so that the
+    front end sees running-window matches, near-chain links and loop-closure candidates.  Odometry = the true motion
+    composed with a small seeded drift per step.  Returns (world, true_poses[n,3], odom_poses[n,3], ranges[n,N])."""
+    rng = np.random.default_rng(9_000_011 * (seed + 1))
+    world = make_world(seed, half_w, half_h, n_boxes)
+    true = np.zeros((n_poses, 3))
+    odom = np.zeros((n_poses, 3))
+    ranges = np.zeros((n_poses, laser.n_readings))
+    dphi = step / radius
+    for i in range(n_poses):
+        phi = i * dphi
+        true[i] = (radius * np.cos(phi), radius * np.sin(phi), (phi + np.pi / 2 + np.pi) % (2 * np.pi) - np.pi)
+        ranges[i] = cast_scan(world, true[i], laser, rng, 0.01, 0.0)
+        if i == 0:
+            odom[i] = true[i]
+        else:  # relative true motion in the previous true frame, perturbed, re-composed onto the previous odometry
+            c, s = np.cos(true[i - 1, 2]), np.sin(true[i - 1, 2])
+            d = true[i, :2] - true[i - 1, :2]
+            local = np.array([c * d[0] + s * d[1], -s * d[0] + c * d[1]]) + rng.normal(0, drift[:2])
+            dth = (true[i, 2] - true[i - 1, 2] + np.pi) % (2 * np.pi) - np.pi + rng.normal(0, drift[2])
+            co, so = np.cos(odom[i - 1, 2]), np.sin(odom[i - 1, 2])
+            odom[i, 0] = odom[i - 1, 0] + co * local[0] - so * local[1]
+            odom[i, 1] = odom[i - 1, 1] + so * local[0] + co * local[1]
+            odom[i, 2] = (odom[i - 1, 2] + dth + np.pi) % (2 * np.pi) - np.pi
+    return world, true, odom, ranges

@@ -185,6 +185,100 @@ b2s_status b2s_matcher_sync(b2s_matcher *m);
  * 3 = window kernel without dropping empty windows (every beam is swept) */
 b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which);
 
+/* ---------------------------------------------------------------- lesson6 front end: karto::Mapper / MapperGraph
+ * The host driver that feeds K1: key-frame gate, running-scan window, sequential MatchScan,
+ * pose-graph vertices / edges, near-chain links and loop-closure candidates (Mapper.cpp:883-1414, 1999-2125;
+ * Mapper.h:1288-1404).  Every MatchScan runs on the device; independent matches of one Process call (all near
+ * chains of LinkNearChains, all candidate chains of TryCloseLoop up to the first accepted closure) go out as ONE
+ * batch.  One sensor per mapper (the reference's multi-robot first-scan linking, Mapper.cpp:920-952, is not built). */
+
+/* Values as the Mapper STORES them (Mapper.cpp:1448-1653); the setParam* squaring of distance_variance_penalty,
+ * angle_variance_penalty and loop_match_maximum_variance_coarse (Mapper.cpp:1871-1874,1919-1927) is the caller's job. */
+typedef struct b2s_mapper_params {
+  int32_t use_scan_matching;                 /* true */
+  int32_t use_scan_barycenter;               /* true */
+  double minimum_time_interval;              /* 3600 s */
+  double minimum_travel_distance;            /* 0.2 m */
+  double minimum_travel_heading;             /* 10 deg in rad */
+  int32_t scan_buffer_size;                  /* 70 */
+  int32_t do_loop_closing;                   /* true */
+  double scan_buffer_maximum_scan_distance;  /* 20 m */
+  double link_match_minimum_response_fine;   /* 0.8 */
+  double link_scan_maximum_distance;         /* 10 m */
+  double loop_search_maximum_distance;       /* 4 m */
+  int32_t loop_match_minimum_chain_size;     /* 10 */
+  int32_t reserved;
+  double loop_match_maximum_variance_coarse; /* 0.4^2 */
+  double loop_match_minimum_response_coarse; /* 0.8 */
+  double loop_match_minimum_response_fine;   /* 0.8 */
+  b2s_matcher_params sequential;             /* CorrelationSearchSpace* 0.3 / 0.01 / 0.03 + the shared tuning values */
+  b2s_matcher_params loop;                   /* LoopSearchSpace* 8.0 / 0.05 / 0.03 + the same tuning values */
+} b2s_mapper_params;
+
+/* Mapper::InitializeParameters defaults (Mapper.cpp:1448-1653); range_threshold of both matchers = the laser's */
+void b2s_mapper_default_params(b2s_mapper_params *out, double range_threshold);
+
+/* The matcher plug-in: ScanMatcher::MatchScan (Mapper.cpp:184-291) for a batch of independent matches.
+ * which = 0 the sequential matcher (Mapper::m_pSequentialScanMatcher), 1 the loop matcher
+ * (MapperGraph::m_pLoopScanMatcher).  ranges [batch][N], poses [batch][3] (robot poses); the base scans of match b are
+ * base_ranges/base_poses[base_first[b] .. base_first[b] + n_base[b]).  The in-tree implementation is the CUDA matcher
+ * (b2s_mapper_create); the hook exists so that the graph logic can be exercised without a device. */
+typedef b2s_status (*b2s_match_scan_fn)(void *user, int which, int batch, const double *ranges, const double *poses,
+                                        const int32_t *base_first, const int32_t *n_base, const double *base_ranges,
+                                        const double *base_poses, int do_penalize, int do_refine,
+                                        b2s_match_result *results);
+
+/* karto::ScanSolver (Mapper.h:825-891) as a C vtable — the reference's own back-end plug-in interface. */
+typedef struct b2s_scan_solver {
+  void *user;
+  void (*add_node)(void *user, int32_t unique_id, const double corrected_pose[3]);          /* AddNode */
+  void (*add_constraint)(void *user, int32_t source_id, int32_t target_id, const double pose_difference[3],
+                         const double covariance[9]);                                       /* AddConstraint(LinkInfo) */
+  int32_t (*compute)(void *user, int32_t capacity, int32_t *ids, double *poses /* [capacity][3] */);
+                                                                                             /* Compute + GetCorrections */
+  void (*clear)(void *user);                                                                /* Clear */
+} b2s_scan_solver;
+
+typedef struct b2s_mapper b2s_mapper; /* opaque: replaces karto::Mapper (+ MapperGraph, MapperSensorManager) */
+
+b2s_status b2s_mapper_create(const b2s_mapper_params *params, const b2s_laser *laser, int device, b2s_mapper **out);
+b2s_status b2s_mapper_create_with_matcher(const b2s_mapper_params *params, const b2s_laser *laser,
+                                          b2s_match_scan_fn match, void *user, b2s_mapper **out);
+void b2s_mapper_destroy(b2s_mapper *m);
+/* Mapper::SetScanSolver (Mapper.cpp:2220); NULL = no back end (poses are never corrected, as with use_back_end false) */
+b2s_status b2s_mapper_set_scan_solver(b2s_mapper *m, const b2s_scan_solver *solver);
+/* Mapper::Process(LocalizedRangeScan*) (Mapper.cpp:1999-2079): ranges[n_readings], odometric robot pose, time stamp (s).
+ * out_processed = the kt_bool it returns (false: rejected by HasMovedEnough); out_corrected_pose = GetCorrectedPose(). */
+b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double odometric_pose[3], double time,
+                              int32_t *out_processed, double out_corrected_pose[3]);
+int32_t b2s_mapper_scan_count(const b2s_mapper *m);   /* GetAllProcessedScans().size() */
+/* corrected poses of every processed scan, [count][3] (they move when a loop closes and a solver is set) */
+b2s_status b2s_mapper_get_poses(const b2s_mapper *m, double *out);
+int32_t b2s_mapper_edge_count(const b2s_mapper *m);
+/* graph edges in creation order: ids [count][2] (source, target), LinkInfo pose difference [count][3] and covariance
+ * [count][9] (Mapper.h:108-175) */
+b2s_status b2s_mapper_get_edges(const b2s_mapper *m, int32_t *ids, double *pose_difference, double *covariance);
+/* out[0] = MatchScan calls so far, out[1] = device batches they were sent in, out[2] = loop-closure candidate chains
+ * examined, out[3] = loops closed, out[4] = running-scan window size */
+b2s_status b2s_mapper_stats(const b2s_mapper *m, double out[5]);
+
+/* ---------------------------------------------------------------- back end: a ScanSolver for the mapper (host only)
+ * the reference's back ends (sparse bundle adjustment / g2o / Ceres / GTSAM, lesson6/src/*_solver)
+ * need Eigen + SuiteSparse and stay on the CPU in every BASELINE config.  This is a small dependency-free 2-D pose-graph
+ * optimiser with the same role: nodes = scan poses, constraints = LinkInfo pose differences weighted by the inverse
+ * covariance (lesson6/src/spa_solver/spa_solver.cc:65-93), Levenberg-Marquardt outer loop, block-Jacobi preconditioned
+ * conjugate gradients inside, first node fixed.  It is NOT a restatement of sba::SysSPA2d (parity unpinned: that
+ * library is not under /root/reference); tests plug the SAME solver into the reference Mapper and into ours. */
+typedef struct b2s_pose_graph b2s_pose_graph;
+b2s_status b2s_pose_graph_create(b2s_pose_graph **out);
+void b2s_pose_graph_destroy(b2s_pose_graph *g);
+/* fills `out` with callbacks bound to `g` (valid while g lives): pass it to b2s_mapper_set_scan_solver */
+b2s_status b2s_pose_graph_as_scan_solver(b2s_pose_graph *g, b2s_scan_solver *out);
+/* SpaSolver::Compute runs doSPA(40) (spa_solver.cc:44-63): max LM iterations (default 40), PCG iterations per step */
+b2s_status b2s_pose_graph_set_iterations(b2s_pose_graph *g, int lm_iterations, int cg_iterations);
+/* out[0] = nodes, out[1] = constraints, out[2] = chi^2 before the last Compute, out[3] = after, out[4] = LM steps taken */
+b2s_status b2s_pose_graph_stats(const b2s_pose_graph *g, double out[5]);
+
 /* ---------------------------------------------------------------- K2c: karto::OccupancyGrid */
 
 typedef struct b2s_occ_grid_info {

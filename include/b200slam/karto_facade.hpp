@@ -10,6 +10,8 @@
 //                       const Vector2<double>& resolution, double angleOffset, double angleRes,
 //                       bool doPenalize, Pose2& mean, Matrix3& cov, bool doingFineMatch)
 //   OccupancyGrid* OccupancyGrid::CreateFromScans(const LocalizedRangeScanVector&, resolution)    same argument list
+//   kt_bool Mapper::Process(LocalizedRangeScan*) (Mapper.cpp:1999), SetScanSolver (:2220)           b200slam::Mapper
+//   hectorslam::HectorSlamProcessor::update(dataContainer, poseHint, map_without_matching)          b200slam::HectorSlamProcessor
 //
 // Errors: where the reference returns NULL the façade returns nullptr; where it throws (std::runtime_error,
 // karto::Exception) the façade throws b200slam::Exception carrying the b2s_status.  Like the reference's
@@ -215,6 +217,89 @@ class OccupancyGrid {
   b2s_occ_grid *g_;
   b2s_occ_grid_info info_;
   std::vector<unsigned char> cells_;
+};
+
+// karto::Mapper as SlamKarto::addScan drives it (karto_slam.cc:407-481; Mapper.cpp:1999-2079): one Process call per
+// LaserScan.  The scan object keeps the reference's accessors; Process fills its corrected pose.
+class MapperScan {
+ public:
+  MapperScan(const std::vector<double> &readings) : readings_(readings) {}
+  void SetOdometricPose(const Pose2 &p) { odometric_ = p; }
+  void SetCorrectedPose(const Pose2 &p) { corrected_ = p; }
+  void SetTime(double t) { time_ = t; }
+  const Pose2 &GetOdometricPose() const { return odometric_; }
+  const Pose2 &GetCorrectedPose() const { return corrected_; }
+  double GetTime() const { return time_; }
+  const std::vector<double> &GetRangeReadings() const { return readings_; }
+
+ private:
+  std::vector<double> readings_;
+  Pose2 odometric_, corrected_;
+  double time_ = 0;
+};
+
+class Mapper {
+ public:
+  // Mapper() + Initialize(rangeThreshold) + the setParam* calls of karto_slam.cc:81-252 (values already in their
+  // stored form, see b2s_mapper_params); device matchers are created on the first match
+  Mapper(const b2s_mapper_params &params, const b2s_laser &laser, int device = 0) { check(b2s_mapper_create(&params, &laser, device, &h_)); }
+  ~Mapper() { b2s_mapper_destroy(h_); }
+  Mapper(const Mapper &) = delete;
+  Mapper &operator=(const Mapper &) = delete;
+  // Mapper::SetScanSolver (Mapper.cpp:2220)
+  void SetScanSolver(const b2s_scan_solver *solver) { check(b2s_mapper_set_scan_solver(h_, solver)); }
+  // kt_bool Mapper::Process(LocalizedRangeScan*) (Mapper.cpp:1999)
+  bool Process(MapperScan *pScan) {
+    if (!pScan) return false;
+    const Pose2 &o = pScan->GetOdometricPose();
+    const double odom[3] = {o.x, o.y, o.heading};
+    double corrected[3];
+    int32_t ok = 0;
+    check(b2s_mapper_process(h_, pScan->GetRangeReadings().data(), odom, pScan->GetTime(), &ok, corrected));
+    pScan->SetCorrectedPose(Pose2(corrected[0], corrected[1], corrected[2]));
+    return ok != 0;
+  }
+  // corrected poses of Mapper::GetAllProcessedScans() (Mapper.cpp:2126), as SlamKarto::updateMap reads them
+  std::vector<Pose2> GetAllProcessedPoses() const {
+    std::vector<double> p(3 * (size_t)b2s_mapper_scan_count(h_));
+    if (!p.empty()) check(b2s_mapper_get_poses(h_, p.data()));
+    std::vector<Pose2> out;
+    for (size_t i = 0; i + 2 < p.size(); i += 3) out.emplace_back(p[i], p[i + 1], p[i + 2]);
+    return out;
+  }
+  b2s_mapper *handle() { return h_; }
+
+ private:
+  b2s_mapper *h_ = nullptr;
+};
+
+// hectorslam::HectorSlamProcessor (lesson4/include/lesson4/hector_mapping/slam_main/HectorSlamProcessor.h:50-150)
+class HectorSlamProcessor {
+ public:
+  HectorSlamProcessor(float mapResolution, int mapSizeX, int mapSizeY, float startX, float startY, int multi_res_size,
+                      int device = 0) {
+    check(b2s_hector_slam_create(mapResolution, mapSizeX, mapSizeY, startX, startY, multi_res_size, device, nullptr, &h_));
+  }
+  ~HectorSlamProcessor() { b2s_hector_slam_destroy(h_); }
+  HectorSlamProcessor(const HectorSlamProcessor &) = delete;
+  HectorSlamProcessor &operator=(const HectorSlamProcessor &) = delete;
+  // update(dataContainer, poseHintWorld, map_without_matching) (:81-108); points = DataContainer entries [n][2]
+  void update(const std::vector<float> &points, const float origo[2], const float poseHintWorld[3], bool map_without_matching = false) {
+    check(b2s_hector_slam_update(h_, points.data(), (int)(points.size() / 2), origo, poseHintWorld, map_without_matching, pose_, cov_, nullptr));
+  }
+  void reset() { check(b2s_hector_slam_reset(h_)); }
+  const float *getLastScanMatchPose() const { return pose_; }
+  const float *getLastScanMatchCovariance() const { return cov_; }
+  void setUpdateFactorFree(float f) { free_ = f; check(b2s_hector_slam_set_update_factors(h_, free_, occ_)); }
+  void setUpdateFactorOccupied(float f) { occ_ = f; check(b2s_hector_slam_set_update_factors(h_, free_, occ_)); }
+  void setMapUpdateMinDistDiff(float d) { dist_ = d; check(b2s_hector_slam_set_map_update_min_diff(h_, dist_, angle_)); }
+  void setMapUpdateMinAngleDiff(float a) { angle_ = a; check(b2s_hector_slam_set_map_update_min_diff(h_, dist_, angle_)); }
+  b2s_hector_slam *handle() { return h_; }
+
+ private:
+  b2s_hector_slam *h_ = nullptr;
+  float pose_[3] = {0, 0, 0}, cov_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  float free_ = 0.4f, occ_ = 0.6f, dist_ = 0.4f, angle_ = 0.13f;
 };
 
 }  // namespace b200slam

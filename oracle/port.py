@@ -202,6 +202,31 @@ def gmap_grid_line(x0, y0, x1, y1):
     return out[:n].copy()
 
 
+def mapper_match_hook(mapper_params, laser):
+    """A b2s_match_scan_fn (include/b200slam.h) served by the CPU restatement's MatchScan — TESTS ONLY: it lets the
+    host-side graph logic of the product's mapper (karto_mapper.cu) run on a machine without a GPU.  Returns a Python
+    callable for creating-..._b200.mapper.Mapper(match_fn=...)."""
+    L = lib()
+    n = laser.n_readings
+    matchers = [PortMatcher(mapper_params.sequential, laser), PortMatcher(mapper_params.loop, laser)]
+
+    def hook(user, which, batch, ranges, poses, base_first, n_base, base_ranges, base_poses, do_penalize, do_refine, results):
+        pm = matchers[which]
+        for b in range(batch):
+            r = np.ctypeslib.as_array(ranges, shape=((b + 1) * n,))[b * n:(b + 1) * n]
+            p = np.ctypeslib.as_array(poses, shape=((b + 1) * 3,))[b * 3:(b + 1) * 3]
+            f, c = base_first[b], n_base[b]
+            br = np.ctypeslib.as_array(base_ranges, shape=((f + c) * n,))[f * n:(f + c) * n]
+            bp = np.ctypeslib.as_array(base_poses, shape=((f + c) * 3,))[f * 3:(f + c) * 3]
+            rc, res = pm.match_scan(r, p, br, bp, bool(do_penalize), bool(do_refine))
+            if rc:
+                return rc
+            C.memmove(C.byref(results[b]), C.byref(res), C.sizeof(res))
+        return 0
+
+    return hook
+
+
 # ---------------------------------------------------------------- Hector (hector_oracle.c) — pinned against
 # oracle/ref_hector.cpp (the reference headers compiled with the Eigen stand-in) by tests/test_oracle_hector_reference.py
 

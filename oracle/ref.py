@@ -273,3 +273,55 @@ def _karto_round(v: float) -> float:
     """math::Round (Math.h:87-90)."""
     import math
     return math.floor(v + 0.5) if v >= 0.0 else math.ceil(v - 0.5)
+
+
+# ---------------------------------------------------------------- the whole front end: karto::Mapper::Process
+
+class RefMapper:
+    """karto::Mapper (Mapper.cpp:1999-2079) fed one LaserScan at a time, as karto_slam.cc:437-475 does.  `params` is a
+    creating-..._b200.mapper.MapperParams (ref_mapper_params has the same layout); `laser` a synth.Laser."""
+
+    def __init__(self, params, laser, ndebug: bool = False):
+        self.L = _lib(ndebug)
+        self.L.ref_mapper_create.restype = C.c_void_p
+        self.lp = laser_params(laser)
+        self.h = C.c_void_p(self.L.ref_mapper_create(C.byref(params), C.byref(self.lp)))
+        self.n = laser.n_readings
+        self._keep = []
+
+    def set_scan_solver(self, solver):
+        """solver: any ctypes struct laid out as b2s_scan_solver / ref_scan_solver."""
+        self._keep.append(solver)
+        self.L.ref_mapper_set_solver(self.h, C.byref(solver))
+
+    def process(self, ranges, odometric_pose, time=0.0):
+        r, o, out = np.ascontiguousarray(ranges, np.float64), np.ascontiguousarray(odometric_pose, np.float64), np.zeros(3)
+        ok = self.L.ref_mapper_process(self.h, _dp(r), self.n, _dp(o), C.c_double(time), _dp(out))
+        return bool(ok), out
+
+    def poses(self):
+        out = np.zeros((self.L.ref_mapper_scan_count(self.h), 3))
+        if len(out):
+            self.L.ref_mapper_get_poses(self.h, _dp(out))
+        return out
+
+    def edges(self):
+        n = self.L.ref_mapper_edge_count(self.h)
+        ids, diff, cov = np.zeros((n, 2), np.int32), np.zeros((n, 3)), np.zeros((n, 9))
+        if n:
+            self.L.ref_mapper_get_edges(self.h, _ip(ids), _dp(diff), _dp(cov))
+        return ids, diff, cov.reshape(n, 3, 3)
+
+    def running_count(self):
+        return self.L.ref_mapper_running_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.ref_mapper_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

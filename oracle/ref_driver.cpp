@@ -442,3 +442,202 @@ int ref_trace_line(int w, int hgt, int x0, int y0, int x1, int y1, int32_t* out_
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// The whole lesson6 front end: karto::Mapper::Process (Mapper.cpp:1999-2079) on a stream of scans, with the
+// reference's own MapperGraph / ScanManager / ScanMatchers.  The struct mirrors b2s_mapper_params (include/b200slam.h);
+// values are the ones STORED in the Mapper.  A ScanSolver can be plugged in as four C callbacks (the reference's own
+// plug-in interface, Mapper.h:825-891), which lets tests give both sides the same back end.
+extern "C" {
+
+struct ref_mapper_params {
+  int32_t use_scan_matching, use_scan_barycenter;
+  double minimum_time_interval, minimum_travel_distance, minimum_travel_heading;
+  int32_t scan_buffer_size, do_loop_closing;
+  double scan_buffer_maximum_scan_distance, link_match_minimum_response_fine, link_scan_maximum_distance,
+      loop_search_maximum_distance;
+  int32_t loop_match_minimum_chain_size, reserved;
+  double loop_match_maximum_variance_coarse, loop_match_minimum_response_coarse, loop_match_minimum_response_fine;
+  ref_matcher_params sequential, loop;
+};
+
+struct ref_scan_solver {
+  void* user;
+  void (*add_node)(void*, int32_t, const double*);
+  void (*add_constraint)(void*, int32_t, int32_t, const double*, const double*);
+  int32_t (*compute)(void*, int32_t, int32_t*, double*);
+  void (*clear)(void*);
+};
+
+}  // extern "C"
+
+namespace {
+
+struct CallbackSolver : ScanSolver {
+  ref_scan_solver cb;
+  IdPoseVector corrections;
+  int n_nodes = 0;
+  void Compute() override {
+    corrections.clear();
+    std::vector<int32_t> ids(n_nodes);
+    std::vector<double> poses(3 * static_cast<size_t>(n_nodes));
+    int n = cb.compute(cb.user, n_nodes, ids.data(), poses.data());
+    for (int i = 0; i < n; i++) corrections.push_back(std::make_pair(ids[i], Pose2(poses[3 * i], poses[3 * i + 1], poses[3 * i + 2])));
+  }
+  const IdPoseVector& GetCorrections() const override { return corrections; }
+  void AddNode(Vertex<LocalizedRangeScan>* v) override {
+    Pose2 p = v->GetObject()->GetCorrectedPose();  // as lesson6/src/spa_solver/spa_solver.cc:65-70
+    double c[3] = {p.GetX(), p.GetY(), p.GetHeading()};
+    n_nodes++;
+    cb.add_node(cb.user, v->GetObject()->GetUniqueId(), c);
+  }
+  void AddConstraint(Edge<LocalizedRangeScan>* e) override {  // as spa_solver.cc:72-93 (pose difference + covariance)
+    LinkInfo* li = (LinkInfo*)(e->GetLabel());
+    Pose2 d = li->GetPoseDifference();
+    double diff[3] = {d.GetX(), d.GetY(), d.GetHeading()}, cov[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) cov[3 * i + j] = li->GetCovariance()(i, j);
+    cb.add_constraint(cb.user, e->GetSource()->GetObject()->GetUniqueId(), e->GetTarget()->GetObject()->GetUniqueId(), diff, cov);
+  }
+  void Clear() override {
+    corrections.clear();
+    if (cb.clear) cb.clear(cb.user);
+  }
+};
+
+struct MapperSession {
+  Mapper* mapper = nullptr;
+  LaserRangeFinder* lrf = nullptr;
+  CallbackSolver* solver = nullptr;
+  Name name;
+  std::vector<LocalizedRangeScan*> all;  // every scan handed to Process (rejected ones too), for deletion
+};
+
+}  // namespace
+
+extern "C" {
+
+void* ref_mapper_create(const ref_mapper_params* p, const ref_laser_params* l) {
+  CoutSilencer quiet;
+  MapperSession* s = new MapperSession();
+  std::stringstream nm;
+  nm << "ref_mapper_laser_" << (g_session_counter++);
+  s->name = Name(nm.str());
+  s->lrf = LaserRangeFinder::CreateLaserRangeFinder(static_cast<LaserRangeFinderType>(l->type), s->name);
+  if (l->type == LaserRangeFinder_Custom) {
+    s->lrf->SetMinimumRange(l->min_range);
+    s->lrf->SetMaximumRange(l->max_range);
+    s->lrf->SetMinimumAngle(l->min_angle);
+    s->lrf->SetMaximumAngle(l->max_angle);
+    s->lrf->SetAngularResolution(l->angular_resolution);
+  }
+  s->lrf->SetRangeThreshold(l->range_threshold);
+  s->lrf->SetOffsetPose(Pose2(l->offset_pose[0], l->offset_pose[1], l->offset_pose[2]));
+  SensorManager::GetInstance()->RegisterSensor(s->lrf);
+  Mapper* m = s->mapper = new Mapper();
+  m->m_pUseScanMatching->SetValue(p->use_scan_matching != 0);
+  m->m_pUseScanBarycenter->SetValue(p->use_scan_barycenter != 0);
+  m->m_pMinimumTimeInterval->SetValue(p->minimum_time_interval);
+  m->m_pMinimumTravelDistance->SetValue(p->minimum_travel_distance);
+  m->m_pMinimumTravelHeading->SetValue(p->minimum_travel_heading);
+  m->m_pScanBufferSize->SetValue(p->scan_buffer_size);
+  m->m_pScanBufferMaximumScanDistance->SetValue(p->scan_buffer_maximum_scan_distance);
+  m->m_pLinkMatchMinimumResponseFine->SetValue(p->link_match_minimum_response_fine);
+  m->m_pLinkScanMaximumDistance->SetValue(p->link_scan_maximum_distance);
+  m->m_pLoopSearchMaximumDistance->SetValue(p->loop_search_maximum_distance);
+  m->m_pDoLoopClosing->SetValue(p->do_loop_closing != 0);
+  m->m_pLoopMatchMinimumChainSize->SetValue(p->loop_match_minimum_chain_size);
+  m->m_pLoopMatchMaximumVarianceCoarse->SetValue(p->loop_match_maximum_variance_coarse);
+  m->m_pLoopMatchMinimumResponseCoarse->SetValue(p->loop_match_minimum_response_coarse);
+  m->m_pLoopMatchMinimumResponseFine->SetValue(p->loop_match_minimum_response_fine);
+  m->m_pCorrelationSearchSpaceDimension->SetValue(p->sequential.search_size);
+  m->m_pCorrelationSearchSpaceResolution->SetValue(p->sequential.resolution);
+  m->m_pCorrelationSearchSpaceSmearDeviation->SetValue(p->sequential.smear_deviation);
+  m->m_pLoopSearchSpaceDimension->SetValue(p->loop.search_size);
+  m->m_pLoopSearchSpaceResolution->SetValue(p->loop.resolution);
+  m->m_pLoopSearchSpaceSmearDeviation->SetValue(p->loop.smear_deviation);
+  m->m_pDistanceVariancePenalty->SetValue(p->sequential.distance_variance_penalty);
+  m->m_pAngleVariancePenalty->SetValue(p->sequential.angle_variance_penalty);
+  m->m_pFineSearchAngleOffset->SetValue(p->sequential.fine_search_angle_offset);
+  m->m_pCoarseSearchAngleOffset->SetValue(p->sequential.coarse_search_angle_offset);
+  m->m_pCoarseAngleResolution->SetValue(p->sequential.coarse_angle_resolution);
+  m->m_pMinimumAnglePenalty->SetValue(p->sequential.minimum_angle_penalty);
+  m->m_pMinimumDistancePenalty->SetValue(p->sequential.minimum_distance_penalty);
+  m->m_pUseResponseExpansion->SetValue(p->sequential.use_response_expansion != 0);
+  return s;
+}
+
+void ref_mapper_set_solver(void* h, const ref_scan_solver* cb) {
+  MapperSession* s = static_cast<MapperSession*>(h);
+  s->solver = new CallbackSolver();
+  s->solver->cb = *cb;
+  s->mapper->SetScanSolver(s->solver);
+}
+
+void ref_mapper_destroy(void* h) {
+  CoutSilencer quiet;
+  MapperSession* s = static_cast<MapperSession*>(h);
+  if (!s) return;
+  delete s->mapper;
+  for (auto* p : s->all) delete p;
+  delete s->solver;
+  SensorManager::GetInstance()->UnregisterSensor(s->lrf);
+  delete s->lrf;
+  delete s;
+}
+
+// what karto_slam.cc:437-475 does per LaserScan: build the LocalizedRangeScan, set both poses from odometry, Process
+int ref_mapper_process(void* h, const double* ranges, int n, const double* odom, double time, double* out_corrected) {
+  CoutSilencer quiet;
+  MapperSession* s = static_cast<MapperSession*>(h);
+  std::vector<kt_double> r(ranges, ranges + n);
+  LocalizedRangeScan* scan = new LocalizedRangeScan(s->name, r);
+  scan->SetOdometricPose(Pose2(odom[0], odom[1], odom[2]));
+  scan->SetCorrectedPose(Pose2(odom[0], odom[1], odom[2]));
+  scan->SetTime(time);
+  s->all.push_back(scan);
+  bool ok = s->mapper->Process(scan);
+  Pose2 c = scan->GetCorrectedPose();
+  if (out_corrected) { out_corrected[0] = c.GetX(); out_corrected[1] = c.GetY(); out_corrected[2] = c.GetHeading(); }
+  return ok ? 1 : 0;
+}
+
+int ref_mapper_scan_count(void* h) {
+  MapperSession* s = static_cast<MapperSession*>(h);
+  return s->mapper->m_Initialized ? static_cast<int>(s->mapper->GetAllProcessedScans().size()) : 0;
+}
+
+void ref_mapper_get_poses(void* h, double* out) {
+  MapperSession* s = static_cast<MapperSession*>(h);
+  LocalizedRangeScanVector v = s->mapper->GetAllProcessedScans();
+  for (size_t i = 0; i < v.size(); i++) {
+    Pose2 c = v[i]->GetCorrectedPose();
+    out[3 * i] = c.GetX(); out[3 * i + 1] = c.GetY(); out[3 * i + 2] = c.GetHeading();
+  }
+}
+
+int ref_mapper_edge_count(void* h) {
+  MapperSession* s = static_cast<MapperSession*>(h);
+  return s->mapper->m_Initialized ? static_cast<int>(s->mapper->GetGraph()->GetEdges().size()) : 0;
+}
+
+void ref_mapper_get_edges(void* h, int32_t* ids, double* diff, double* cov) {
+  MapperSession* s = static_cast<MapperSession*>(h);
+  const std::vector<Edge<LocalizedRangeScan>*>& e = s->mapper->GetGraph()->GetEdges();
+  for (size_t i = 0; i < e.size(); i++) {
+    LinkInfo* li = (LinkInfo*)(e[i]->GetLabel());
+    ids[2 * i] = e[i]->GetSource()->GetObject()->GetUniqueId();
+    ids[2 * i + 1] = e[i]->GetTarget()->GetObject()->GetUniqueId();
+    Pose2 d = li->GetPoseDifference();
+    diff[3 * i] = d.GetX(); diff[3 * i + 1] = d.GetY(); diff[3 * i + 2] = d.GetHeading();
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) cov[9 * i + 3 * r + c] = li->GetCovariance()(r, c);
+  }
+}
+
+int ref_mapper_running_count(void* h) {
+  MapperSession* s = static_cast<MapperSession*>(h);
+  return static_cast<int>(s->mapper->m_pMapperSensorManager->GetRunningScans(s->name).size());
+}
+
+}  // extern "C"

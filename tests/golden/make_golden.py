@@ -197,8 +197,27 @@ def hector_case():
     np.savez_compressed(os.path.join(HERE, "hector.npz"), **out)
 
 
+def mapper_case():
+    """The whole lesson6 front end: karto::Mapper::Process over a seeded 150-scan, 3-lap workload (tests/mapper_cases.py);
+    poses and graph edges as the reference leaves them (no back end)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mapper_cases as mc
+    seed, n = 3, 150
+    laser, prm, true, odom, ranges = mc.workload(pkg, seed, n)
+    r = ref.RefMapper(prm, laser)
+    flags, _ = mc.run(r, odom, ranges)
+    ids, diff, cov = r.edges()
+    np.savez_compressed(os.path.join(HERE, "karto_mapper.npz"), seed=np.int32(seed), n=np.int32(n), flags=flags,
+                        poses=r.poses(), edge_ids=ids, edge_diff=diff, edge_cov=cov, ranges_sample=ranges[::17])
+    r.close()
+
+
 if __name__ == "__main__":
     assert ref.available(), "run `make -C oracle ref` first"
+    if sys.argv[1:] == ["mapper"]:
+        mapper_case()
+        print("karto_mapper.npz", os.path.getsize(os.path.join(HERE, "karto_mapper.npz")))
+        sys.exit(0)
     if sys.argv[1:] == ["hector"]:
         hector_case()
         print("hector.npz", os.path.getsize(os.path.join(HERE, "hector.npz")))
@@ -209,6 +228,7 @@ if __name__ == "__main__":
     trace_lines()
     gmapping_case()
     hector_case()
+    mapper_case()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

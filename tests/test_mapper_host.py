@@ -1,0 +1,142 @@
+"""CPU tests of the mapper's HOST logic (karto_mapper.cu: key-frame gate, running window, graph edges, near chains,
+loop-closure candidates, ScanSolver plug-in) against the UNMODIFIED reference karto::Mapper (oracle/_ref/libkarto_ref.so).
+No GPU here: the product's matcher plug-in point is served by the CPU restatement's MatchScan (tests only), the
+reference uses its own ScanMatcher — so every difference would come from the graph / pose logic under test."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port, ref
+import mapper_cases as mc
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+live = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libkarto_ref.so not built")
+
+
+def compare(r, m, tol=1e-9):
+    pr, pm = r.poses(), m.poses()
+    assert pr.shape == pm.shape and np.abs(pr - pm).max() <= tol
+    (ir, dr, cr), (im, dm, cm) = r.edges(), m.edges()
+    assert np.array_equal(ir, im), "graph edges differ"
+    assert np.abs(dr - dm).max() <= tol and np.abs(cr - cm).max() <= tol
+
+
+@live
+def test_mapper_matches_reference_without_back_end(pkg):
+    """150 scans, 3 laps: sequential matches against the running window, near-chain links (batched), loop closures
+    accepted without a solver (the lesson6 indoor yaml: use_back_end false)."""
+    MP, abi = pkg.load("mapper"), pkg.abi
+    laser, prm, true, odom, ranges = mc.workload(pkg, 3, 150)
+    al = abi.laser_from(laser)
+    r = ref.RefMapper(prm, laser)
+    m = MP.Mapper(prm, al, match_fn=port.mapper_match_hook(prm, al))
+    fr, cr = mc.run(r, odom, ranges)
+    fm, cm = mc.run(m, odom, ranges)
+    assert np.array_equal(fr, fm) and fr.all() and np.abs(cr - cm).max() <= 1e-9
+    compare(r, m)
+    st = m.stats()
+    assert st["loops_closed"] >= 1 and st["running_scans"] == r.running_count() == 20
+    assert st["batches"] < st["match_calls"]  # near chains / candidates went out batched
+    ids = m.edges()[0]
+    assert (ids[:, 1] - ids[:, 0] > 30).any()  # links across laps exist
+    assert np.abs(m.poses()[:, :2] - true[:, :2]).max() < np.abs(odom[:, :2] - true[:, :2]).max()
+    r.close(), m.close()
+
+
+@live
+def test_mapper_with_scan_solver_plugin(pkg):
+    """The same back end (the library's pose-graph optimiser, one instance per side) plugged into the reference Mapper
+    through karto::ScanSolver and into ours through b2s_scan_solver: corrected poses agree after every loop closure."""
+    MP, abi = pkg.load("mapper"), pkg.abi
+    laser, prm, true, odom, ranges = mc.workload(pkg, 5, 130, drift=(0.01, 0.008, 0.004))
+    al = abi.laser_from(laser)
+    g1, g2 = MP.PoseGraph(), MP.PoseGraph()
+    r = ref.RefMapper(prm, laser)
+    r.set_scan_solver(g1.as_scan_solver())
+    m = MP.Mapper(prm, al, match_fn=port.mapper_match_hook(prm, al))
+    m.set_scan_solver(g2.as_scan_solver())
+    for i in range(len(ranges)):
+        a, b = r.process(ranges[i], odom[i], 0.1 * i), m.process(ranges[i], odom[i], 0.1 * i)
+        assert a[0] == b[0] and np.abs(a[1] - b[1]).max() <= 1e-9, i
+    compare(r, m)
+    s1, s2 = g1.stats(), g2.stats()
+    assert s1 == s2 and s2["constraints"] == len(m.edges()[0]) and s2["chi2_after"] < 0.5 * s2["chi2_before"]
+    assert m.stats()["loops_closed"] >= 1
+    assert np.abs(m.poses()[:, :2] - true[:, :2]).max() < 0.5 * np.abs(odom[:, :2] - true[:, :2]).max()
+    r.close(), m.close()
+
+
+@live
+def test_mapper_key_frame_gate(pkg):
+    """Mapper::HasMovedEnough (Mapper.cpp:2087-2119): travel distance, heading and time interval."""
+    MP, abi = pkg.load("mapper"), pkg.abi
+    laser, prm, true, odom, ranges = mc.workload(pkg, 7, 12)
+    prm.minimum_time_interval = 5.0
+    al = abi.laser_from(laser)
+    r = ref.RefMapper(prm, laser)
+    m = MP.Mapper(prm, al, match_fn=port.mapper_match_hook(prm, al))
+    seq = [(0, 0.0), (0, 1.0), (1, 2.0), (1, 3.0), (1, 9.0), (2, 9.5)]  # (pose index, time): repeats are rejected
+    tiny = odom[2] + np.array([0.05, 0.0, 0.02])
+    for k, (i, t) in enumerate(seq):
+        a, b = r.process(ranges[i], odom[i], t), m.process(ranges[i], odom[i], t)
+        assert a[0] == b[0] and np.abs(a[1] - b[1]).max() <= 1e-9, k
+    a, b = r.process(ranges[2], tiny, 10.0), m.process(ranges[2], tiny, 10.0)  # moved 5 cm / 0.02 rad: rejected
+    assert a[0] == b[0] == False and np.abs(a[1] - b[1]).max() <= 1e-9
+    turn = odom[2] + np.array([0.0, 0.0, 0.2])
+    a, b = r.process(ranges[2], turn, 10.5), m.process(ranges[2], turn, 10.5)  # turned 0.2 rad >= 10 deg: accepted
+    assert a[0] == b[0] == True
+    assert len(m.poses()) == len(r.poses()) == 5
+    compare(r, m)
+    r.close(), m.close()
+
+
+def test_mapper_golden(pkg):
+    """Poses and edges the reference Mapper produced for the seeded workload (tests/golden/make_golden.py mapper),
+    checked wherever the library loads — e.g. on the GPU box, where /root/reference does not exist."""
+    MP, abi = pkg.load("mapper"), pkg.abi
+    g = np.load(os.path.join(G, "karto_mapper.npz"))
+    laser, prm, true, odom, ranges = mc.workload(pkg, int(g["seed"]), int(g["n"]))
+    assert np.array_equal(ranges[::17], g["ranges_sample"]), "the synthetic workload changed: regenerate the golden file"
+    al = abi.laser_from(laser)
+    m = MP.Mapper(prm, al, match_fn=port.mapper_match_hook(prm, al))
+    flags, _ = mc.run(m, odom, ranges)
+    assert np.array_equal(flags, g["flags"])
+    assert np.abs(m.poses() - g["poses"]).max() <= 1e-9
+    ids, diff, cov = m.edges()
+    assert np.array_equal(ids, g["edge_ids"]) and np.abs(diff - g["edge_diff"]).max() <= 1e-9
+    assert np.abs(cov - g["edge_cov"]).max() <= 1e-9
+    m.close()
+
+
+def test_pose_graph_solver_recovers_ring(pkg):
+    """The back-end optimiser on its own: a ring of 40 poses with exact relative constraints and a corrupted initial
+    guess converges back to the ring (chi^2 -> 0) with the first node fixed."""
+    import ctypes as C
+    MP = pkg.load("mapper")
+    n = 40
+    th = np.arange(n) * 2 * np.pi / n
+    truth = np.stack([3 * np.cos(th), 3 * np.sin(th), (th + np.pi / 2 + np.pi) % (2 * np.pi) - np.pi], 1)
+    rng = np.random.default_rng(1)
+    guess = truth + np.concatenate([np.zeros((1, 3)), rng.normal(0, [0.2, 0.2, 0.1], (n - 1, 3))])
+    g = MP.PoseGraph()
+    s = g.as_scan_solver()
+    for i in range(n):
+        s.add_node(s.user, i, guess[i].ctypes.data_as(C.POINTER(C.c_double)))
+    cov = (np.eye(3) * [1e-3, 1e-3, 1e-4]).ravel()
+    for i in range(n):
+        for j in ((i + 1) % n, (i + 3) % n):
+            a, b = truth[i], truth[j]
+            c, sn = np.cos(a[2]), np.sin(a[2])
+            d = np.array([c * (b[0] - a[0]) + sn * (b[1] - a[1]), -sn * (b[0] - a[0]) + c * (b[1] - a[1]),
+                          (b[2] - a[2] + np.pi) % (2 * np.pi) - np.pi])
+            s.add_constraint(s.user, i, j, d.ctypes.data_as(C.POINTER(C.c_double)), cov.ctypes.data_as(C.POINTER(C.c_double)))
+    ids, poses = np.zeros(n, np.int32), np.zeros((n, 3))
+    got = s.compute(s.user, n, ids.ctypes.data_as(C.POINTER(C.c_int32)), poses.ctypes.data_as(C.POINTER(C.c_double)))
+    st = g.stats()
+    assert got == n and list(ids) == list(range(n))
+    assert st["chi2_after"] < 1e-12 * max(1.0, st["chi2_before"]) and st["chi2_before"] > 100
+    d = poses - truth
+    d[:, 2] = (d[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(d).max() < 1e-6
+    g.close()
