@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "b200slam.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(", text)))
+    # function declarations only: `b2s_status (*callback)(...)` typedefs and struct members are not symbols
+    return sorted(set(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\((?!\s*\*)", text)))
 
 
 def test_all_declared_symbols_exported(pkg):
