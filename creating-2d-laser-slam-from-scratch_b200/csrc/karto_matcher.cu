@@ -1425,7 +1425,7 @@ static b2s_status build_sat(b2s_matcher *m) {
   const size_t sm = sizeof(uint32_t) * (size_t)(m->sbx + 1) * (m->sby + 1);
   m->sat_valid = false;
   if (sm > 200 * 1024 || (m->g.width_step % 4) != 0 || (long long)m->sbx * m->sby >= 65535) return B2S_OK;  // no skipping
-  if (sm > 48 * 1024) B2S_CUDA_CHECK(cudaFuncSetAttribute(k_grid_sat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  if (sm > 16 * 1024) B2S_CUDA_CHECK(cudaFuncSetAttribute(k_grid_sat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   k_grid_sat<<<m->batch, 256, sm, m->stream>>>(m->d_grids, m->grid_pitch, m->g.width_step, m->g.height, m->sbx, m->sby, m->d_sat);
   B2S_CUDA_CHECK(cudaGetLastError());
   m->sat_valid = true;
@@ -1614,7 +1614,7 @@ b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_
     k_scan_points<<<(unsigned)need, 256, 0, m->stream>>>(m->d_base_ranges, m->d_base_poses, m->l, nullptr, m->d_base_pts, nullptr);
     if (!m->smear_degenerate) {
       size_t smem = n * (2 * sizeof(double) + 1) + 16;
-      if (smem > 48 * 1024)
+      if (smem > 16 * 1024)
         B2S_CUDA_CHECK(cudaFuncSetAttribute(k_add_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_add_scan<<<(unsigned)need, 128, smem, m->stream>>>(m->d_base_pts, m->d_sensor, m->d_grid_off, m->d_grids,
                                                            m->grid_pitch, m->d_kernel, m->g, scale, (int)n, n_base);
@@ -1994,7 +1994,7 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     const size_t sat_bytes = skip_empty ? sizeof(uint16_t) * (size_t)((((m->sbx + 1) * (m->sby + 1)) + 7) & ~7) : 0;
     const size_t osm = (((size_t)n * OFF_SMEM_PER_BEAM + 15) & ~(size_t)15) + sat_bytes + 64;
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_stats, 0, sizeof(unsigned long long), m->stream));
-    if (osm > 48 * 1024)
+    if (osm > 16 * 1024)  // static + dynamic shared memory together must stay under the 48 KB default: opt in early
       B2S_CUDA_CHECK(cudaFuncSetAttribute(k_offsets_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
     k_offsets_sorted<<<B * ((na + OFF_CHUNK - 1) / OFF_CHUNK), 256, osm, m->stream>>>(
         m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases, m->d_flags, s->angle_offset, s->angle_res, na, n,
