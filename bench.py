@@ -405,6 +405,50 @@ def bench_k2(pkg, local, quick=False):
         m5.close()
     except Exception as e:
         out["k1_extras_error"] = repr(e)
+    # --- lesson6 front end: karto::Mapper::Process per key frame through b2s_mapper_process with the
+    #     shipped indoor yaml (lesson6/config/mapper_params.yaml: 0.3 m / 0.01 m sequential window on a 2431^2 grid,
+    #     110-scan running buffer, 10 m / 0.05 m loop window, response expansion on); near chains / loop candidates batched
+    try:
+        MPm = pkg.load("mapper")
+        lm = synth.Laser(range_threshold=12.0)
+        n_map = 120 if quick else 400
+        _, tru, odo, rng_m = synth.make_loop_trajectory(17, n_map, lm, radius=2.0, step=0.25)
+        yaml = dict(scan_buffer_size=110, scan_buffer_maximum_scan_distance=100.0, link_match_minimum_response_fine=0.1,
+                    link_scan_maximum_distance=1.5, loop_search_maximum_distance=10.0, loop_match_minimum_chain_size=5,
+                    loop_match_maximum_variance_coarse=9.0, loop_match_minimum_response_coarse=0.35,
+                    loop_match_minimum_response_fine=0.45, minimum_travel_heading=0.174, loop_search_size=10.0,
+                    both_distance_variance_penalty=0.25, both_angle_variance_penalty=0.01,
+                    both_fine_search_angle_offset=0.00349, both_coarse_search_angle_offset=0.349,
+                    both_coarse_angle_resolution=0.0349, both_use_response_expansion=1)
+        prm = MPm.default_params(12.0, **yaml)
+        mp_ = MPm.Mapper(prm, abi.laser_from(lm), device=local)
+        mp_.process(rng_m[0], odo[0], 0.0)
+        mp_.process(rng_m[1], odo[1], 0.1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(2, n_map):
+            mp_.process(rng_m[i], odo[i], 0.1 * i)
+        dt = time.perf_counter() - t0
+        stm = mp_.stats()
+        out["karto_mapper_stream"] = {"key_frames": n_map - 2, "scans_per_s": (n_map - 2) / dt, "ms_per_scan": 1e3 * dt / (n_map - 2),
+                                      "match_scan_calls": stm["match_calls"], "device_batches": stm["batches"],
+                                      "loops_closed": stm["loops_closed"], "edges": int(len(mp_.edges()[0])),
+                                      "max_xy_err_m": float(np.abs(mp_.poses()[:, :2] - tru[:, :2]).max()),
+                                      "config": "lesson6/config/mapper_params.yaml (no back end), 1081 beams, range threshold 12 m"}
+        mp_.close()
+        from oracle import ref as _ref
+        if _ref.available(ndebug=True):
+            n_ref = min(n_map, 150)
+            rm = _ref.RefMapper(prm, lm, ndebug=True)
+            t0 = time.perf_counter()
+            for i in range(n_ref):
+                rm.process(rng_m[i], odo[i], 0.1 * i)
+            dt = time.perf_counter() - t0
+            rm.close()
+            out["karto_mapper_stream"]["cpu_reference"] = {"scans_per_s": n_ref / dt, "sample": f"first {n_ref} key frames of the same "
+                                                           "stream, karto::Mapper::Process, -O2 -DNDEBUG, 1 thread"}
+    except Exception as e:
+        out["karto_mapper_stream"] = {"error": repr(e)}
     # --- K3 (lesson3): batched PL-ICP, 1024 independent scan pairs with odometry-like motion
     P = pkg.load("plicp")
     nb = 256 if quick else 1024
