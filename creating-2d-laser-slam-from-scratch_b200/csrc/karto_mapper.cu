@@ -15,7 +15,10 @@
 // All pose arithmetic is double precision in the reference's operation order, so poses, link means and covariances agree
 // with the reference to the matcher's own tolerance (1e-9 in the parity tests) and every threshold decision is the same.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <list>
@@ -149,8 +152,14 @@ struct CudaBackend {  // the two ScanMatcher instances a Mapper owns, as b2s_mat
   b2s_matcher_params params[2]{};
   b2s_matcher *h[2] = {nullptr, nullptr};
   int cap_batch[2] = {0, 0}, cap_base[2] = {0, 0};
+  int min_base = 32;  // scan_buffer_size + 1: the sequential matcher's base set is the running window
   std::vector<double> base_r, base_p;
+  double t_pad = 0, t_match = 0, t_create = 0;  // seconds, reported at destroy when B2S_MAPPER_PROFILE is set
+  long n_create = 0, n_calls = 0;
   ~CudaBackend() {
+    if (std::getenv("B2S_MAPPER_PROFILE"))
+      std::fprintf(stderr, "[b2s_mapper] backend: %ld calls, pad-copy %.1f ms, match_scan_host %.1f ms, %ld handle (re)creations %.1f ms\n",
+                   n_calls, 1e3 * t_pad, 1e3 * t_match, n_create, 1e3 * t_create);
     for (auto *p : h)
       if (p) b2s_matcher_destroy(p);
   }
@@ -255,18 +264,27 @@ b2s_status cuda_match(void *user, int which, int batch, const double *ranges, co
                       int do_refine, b2s_match_result *results) {
   CudaBackend *c = static_cast<CudaBackend *>(user);
   const int N = c->laser.n_readings;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const auto t0 = now();
+  c->n_calls++;
   int max_base = 1;
   for (int b = 0; b < batch; b++) max_base = std::max(max_base, (int)n_base[b]);
   if (!c->h[which] || batch > c->cap_batch[which] || max_base > c->cap_base[which]) {
     if (c->h[which]) b2s_matcher_destroy(c->h[which]);
     c->h[which] = nullptr;
-    const int cb = std::max(std::max(batch, c->cap_batch[which]), 8);
-    const int cs = std::max(std::max(max_base, c->cap_base[which]) * 5 / 4, 32);
+    // (re)creating a handle costs tens of ms (device + pinned allocations): size it for the running window up front and
+    // double on growth so that a stream re-creates it a handful of times at most
+    const int cb = std::max(std::max(batch, c->cap_batch[which] * 2), 8);
+    const int cs = std::max(std::max(max_base, c->cap_base[which] * 2), c->min_base);
     b2s_status st = b2s_matcher_create(&c->params[which], &c->laser, c->device, cb, cs, nullptr, &c->h[which]);
     if (st) return st;
     c->cap_batch[which] = cb;
     c->cap_base[which] = cs;
+    c->n_create++;
+    c->t_create += secs(t0, now());
   }
+  const auto t1 = now();
   for (int b = 0; b < batch; b++)
     if (n_base[b] <= 0) B2S_FAIL(B2S_ERR_BAD_PARAMS, "mapper: MatchScan against an empty chain");
   c->base_r.resize((size_t)batch * max_base * N);
@@ -277,8 +295,12 @@ b2s_status cuda_match(void *user, int which, int batch, const double *ranges, co
       std::memcpy(&c->base_r[dst * N], base_ranges + src * N, sizeof(double) * N);
       std::memcpy(&c->base_p[dst * 3], base_poses + src * 3, sizeof(double) * 3);
     }
-  return b2s_matcher_match_scan_host(c->h[which], batch, ranges, poses, max_base, c->base_r.data(), c->base_p.data(),
-                                     do_penalize, do_refine, results);
+  const auto t2 = now();
+  const b2s_status st = b2s_matcher_match_scan_host(c->h[which], batch, ranges, poses, max_base, c->base_r.data(), c->base_p.data(),
+                                                    do_penalize, do_refine, results);
+  c->t_pad += secs(t1, t2);
+  c->t_match += secs(t2, now());
+  return st;
 }
 
 // ---- MapperGraph
@@ -659,6 +681,7 @@ b2s_status b2s_mapper_create(const b2s_mapper_params *params, const b2s_laser *l
   c->laser = *laser;
   c->params[0] = params->sequential;
   c->params[1] = params->loop;
+  c->min_base = std::max(32, params->scan_buffer_size + 1);
   st = b2s_mapper_create_with_matcher(params, laser, cuda_match, c, out);
   if (st) {
     delete c;

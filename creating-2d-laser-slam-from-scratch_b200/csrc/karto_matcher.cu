@@ -88,16 +88,18 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 
 // per-byte atomic max on a u8 array (no native byte atomics): CAS on the containing aligned word
-__device__ __forceinline__ void atomic_max_u8(uint8_t *base, int idx, uint32_t val) {
+// returns the byte's previous value
+__device__ __forceinline__ uint32_t atomic_max_u8(uint8_t *base, int idx, uint32_t val) {
   uint32_t *w = reinterpret_cast<uint32_t *>(base + (idx & ~3));
   uint32_t shift = (idx & 3) * 8;
   uint32_t v = val << shift;
   uint32_t old = *w, assumed;
   do {
-    if (((old >> shift) & 0xffu) >= val) return;
+    if (((old >> shift) & 0xffu) >= val) return (old >> shift) & 0xffu;
     assumed = old;
     old = atomicCAS(w, assumed, __vmaxu4(assumed, v));
   } while (assumed != old);
+  return (old >> shift) & 0xffu;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -177,71 +179,96 @@ __global__ void k_grid_offsets(const double *__restrict__ sensor, double *__rest
 
 // ----------------------------------------------------------------------------------------------
 // k_add_scan: ScanMatcher::AddScan (Mapper.cpp:716-748) for one (match, base scan) per block:
-// thread 0 runs the FindValidPoints state machine (Mapper.cpp:756-811) over points staged in shared memory,
+// the FindValidPoints state machine (Mapper.cpp:756-811) runs over points staged in shared memory (see below),
 // then all threads rasterise the valid points and max-stamp the smear kernel (Mapper.h:971-1005).
 // The result is a per-byte maximum, hence independent of the order in which points / scans are applied,
 // EXCEPT when an off-centre kernel value equals 100 (sigma ~ 10*res); that case takes k_add_scans_seq.
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void find_valid_points(const double *px, const double *py, int n, double vx, double vy,
-                                                  uint8_t *valid) {
-  const double min_sq = 0.1 * 0.1;
-  int trailing = 0;
-  double fx = 0.0, fy = 0.0;
-  bool first_time = true;
-  for (int it = 0; it < n; it++) {
-    double cx = px[it], cy = py[it];
-    if (first_time && !isnan(cx) && !isnan(cy)) {
-      fx = cx; fy = cy;
-      first_time = false;
-    }
-    double dx = fx - cx, dy = fy - cy;
-    if (dx * dx + dy * dy > min_sq) {
-      double a = vy - fy;
-      double bb = fx - vx;
-      double c = fy * vx - fx * vy;
-      double ss = cx * a + cy * bb + c;
-      fx = cx; fy = cy;
-      if (ss < 0.0) {
-        trailing = it;
-      } else {
-        for (; trailing != it; ++trailing) valid[trailing] = 1;
-      }
-    }
-  }
-}
-
+// The state machine in parallel.  Its only carried state is the "first point of the current segment" f and the
+// trailing index, and after every segment boundary (a point farther than 0.1 m from f) trailing == that boundary's
+// index whichever branch ran.  Hence: (1) next[i] = first j > i with |p_i - p_j|^2 > 0.01 (same expression, so NaN /
+// inf readings behave as in the loop) is computed for all i at once; (2) one thread follows f -> next[f] from the first
+// non-NaN point — a chain of ~n/5 dependent shared-memory loads instead of n iterations of fp64 arithmetic; (3) for
+// boundary k (f = b[k-1], c = b[k]) the side test is evaluated in parallel and the points [b[k-1]', b[k]) — from index 0
+// for the first boundary — are valid iff ss >= 0 (i.e. !(ss < 0), NaN included).  Points after the last boundary are
+// never pushed (the reference drops the tail).  Bit-identical flags to the sequential loop (kept verbatim in k_add_scans_seq).
 __global__ void k_add_scan(const double *__restrict__ base_pts, const double *__restrict__ sensor,
                            const double *__restrict__ grid_off, uint8_t *__restrict__ grids, size_t grid_pitch,
                            const uint8_t *__restrict__ kernel, b2s_grid_info g, double scale, int n, int n_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *px = reinterpret_cast<double *>(smem_raw);
   double *py = px + n;
-  uint8_t *valid = reinterpret_cast<uint8_t *>(py + n);
+  int *nxt = reinterpret_cast<int *>(py + n);  // next[i]; reused as the boundary list b[k]
+  int *bnd = nxt + n;
+  uint8_t *valid = reinterpret_cast<uint8_t *>(bnd + n + 1);
+  __shared__ int n_bnd, first_pt;
   const int bs = blockIdx.x;  // b * n_base + s
   const int b = bs / n_base;
+  if (threadIdx.x == 0) first_pt = n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     px[i] = base_pts[((size_t)bs * n + i) * 2];
     py[i] = base_pts[((size_t)bs * n + i) * 2 + 1];
     valid[i] = 0;
   }
   __syncthreads();
-  if (threadIdx.x == 0) find_valid_points(px, py, n, sensor[3 * b], sensor[3 * b + 1], valid);
+  const double min_sq = 0.1 * 0.1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double fx = px[i], fy = py[i];
+    if (!isnan(fx) && !isnan(fy)) atomicMin(&first_pt, i);
+    int j = i + 1;
+    for (; j < n; j++) {
+      const double dx = fx - px[j], dy = fy - py[j];
+      if (dx * dx + dy * dy > min_sq) break;
+    }
+    nxt[i] = j;
+  }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    int k = 0;
+    for (int f = first_pt; f < n; f = nxt[f]) bnd[k++] = f;
+    n_bnd = k;
+  }
+  __syncthreads();
+  const double vx = sensor[3 * b], vy = sensor[3 * b + 1];
+  for (int k = 1 + threadIdx.x; k < n_bnd; k += blockDim.x) {
+    const int f = bnd[k - 1], c = bnd[k];
+    const double fx = px[f], fy = py[f], cx = px[c], cy = py[c];
+    const double a = vy - fy;
+    const double bb = fx - vx;
+    const double cc = fy * vx - fx * vy;
+    const double ss = cx * a + cy * bb + cc;
+    if (!(ss < 0.0))
+      for (int t = (k == 1 ? 0 : f); t < c; t++) valid[t] = 1;
+  }
+  __syncthreads();
+  // Rasterise + smear.  The result is max over occupied cells of the kernel stamped around them, and a cell holds 100
+  // only as the centre of some point (no off-centre kernel value reaches 100 on this path), so each occupied cell is
+  // stamped ONCE, by whichever thread raises its centre byte to 100 (running-window base scans hit the same walls many
+  // times over).  Winners are queued in shared memory and stamped a warp at a time, lanes over the kernel cells.
   const double ox = grid_off[2 * b], oy = grid_off[2 * b + 1];
   uint8_t *grid = grids + (size_t)b * grid_pitch;
-  const int half = g.kernel_size / 2;
+  const int half = g.kernel_size / 2, ksz = g.kernel_size * g.kernel_size;
+  int *win = nxt;  // the chain arrays are free again
+  if (threadIdx.x == 0) n_bnd = 0;
+  __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     if (!valid[i]) continue;
     double gxd = kround((px[i] - ox) * scale);
     double gyd = kround((py[i] - oy) * scale);
     // IsUpTo on static_cast<int>: non-finite / out-of-int-range values are rejected
     if (!(gxd >= 0.0 && gxd < (double)g.roi_w) || !(gyd >= 0.0 && gyd < (double)g.roi_h)) continue;
-    int gx = (int)gxd + g.roi_x, gy = (int)gyd + g.roi_y;
-    for (int j = -half; j <= half; j++)
-      for (int k = -half; k <= half; k++) {
-        uint32_t kv = kernel[(k + half) + g.kernel_size * (j + half)];
-        if (kv) atomic_max_u8(grid, (gx + k) + (gy + j) * g.width_step, kv);
-      }
+    const int idx = ((int)gxd + g.roi_x) + ((int)gyd + g.roi_y) * g.width_step;
+    if (atomic_max_u8(grid, idx, GRID_OCCUPIED) != GRID_OCCUPIED) win[atomicAdd(&n_bnd, 1)] = idx;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, n_win = n_bnd;
+  for (int w = warp; w < n_win; w += nwarps) {
+    const int idx = win[w];
+    for (int c = lane; c < ksz; c += 32) {
+      const int j = c / g.kernel_size - half, k = c % g.kernel_size - half;
+      const uint32_t kv = kernel[c];
+      if (kv && (j | k)) atomic_max_u8(grid, idx + k + j * g.width_step, kv);
+    }
   }
 }
 
@@ -1613,10 +1640,10 @@ b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_
     B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_base_poses, base_poses, sizeof(double) * need * 3, cudaMemcpyHostToDevice, m->stream));
     k_scan_points<<<(unsigned)need, 256, 0, m->stream>>>(m->d_base_ranges, m->d_base_poses, m->l, nullptr, m->d_base_pts, nullptr);
     if (!m->smear_degenerate) {
-      size_t smem = n * (2 * sizeof(double) + 1) + 16;
+      size_t smem = n * (2 * sizeof(double) + 2 * sizeof(int) + 1) + sizeof(int) + 16;
       if (smem > 16 * 1024)
         B2S_CUDA_CHECK(cudaFuncSetAttribute(k_add_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_add_scan<<<(unsigned)need, 128, smem, m->stream>>>(m->d_base_pts, m->d_sensor, m->d_grid_off, m->d_grids,
+      k_add_scan<<<(unsigned)need, 256, smem, m->stream>>>(m->d_base_pts, m->d_sensor, m->d_grid_off, m->d_grids,
                                                            m->grid_pitch, m->d_kernel, m->g, scale, (int)n, n_base);
     } else {
       uint8_t *scratch = nullptr;
