@@ -394,6 +394,34 @@ b2s_status b2s_hector_slam_copy_level_ros(b2s_hector_slam *p, int level, int8_t 
  * out[3] / out[4] = ms of the last match / update kernels */
 b2s_status b2s_hector_slam_stats(b2s_hector_slam *p, double out[5]);
 
+/* ---------------------------------------------------------------- ROS-shaped input adapters (host only)
+ * The wire formats either side of the path: sensor_msgs/LaserScan in (here), nav_msgs/OccupancyGrid payloads out
+ * (b2s_occ_grid_copy_ros, b2s_hector_map_copy_ros / b2s_hector_slam_copy_level_ros, b2s_gmap_copy_ros).  ROS itself is
+ * out of scope; these are the conversions the lesson nodes perform on the message fields. */
+typedef struct b2s_laser_scan_msg { /* the sensor_msgs/LaserScan fields the nodes read */
+  float angle_min, angle_max, angle_increment, range_min, range_max;
+  int32_t n_ranges;
+  const float *ranges;
+} b2s_laser_scan_msg;
+/* SlamKarto::getLaser (lesson6/src/karto_slam.cc:323-395): the Custom LaserRangeFinder made from the first scan —
+ * angles / ranges from the message, offset = laser pose in base_link (x, y, yaw), range threshold clipped into
+ * [range_min, range_max] (Karto.h:3778-3787), n_readings = Round((max - min) / resolution) WITHOUT + 1
+ * (LaserRangeFinder::Update, Karto.h:4152-4161).  Returns B2S_ERR_BAD_PARAMS if the message carries a different
+ * number of ranges than that (LaserRangeFinder::Validate would reject every scan). */
+b2s_status b2s_ros_karto_laser(const b2s_laser_scan_msg *scan, const double laser_pose_in_base[3], double use_scan_range,
+                               b2s_laser *out);
+/* SlamKarto::addScan (karto_slam.cc:407-434): float32 ranges -> kt_double readings, in reverse order for a laser
+ * mounted upside-down (lasers_inverted_) */
+b2s_status b2s_ros_karto_readings(const b2s_laser_scan_msg *scan, int inverted, double *out_readings);
+/* HectorMappingRos::rosPointCloudToDataContainer (lesson4/src/hector_mapping/hector_slam.cc:320-362): laser-frame points
+ * ([n][3] float x, y, z as laser_geometry projected them) -> DataContainer entries in map-cell units.  laser_in_base =
+ * (x, y, z, yaw) of the laser in base_link.  Filters: squared distance in (min_dist^2, max_dist^2), not behind the robot
+ * within 0.5 m^2, not beyond use_max_scan_range, height window (z_min, z_max).  out_points [n][2] (capacity n),
+ * out_origo[2] = laser position * scale_to_map.  Returns the number of points kept in *out_n. */
+b2s_status b2s_ros_hector_points(const float *points_xyz, int n, const float laser_in_base[4], float scale_to_map,
+                                 float min_dist, float max_dist, double use_max_scan_range, float z_min, float z_max,
+                                 float *out_points, float out_origo[2], int32_t *out_n);
+
 /* ---------------------------------------------------------------- K2b: GMapping hit/visit map */
 
 typedef struct b2s_gmap b2s_gmap; /* opaque: replaces GMapping::ScanMatcherMap (gmapping.cc:135) */
