@@ -154,12 +154,14 @@ struct CudaBackend {  // the two ScanMatcher instances a Mapper owns, as b2s_mat
   int cap_batch[2] = {0, 0}, cap_base[2] = {0, 0};
   int min_base = 32;  // scan_buffer_size + 1: the sequential matcher's base set is the running window
   std::vector<double> base_r, base_p;
-  double t_pad = 0, t_match = 0, t_create = 0;  // seconds, reported at destroy when B2S_MAPPER_PROFILE is set
+  double t_pad = 0, t_match = 0, t_create = 0, t_add = 0, t_sweeps = 0;  // seconds, reported at destroy when B2S_MAPPER_PROFILE is set
+  bool profile = std::getenv("B2S_MAPPER_PROFILE") != nullptr;
   long n_create = 0, n_calls = 0;
   ~CudaBackend() {
-    if (std::getenv("B2S_MAPPER_PROFILE"))
-      std::fprintf(stderr, "[b2s_mapper] backend: %ld calls, pad-copy %.1f ms, match_scan_host %.1f ms, %ld handle (re)creations %.1f ms\n",
-                   n_calls, 1e3 * t_pad, 1e3 * t_match, n_create, 1e3 * t_create);
+    if (profile)
+      std::fprintf(stderr, "[b2s_mapper] backend: %ld calls, pad-copy %.1f ms, match %.1f ms (upload + rasterise %.1f, sweeps + results %.1f), "
+                           "%ld handle (re)creations %.1f ms\n",
+                   n_calls, 1e3 * t_pad, 1e3 * t_match, 1e3 * t_add, 1e3 * t_sweeps, n_create, 1e3 * t_create);
     for (auto *p : h)
       if (p) b2s_matcher_destroy(p);
   }
@@ -296,8 +298,19 @@ b2s_status cuda_match(void *user, int which, int batch, const double *ranges, co
       std::memcpy(&c->base_p[dst * 3], base_poses + src * 3, sizeof(double) * 3);
     }
   const auto t2 = now();
-  const b2s_status st = b2s_matcher_match_scan_host(c->h[which], batch, ranges, poses, max_base, c->base_r.data(), c->base_p.data(),
-                                                    do_penalize, do_refine, results);
+  b2s_status st;
+  if (c->profile) {  // B2S_MAPPER_PROFILE: the three stages separately, with a stream sync after each
+    st = b2s_matcher_set_scans(c->h[which], batch, ranges, poses);
+    if (!st) st = b2s_matcher_add_scans(c->h[which], max_base, c->base_r.data(), c->base_p.data());
+    if (!st) st = b2s_matcher_sync(c->h[which]);
+    const auto t3 = now();
+    if (!st) st = b2s_matcher_match_scan(c->h[which], do_penalize, do_refine, results);
+    c->t_add += secs(t2, t3);
+    c->t_sweeps += secs(t3, now());
+  } else {
+    st = b2s_matcher_match_scan_host(c->h[which], batch, ranges, poses, max_base, c->base_r.data(), c->base_p.data(),
+                                     do_penalize, do_refine, results);
+  }
   c->t_pad += secs(t1, t2);
   c->t_match += secs(t2, now());
   return st;

@@ -263,7 +263,7 @@ b2s_status b2s_mapper_get_edges(const b2s_mapper *m, int32_t *ids, double *pose_
 b2s_status b2s_mapper_stats(const b2s_mapper *m, double out[5]);
 
 /* ---------------------------------------------------------------- back end: a ScanSolver for the mapper (host only)
- * the reference's back ends (sparse bundle adjustment / g2o / Ceres / GTSAM, lesson6/src/*_solver)
+ * the reference's back ends (sparse bundle adjustment / g2o / Ceres / GTSAM, lesson6/src/<name>_solver)
  * need Eigen + SuiteSparse and stay on the CPU in every BASELINE config.  This is a small dependency-free 2-D pose-graph
  * optimiser with the same role: nodes = scan poses, constraints = LinkInfo pose differences weighted by the inverse
  * covariance (lesson6/src/spa_solver/spa_solver.cc:65-93), Levenberg-Marquardt outer loop, block-Jacobi preconditioned
