@@ -247,7 +247,7 @@ __global__ void k_add_scan(const double *__restrict__ base_pts, const double *__
   // times over).  Winners are queued in shared memory and stamped a warp at a time, lanes over the kernel cells.
   const double ox = grid_off[2 * b], oy = grid_off[2 * b + 1];
   uint8_t *grid = grids + (size_t)b * grid_pitch;
-  const int half = g.kernel_size / 2, ksz = g.kernel_size * g.kernel_size;
+  const int half = g.kernel_size / 2;
   int *win = nxt;  // the chain arrays are free again
   if (threadIdx.x == 0) n_bnd = 0;
   __syncthreads();
@@ -261,13 +261,31 @@ __global__ void k_add_scan(const double *__restrict__ base_pts, const double *__
     if (atomic_max_u8(grid, idx, GRID_OCCUPIED) != GRID_OCCUPIED) win[atomicAdd(&n_bnd, 1)] = idx;
   }
   __syncthreads();
+  // one lane per aligned 32-bit WORD of the stamp (a kernel row covers <= kernel_size/4 + 2 words): the four byte
+  // maxima of a word go out as one packed CAS, so lanes of a warp never contend with each other
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, n_win = n_bnd;
+  const int ks = g.kernel_size, wpr = (ks + 3) / 4 + 1;  // words per kernel row, whatever the alignment
   for (int w = warp; w < n_win; w += nwarps) {
     const int idx = win[w];
-    for (int c = lane; c < ksz; c += 32) {
-      const int j = c / g.kernel_size - half, k = c % g.kernel_size - half;
-      const uint32_t kv = kernel[c];
-      if (kv && (j | k)) atomic_max_u8(grid, idx + k + j * g.width_step, kv);
+    for (int t = lane; t < ks * wpr; t += 32) {
+      const int j = t / wpr - half, q = t % wpr;
+      const int row0 = idx - half + j * g.width_step;   // byte index of the stamp row's first cell
+      const int wbase = (row0 & ~3) + 4 * q;            // this lane's aligned word
+      uint32_t v = 0;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int k = wbase + e - row0;                 // kernel column of byte e
+        if (k >= 0 && k < ks) v |= (uint32_t)kernel[k + ks * (j + half)] << (8 * e);
+      }
+      if (v == 0) continue;
+      uint32_t *wp = reinterpret_cast<uint32_t *>(grid + wbase);
+      uint32_t old = *wp, assumed;
+      do {
+        const uint32_t mx = __vmaxu4(old, v);
+        if (mx == old) break;
+        assumed = old;
+        old = atomicCAS(wp, assumed, mx);
+      } while (assumed != old);
     }
   }
 }
