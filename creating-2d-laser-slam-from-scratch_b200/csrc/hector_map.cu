@@ -189,6 +189,20 @@ __device__ __forceinline__ void hc_interp(const float *__restrict__ lo, int sx, 
   out[2] = -((dy1 * xfi) + (dy2 * fx));
 }
 
+__device__ __forceinline__ void hs_interp(const float *__restrict__ prob, int sx, int sy, float x, float y, float out[3]) {
+  const float lim_x = (float)sx - 2.0f, lim_y = (float)sy - 2.0f;  // setMapCellDims: dims - 2
+  if (x < 0.0f || x > lim_x || y < 0.0f || y > lim_y) { out[0] = out[1] = out[2] = 0.0f; return; }
+  const int ix = (int)x, iy = (int)y;
+  const float fx = x - (float)ix, fy = y - (float)iy;
+  const int index = iy * sx + ix;
+  const float i0 = prob[index], i1 = prob[index + 1], i2 = prob[index + sx], i3 = prob[index + sx + 1];
+  const float dx1 = i0 - i1, dx2 = i2 - i3, dy1 = i0 - i2, dy2 = i1 - i3;
+  const float xfi = 1.0f - fx, yfi = 1.0f - fy;
+  out[0] = ((i0 * xfi + i1 * fx) * yfi) + ((i2 * xfi + i3 * fx) * fy);
+  out[1] = -((dx1 * yfi) + (dx2 * fy));
+  out[2] = -((dy1 * xfi) + (dy2 * fx));
+}
+
 __device__ inline void hc_inv3_mul(const float m[9], const float v[3], float out[3]) {  // Matrix3f::inverse() * v
   const float c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
   const float det = c00 * m[0] + (c10 * m[1] + c20 * m[2]);  /* Eigen's unrolled 3-term redux: a0 + (a1 + a2) */
@@ -288,6 +302,8 @@ __global__ void k_hc_ros(const float *__restrict__ lo, int n, int8_t *__restrict
 // ---- lesson4 front end (HectorSlamProcessor): all pyramid levels per launch ------------------------------------
 
 struct HsLevel {  // one MapRepMultiMap level as the kernels see it
+  float *prob;  // getGridProbability(cell) = e^lo / (e^lo + 1) (GridMapLogOdds.h:136-140), refreshed whenever lo changes —
+                // the device-side form of the reference's per-scan GridMapCacheArray (4 expf + 4 divisions per point less)
   float *lo;
   int32_t *ui;
   unsigned long long *free_st, *occ_st;
@@ -322,11 +338,11 @@ constexpr int HS_PPT = 2;                        // points per thread held in re
 constexpr int HS_SMEM_PTS = HS_THREADS * HS_PPT; // scans up to 2048 points take the staged path
 constexpr int HS_SMEM_BYTES = (int)sizeof(float2) * HS_SMEM_PTS + 9 * HS_THREADS * (int)sizeof(float);
 
-__device__ __forceinline__ void hs_point_terms(const float *__restrict__ lo, int sx, int sy, float2 p, float c, float s,
+__device__ __forceinline__ void hs_point_terms(const float *__restrict__ prob, int sx, int sy, float2 p, float c, float s,
                                                float e0, float e1, float a[9]) {
   const float tx = (c * p.x + (-s) * p.y) + e0, ty = (s * p.x + c * p.y) + e1;
   float t[3];
-  hc_interp(lo, sx, sy, tx, ty, t);
+  hs_interp(prob, sx, sy, tx, ty, t);
   const float rot = ((-s * p.x - c * p.y) * t[1] + (c * p.x - s * p.y) * t[2]);
   const float fun = 1.0f - t[0];
   a[0] += t[1] * fun; a[1] += t[2] * fun; a[2] += rot * fun;    // dTr
@@ -340,6 +356,7 @@ __global__ void __launch_bounds__(HS_THREADS)
   float2 *spts = reinterpret_cast<float2 *>(hs_smem);                                                   // [HS_SMEM_PTS]
   float(*part)[HS_THREADS] = reinterpret_cast<float(*)[HS_THREADS]>(hs_smem + sizeof(float2) * HS_SMEM_PTS);  // [9][HS_THREADS]
   __shared__ float tot[9];
+  __shared__ float bc[5];  // new estimate + cos / sin of its heading, published by thread 0
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = L.l[0].n;
   const bool staged = n <= HS_SMEM_PTS;
@@ -374,18 +391,18 @@ __global__ void __launch_bounds__(HS_THREADS)
     float e0 = (m.tw_lin * world0 + 0.0f * world1) + m.tw_tx;
     float e1 = (0.0f * world0 + m.tw_lin * world1) + m.tw_ty;
     float e2 = world2;
+    float c = cosf(e2), s = sinf(e2);
     for (int it = 0; it < m.iterations; it++) {
-      const float c = cosf(e2), s = sinf(e2);
       float a[9];
 #pragma unroll
       for (int q = 0; q < 9; q++) a[q] = 0.0f;
       if (staged) {
 #pragma unroll
         for (int j = 0; j < HS_PPT; j++)
-          if (tid + j * HS_THREADS < n) hs_point_terms(m.lo, m.sx, m.sy, p[j], c, s, e0, e1, a);
+          if (tid + j * HS_THREADS < n) hs_point_terms(m.prob, m.sx, m.sy, p[j], c, s, e0, e1, a);
       } else {
         for (int i = tid; i < n; i += HS_THREADS)
-          hs_point_terms(m.lo, m.sx, m.sy, make_float2(__fmul_rn(gp[i].x, factor), __fmul_rn(gp[i].y, factor)), c, s, e0, e1, a);
+          hs_point_terms(m.prob, m.sx, m.sy, make_float2(__fmul_rn(gp[i].x, factor), __fmul_rn(gp[i].y, factor)), c, s, e0, e1, a);
       }
 #pragma unroll
       for (int q = 0; q < 9; q++) part[q][tid] = a[q];
@@ -399,17 +416,27 @@ __global__ void __launch_bounds__(HS_THREADS)
         if (lane == 0) tot[warp] = v;
       }
       __syncthreads();
-      const float dTr[3] = {tot[0], tot[1], tot[2]};
-      H[0] = tot[3]; H[4] = tot[4]; H[8] = tot[5];
-      H[1] = H[3] = tot[6]; H[2] = H[6] = tot[7]; H[5] = H[7] = tot[8];
-      if (H[0] != 0.0f && H[4] != 0.0f) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
-        float dir[3];
-        hc_inv3_mul(H, dTr, dir);
-        if (dir[2] > 0.2f) dir[2] = 0.2f;
-        else if (dir[2] < -0.2f) dir[2] = -0.2f;
-        e0 += dir[0]; e1 += dir[1]; e2 += dir[2];
+      if (tid == 0) {  // one thread solves and publishes the new estimate with its cosine / sine (the kernel is issue-bound:
+                       // 32 warps repeating the 3x3 solve and the range reductions cost more than a third barrier)
+        const float dTr[3] = {tot[0], tot[1], tot[2]};
+        float Hm[9];
+        Hm[0] = tot[3]; Hm[4] = tot[4]; Hm[8] = tot[5];
+        Hm[1] = Hm[3] = tot[6]; Hm[2] = Hm[6] = tot[7]; Hm[5] = Hm[7] = tot[8];
+        float n0 = e0, n1 = e1, n2 = e2;
+        if (Hm[0] != 0.0f && Hm[4] != 0.0f) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
+          float dir[3];
+          hc_inv3_mul(Hm, dTr, dir);
+          if (dir[2] > 0.2f) dir[2] = 0.2f;
+          else if (dir[2] < -0.2f) dir[2] = -0.2f;
+          n0 += dir[0]; n1 += dir[1]; n2 += dir[2];
+        }
+        bc[0] = n0; bc[1] = n1; bc[2] = n2; bc[3] = cosf(n2); bc[4] = sinf(n2);
       }
+      __syncthreads();
+      e0 = bc[0]; e1 = bc[1]; e2 = bc[2]; c = bc[3]; s = bc[4];
     }
+    H[0] = tot[3]; H[4] = tot[4]; H[8] = tot[5];  // the Hessian of the level's last iteration (covMatrix = H)
+    H[1] = H[3] = tot[6]; H[2] = H[6] = tot[7]; H[5] = H[7] = tot[8];
     {
       const double two_pi = 2.0f * 3.14159265358979323846;  // util::normalize_angle (UtilFunctions.h:36-48)
       float a = (float)fmod(fmod((double)e2, two_pi) + two_pi, two_pi);
@@ -425,6 +452,11 @@ __global__ void __launch_bounds__(HS_THREADS)
     for (int q = 0; q < 9; q++) out[3 + q] = H[q];  // covMatrix = H of the last level matched (level 0)
     out[12] = any ? 1.0f : 0.0f;
   }
+}
+
+__device__ __forceinline__ float hs_prob_of(float lo) {  // getGridProbability (GridMapLogOdds.h:136-140)
+  const float odds = expf(lo);
+  return odds / (odds + 1.0f);
 }
 
 // MapRepMultiMap::updateByScan (:174-191): mark / apply passes of every level in one launch each (blockIdx.y = level)
@@ -470,7 +502,9 @@ __global__ void __launch_bounds__(256)
       const int off = start + (int)k * ln.off_a + (int)inc * ln.off_b;
       my_visits++;
       if (m.free_st[off] == stamp && (m.occ_st[off] >> 32) != (epoch_hi >> 32)) {  // bresenhamCellFree (:302-312)
-        m.lo[off] = __fadd_rn(m.lo[off], lo_free);
+        const float v = __fadd_rn(m.lo[off], lo_free);
+        m.lo[off] = v;
+        m.prob[off] = hs_prob_of(v);
         m.ui[off] = mark_free;
       }
     }
@@ -486,6 +520,7 @@ __global__ void __launch_bounds__(256)
         }
         if (v < 50.0f) v = __fadd_rn(v, lo_occ);
         m.lo[off] = v;
+        m.prob[off] = hs_prob_of(v);
         m.ui[off] = mark_occ;
       }
     }
@@ -493,6 +528,11 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) my_visits += __shfl_xor_sync(0xffffffffu, my_visits, d);
   if (lane == 0 && my_visits) atomicAdd(visits, my_visits);
+}
+
+__global__ void k_hs_fill(float *__restrict__ p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 }  // namespace b2s
@@ -702,6 +742,7 @@ struct b2s_hector_slam {
   bool own_stream = false;
   int levels = 0;
   b2s_hector_map *map[B2S_HECTOR_MAX_LEVELS] = {};
+  float *d_prob[B2S_HECTOR_MAX_LEVELS] = {};  // per-level probability planes (see HsLevel::prob)
   float *d_pts[B2S_HECTOR_MAX_LEVELS] = {};  // dataContainer (level 0) and dataContainers[l-1]
   int n_pts[B2S_HECTOR_MAX_LEVELS] = {};
   float origo[B2S_HECTOR_MAX_LEVELS][2] = {};
@@ -742,6 +783,7 @@ static HsLevels hs_levels(const b2s_hector_slam *p) {
   for (int l = 0; l < p->levels; l++) {
     const b2s_hector_map *m = p->map[l];
     HsLevel &o = L.l[l];
+    o.prob = p->d_prob[l];
     o.lo = m->d_lo; o.ui = m->d_ui; o.free_st = m->d_free; o.occ_st = m->d_occ;
     o.pts = p->d_pts[l]; o.n = p->n_pts[l];
     o.sx = m->sx; o.sy = m->sy;
@@ -786,6 +828,9 @@ b2s_status b2s_hector_slam_create(float map_resolution, int map_size_x, int map_
     const float det = m->tw_lin * m->tw_lin - 0.0f * 0.0f, invdet = 1.0f / det, i01 = -0.0f * invdet;
     m->wt_tx = -(m->wt_lin * m->tw_tx + i01 * m->tw_ty);
     m->wt_ty = -(i01 * m->tw_tx + m->wt_lin * m->tw_ty);
+    const int cells = sx * sy;
+    B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaMalloc(reinterpret_cast<void **>(&p->d_prob[l]), sizeof(float) * (size_t)cells));
+    k_hs_fill<<<ceil_div(cells, 256), 256, 0, p->stream>>>(p->d_prob[l], cells, 0.5f);  // logOdds 0 -> e^0 / (e^0 + 1)
     sx /= 2; sy /= 2;
     res *= 2.0f;
   }
@@ -812,6 +857,7 @@ void b2s_hector_slam_destroy(b2s_hector_slam *p) {
   for (int l = 0; l < B2S_HECTOR_MAX_LEVELS; l++) {
     if (p->map[l]) b2s_hector_map_destroy(p->map[l]);
     if (p->d_pts[l]) cudaFree(p->d_pts[l]);
+    if (p->d_prob[l]) cudaFree(p->d_prob[l]);
   }
   if (p->d_out) cudaFree(p->d_out);
   if (p->d_visits) cudaFree(p->d_visits);
@@ -846,7 +892,9 @@ b2s_status b2s_hector_slam_reset(b2s_hector_slam *p) {
     const size_t cells = (size_t)m->sx * m->sy;
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_lo, 0, cells * 4, p->stream));
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_ui, 0xff, cells * 4, p->stream));
+    k_hs_fill<<<ceil_div((long long)cells, 256), 256, 0, p->stream>>>(p->d_prob[l], (int)cells, 0.5f);
   }
+  B2S_CUDA_CHECK(cudaGetLastError());
   return B2S_OK;
 }
 
