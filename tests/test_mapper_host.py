@@ -140,3 +140,56 @@ def test_pose_graph_solver_recovers_ring(pkg):
     d[:, 2] = (d[:, 2] + np.pi) % (2 * np.pi) - np.pi
     assert np.abs(d).max() < 1e-6
     g.close()
+
+
+@live
+def test_mapper_with_dropouts(pkg):
+    """1 % of the readings replaced by NaN / 0.0 (below min range): unfiltered points, barycenters and every decision
+    still agree with the reference exactly."""
+    MP, abi = pkg.load("mapper"), pkg.abi
+    laser, prm, true, odom, ranges = mc.workload(pkg, 3, 70)
+    rng = np.random.default_rng(4)
+    r2 = ranges.copy()
+    for k, (i, j) in enumerate(np.argwhere(rng.random(r2.shape) < 0.01)):
+        r2[i, j] = np.nan if k % 2 == 0 else 0.0
+    al = abi.laser_from(laser)
+    r = ref.RefMapper(prm, laser)
+    m = MP.Mapper(prm, al, match_fn=port.mapper_match_hook(prm, al))
+    fr, _ = mc.run(r, odom, r2)
+    fm, _ = mc.run(m, odom, r2)
+    assert np.array_equal(fr, fm)
+    compare(r, m)
+    r.close(), m.close()
+
+
+@live
+def test_mapper_singular_covariance_is_an_error_where_the_reference_asserts(pkg, tmp_path):
+    """ComputeWeightedMean inverts the link covariances with Matrix3::Inverse, which ASSERTS when |det| <= 1e-14
+    (Karto.h:2445-2453; the catkin build keeps asserts).  On this seeded stream the reference aborts at some scan; ours
+    must report B2S_ERR_BAD_STATE at the same scan instead of continuing with garbage."""
+    import subprocess
+    import sys
+    MP, abi = pkg.load("mapper"), pkg.abi
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import importlib, mapper_cases as mc\nfrom oracle import ref\n"
+            "pkg = importlib.import_module('creating-2d-laser-slam-from-scratch_b200')\n"
+            "laser, prm, true, odom, ranges = mc.workload(pkg, 9, 70)\nr = ref.RefMapper(prm, laser)\n"
+            "for i in range(70):\n    print(i, flush=True)\n    r.process(ranges[i], odom[i], 0.1 * i)\nprint('done', flush=True)\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    lines = out.stdout.split()
+    assert out.returncode != 0 and lines[-1] != "done" and "Assertion" in out.stderr
+    ref_fail = int(lines[-1])
+    laser, prm, true, odom, ranges = mc.workload(pkg, 9, 70)
+    al = abi.laser_from(laser)
+    m = MP.Mapper(prm, al, match_fn=port.mapper_match_hook(prm, al))
+    ours_fail = None
+    for i in range(70):
+        try:
+            m.process(ranges[i], odom[i], 0.1 * i)
+        except pkg.load("matcher").B2SError as e:
+            assert e.status == abi.B2S_ERR_BAD_STATE
+            ours_fail = i
+            break
+    assert ours_fail == ref_fail
+    m.close()
