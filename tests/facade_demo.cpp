@@ -43,5 +43,44 @@ int main() {
   printf("grid %d %d %ld %ld\n", g->GetWidth(), g->GetHeight(), occ, fre);
   delete g;
   delete m;
+
+  // the two front ends, with the reference's own call shapes: karto::Mapper::Process per scan (odometric pose = the
+  // pose read in), hectorslam::HectorSlamProcessor::update per scan
+  b2s_mapper_params mp;
+  b2s_mapper_default_params(&mp, 9.25);
+  mp.sequential.search_size = 0.5; mp.sequential.resolution = 0.05;  // small windows keep the demo quick
+  mp.loop.search_size = 4.0;
+  mp.minimum_travel_distance = 0.0; mp.minimum_travel_heading = 0.0;
+  Mapper mapper(mp, laser);
+  int processed = 0;
+  for (int s = 0; s < n; s++) {
+    MapperScan ms(scans[s]->GetRangeReadings());
+    ms.SetOdometricPose(scans[s]->GetCorrectedPose());
+    ms.SetCorrectedPose(scans[s]->GetCorrectedPose());
+    ms.SetTime(0.1 * s);
+    processed += mapper.Process(&ms) ? 1 : 0;
+  }
+  std::vector<Pose2> poses = mapper.GetAllProcessedPoses();
+  printf("mapper %d %zu %.17g %.17g %.17g\n", processed, poses.size(), poses.back().x, poses.back().y, poses.back().heading);
+
+  HectorSlamProcessor hector(0.05f, 1024, 1024, 0.5f, 0.5f, 3);
+  hector.setUpdateFactorFree(0.4f);
+  hector.setUpdateFactorOccupied(0.9f);
+  hector.setMapUpdateMinDistDiff(0.0f);
+  float hint[3] = {(float)scans[0]->GetCorrectedPose().x, (float)scans[0]->GetCorrectedPose().y, (float)scans[0]->GetCorrectedPose().heading};
+  const float origo[2] = {0.f, 0.f};
+  for (int s = 0; s < n; s++) {
+    std::vector<float> pts;
+    const std::vector<double> &r = scans[s]->GetRangeReadings();
+    for (int i = 0; i < 1081; i++) {
+      const double a = -2.356194490192345 + i * 0.004363323129985824;
+      if (!(r[i] > 0.4 && r[i] < 20.0)) continue;
+      pts.push_back((float)(r[i] * std::cos(a)) * 20.0f);
+      pts.push_back((float)(r[i] * std::sin(a)) * 20.0f);
+    }
+    hector.update(pts, origo, hint, s == 0);
+    for (int k = 0; k < 3; k++) hint[k] = hector.getLastScanMatchPose()[k];
+  }
+  printf("hector %.9g %.9g %.9g\n", hint[0], hint[1], hint[2]);
   return 0;
 }

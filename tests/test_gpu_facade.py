@@ -52,3 +52,7 @@ def test_facade_runs_reference_call_sequence(tmp_path, pkg):
     og = port.occupancy_grid(laser, ranges, poses_in, 0.05)
     c = og["cells"][:, :og["width"]]
     assert lines["grid"] == [og["width"], og["height"], int((c == 100).sum()), int((c == 255).sum())]
+    # the front-end classes: every scan becomes a key frame; the last corrected pose stays near the true pose, and the
+    # Hector processor (first scan mapped at its true pose, then self-driven) tracks the trajectory
+    assert lines["mapper"][:2] == [6, 6] and np.abs(np.array(lines["mapper"][2:4]) - poses[5][:2]).max() < 0.1
+    assert np.abs(np.array(lines["hector"][:2]) - poses[5][:2]).max() < 0.1
