@@ -386,7 +386,7 @@ def bench_k2(pkg, local, quick=False):
         m5.add_scans(mbr, mbp)
         se5 = abi.Search(7.5, 7.5, 0.2, 0.2, 20 * D, 2 * D, 1, 0)
         rows5 = {}
-        for name, kern in (("window", 0), ("generic", 1)):
+        for name, kern in (("window_kernel", 0), ("generic_kernel", 1)):
             m5.set_kernel(kern)
             m5.correlate_scan(mp, se5)
             torch.cuda.synchronize()
