@@ -299,6 +299,7 @@ def bench_k2(pkg, local, quick=False):
                                     "one H2D of the scan, one launch for the 3-level Gauss-Newton match (4+4+6 iterations), "
                                     "a 13-float D2H, the map-update gate on the host, two launches for the 3-level update"}
     hs.close()
+    stream_ranges, stream_poses = ranges, poses  # reused by the PL-ICP odometry stream below
     # every-scan mapping (gate off): the K2a update rate itself
     hs = H.HectorSlam(device=local, **dict(kw, min_dist=0.0, min_angle=0.0))
     n_map = min(n_stream, 1000)
@@ -476,6 +477,69 @@ def bench_k2(pkg, local, quick=False):
                           "mean_iterations": float(iters.mean()),
                           "median_xy_err_m": float(np.median(np.abs(x[:, :2] - truth[:, :2]).max(axis=1))),
                           "note": "sigma = 1 cm range noise; host buffers in, results out (H2D + kernel + D2H); parity unpinned"}
+    # --- cfg 3's other half: the lesson3 PL-ICP odometry over the same 10 000-scan stream (plicp_odometry.cc:191-436): scan i
+    #     against scan i-1 with a zero first guess; consecutive pairs are independent, so the stream is ONE batched call
+    try:
+        n_od = len(stream_ranges) - 1
+        t0 = time.perf_counter()
+        xo, vo, _, _, _ = P.match(ip, stream_ranges[:-1], stream_ranges[1:], theta, 0.1, 30.0, np.zeros((n_od, 3)), device=local)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        pose = stream_poses[0].copy()  # dead-reckon the increments
+        for i in range(n_od):
+            c, s_ = np.cos(pose[2]), np.sin(pose[2])
+            pose = np.array([pose[0] + c * xo[i, 0] - s_ * xo[i, 1], pose[1] + s_ * xo[i, 0] + c * xo[i, 1], pose[2] + xo[i, 2]])
+        out["plicp_odometry_stream"] = {"pairs": n_od, "pairs_per_s_e2e": n_od / dt, "ms": dt * 1e3, "valid": int(vo.sum()),
+                                        "final_xy_drift_m": float(np.abs(pose[:2] - stream_poses[-1][:2]).max()),
+                                        "note": "pure scan-to-scan odometry, no map: drift accumulates; parity unpinned"}
+    except Exception as e:
+        out["plicp_odometry_stream"] = {"error": repr(e)}
+    # --- cfg 5's back end: the CPU pose-graph solve that follows the batched loop-closure matches (here the library's own
+    #     LM + PCG optimiser; the reference uses sba / SuiteSparse) on a synthetic 5 000-node, 4-lap graph
+    try:
+        MPg = pkg.load("mapper")
+        nn = 1000 if quick else 5000
+        per_lap = nn // 4
+        th = np.arange(nn) * 2 * np.pi / per_lap
+        tru = np.stack([20 * np.cos(th), 20 * np.sin(th), (th + np.pi / 2 + np.pi) % (2 * np.pi) - np.pi], 1)
+        rg = np.random.default_rng(3)
+        def rel(a, b):
+            c, s_ = np.cos(a[2]), np.sin(a[2])
+            return np.array([c * (b[0] - a[0]) + s_ * (b[1] - a[1]), -s_ * (b[0] - a[0]) + c * (b[1] - a[1]),
+                             (b[2] - a[2] + np.pi) % (2 * np.pi) - np.pi])
+        guess = np.zeros((nn, 3))
+        guess[0] = tru[0]
+        for i in range(1, nn):  # drifting odometry as the initial guess
+            d = rel(tru[i - 1], tru[i]) + rg.normal(0, [0.002, 0.002, 0.0005])
+            c, s_ = np.cos(guess[i - 1, 2]), np.sin(guess[i - 1, 2])
+            guess[i] = [guess[i - 1, 0] + c * d[0] - s_ * d[1], guess[i - 1, 1] + s_ * d[0] + c * d[1], guess[i - 1, 2] + d[2]]
+        pg = MPg.PoseGraph(lm_iterations=40, cg_iterations=2000)
+        sv = pg.as_scan_solver()
+        dp = C.POINTER(C.c_double)
+        for i in range(nn):
+            sv.add_node(sv.user, i, np.ascontiguousarray(guess[i]).ctypes.data_as(dp))
+        cov = np.ascontiguousarray((np.eye(3) * [2.5e-4, 2.5e-4, 1e-5]).ravel())
+        n_con = 0
+        for i in range(nn):
+            for j in ([i + 1, i + 2] + ([i - per_lap] if i >= per_lap and i % 5 == 0 else [])):
+                if 0 <= j < nn and j != i:
+                    a, b = (i, j) if j > i else (j, i)
+                    d = np.ascontiguousarray(rel(tru[a], tru[b]) + rg.normal(0, [0.005, 0.005, 0.001]))
+                    sv.add_constraint(sv.user, a, b, d.ctypes.data_as(dp), cov.ctypes.data_as(dp))
+                    n_con += 1
+        ids, outp = np.zeros(nn, np.int32), np.zeros((nn, 3))
+        t0 = time.perf_counter()
+        sv.compute(sv.user, nn, ids.ctypes.data_as(C.POINTER(C.c_int32)), outp.ctypes.data_as(dp))
+        dt = time.perf_counter() - t0
+        st = pg.stats()
+        out["cfg5_pose_graph_solve_cpu"] = {"nodes": nn, "constraints": n_con, "solve_ms": dt * 1e3, "lm_steps": st["lm_steps"],
+                                            "chi2_before": st["chi2_before"], "chi2_after": st["chi2_after"],
+                                            "max_xy_err_before_m": float(np.abs(guess[:, :2] - tru[:, :2]).max()),
+                                            "max_xy_err_after_m": float(np.abs(outp[:, :2] - tru[:, :2]).max()),
+                                            "note": "host only (1 thread): LM + block-Jacobi PCG, first node fixed"}
+        pg.close()
+    except Exception as e:
+        out["cfg5_pose_graph_solve_cpu"] = {"error": repr(e)}
     return out
 
 
