@@ -146,6 +146,8 @@ struct b2s_matcher {
   int sbx = 0, sby = 0;
   bool sat_valid = false;
   unsigned long long *d_stats = nullptr;  // [0] beam-angle pairs dropped as empty windows in the last sweep
+  unsigned long long *h_stats = nullptr;  // pinned copy, read back with the results
+  bool pending = false;                   // a correlate_scan_begin awaits its _end
   double last_empty_frac = 0.0;
   bool grid_high_bytes = false;  // set_grids saw a byte > 127: the packed-byte window kernel is not applicable
   int32_t *d_sums = nullptr;
@@ -1551,6 +1553,8 @@ static b2s_status matcher_create_impl(const b2s_matcher_params *params, const b2
   if ((st = dev_alloc(&m->d_glob_best, B))) return st;
   if ((st = dev_alloc(&m->d_tie, B * 5))) return st;
   B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m->h_results), B * sizeof(b2s_match_result)));
+  B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m->h_stats), sizeof(unsigned long long)));
+  *m->h_stats = 0;
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_grids, 0, B * m->grid_pitch, m->stream));
   B2S_CUDA_CHECK(cudaMemsetAsync(m->d_results, 0, B * sizeof(b2s_match_result), m->stream));
   B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
@@ -1590,6 +1594,7 @@ void b2s_matcher_destroy(b2s_matcher *m) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (m->h_results) cudaFreeHost(m->h_results);
+  if (m->h_stats) cudaFreeHost(m->h_stats);
   for (auto &e : m->ev)
     if (e) cudaEventDestroy(e);
   if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
@@ -1740,29 +1745,39 @@ b2s_status b2s_matcher_compute_offsets(b2s_matcher *m, int b, double angle_cente
   return B2S_OK;
 }
 
-b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, const b2s_search *search,
-                                      b2s_match_result *results) {
-  if (!m || !centers || !search || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+// Enqueue a CorrelateScan (centers H2D, lookup lists, sweep, reduce, results D2H into the handle's pinned buffer) on the
+// handle's stream and return without waiting: a caller with two handles overlaps one batch's uploads and small kernels
+// with the other batch's sweep.  b2s_matcher_correlate_scan_end waits and hands the results out.
+b2s_status b2s_matcher_correlate_scan_begin(b2s_matcher *m, const double *centers, const b2s_search *search,
+                                            const b2s_match_result *cov_in) {
+  if (!m || !centers || !search) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
+  if (search->fine && !cov_in) B2S_FAIL(B2S_ERR_BAD_PARAMS, "the fine stage needs the incoming covariances (rCovariance is IN/OUT)");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
   const int B = m->batch;
   B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_centers, centers, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, m->stream));
   if (search->fine) {  // rCovariance is IN/OUT for the fine stage (Mapper.cpp:648)
-    for (int b = 0; b < B; b++) m->h_results[b] = results[b];
+    for (int b = 0; b < B; b++) m->h_results[b] = cov_in[b];
     B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_results, m->h_results, sizeof(b2s_match_result) * B, cudaMemcpyHostToDevice, m->stream));
   }
   b2s_status st = run_correlate(m, search, true);
   if (st) return st;
   B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_stats, m->d_stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+  m->pending = true;
+  return B2S_OK;
+}
+
+b2s_status b2s_matcher_correlate_scan_end(b2s_matcher *m, b2s_match_result *results) {
+  if (!m || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (!m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_correlate_scan_end without a pending b2s_matcher_correlate_scan_begin");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const int B = m->batch;
   B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  m->pending = false;
   std::memcpy(results, m->h_results, sizeof(b2s_match_result) * B);
-  if (m->last_path == 2 && m->last.na > 0 && m->n > 0) {
-    unsigned long long dropped = 0;
-    B2S_CUDA_CHECK(cudaMemcpy(&dropped, m->d_stats, sizeof(dropped), cudaMemcpyDeviceToHost));
-    m->last_empty_frac = (double)dropped / ((double)B * m->last.na * m->n);
-  } else {
-    m->last_empty_frac = 0.0;
-  }
+  if (m->last_path == 2 && m->last.na > 0 && m->n > 0) m->last_empty_frac = (double)*m->h_stats / ((double)B * m->last.na * m->n);
+  else m->last_empty_frac = 0.0;
   for (int i = 1; i < 3; i++) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, m->ev[i - 1], m->ev[i]) == cudaSuccess) m->last_ms[i - 1] = ms;
@@ -1772,6 +1787,14 @@ b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, con
     if (cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->last_ms[2] = ms;
   }
   return B2S_OK;
+}
+
+b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, const b2s_search *search,
+                                      b2s_match_result *results) {
+  if (!results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  b2s_status st = b2s_matcher_correlate_scan_begin(m, centers, search, results);
+  if (st) return st;
+  return b2s_matcher_correlate_scan_end(m, results);
 }
 
 b2s_status b2s_matcher_match_scan(b2s_matcher *m, int do_penalize, int do_refine, b2s_match_result *results) {

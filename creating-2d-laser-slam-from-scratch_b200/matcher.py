@@ -45,6 +45,8 @@ def lib():
     L.b2s_matcher_add_scans.argtypes = [vp, C.c_int, dp, dp]
     L.b2s_matcher_set_grids.argtypes = [vp, u8p, dp]
     L.b2s_matcher_correlate_scan.argtypes = [vp, dp, C.POINTER(abi.Search), C.POINTER(abi.MatchResult)]
+    L.b2s_matcher_correlate_scan_begin.argtypes = [vp, dp, C.POINTER(abi.Search), C.POINTER(abi.MatchResult)]
+    L.b2s_matcher_correlate_scan_end.argtypes = [vp, C.POINTER(abi.MatchResult)]
     i32p = C.POINTER(C.c_int32)
     L.b2s_matcher_correlate_split_begin.argtypes = [vp, dp, C.POINTER(abi.Search), C.c_int, C.c_int, dp, dp, i32p]
     L.b2s_matcher_correlate_split_ties.argtypes = [vp, dp, dp]
@@ -145,6 +147,16 @@ class ScanMatcher:
                 for i in range(9):
                     res[b].cov[i] = ci[b, i]
         check(self.L.b2s_matcher_correlate_scan(self.h, _d(c), C.byref(search), res))
+        return results_to_arrays(res, self.batch)
+
+    def correlate_scan_begin(self, centers, search: abi.Search):
+        """Enqueue a coarse CorrelateScan and return; pair with correlate_scan_end (two handles pipeline batches)."""
+        self._pending_centers = f64(centers).reshape(self.batch, 3)  # keep the host buffer alive until _end
+        check(self.L.b2s_matcher_correlate_scan_begin(self.h, _d(self._pending_centers), C.byref(search), None))
+
+    def correlate_scan_end(self):
+        res = (abi.MatchResult * self.batch)()
+        check(self.L.b2s_matcher_correlate_scan_end(self.h, res))
         return results_to_arrays(res, self.batch)
 
     # ---- a coarse sweep whose ANGLES are split over ranks (three phases, see include/b200slam.h) ----

@@ -139,6 +139,13 @@ b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const dou
 b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, const b2s_search *search,
                                       b2s_match_result *results);
 
+/* The same call split in two so that a caller can pipeline batches on two handles (one batch's uploads, rasterisation and
+ * lookup lists overlap the other batch's sweep): _begin enqueues everything incl. the result read-back on the handle's
+ * stream and returns; _end waits and hands the results out.  cov_in is only read for fine = 1 (may be NULL otherwise). */
+b2s_status b2s_matcher_correlate_scan_begin(b2s_matcher *m, const double *centers, const b2s_search *search,
+                                            const b2s_match_result *cov_in);
+b2s_status b2s_matcher_correlate_scan_end(b2s_matcher *m, b2s_match_result *results);
+
 /* ScanMatcher::MatchScan (Mapper.cpp:184-291): coarse sweep (+ optional response expansion) + fine sweep.
  * Requires set_scans + add_scans (or set_grids). */
 b2s_status b2s_matcher_match_scan(b2s_matcher *m, int do_penalize, int do_refine, b2s_match_result *results);

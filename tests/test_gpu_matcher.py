@@ -520,3 +520,40 @@ def test_angle_split_sweep_matches_whole_sweep(pkg, M, world, kernel):
     for a, b_ in zip(got1, whole):
         assert np.allclose(a, b_, rtol=0, atol=TOL)
     m.close()
+
+
+def test_correlate_begin_end_pipelined_over_two_handles(pkg):
+    """b2s_matcher_correlate_scan_begin/_end on two handles, interleaved as a 2-deep pipeline: identical results to the
+    synchronous call, and _end without _begin is a BAD_STATE error."""
+    abi, synth, M = pkg.abi, pkg.synth, pkg.load("matcher")
+    params, laser = abi.matcher_params(1.5, 0.05, 0.03, 9.25), abi.laser_from(synth.Laser())
+    se = abi.Search(0.75, 0.75, 0.05, 0.05, 22.5 * D, 0.25 * D, 1, 0)
+    sets = []
+    for k in range(4):
+        cases = [synth.make_match_case(7000 + 10 * k + i) for i in range(6)]
+        sets.append((np.stack([c.ranges for c in cases]), np.stack([c.odom_pose for c in cases]),
+                     np.stack([c.base_ranges for c in cases])[:, None, :], np.stack([c.base_pose for c in cases])[:, None, :]))
+    ms = [M.ScanMatcher(params, laser, max_batch=6, max_base_scans=1) for _ in range(2)]
+    with pytest.raises(M.B2SError) as e:
+        ms[0].set_scans(sets[0][0], sets[0][1]); ms[0].add_scans(sets[0][2], sets[0][3]); ms[0].correlate_scan_end()
+    assert e.value.status == abi.B2S_ERR_BAD_STATE
+    want = []
+    for r, p, br, bp in sets:
+        ms[0].set_scans(r, p); ms[0].add_scans(br, bp)
+        want.append(ms[0].correlate_scan(p, se))
+
+    def begin(i):
+        r, p, br, bp = sets[i]
+        ms[i % 2].set_scans(r, p); ms[i % 2].add_scans(br, bp); ms[i % 2].correlate_scan_begin(p, se)
+
+    got = []
+    begin(0)
+    for i in range(4):
+        if i + 1 < 4:
+            begin(i + 1)
+        got.append(ms[i % 2].correlate_scan_end())
+    for w, g in zip(want, got):
+        for a, b in zip(w, g):
+            assert np.array_equal(a, b)
+    for m in ms:
+        m.close()
