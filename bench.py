@@ -423,15 +423,17 @@ def bench_k2(pkg, local, quick=False):
                     both_coarse_angle_resolution=0.0349, both_use_response_expansion=1)
         prm = MPm.default_params(12.0, **yaml)
         mp_ = MPm.Mapper(prm, abi.laser_from(lm), device=local)
-        mp_.process(rng_m[0], odo[0], 0.0)
-        mp_.process(rng_m[1], odo[1], 0.1)
+        n_warm = 30  # the first frames create the matcher handles (device + pinned allocations, ~0.2-1.5 s once per mapper)
+        for i in range(n_warm):
+            mp_.process(rng_m[i], odo[i], 0.1 * i)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for i in range(2, n_map):
+        for i in range(n_warm, n_map):
             mp_.process(rng_m[i], odo[i], 0.1 * i)
         dt = time.perf_counter() - t0
         stm = mp_.stats()
-        out["karto_mapper_stream"] = {"key_frames": n_map - 2, "scans_per_s": (n_map - 2) / dt, "ms_per_scan": 1e3 * dt / (n_map - 2),
+        out["karto_mapper_stream"] = {"key_frames": n_map - n_warm, "scans_per_s": (n_map - n_warm) / dt, "ms_per_scan": 1e3 * dt / (n_map - n_warm),
+                                      "untimed_first_frames": n_warm,
                                       "match_scan_calls": stm["match_calls"], "device_batches": stm["batches"],
                                       "loops_closed": stm["loops_closed"], "edges": int(len(mp_.edges()[0])),
                                       "max_xy_err_m": float(np.abs(mp_.poses()[:, :2] - tru[:, :2]).max()),
