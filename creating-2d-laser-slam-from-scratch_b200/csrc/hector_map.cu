@@ -757,6 +757,8 @@ struct b2s_hector_slam {
   unsigned long long *d_visits = nullptr;
   double n_matched = 0, n_updated = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_h2d = nullptr;  // completion of the last upload out of h_pts
+  bool h2d_pending = false;
   bool ev_match = false, ev_update = false;
 };
 
@@ -839,6 +841,7 @@ b2s_status b2s_hector_slam_create(float map_resolution, int map_size_x, int map_
   hs_reset_poses(p);
   std::memset(p->last_cov, 0, sizeof(p->last_cov));
   for (auto &e : p->ev) B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaEventCreate(&e));
+  B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaEventCreateWithFlags(&p->ev_h2d, cudaEventDisableTiming));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p),
                        cudaFuncSetAttribute(k_hs_match, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM_BYTES));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaMalloc(reinterpret_cast<void **>(&p->d_out), 16 * sizeof(float)));
@@ -865,6 +868,7 @@ void b2s_hector_slam_destroy(b2s_hector_slam *p) {
   if (p->h_pts) cudaFreeHost(p->h_pts);
   for (auto &e : p->ev)
     if (e) cudaEventDestroy(e);
+  if (p->ev_h2d) cudaEventDestroy(p->ev_h2d);
   if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -919,6 +923,7 @@ b2s_status b2s_hector_slam_update(b2s_hector_slam *p, const float *points, int n
     p->pts_cap = cap;
   }
   if ((size_t)n_points > p->h_pts_cap) {
+    if (p->h2d_pending) B2S_CUDA_CHECK(cudaEventSynchronize(p->ev_h2d));
     if (p->h_pts) B2S_CUDA_CHECK(cudaFreeHost(p->h_pts));
     p->h_pts = nullptr;
     const size_t cap = std::max<size_t>(2048, (size_t)n_points);
@@ -927,8 +932,13 @@ b2s_status b2s_hector_slam_update(b2s_hector_slam *p, const float *points, int n
   }
   // level 0 always sees the scan passed in; the coarse levels see the last MATCHED scan (MapRepMultiMap.h:144-191)
   if (n_points > 0) {
+    // the pinned staging buffer may still be the source of the PREVIOUS call's upload (a map_without_matching call
+    // returns without waiting for the stream): wait for that copy — not for the kernels behind it — before reusing it
+    if (p->h2d_pending) B2S_CUDA_CHECK(cudaEventSynchronize(p->ev_h2d));
     std::memcpy(p->h_pts, points, sizeof(float) * 2 * (size_t)n_points);
     B2S_CUDA_CHECK(cudaMemcpyAsync(p->d_pts[0], p->h_pts, sizeof(float) * 2 * (size_t)n_points, cudaMemcpyHostToDevice, p->stream));
+    B2S_CUDA_CHECK(cudaEventRecord(p->ev_h2d, p->stream));
+    p->h2d_pending = true;
   }
   p->n_pts[0] = n_points;
   p->origo[0][0] = origo[0]; p->origo[0][1] = origo[1];

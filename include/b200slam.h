@@ -141,7 +141,9 @@ b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, con
 
 /* The same call split in two so that a caller can pipeline batches on two handles (one batch's uploads, rasterisation and
  * lookup lists overlap the other batch's sweep): _begin enqueues everything incl. the result read-back on the handle's
- * stream and returns; _end waits and hands the results out.  cov_in is only read for fine = 1 (may be NULL otherwise). */
+ * stream and returns; _end waits and hands the results out.  cov_in is only read for fine = 1 (may be NULL otherwise).
+ * Host buffers handed to set_scans / add_scans / _begin must stay unchanged until _end returns when they are pinned
+ * (uploads out of pinned memory are asynchronous). */
 b2s_status b2s_matcher_correlate_scan_begin(b2s_matcher *m, const double *centers, const b2s_search *search,
                                             const b2s_match_result *cov_in);
 b2s_status b2s_matcher_correlate_scan_end(b2s_matcher *m, b2s_match_result *results);
