@@ -110,7 +110,10 @@ int b2s_abi_version(void);
 const char *b2s_last_error(void);              /* thread-local text of the last failure */
 int b2s_device_count(void);                    /* 0 when no usable CUDA device */
 
-/* ---------------------------------------------------------------- K1: Karto correlative scan matcher */
+/* ---------------------------------------------------------------- K1: Karto correlative scan matcher
+ * Host arrays are caller-owned.  Uploads are enqueued on the handle's stream: out of pageable memory the CUDA runtime
+ * stages them before the call returns; out of PINNED memory they are asynchronous, so such buffers must stay unchanged
+ * until the next call that waits for the stream (correlate_scan, match_scan, _end, sync). */
 
 /* ScanMatcher::Create (Mapper.cpp:126-172).  `max_batch` matches share one handle; `max_angles`
  * bounds nAngles of any later search (0 = derive from params).  `cuda_stream` may be NULL
