@@ -154,6 +154,8 @@ struct CudaBackend {  // the two ScanMatcher instances a Mapper owns, as b2s_mat
   int cap_batch[2] = {0, 0}, cap_base[2] = {0, 0};
   int min_base = 32;  // scan_buffer_size + 1: the sequential matcher's base set is the running window
   std::vector<double> base_r, base_p;
+  std::vector<int32_t> base_rows;
+  size_t pool_n[2] = {0, 0};  // scans of the mapper already appended to each handle's device-resident pool
   double t_pad = 0, t_match = 0, t_create = 0, t_add = 0, t_sweeps = 0;  // seconds, reported at destroy when B2S_MAPPER_PROFILE is set
   bool profile = std::getenv("B2S_MAPPER_PROFILE") != nullptr;
   long n_create = 0, n_calls = 0;
@@ -229,11 +231,69 @@ struct MatchJob {
   std::vector<int> chain;        // base scans (indices into m->scans)
 };
 
+b2s_status cuda_ensure_handle(CudaBackend *c, int which, int batch, int max_base);
+
+// The CUDA path proper: base scans are referenced by their row in the handle's device-resident scan pool (every scan
+// of the mapper is uploaded once per handle), so a match uploads only the matched scans, the chain rows and the
+// chain poses.  Ragged chains are padded to the longest chain of the batch by repeating the last row.
+b2s_status cuda_match_ids(b2s_mapper *m, int which, const std::vector<MatchJob> &jobs, bool do_penalize, bool do_refine,
+                          std::vector<b2s_match_result> &out) {
+  CudaBackend *c = m->cuda;
+  const int B = (int)jobs.size(), N = m->laser.n_readings;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const auto t1 = now();
+  c->n_calls++;
+  int max_base = 1;
+  for (const MatchJob &j : jobs) {
+    if (j.chain.empty()) B2S_FAIL(B2S_ERR_BAD_PARAMS, "mapper: MatchScan against an empty chain");
+    max_base = std::max(max_base, (int)j.chain.size());
+  }
+  b2s_status st = cuda_ensure_handle(c, which, B, max_base);
+  if (st) return st;
+  for (; c->pool_n[which] < m->scans.size(); c->pool_n[which]++) {  // new scans (all of them after a handle re-creation)
+    st = b2s_matcher_pool_append(c->h[which], m->scans[c->pool_n[which]].ranges.data(), nullptr);
+    if (st) return st;
+  }
+  std::vector<double> ranges((size_t)B * N), poses((size_t)B * 3);
+  c->base_rows.resize((size_t)B * max_base);
+  c->base_p.resize((size_t)B * max_base * 3);
+  for (int b = 0; b < B; b++) {
+    std::memcpy(&ranges[(size_t)b * N], jobs[b].ranges->data(), sizeof(double) * N);
+    poses[3 * b] = jobs[b].robot_pose.x; poses[3 * b + 1] = jobs[b].robot_pose.y; poses[3 * b + 2] = jobs[b].robot_pose.h;
+    const int nb = (int)jobs[b].chain.size();
+    for (int j = 0; j < max_base; j++) {
+      const int id = jobs[b].chain[std::min(j, nb - 1)];
+      const MScan &sc = m->scans[id];
+      const size_t k = (size_t)b * max_base + j;
+      c->base_rows[k] = id;
+      c->base_p[3 * k] = sc.corrected.x; c->base_p[3 * k + 1] = sc.corrected.y; c->base_p[3 * k + 2] = sc.corrected.h;
+    }
+  }
+  const auto t2 = now();
+  st = b2s_matcher_set_scans(c->h[which], B, ranges.data(), poses.data());
+  if (!st) st = b2s_matcher_add_scans_pool(c->h[which], max_base, c->base_rows.data(), c->base_p.data());
+  if (!st && c->profile) st = b2s_matcher_sync(c->h[which]);
+  const auto t3 = now();
+  if (!st) st = b2s_matcher_match_scan(c->h[which], do_penalize ? 1 : 0, do_refine ? 1 : 0, out.data());
+  const auto t4 = now();
+  c->t_pad += secs(t1, t2);
+  c->t_add += secs(t2, t3);
+  c->t_sweeps += secs(t3, t4);
+  c->t_match += secs(t2, t4);
+  return st;
+}
+
 b2s_status run_matches(b2s_mapper *m, int which, const std::vector<MatchJob> &jobs, bool do_penalize, bool do_refine,
                        std::vector<b2s_match_result> &out) {
   const int B = (int)jobs.size(), N = m->laser.n_readings;
   out.assign(B, b2s_match_result{});
   if (B == 0) return B2S_OK;
+  if (m->cuda) {
+    m->n_match_calls += B;
+    m->n_batches += 1;
+    return cuda_match_ids(m, which, jobs, do_penalize, do_refine, out);
+  }
   std::vector<double> ranges((size_t)B * N), poses((size_t)B * 3);
   std::vector<int32_t> first(B), count(B);
   size_t total = 0;
@@ -259,7 +319,27 @@ b2s_status run_matches(b2s_mapper *m, int which, const std::vector<MatchJob> &jo
                   do_penalize ? 1 : 0, do_refine ? 1 : 0, out.data());
 }
 
-// ---- the CUDA matcher as the plug-in: ragged chains are padded to the longest chain of the batch by repeating each
+// (re)creating a handle costs tens of ms (device + pinned allocations): size it for the running window up front and
+// double on growth so that a stream re-creates it a handful of times at most
+b2s_status cuda_ensure_handle(CudaBackend *c, int which, int batch, int max_base) {
+  if (c->h[which] && batch <= c->cap_batch[which] && max_base <= c->cap_base[which]) return B2S_OK;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (c->h[which]) b2s_matcher_destroy(c->h[which]);
+  c->h[which] = nullptr;
+  c->pool_n[which] = 0;
+  const int cb = std::max(std::max(batch, c->cap_batch[which] * 2), 8);
+  const int cs = std::max(std::max(max_base, c->cap_base[which] * 2), c->min_base);
+  b2s_status st = b2s_matcher_create(&c->params[which], &c->laser, c->device, cb, cs, nullptr, &c->h[which]);
+  if (st) return st;
+  c->cap_batch[which] = cb;
+  c->cap_base[which] = cs;
+  c->n_create++;
+  c->t_create += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return B2S_OK;
+}
+
+// ---- the CUDA matcher behind the generic plug-in signature (host arrays in; the mapper itself takes the pooled path
+// above, this form serves callers that drive b2s_match_scan_fn directly): ragged chains are padded to the longest chain of the batch by repeating each
 // match's last base scan (rasterising a scan twice leaves the correlation grid unchanged)
 b2s_status cuda_match(void *user, int which, int batch, const double *ranges, const double *poses, const int32_t *base_first,
                       const int32_t *n_base, const double *base_ranges, const double *base_poses, int do_penalize,
@@ -268,23 +348,12 @@ b2s_status cuda_match(void *user, int which, int batch, const double *ranges, co
   const int N = c->laser.n_readings;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-  const auto t0 = now();
   c->n_calls++;
   int max_base = 1;
   for (int b = 0; b < batch; b++) max_base = std::max(max_base, (int)n_base[b]);
-  if (!c->h[which] || batch > c->cap_batch[which] || max_base > c->cap_base[which]) {
-    if (c->h[which]) b2s_matcher_destroy(c->h[which]);
-    c->h[which] = nullptr;
-    // (re)creating a handle costs tens of ms (device + pinned allocations): size it for the running window up front and
-    // double on growth so that a stream re-creates it a handful of times at most
-    const int cb = std::max(std::max(batch, c->cap_batch[which] * 2), 8);
-    const int cs = std::max(std::max(max_base, c->cap_base[which] * 2), c->min_base);
-    b2s_status st = b2s_matcher_create(&c->params[which], &c->laser, c->device, cb, cs, nullptr, &c->h[which]);
+  {
+    b2s_status st = cuda_ensure_handle(c, which, batch, max_base);
     if (st) return st;
-    c->cap_batch[which] = cb;
-    c->cap_base[which] = cs;
-    c->n_create++;
-    c->t_create += secs(t0, now());
   }
   const auto t1 = now();
   for (int b = 0; b < batch; b++)

@@ -136,6 +136,10 @@ struct b2s_matcher {
   double *d_grid_off = nullptr;
   double *d_base_ranges = nullptr, *d_base_poses = nullptr, *d_base_pts = nullptr;
   size_t base_cap = 0;
+  double *d_pool = nullptr;        // scan pool: readings of scans that serve as base scans again and again
+  size_t pool_cap = 0, pool_count = 0;
+  int32_t *d_base_src = nullptr;   // [batch * n_base] pool rows of the current base sets
+  size_t base_src_cap = 0;
   int32_t *d_lut = nullptr;
   size_t lut_cap = 0;
   int32_t *d_lists = nullptr, *d_counts = nullptr, *d_starts = nullptr;  // window kernel: per-(match, angle) grouped window origins
@@ -1589,7 +1593,7 @@ void b2s_matcher_destroy(b2s_matcher *m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   void *ptrs[] = {m->d_kernel, m->d_ranges, m->d_poses, m->d_sensor, m->d_pts, m->d_local, m->d_grids,
-                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_lut, m->d_lists, m->d_counts, m->d_starts, m->d_sat, m->d_stats, m->d_part_best, m->d_glob_best, m->d_tie, m->d_sums, m->d_bases,
+                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_pool, m->d_base_src, m->d_lut, m->d_lists, m->d_counts, m->d_starts, m->d_sat, m->d_stats, m->d_part_best, m->d_glob_best, m->d_tie, m->d_sums, m->d_bases,
                   m->d_flags, m->d_probs, m->d_centers, m->d_results, m->d_work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1627,7 +1631,7 @@ b2s_status b2s_matcher_set_scans(b2s_matcher *m, int batch, const double *ranges
   const size_t n = (size_t)m->n;
   B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_ranges, ranges, sizeof(double) * batch * n, cudaMemcpyHostToDevice, m->stream));
   B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_poses, poses, sizeof(double) * batch * 3, cudaMemcpyHostToDevice, m->stream));
-  k_scan_points<<<batch, 256, 0, m->stream>>>(m->d_ranges, m->d_poses, m->l, m->d_sensor, m->d_pts, m->d_local);
+  k_scan_points<<<batch, 256, 0, m->stream>>>(m->d_ranges, m->d_poses, m->l, m->d_sensor, m->d_pts, m->d_local, nullptr);
   B2S_CUDA_CHECK(cudaGetLastError());
   m->scans_set = true;
   m->grids_set = false;
@@ -1635,8 +1639,11 @@ b2s_status b2s_matcher_set_scans(b2s_matcher *m, int batch, const double *ranges
   return B2S_OK;
 }
 
-b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_ranges, const double *base_poses) {
-  if (!m || n_base < 0 || (n_base > 0 && (!base_ranges || !base_poses))) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+// base_ranges != NULL: the base scans' readings come from the host; otherwise pool_rows ([batch * n_base], host) names
+// rows of the handle's device-resident scan pool
+static b2s_status add_scans_impl(b2s_matcher *m, int n_base, const double *base_ranges, const int32_t *pool_rows,
+                                 const double *base_poses) {
+  if (!m || n_base < 0 || (n_base > 0 && ((!base_ranges && !pool_rows) || !base_poses))) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->scans_set) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_set_scans must precede b2s_matcher_add_scans");
   if (n_base > m->max_base) B2S_FAIL(B2S_ERR_TOO_LARGE, "n_base exceeds the handle's max_base_scans");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
@@ -1659,9 +1666,21 @@ b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_
       if ((st = dev_alloc(&m->d_base_pts, need * n * 2))) return st;
       m->base_cap = need;
     }
-    B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_base_ranges, base_ranges, sizeof(double) * need * n, cudaMemcpyHostToDevice, m->stream));
     B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_base_poses, base_poses, sizeof(double) * need * 3, cudaMemcpyHostToDevice, m->stream));
-    k_scan_points<<<(unsigned)need, 256, 0, m->stream>>>(m->d_base_ranges, m->d_base_poses, m->l, nullptr, m->d_base_pts, nullptr);
+    if (base_ranges) {
+      B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_base_ranges, base_ranges, sizeof(double) * need * n, cudaMemcpyHostToDevice, m->stream));
+      k_scan_points<<<(unsigned)need, 256, 0, m->stream>>>(m->d_base_ranges, m->d_base_poses, m->l, nullptr, m->d_base_pts, nullptr, nullptr);
+    } else {
+      for (size_t i = 0; i < need; i++)
+        if (pool_rows[i] < 0 || (size_t)pool_rows[i] >= m->pool_count) B2S_FAIL(B2S_ERR_OUT_OF_RANGE, "scan pool row out of range");
+      if (need > m->base_src_cap) {
+        if (m->d_base_src) { B2S_CUDA_CHECK(cudaFree(m->d_base_src)); m->d_base_src = nullptr; }
+        B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&m->d_base_src), sizeof(int32_t) * need));
+        m->base_src_cap = need;
+      }
+      B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_base_src, pool_rows, sizeof(int32_t) * need, cudaMemcpyHostToDevice, m->stream));
+      k_scan_points<<<(unsigned)need, 256, 0, m->stream>>>(m->d_pool, m->d_base_poses, m->l, nullptr, m->d_base_pts, nullptr, m->d_base_src);
+    }
     if (!m->smear_degenerate) {
       size_t smem = n * (2 * sizeof(double) + 2 * sizeof(int) + 1) + sizeof(int) + 16;
       if (smem > 16 * 1024)
@@ -1682,6 +1701,42 @@ b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_
   m->grid_high_bytes = false;
   m->have_sweep = false;
   return build_sat(m);
+}
+
+b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_ranges, const double *base_poses) {
+  if (n_base > 0 && !base_ranges) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  return add_scans_impl(m, n_base, base_ranges, nullptr, base_poses);
+}
+
+// ---- scan pool: readings that serve as base scans of many matches (a mapper's running window, near chains, loop
+// candidates) are uploaded once and referenced by row afterwards
+b2s_status b2s_matcher_pool_append(b2s_matcher *m, const double *ranges, int32_t *out_row) {
+  if (!m || !ranges) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  const size_t n = (size_t)std::max(m->l.n_readings, 1);
+  if (m->pool_count == m->pool_cap) {
+    const size_t cap = std::max<size_t>(256, m->pool_cap * 2);
+    double *fresh = nullptr;
+    b2s_status st = dev_alloc(&fresh, cap * n);
+    if (st) return st;
+    if (m->pool_count)
+      B2S_CUDA_CHECK(cudaMemcpyAsync(fresh, m->d_pool, sizeof(double) * m->pool_count * n, cudaMemcpyDeviceToDevice, m->stream));
+    B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    if (m->d_pool) B2S_CUDA_CHECK(cudaFree(m->d_pool));
+    m->d_pool = fresh;
+    m->pool_cap = cap;
+  }
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_pool + m->pool_count * n, ranges, sizeof(double) * n, cudaMemcpyHostToDevice, m->stream));
+  if (out_row) *out_row = (int32_t)m->pool_count;
+  m->pool_count++;
+  return B2S_OK;
+}
+
+int32_t b2s_matcher_pool_count(const b2s_matcher *m) { return m ? (int32_t)m->pool_count : 0; }
+
+b2s_status b2s_matcher_add_scans_pool(b2s_matcher *m, int n_base, const int32_t *pool_rows, const double *base_poses) {
+  if (n_base > 0 && !pool_rows) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  return add_scans_impl(m, n_base, nullptr, pool_rows, base_poses);
 }
 
 b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const double *offsets) {

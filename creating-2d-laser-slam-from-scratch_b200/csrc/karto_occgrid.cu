@@ -226,7 +226,7 @@ static b2s_status occ_create_impl(const b2s_laser *laser, int n_scans, const dou
   if (M) B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemcpyAsync(d_poses, poses, sizeof(double) * M * 3, cudaMemcpyHostToDevice, st));
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaMemsetAsync(d_visits, 0, sizeof(unsigned long long), st));
   double bb[4];
-  if (M) k_scan_points<<<(unsigned)M, 256, 0, st>>>(d_ranges, d_poses, *laser, d_sensor, d_pts, nullptr);
+  if (M) k_scan_points<<<(unsigned)M, 256, 0, st>>>(d_ranges, d_poses, *laser, d_sensor, d_pts, nullptr, nullptr);
   if (given_bbox) {
     for (int i = 0; i < 4; i++) bb[i] = given_bbox[i];
   } else {

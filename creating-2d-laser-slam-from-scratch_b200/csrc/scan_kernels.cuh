@@ -10,9 +10,12 @@ namespace b2s {
 // scan-local points of GridIndexLookup::ComputeOffsets (Karto.h:6423-6434, Transform::InverseTransformPose
 // Karto.h:2894-2901).  One block per scan.
 // ----------------------------------------------------------------------------------------------
+// `src` (may be NULL): row of `ranges` scan b reads (a scan pool shared by many base sets); NULL = row b.
 static __global__ void k_scan_points(const double *__restrict__ ranges, const double *__restrict__ poses, b2s_laser l,
-                              double *__restrict__ sensor, double *__restrict__ pts, double *__restrict__ local) {
+                              double *__restrict__ sensor, double *__restrict__ pts, double *__restrict__ local,
+                              const int32_t *__restrict__ src) {
   const int b = blockIdx.x;
+  const size_t row = src ? (size_t)src[b] : (size_t)b;
   const int n = l.n_readings;
   __shared__ double sp[3];
   __shared__ double inv[6];
@@ -41,7 +44,7 @@ static __global__ void k_scan_points(const double *__restrict__ ranges, const do
   __syncthreads();
   const double dh = normalize_angle(0.0 - tr[2]);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double r = ranges[(size_t)b * n + i];
+    double r = ranges[row * n + i];
     double angle = sp[2] + l.min_angle + (double)(uint32_t)i * l.angular_resolution;
     double x = sp[0] + (r * cos(angle));
     double y = sp[1] + (r * sin(angle));

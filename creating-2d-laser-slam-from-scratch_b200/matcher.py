@@ -133,6 +133,19 @@ class ScanMatcher:
         br = f64(base_ranges).reshape(self.batch, n_base, self.n)
         check(self.L.b2s_matcher_add_scans(self.h, n_base, _d(br), _d(bp)))
 
+    def pool_append(self, ranges) -> int:
+        """Upload one scan's readings into the handle's device-resident scan pool; returns its row."""
+        r, row = f64(ranges).reshape(self.n), C.c_int32(-1)
+        self.L.b2s_matcher_pool_append.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+        check(self.L.b2s_matcher_pool_append(self.h, _d(r), C.byref(row)))
+        return row.value
+
+    def add_scans_pool(self, pool_rows, base_poses):
+        bp = f64(base_poses).reshape(self.batch, -1, 3)
+        rows = np.ascontiguousarray(pool_rows, np.int32).reshape(self.batch, bp.shape[1])
+        self.L.b2s_matcher_add_scans_pool.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        check(self.L.b2s_matcher_add_scans_pool(self.h, bp.shape[1], rows.ctypes.data_as(C.POINTER(C.c_int32)), _d(bp)))
+
     def set_grids(self, grids, offsets):
         g = np.ascontiguousarray(grids, dtype=np.uint8).reshape(self.batch, self.g.data_size)
         o = f64(offsets).reshape(self.batch, 2)

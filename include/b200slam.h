@@ -133,6 +133,13 @@ b2s_status b2s_matcher_set_scans(b2s_matcher *m, int batch, const double *ranges
  * base_poses: [batch][n_base][3]. */
 b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_ranges, const double *base_poses);
 
+/* Scan pool: readings that serve as base scans of many matches (a mapper's running window, near chains, loop-closure
+ * candidate chains) are uploaded once (_pool_append returns the row) and referenced by row afterwards;
+ * _add_scans_pool is b2s_matcher_add_scans with pool rows ([batch][n_base], host) in place of base_ranges. */
+b2s_status b2s_matcher_pool_append(b2s_matcher *m, const double *ranges, int32_t *out_row);
+int32_t b2s_matcher_pool_count(const b2s_matcher *m);
+b2s_status b2s_matcher_add_scans_pool(b2s_matcher *m, int n_base, const int32_t *pool_rows, const double *base_poses);
+
 /* Alternative to add_scans for callers that keep grids themselves: upload ready-made correlation grids
  * ([batch][data_size] bytes) and their world offsets ([batch][2], CoordinateConverter::SetOffset). */
 b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const double *offsets);

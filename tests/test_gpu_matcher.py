@@ -557,3 +557,33 @@ def test_correlate_begin_end_pipelined_over_two_handles(pkg):
             assert np.array_equal(a, b)
     for m in ms:
         m.close()
+
+
+def test_scan_pool_base_sets(pkg):
+    """b2s_matcher_pool_append + _add_scans_pool: base scans referenced by pool row give the same correlation grids and
+    the same MatchScan results as uploading their readings; rows out of range are refused."""
+    abi, synth, M = pkg.abi, pkg.synth, pkg.load("matcher")
+    laser = synth.Laser()
+    world, poses, ranges = synth.make_trajectory(12, 9, laser, step_xy=0.1, step_th_deg=2)
+    params = abi.matcher_params(1.5, 0.05, 0.03, 9.25)
+    chains = [[0, 1, 2, 3], [2, 3, 4, 4], [5, 6, 7, 7]]          # ragged chains padded by repetition
+    cur = [4, 5, 8]
+    cr, cp = ranges[cur], poses[cur] + np.array([0.05, -0.04, 0.02])
+    a = M.ScanMatcher(params, abi.laser_from(laser), max_batch=3, max_base_scans=4)
+    a.set_scans(cr, cp)
+    a.add_scans(np.stack([ranges[c] for c in chains]), np.stack([poses[c] for c in chains]))
+    want = a.match_scan()
+    b = M.ScanMatcher(params, abi.laser_from(laser), max_batch=3, max_base_scans=4)
+    rows = [b.pool_append(ranges[i]) for i in range(9)]
+    assert rows == list(range(9))
+    b.set_scans(cr, cp)
+    b.add_scans_pool(chains, np.stack([poses[c] for c in chains]))
+    got = b.match_scan()
+    for k in range(3):
+        assert np.array_equal(a.grid(k)[0], b.grid(k)[0])
+    for x, y in zip(want, got):
+        assert np.array_equal(x, y)
+    with pytest.raises(M.B2SError) as e:
+        b.add_scans_pool([[0, 1, 2, 9]] * 3, np.stack([poses[c] for c in chains]))
+    assert e.value.status == abi.B2S_ERR_OUT_OF_RANGE
+    a.close(), b.close()
