@@ -635,6 +635,46 @@ void ref_mapper_get_edges(void* h, int32_t* ids, double* diff, double* cov) {
   }
 }
 
+// Mapper::InitializeParameters (Mapper.cpp:1448-1653): the defaults as a fresh reference Mapper holds them
+void ref_mapper_default_params(ref_mapper_params* p) {
+  CoutSilencer quiet;
+  Mapper m;
+  std::memset(p, 0, sizeof(*p));
+  p->use_scan_matching = m.m_pUseScanMatching->GetValue();
+  p->use_scan_barycenter = m.m_pUseScanBarycenter->GetValue();
+  p->minimum_time_interval = m.m_pMinimumTimeInterval->GetValue();
+  p->minimum_travel_distance = m.m_pMinimumTravelDistance->GetValue();
+  p->minimum_travel_heading = m.m_pMinimumTravelHeading->GetValue();
+  p->scan_buffer_size = m.m_pScanBufferSize->GetValue();
+  p->do_loop_closing = m.m_pDoLoopClosing->GetValue();
+  p->scan_buffer_maximum_scan_distance = m.m_pScanBufferMaximumScanDistance->GetValue();
+  p->link_match_minimum_response_fine = m.m_pLinkMatchMinimumResponseFine->GetValue();
+  p->link_scan_maximum_distance = m.m_pLinkScanMaximumDistance->GetValue();
+  p->loop_search_maximum_distance = m.m_pLoopSearchMaximumDistance->GetValue();
+  p->loop_match_minimum_chain_size = m.m_pLoopMatchMinimumChainSize->GetValue();
+  p->loop_match_maximum_variance_coarse = m.m_pLoopMatchMaximumVarianceCoarse->GetValue();
+  p->loop_match_minimum_response_coarse = m.m_pLoopMatchMinimumResponseCoarse->GetValue();
+  p->loop_match_minimum_response_fine = m.m_pLoopMatchMinimumResponseFine->GetValue();
+  ref_matcher_params t;
+  std::memset(&t, 0, sizeof(t));
+  t.distance_variance_penalty = m.m_pDistanceVariancePenalty->GetValue();
+  t.angle_variance_penalty = m.m_pAngleVariancePenalty->GetValue();
+  t.fine_search_angle_offset = m.m_pFineSearchAngleOffset->GetValue();
+  t.coarse_search_angle_offset = m.m_pCoarseSearchAngleOffset->GetValue();
+  t.coarse_angle_resolution = m.m_pCoarseAngleResolution->GetValue();
+  t.minimum_angle_penalty = m.m_pMinimumAnglePenalty->GetValue();
+  t.minimum_distance_penalty = m.m_pMinimumDistancePenalty->GetValue();
+  t.use_response_expansion = m.m_pUseResponseExpansion->GetValue();
+  p->sequential = t;
+  p->sequential.search_size = m.m_pCorrelationSearchSpaceDimension->GetValue();
+  p->sequential.resolution = m.m_pCorrelationSearchSpaceResolution->GetValue();
+  p->sequential.smear_deviation = m.m_pCorrelationSearchSpaceSmearDeviation->GetValue();
+  p->loop = t;
+  p->loop.search_size = m.m_pLoopSearchSpaceDimension->GetValue();
+  p->loop.resolution = m.m_pLoopSearchSpaceResolution->GetValue();
+  p->loop.smear_deviation = m.m_pLoopSearchSpaceSmearDeviation->GetValue();
+}
+
 int ref_mapper_running_count(void* h) {
   MapperSession* s = static_cast<MapperSession*>(h);
   return static_cast<int>(s->mapper->m_pMapperSensorManager->GetRunningScans(s->name).size());

@@ -193,3 +193,27 @@ def test_mapper_singular_covariance_is_an_error_where_the_reference_asserts(pkg,
             break
     assert ours_fail == ref_fail
     m.close()
+
+
+@live
+def test_mapper_default_params_equal_the_reference(pkg):
+    """b2s_mapper_default_params vs the values a fresh karto::Mapper holds (Mapper::InitializeParameters)."""
+    import ctypes as C
+    MP = pkg.load("mapper")
+    ours = MP.default_params(12.0)
+    theirs = MP.MapperParams()
+    ref._lib(False).ref_mapper_default_params(C.byref(theirs))
+    theirs.sequential.range_threshold = theirs.loop.range_threshold = 12.0  # comes from the laser, not from the Mapper
+    def flat(p):
+        out = {}
+        for name, _ in p._fields_:
+            v = getattr(p, name)
+            if hasattr(v, "_fields_"):
+                out.update({f"{name}.{k}": getattr(v, k) for k, _ in v._fields_})
+            else:
+                out[name] = v
+        return out
+    a, b = flat(ours), flat(theirs)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k] == b[k], (k, a[k], b[k])
