@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
 // (iy, ix, k) with linear index (iy*nx + ix)*na + k; ties are summed sequentially in that order when there are
 // at most RED_MAX_TIES of them (bit-identical to the reference), otherwise by a fixed-order tree.
 // ----------------------------------------------------------------------------------------------
-constexpr int RED_THREADS = 1024;
+constexpr int RED_THREADS = 512;   // 60 registers: two CTAs per SM, so one match's serial tail overlaps another's streaming pass
 constexpr int RED_MAX_TIES = 512;
 constexpr int RED_UNROLL = 8;
 
@@ -1086,8 +1086,8 @@ __global__ void __launch_bounds__(RED_THREADS)
   // evaluation, otherwise (near-ties, e.g. equal sums under the clamped penalty) the row is re-read and every
   // candidate inside the margin is evaluated exactly.
   double best = -1.0;
-  float first_fmax = 0.0f;      // float maximum of this thread's first cell, kept for pass 2
-  bool first_known = false;
+  float fmax0 = 0.0f, fmax1 = 0.0f;  // float maxima of this thread's first two cells, kept for pass 2
+  bool known0 = false, known1 = false;
   for (int c = tid; c < ncell && mode <= 1; c += RED_THREADS) {
     const int iy = c / nx, ix = c % nx;
     const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
@@ -1117,7 +1117,8 @@ __global__ void __launch_bounds__(RED_THREADS)
           }
         }
       }
-      if (c == tid) { first_fmax = fmax; first_known = !any_amb; }
+      if (c == tid) { fmax0 = fmax; known0 = !any_amb; }
+      else if (c == tid + RED_THREADS) { fmax1 = fmax; known1 = !any_amb; }
       if (!near && !any_amb) {
         const double angle = start_a + (double)(uint32_t)(k_first + kmax) * s.angle_res;
         cell_best = candidate_response(vmax, n, pen, sq, angle, ch, p);
@@ -1181,7 +1182,8 @@ __global__ void __launch_bounds__(RED_THREADS)
   double ax = 0, ay = 0, tx = 0, ty = 0;
   const float tie_thr = (float)((best - KT_TOLERANCE) * (1.0 - 1.0e-6)) - 1.0e-9f;
   for (int c = tid; c < ncell && mode != 3; c += RED_THREADS) {
-    if (c == tid && first_known && first_fmax < tie_thr) continue;  // no candidate of this cell can tie (pass 1's maximum)
+    if (c == tid && known0 && fmax0 < tie_thr) continue;  // no candidate of this cell can tie (pass 1's maximum)
+    if (c == tid + RED_THREADS && known1 && fmax1 < tie_thr) continue;
     const int iy = c / nx, ix = c % nx;
     const double y = start_y + (double)(uint32_t)iy * s.res_y, x = start_x + (double)(uint32_t)ix * s.res_x;
     const double sq = x * x + y * y;
