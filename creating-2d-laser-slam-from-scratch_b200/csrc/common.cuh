@@ -10,7 +10,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 
 #include "../../include/b200slam.h"
 
@@ -148,6 +151,24 @@ struct StreamRef {
   cudaStream_t s = nullptr;
   bool owned = false;
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is one value per (kernel, device), shared by every handle of the process.
+// Handles of different sizes used from different threads must therefore never LOWER it between another thread's set
+// and launch: keep a process-wide running maximum per (kernel, device) and only ever raise the attribute.
+template <class K>
+inline cudaError_t raise_dyn_smem(K kern, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, size_t> seen;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &cur = seen[std::make_pair(reinterpret_cast<const void *>(kern), dev)];
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

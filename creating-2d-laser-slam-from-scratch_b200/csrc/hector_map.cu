@@ -843,7 +843,7 @@ b2s_status b2s_hector_slam_create(float map_resolution, int map_size_x, int map_
   for (auto &e : p->ev) B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaEventCreate(&e));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaEventCreateWithFlags(&p->ev_h2d, cudaEventDisableTiming));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p),
-                       cudaFuncSetAttribute(k_hs_match, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM_BYTES));
+                       raise_dyn_smem(k_hs_match, HS_SMEM_BYTES));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaMalloc(reinterpret_cast<void **>(&p->d_out), 16 * sizeof(float)));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaMallocHost(reinterpret_cast<void **>(&p->h_out), 16 * sizeof(float)));
   B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), cudaMalloc(reinterpret_cast<void **>(&p->d_visits), sizeof(unsigned long long)));

@@ -172,6 +172,7 @@ struct CudaBackend {  // the two ScanMatcher instances a Mapper owns, as b2s_mat
 }  // namespace
 
 struct b2s_mapper {
+  bool failed = false;  // a Process call failed after the scan entered the graph: the handle must be discarded
   b2s_mapper_params prm{};
   b2s_laser laser{};
   b2s_match_scan_fn match = nullptr;
@@ -794,6 +795,8 @@ b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double 
                               int32_t *out_processed, double out_corrected_pose[3]) {
   if (!m || !ranges || !odometric_pose) B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_mapper_process: null argument");
   if (out_processed) *out_processed = 0;
+  if (m->failed)
+    B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_mapper_process: an earlier call failed half-way (the reference aborts there); destroy the handle");
   MScan scan;
   scan.ranges.assign(ranges, ranges + m->laser.n_readings);
   scan.odom = p3(odometric_pose);
@@ -823,12 +826,14 @@ b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double 
       const double c[3] = {s.corrected.x, s.corrected.y, s.corrected.h};
       m->solver.add_node(m->solver.user, id, c);
     }
+    // from here on the scan is part of the graph: a failure leaves a vertex without its edges / running-window entry,
+    // so the handle is marked failed and every later Process returns B2S_ERR_BAD_STATE
     b2s_status st = add_edges(m, id, cov);
-    if (st) return st;
+    if (st) { m->failed = true; return st; }
     add_running_scan(m, id);
     if (m->prm.do_loop_closing) {
       st = try_close_loop(m, id);
-      if (st) return st;
+      if (st) { m->failed = true; return st; }
     }
   }
   m->last_scan = id;

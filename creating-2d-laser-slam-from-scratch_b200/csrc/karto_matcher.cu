@@ -152,6 +152,7 @@ struct b2s_matcher {
   unsigned long long *d_stats = nullptr;  // [0] beam-angle pairs dropped as empty windows in the last sweep
   unsigned long long *h_stats = nullptr;  // pinned copy, read back with the results
   bool pending = false;                   // a correlate_scan_begin awaits its _end
+  int pending_batch = 0;                  // batch size that _begin enqueued
   double last_empty_frac = 0.0;
   bool grid_high_bytes = false;  // set_grids saw a byte > 127: the packed-byte window kernel is not applicable
   int32_t *d_sums = nullptr;
@@ -1478,7 +1479,7 @@ static b2s_status build_sat(b2s_matcher *m) {
   const size_t sm = sizeof(uint32_t) * (size_t)(m->sbx + 1) * (m->sby + 1);
   m->sat_valid = false;
   if (sm > 200 * 1024 || (m->g.width_step % 4) != 0 || (long long)m->sbx * m->sby >= 65535) return B2S_OK;  // no skipping
-  if (sm > 16 * 1024) B2S_CUDA_CHECK(cudaFuncSetAttribute(k_grid_sat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  if (sm > 16 * 1024) B2S_CUDA_CHECK(raise_dyn_smem(k_grid_sat, sm));
   k_grid_sat<<<m->batch, 256, sm, m->stream>>>(m->d_grids, m->grid_pitch, m->g.width_step, m->g.height, m->sbx, m->sby, m->d_sat);
   B2S_CUDA_CHECK(cudaGetLastError());
   m->sat_valid = true;
@@ -1626,6 +1627,7 @@ b2s_status b2s_matcher_sync(b2s_matcher *m) {
 }
 
 b2s_status b2s_matcher_set_scans(b2s_matcher *m, int batch, const double *ranges, const double *poses) {
+  if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || !ranges || !poses) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (batch <= 0 || batch > m->max_batch) B2S_FAIL(B2S_ERR_TOO_LARGE, "batch exceeds the handle's max_batch");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
@@ -1645,6 +1647,7 @@ b2s_status b2s_matcher_set_scans(b2s_matcher *m, int batch, const double *ranges
 // rows of the handle's device-resident scan pool
 static b2s_status add_scans_impl(b2s_matcher *m, int n_base, const double *base_ranges, const int32_t *pool_rows,
                                  const double *base_poses) {
+  if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || n_base < 0 || (n_base > 0 && ((!base_ranges && !pool_rows) || !base_poses))) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->scans_set) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_set_scans must precede b2s_matcher_add_scans");
   if (n_base > m->max_base) B2S_FAIL(B2S_ERR_TOO_LARGE, "n_base exceeds the handle's max_base_scans");
@@ -1686,7 +1689,7 @@ static b2s_status add_scans_impl(b2s_matcher *m, int n_base, const double *base_
     if (!m->smear_degenerate) {
       size_t smem = n * (2 * sizeof(double) + 2 * sizeof(int) + 1) + sizeof(int) + 16;
       if (smem > 16 * 1024)
-        B2S_CUDA_CHECK(cudaFuncSetAttribute(k_add_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2S_CUDA_CHECK(raise_dyn_smem(k_add_scan, smem));
       k_add_scan<<<(unsigned)need, 256, smem, m->stream>>>(m->d_base_pts, m->d_sensor, m->d_grid_off, m->d_grids,
                                                            m->grid_pitch, m->d_kernel, m->g, scale, (int)n, n_base);
     } else {
@@ -1713,6 +1716,7 @@ b2s_status b2s_matcher_add_scans(b2s_matcher *m, int n_base, const double *base_
 // ---- scan pool: readings that serve as base scans of many matches (a mapper's running window, near chains, loop
 // candidates) are uploaded once and referenced by row afterwards
 b2s_status b2s_matcher_pool_append(b2s_matcher *m, const double *ranges, int32_t *out_row) {
+  if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || !ranges) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
   const size_t n = (size_t)std::max(m->l.n_readings, 1);
@@ -1742,6 +1746,7 @@ b2s_status b2s_matcher_add_scans_pool(b2s_matcher *m, int n_base, const int32_t 
 }
 
 b2s_status b2s_matcher_set_grids(b2s_matcher *m, const uint8_t *grids, const double *offsets) {
+  if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || !grids || !offsets) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->scans_set) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_set_scans must precede b2s_matcher_set_grids");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
@@ -1823,6 +1828,7 @@ b2s_status b2s_matcher_correlate_scan_begin(b2s_matcher *m, const double *center
   B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
   B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_stats, m->d_stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
   m->pending = true;
+  m->pending_batch = B;
   return B2S_OK;
 }
 
@@ -1830,7 +1836,7 @@ b2s_status b2s_matcher_correlate_scan_end(b2s_matcher *m, b2s_match_result *resu
   if (!m || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_correlate_scan_end without a pending b2s_matcher_correlate_scan_begin");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
-  const int B = m->batch;
+  const int B = m->pending_batch;  // the batch the _begin enqueued
   B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
   m->pending = false;
   std::memcpy(results, m->h_results, sizeof(b2s_match_result) * B);
@@ -1856,6 +1862,7 @@ b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, con
 }
 
 b2s_status b2s_matcher_match_scan(b2s_matcher *m, int do_penalize, int do_refine, b2s_match_result *results) {
+  if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
@@ -1953,6 +1960,7 @@ b2s_status b2s_matcher_match_scan_host(b2s_matcher *m, int batch, const double *
  *   finish: in global best / tie sums / plane; out the same results as b2s_matcher_correlate_scan (coarse stage). */
 b2s_status b2s_matcher_correlate_split_begin(b2s_matcher *m, const double *centers, const b2s_search *search, int k_first,
                                              int k_count, double *best, double *probs, int32_t *status) {
+  if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || !centers || !search || !best || !probs || !status || k_count < 0) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (search->fine) B2S_FAIL(B2S_ERR_BAD_PARAMS, "only the coarse stage (doingFineMatch = false) can be split");
   if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
@@ -1980,6 +1988,7 @@ static b2s_status split_phase(b2s_matcher *m, int mode) {
 }
 
 b2s_status b2s_matcher_correlate_split_ties(b2s_matcher *m, const double *global_best, double *tie_sums) {
+  if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || !global_best || !tie_sums) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->have_sweep) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_correlate_split_begin must come first");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
@@ -1995,6 +2004,7 @@ b2s_status b2s_matcher_correlate_split_ties(b2s_matcher *m, const double *global
 
 b2s_status b2s_matcher_correlate_split_finish(b2s_matcher *m, const double *global_best, const double *tie_sums,
                                               const double *probs, b2s_match_result *results) {
+  if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || !global_best || !tie_sums || !probs || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->have_sweep) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_correlate_split_begin must come first");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
@@ -2121,7 +2131,7 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     const size_t osm = (((size_t)n * OFF_SMEM_PER_BEAM + 15) & ~(size_t)15) + sat_bytes + 64;
     B2S_CUDA_CHECK(cudaMemsetAsync(m->d_stats, 0, sizeof(unsigned long long), m->stream));
     if (osm > 16 * 1024)  // static + dynamic shared memory together must stay under the 48 KB default: opt in early
-      B2S_CUDA_CHECK(cudaFuncSetAttribute(k_offsets_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
+      B2S_CUDA_CHECK(raise_dyn_smem(k_offsets_sorted, osm));
     k_offsets_sorted<<<B * ((na + OFF_CHUNK - 1) / OFF_CHUNK), 256, osm, m->stream>>>(
         m->d_ranges, m->d_local, m->d_grid_off, m->d_centers, m->d_bases, m->d_flags, s->angle_offset, s->angle_res, na, n,
         ncell, m->g.width_step, m->g.data_size, scale, rows_total, tiles_x_w * 32, m->d_lists, m->d_counts,
@@ -2143,7 +2153,7 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     const int bank_step = ((m->g.width_step >> 2) * std::max(stride, 1)) & 31;
     const bool gen = (bank_step & 3) != 2;
     auto launch = [&](auto kern) -> b2s_status {
-      B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem));
+      B2S_CUDA_CHECK(raise_dyn_smem(kern, win_smem));
       kern<<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes, m->d_lists,
                                                        m->d_counts, m->d_starts, m->d_flags, B, n, na, nx, ny,
                                                        m->g.width_step, m->d_sums, m->d_work, band_rows, nbands,

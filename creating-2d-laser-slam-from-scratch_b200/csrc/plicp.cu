@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(ICP_THREADS)
   unsigned long long *dj = reinterpret_cast<unsigned long long *>(ds + n);  // min squared distance per reference beam
   int *j1 = reinterpret_cast<int *>(dj + n), *j2 = j1 + n;
   uint8_t *rv = reinterpret_cast<uint8_t *>(j2 + n), *sv = rv + n;
-  __shared__ double red[ICP_THREADS][20];
+  __shared__ double red[ICP_THREADS][17];  // 16 used; the odd pitch keeps the tree reduction off one bank group
   __shared__ double xs[8];  // x_old[3], x_new[3], lim, error
   __shared__ int s_cnt[4];  // k (valid before trim), nvalid, ok, done
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -303,8 +303,15 @@ extern "C" b2s_status b2s_plicp_match(const b2s_icp_params *params, int batch, i
     B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_plicp_match: null/invalid argument");
   if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
   B2S_CUDA_CHECK(cudaSetDevice(device));
+  // shared memory: the kernel's static arrays + the per-beam dynamic part must fit the opt-in limit of the device
+  cudaFuncAttributes fa;
+  B2S_CUDA_CHECK(cudaFuncGetAttributes(&fa, k_plicp));
+  int optin = 0;
+  B2S_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   const size_t smem = (size_t)n * (8 * 8 + 8 + 4 + 4 + 1 + 1) + 64;
-  if (smem > 200 * 1024) B2S_FAIL(B2S_ERR_TOO_LARGE, "too many beams for the shared-memory PL-ICP kernel");
+  if (smem + fa.sharedSizeBytes > (size_t)optin) B2S_FAIL(B2S_ERR_TOO_LARGE, "too many beams for the shared-memory PL-ICP kernel");
+  // always opt in: static + dynamic crosses the 48 KB default long before the dynamic part alone does
+  B2S_CUDA_CHECK(cudaFuncSetAttribute(k_plicp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)optin - fa.sharedSizeBytes)));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   bool own = false;
   if (!st) {
@@ -314,21 +321,27 @@ extern "C" b2s_status b2s_plicp_match(const b2s_icp_params *params, int batch, i
   double *d_ref = nullptr, *d_sens = nullptr, *d_theta = nullptr, *d_guess = nullptr;
   b2s_icp_result *d_res = nullptr;
   const size_t bn = (size_t)batch * n;
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_ref), sizeof(double) * bn, st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_sens), sizeof(double) * bn, st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_theta), sizeof(double) * n, st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_guess), sizeof(double) * 3 * batch, st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_res), sizeof(b2s_icp_result) * batch, st));
-  B2S_CUDA_CHECK(cudaMemcpyAsync(d_ref, ref_ranges, sizeof(double) * bn, cudaMemcpyHostToDevice, st));
-  B2S_CUDA_CHECK(cudaMemcpyAsync(d_sens, sens_ranges, sizeof(double) * bn, cudaMemcpyHostToDevice, st));
-  B2S_CUDA_CHECK(cudaMemcpyAsync(d_theta, theta, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  B2S_CUDA_CHECK(cudaMemcpyAsync(d_guess, first_guess, sizeof(double) * 3 * batch, cudaMemcpyHostToDevice, st));
-  if (smem > 48 * 1024) B2S_CUDA_CHECK(cudaFuncSetAttribute(k_plicp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto release = [&]() {  // error paths too: nothing allocated here outlives the call
+    for (void *p : {(void *)d_ref, (void *)d_sens, (void *)d_theta, (void *)d_guess, (void *)d_res})
+      if (p) cudaFreeAsync(p, st);
+    cudaStreamSynchronize(st);
+    if (own) cudaStreamDestroy(st);
+  };
+#define ICP_CHECK(expr) B2S_CUDA_CHECK_CLEAN(release(), expr)
+  ICP_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_ref), sizeof(double) * bn, st));
+  ICP_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_sens), sizeof(double) * bn, st));
+  ICP_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_theta), sizeof(double) * n, st));
+  ICP_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_guess), sizeof(double) * 3 * batch, st));
+  ICP_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_res), sizeof(b2s_icp_result) * batch, st));
+  ICP_CHECK(cudaMemcpyAsync(d_ref, ref_ranges, sizeof(double) * bn, cudaMemcpyHostToDevice, st));
+  ICP_CHECK(cudaMemcpyAsync(d_sens, sens_ranges, sizeof(double) * bn, cudaMemcpyHostToDevice, st));
+  ICP_CHECK(cudaMemcpyAsync(d_theta, theta, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ICP_CHECK(cudaMemcpyAsync(d_guess, first_guess, sizeof(double) * 3 * batch, cudaMemcpyHostToDevice, st));
   k_plicp<<<batch, ICP_THREADS, smem, st>>>(*params, n, d_ref, d_sens, d_theta, range_min, range_max, d_guess, d_res);
-  B2S_CUDA_CHECK(cudaGetLastError());
-  B2S_CUDA_CHECK(cudaMemcpyAsync(results, d_res, sizeof(b2s_icp_result) * batch, cudaMemcpyDeviceToHost, st));
-  for (void *p : {(void *)d_ref, (void *)d_sens, (void *)d_theta, (void *)d_guess, (void *)d_res}) B2S_CUDA_CHECK(cudaFreeAsync(p, st));
-  B2S_CUDA_CHECK(cudaStreamSynchronize(st));
-  if (own) cudaStreamDestroy(st);
+  ICP_CHECK(cudaGetLastError());
+  ICP_CHECK(cudaMemcpyAsync(results, d_res, sizeof(b2s_icp_result) * batch, cudaMemcpyDeviceToHost, st));
+  ICP_CHECK(cudaStreamSynchronize(st));
+#undef ICP_CHECK
+  release();
   return B2S_OK;
 }

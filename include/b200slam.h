@@ -115,8 +115,8 @@ int b2s_device_count(void);                    /* 0 when no usable CUDA device *
  * stages them before the call returns; out of PINNED memory they are asynchronous, so such buffers must stay unchanged
  * until the next call that waits for the stream (correlate_scan, match_scan, _end, sync). */
 
-/* ScanMatcher::Create (Mapper.cpp:126-172).  `max_batch` matches share one handle; `max_angles`
- * bounds nAngles of any later search (0 = derive from params).  `cuda_stream` may be NULL
+/* ScanMatcher::Create (Mapper.cpp:126-172).  `max_batch` matches share one handle, each with up to
+ * `max_base_scans` base scans; buffers that depend on the search volume grow on demand.  `cuda_stream` may be NULL
  * (the handle then creates its own non-blocking stream) or a cudaStream_t owned by the caller. */
 b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser *laser, int device,
                               int max_batch, int max_base_scans, void *cuda_stream, b2s_matcher **out);
@@ -267,7 +267,11 @@ void b2s_mapper_destroy(b2s_mapper *m);
 /* Mapper::SetScanSolver (Mapper.cpp:2220); NULL = no back end (poses are never corrected, as with use_back_end false) */
 b2s_status b2s_mapper_set_scan_solver(b2s_mapper *m, const b2s_scan_solver *solver);
 /* Mapper::Process(LocalizedRangeScan*) (Mapper.cpp:1999-2079): ranges[n_readings], odometric robot pose, time stamp (s).
- * out_processed = the kt_bool it returns (false: rejected by HasMovedEnough); out_corrected_pose = GetCorrectedPose(). */
+ * out_processed = the kt_bool it returns (false: rejected by HasMovedEnough); out_corrected_pose = GetCorrectedPose().
+ * A non-OK status returned after the scan entered the graph (edge building / loop closing failed: CUDA error,
+ * B2S_ERR_NO_BEST_POSE, or B2S_ERR_BAD_STATE where the reference's Matrix3::Inverse asserts) leaves the mapper where
+ * the reference process would have aborted: the handle is marked failed, later calls return B2S_ERR_BAD_STATE, and it
+ * must be destroyed. */
 b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double odometric_pose[3], double time,
                               int32_t *out_processed, double out_corrected_pose[3]);
 int32_t b2s_mapper_scan_count(const b2s_mapper *m);   /* GetAllProcessedScans().size() */

@@ -76,3 +76,26 @@ def test_gpu_matches_restatement_and_truth(pkg):
     for b in range(5):
         res = port.plicp_match(p2, refs[b], sens[b], theta, 0.1, 30.0, guesses[b])
         assert v2[b] == res.valid and np.allclose(x2[b], res.x[:], rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [90, 360, 598, 720])
+def test_gpu_beam_counts_between_the_shared_memory_defaults(pkg, n):
+    """Beam counts whose static + dynamic shared memory crosses the 48 KB default without the dynamic part alone doing
+    so (86..598 once failed with cudaErrorInvalidValue): a 360-beam lidar must work like the 1081-beam one."""
+    abi, synth = pkg.abi, pkg.synth
+    P = pkg.load("plicp")
+    laser = synth.Laser(n_readings=n, min_angle=-np.pi, max_angle=np.pi - 2 * np.pi / n, angular_resolution=2 * np.pi / n)
+    theta = laser.min_angle + np.arange(n) * laser.angular_resolution
+    world = synth.make_world(4)
+    refs, sens = [], []
+    for d in CASES[:3]:
+        ra, rb = pair(synth, world, d, laser)
+        refs.append(ra); sens.append(rb)
+    params = abi.icp_params()
+    x, valid, iters, nvalid, err = P.match(params, refs, sens, theta, 0.1, 30.0, [[0, 0, 0]] * 3)
+    for b in range(3):
+        res = port.plicp_match(params, refs[b], sens[b], theta, 0.1, 30.0, [0, 0, 0])
+        assert valid[b] == res.valid
+        if res.valid:
+            assert np.allclose(x[b], res.x[:], rtol=0, atol=1e-6), (n, b, x[b], res.x[:])
