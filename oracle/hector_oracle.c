@@ -191,9 +191,20 @@ long orc_hmap_update_by_scan_just_once(orc_hmap *m, const float *points, int n, 
   return visits;
 }
 
+/* getGridProbability (GridMapLogOdds.h:136-140): `float odds = exp(cell.logOddsVal);` — the header includes only
+ * <cmath>, so the unqualified exp / sin / cos on a float resolve to the C library's DOUBLE functions (the reference
+ * build imports exp, sincos, sincosf, log, fmod, pow, round and no expf: `nm -D oracle/_ref/libhector_ref.so`); the
+ * result is rounded to float on assignment.  (float)exp((double)x) and expf(x) differ on ~0.07 % of inputs. */
 static float grid_prob(const orc_hmap *m, int index) {
-  float odds = expf(m->log_odds[index]);
+  float odds = (float)exp((double)m->log_odds[index]);
   return odds / (odds + 1.0f);
+}
+
+void orc_hector_grid_probabilities(const float *log_odds, int n, float *out) {
+  orc_hmap m;
+  memset(&m, 0, sizeof(m));
+  m.log_odds = (float *)log_odds;
+  for (int i = 0; i < n; i++) out[i] = grid_prob(&m, i);
 }
 
 /* interpMapValueWithDerivatives (OccGridMapUtil.h:139-228); the per-scan cache only memoises getGridProbability */
@@ -215,7 +226,7 @@ static void interp(const orc_hmap *m, float x, float y, float out[3]) {
 /* getCompleteHessianDerivs (OccGridMapUtil.h:77-132): H row-major 3x3, dTr[3] */
 static void hessian_derivs(const orc_hmap *m, const float pose[3], const float *pts, int n, float H[9], float dTr[3]) {
   float c = cosf(pose[2]), s = sinf(pose[2]);          /* getTransformForState: Rotation2Df */
-  float sin_rot = (float)sin(pose[2]), cos_rot = (float)cos(pose[2]); /* `sin(pose[2])` with float arg: std::sin(float) */
+  float sin_rot = (float)sin((double)pose[2]), cos_rot = (float)cos((double)pose[2]); /* unqualified sin / cos: ::sin(double), rounded to float */
   memset(H, 0, 9 * sizeof(float));
   memset(dTr, 0, 3 * sizeof(float));
   for (int i = 0; i < n; i++) {

@@ -124,6 +124,17 @@ void ref_hmap_match_data(void *h, const float *pts, int n, const float begin_wor
       for (int j = 0; j < 3; ++j) out_cov[3 * i + j] = cov(i, j);
 }
 
+/* GridMapLogOddsFunctions::getGridProbability (GridMapLogOdds.h:136-140) of the reference, for arbitrary log-odds values:
+ * the values are planted into a scratch map's cells and read back through OccGridMapBase::getGridProbabilityMap. */
+void ref_hector_grid_probabilities(const float *log_odds, int n, float *out) {
+  HGridMap g(1.0f, Eigen::Vector2i(64, 64), Eigen::Vector2f(0.f, 0.f));
+  for (int i = 0; i < n; i += 64 * 64) {
+    const int cnt = n - i < 64 * 64 ? n - i : 64 * 64;
+    for (int j = 0; j < cnt; ++j) g.getCell(j).logOddsVal = log_odds[i + j];
+    for (int j = 0; j < cnt; ++j) out[i + j] = g.getGridProbabilityMap(j);
+  }
+}
+
 /* Bresenham cell list of OccGridMapBase::updateLineBresenhami as the map sees it: run one line on a scratch map and
  * report which cells were freed / occupied (update index stamps), for the per-segment cell-set tests. */
 int ref_hector_line_cells(int size, int x0, int y0, int x1, int y1, int32_t *free_cells, int32_t *n_free, int32_t *occ_cell) {

@@ -170,3 +170,24 @@ def test_hector_golden(pkg):
     idx = np.flatnonzero(ui.ravel() >= 0)
     assert np.array_equal(idx, g["jo_idx"]) and np.array_equal(ui.ravel()[idx], g["jo_ui"])
     assert np.array_equal(lo.ravel()[idx].view(np.int32), g["jo_lo"].view(np.int32))
+
+
+@live
+def test_grid_probability_double_exp(pkg):
+    """getGridProbability (GridMapLogOdds.h:136-140): the unqualified exp() on a float is the C library's double exp,
+    rounded to float (the reference build imports `exp`, not `expf`).  2^20 log-odds values incl. every multiple-sum
+    the update factors can produce: restatement == reference, bit for bit; and the expf reading would NOT be."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    lf, lo_ = np.float32(np.log(np.float32(0.4) / np.float32(0.6))), np.float32(np.log(np.float32(0.9) / np.float32(0.1)))
+    combos = (np.arange(-60, 1, dtype=np.float32)[:, None] * lf + np.arange(0, 40, dtype=np.float32)[None, :] * lo_).ravel()
+    v = np.concatenate([combos, rng.uniform(-60, 60, (1 << 20) - len(combos)).astype(np.float32)]).astype(np.float32)
+    a, b = np.zeros_like(v), np.zeros_like(v)
+    L = port.lib()
+    L.orc_hector_grid_probabilities(v.ctypes.data_as(C.POINTER(C.c_float)), len(v), a.ctypes.data_as(C.POINTER(C.c_float)))
+    rh.lib().ref_hector_grid_probabilities(v.ctypes.data_as(C.POINTER(C.c_float)), len(v), b.ctypes.data_as(C.POINTER(C.c_float)))
+    assert np.array_equal(a.view(np.int32), b.view(np.int32))
+    with np.errstate(all="ignore"):
+        odds_f = np.exp(v)  # numpy float32 exp: the other reading
+        alt = odds_f / (odds_f + np.float32(1.0))
+    assert (alt.view(np.int32) != b.view(np.int32)).any()
