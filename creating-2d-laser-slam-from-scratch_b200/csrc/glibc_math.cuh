@@ -99,7 +99,7 @@ B2S_HD float glibc_cosf(float y, bool use_fma) {
   return cosf(y);
 }
 
-#if !defined(__CUDA_ARCH__)
+// (host function)
 // Which build of s_sincosf does THIS host's libm run?  1 = FMA, 0 = separate multiply / add, -1 = neither restatement
 // reproduces it on the probe inputs (an unknown libm: callers fall back to 1 and report it).  The two builds differ on
 // exactly 34 of the 2 246 049 792 floats with |x| < 120 (all with |x| > 17.2, next to multiples of pi/2 where the
@@ -123,6 +123,5 @@ inline int glibc_sincosf_variant_of_host() {
   if (ok[0]) return 0;
   return -1;
 }
-#endif
 
 }  // namespace b2s

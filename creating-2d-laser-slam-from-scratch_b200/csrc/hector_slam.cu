@@ -1,0 +1,1181 @@
+// lesson4 front end — hectorslam::HectorSlamProcessor on B200 (sm_100a).  Product code: CUDA only.
+//
+// Reference behaviour (paths relative to /root/reference/lesson4/include/lesson4/hector_mapping):
+//   HectorSlamProcessor::update / reset                                  slam_main/HectorSlamProcessor.h:81-116
+//   MapRepMultiMap ctor / matchData / updateByScan                       slam_main/MapRepMultiMap.h:56-191
+//   ScanMatcher::matchData / estimateTransformationLogLh                 matcher/ScanMatcher.h:60-141
+//   OccGridMapUtil::getCompleteHessianDerivs / interpMapValueWithDerivatives / getTransformForState
+//                                                                        map/OccGridMapUtil.h:77-228, 437-440
+//   OccGridMapBase::updateByScan / Bresenham / bresenhamCellFree/Occ     map/OccGridMapBase.h:118-168, 220-330
+//   GridMapLogOddsFunctions::getGridProbability                          map/GridMapLogOdds.h:136-140
+//   util::poseDifferenceLargerThan / normalize_angle                     util/UtilFunctions.h:36-48, 72-90
+//   node loop: update(container, getLastScanMatchPose())                 lesson4/src/hector_mapping/hector_slam.cc:195-204
+//
+// Everything of one LaserScan runs on the device: the coarse-to-fine Gauss-Newton match, the map-update gate, the
+// pose -> cell transform of the update and the Bresenham mark / apply passes.  The processor's state (last poses,
+// update indices, stamp epochs, the coarse levels' data containers) lives in device memory, so a stream of scans needs
+// no host round trip between scans (b2s_hector_slam_process_stream: ONE cooperative kernel walks the whole stream;
+// b2s_hector_slam_update: one launch per scan, the pose comes back through a host-mapped mailbox as soon as the match
+// is done while the map update still runs).  A handle holds B independent processors (independent robots / maps,
+// "shard over independent maps"); B = 1 is the reference's single processor.
+//
+// Arithmetic: float32 in the reference's operation order, no FMA (-fmad=false).  EXACT mode (default) reproduces the
+// reference bit for bit: the nine sums of getCompleteHessianDerivs are accumulated sequentially in point order (one lane
+// per sum), Rotation2Df's std::cos / std::sin(float) are glibc's sincosf restated (glibc_math.cuh), the unqualified
+// sin / cos / exp of the reference (C library DOUBLE functions rounded to float) are the device's double functions
+// rounded to float (both are within 2 ulp of the exact double, so the float agrees unless the exact value lies within
+// ~1e-16 relative of a float rounding boundary: ~5e-9 per evaluation).  FAST mode sums with a tree (poses within 1e-4).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "glibc_math.cuh"
+
+using namespace b2s;
+
+namespace b2s {
+
+constexpr int HS_L = B2S_HECTOR_MAX_LEVELS;
+constexpr int HS_THREADS = 576;          // 18 warps: two points per thread cover a 1081-beam scan in one pass
+constexpr int HS_MAX_PTS = 4096;         // beams per scan (12-bit beam field of the stamps; shared-memory staging)
+constexpr int HS_EPOCH_BITS = 20;
+constexpr unsigned HS_EPOCH_MAX = (1u << HS_EPOCH_BITS) - 1;
+constexpr int HS_STREAM_CTAS = 48;       // cooperative grid of the stream kernel (one CTA per SM, all co-resident)
+
+struct HsLevel {  // one MapRepMultiMap level, all B processors ([b][cells] planes)
+  float *prob;    // getGridProbability(cell), refreshed whenever a cell's log-odds changes: the device-side form of the
+                  // reference's per-scan GridMapCacheArray
+  float *lo;
+  int32_t *ui;
+  uint32_t *free_st, *occ_st;  // per-scan stamps: (epoch << 12) | (4095 - beam)
+  float *pts;                  // [b][cap][2] data container of this level (level 0: the current scan)
+  int sx, sy;
+  float tw_lin, tw_tx, tw_ty, wt_lin, wt_tx, wt_ty;
+  int iterations;  // 1 + maxIterations of MapRepMultiMap::matchData (:144-166): 1+5 on level 0, 1+3 above
+};
+
+struct HsState {  // device-resident state of ONE processor
+  float last_update_pose[3], last_match_pose[3], last_cov[9];
+  int curr_update_index[HS_L];
+  unsigned int epoch[HS_L];
+  int n_pts[HS_L];
+  float origo[HS_L][2];
+  // the update the gate decided for the current scan
+  int do_update;
+  float uc[HS_L], us[HS_L], umx[HS_L], umy[HS_L];
+  int bx[HS_L], by[HS_L];
+  unsigned int epoch_hi[HS_L];
+  int mark_free[HS_L], mark_occ[HS_L];
+  unsigned long long visits, n_matched, n_updated;
+  unsigned long long t_match_ns, t_update_ns;
+};
+
+struct HsBatch {  // kernel parameter
+  HsLevel l[HS_L];
+  int levels, batch, cap;
+  float lo_free, lo_occ, min_dist, min_angle;
+  int exact, use_fma;
+  HsState *state;  // [batch]
+};
+
+struct HsCall {  // one scan per processor
+  const float *pts0;    // [b][pts_stride][2] level-0 points (device, or host-mapped for the per-scan call)
+  const int *n0;        // [b] (device / host-mapped) or NULL -> n0_uniform
+  int n0_uniform, pts_stride;
+  const float *hints;   // [b][3] or NULL -> the processor's last scan-match pose (the node's loop)
+  float origo_x, origo_y;
+  int map_without_matching;
+  float *out;           // [b][16] device: pose[3], cov[9], updated, matched, -, -
+  volatile float *mailbox;  // host-mapped copy of out for processor 0 + sequence word, or NULL
+  unsigned int seq;
+};
+
+__device__ __forceinline__ unsigned long long hs_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void hs_interp(const float *__restrict__ prob, int sx, int sy, float x, float y, float out[3]) {
+  const float lim_x = (float)sx - 2.0f, lim_y = (float)sy - 2.0f;  // setMapCellDims: dims - 2
+  if (x < 0.0f || x > lim_x || y < 0.0f || y > lim_y) { out[0] = out[1] = out[2] = 0.0f; return; }
+  const int ix = (int)x, iy = (int)y;
+  const float fx = x - (float)ix, fy = y - (float)iy;
+  const int index = iy * sx + ix;
+  // L2 loads: the planes are rewritten by other SMs between the scans of one persistent launch
+  const float i0 = __ldcg(prob + index), i1 = __ldcg(prob + index + 1), i2 = __ldcg(prob + index + sx),
+              i3 = __ldcg(prob + index + sx + 1);
+  const float dx1 = i0 - i1, dx2 = i2 - i3, dy1 = i0 - i2, dy2 = i1 - i3;
+  const float xfi = 1.0f - fx, yfi = 1.0f - fy;
+  out[0] = ((i0 * xfi + i1 * fx) * yfi) + ((i2 * xfi + i3 * fx) * fy);
+  out[1] = -((dx1 * yfi) + (dx2 * fy));
+  out[2] = -((dy1 * xfi) + (dy2 * fx));
+}
+
+__device__ inline void hs_inv3_mul(const float m[9], const float v[3], float out[3]) {  // Matrix3f::inverse() * v
+  const float c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
+  const float det = c00 * m[0] + (c10 * m[1] + c20 * m[2]);  /* Eigen's unrolled 3-term redux: a0 + (a1 + a2) */
+  const float invdet = 1.0f / det;
+  float inv[9];
+  inv[0] = c00 * invdet; inv[3] = c10 * invdet; inv[6] = c20 * invdet;
+  inv[1] = (m[2] * m[7] - m[1] * m[8]) * invdet;
+  inv[4] = (m[0] * m[8] - m[2] * m[6]) * invdet;
+  inv[7] = (m[1] * m[6] - m[0] * m[7]) * invdet;
+  inv[2] = (m[1] * m[5] - m[2] * m[4]) * invdet;
+  inv[5] = (m[2] * m[3] - m[0] * m[5]) * invdet;
+  inv[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
+  for (int r = 0; r < 3; r++) out[r] = inv[3 * r] * v[0] + (inv[3 * r + 1] * v[1] + inv[3 * r + 2] * v[2]);
+}
+
+// util::poseDifferenceLargerThan (UtilFunctions.h:72-90).  Only <cmath> is included there, so the unqualified
+// abs(angleDiff) is int abs(int): the difference is truncated to an integer before the compare.
+__device__ inline bool hs_pose_difference_larger_than(const float a[3], const float b[3], float dist_thresh,
+                                                      float angle_thresh) {
+  const float dx = a[0] - b[0], dy = a[1] - b[1];
+  if (sqrtf(dx * dx + dy * dy) > dist_thresh) return true;
+  float d = a[2] - b[2];
+  const double pi = 3.14159265358979323846;
+  if ((double)d > pi) d = (float)((double)d - pi * 2.0f);
+  else if ((double)d < -pi) d = (float)((double)d + pi * 2.0f);
+  const int t = (int)d;
+  return (float)(t < 0 ? -t : t) > angle_thresh;
+}
+
+// terms of one point for getCompleteHessianDerivs (OccGridMapUtil.h:99-126)
+__device__ __forceinline__ void hs_point_terms(const float *__restrict__ prob, int sx, int sy, float2 p, float c, float s,
+                                               float sin_rot, float cos_rot, float e0, float e1, float a[9]) {
+  const float tx = (c * p.x + (-s) * p.y) + e0, ty = (s * p.x + c * p.y) + e1;
+  float t[3];
+  hs_interp(prob, sx, sy, tx, ty, t);
+  const float rot = ((-sin_rot * p.x - cos_rot * p.y) * t[1] + (cos_rot * p.x - sin_rot * p.y) * t[2]);
+  const float fun = 1.0f - t[0];
+  a[0] = t[1] * fun; a[1] = t[2] * fun; a[2] = rot * fun;    // dTr
+  a[3] = t[1] * t[1]; a[4] = t[2] * t[2]; a[5] = rot * rot;  // H00 H11 H22
+  a[6] = t[1] * t[2]; a[7] = t[1] * rot; a[8] = t[2] * rot;  // H01 H02 H12
+}
+
+struct HsTrig {
+  float c, s;              // Rotation2Df(angle): std::cos / std::sin(float) = glibc cosf / sinf
+  float sin_rot, cos_rot;  // OccGridMapUtil.h:87-88: the C library's double sin / cos, rounded to float
+};
+__device__ inline HsTrig hs_trig(float angle, bool exact, bool use_fma) {
+  HsTrig t;
+  if (exact) {
+    t.c = glibc_cosf(angle, use_fma);
+    t.s = glibc_sinf(angle, use_fma);
+    t.sin_rot = (float)sin((double)angle);
+    t.cos_rot = (float)cos((double)angle);
+  } else {
+    t.c = cosf(angle); t.s = sinf(angle);
+    t.sin_rot = t.s; t.cos_rot = t.c;
+  }
+  return t;
+}
+
+// shared memory of the match: [cap] float2 staged scan, then (EXACT) 9 term columns of `pitch` floats / (FAST) per-warp partials
+__host__ __device__ inline int hs_pitch(int cap) { return ((cap + 3) & ~3) + 4; }
+__host__ __device__ inline size_t hs_smem_bytes(int cap) { return sizeof(float2) * (size_t)cap + sizeof(float) * 9 * (size_t)hs_pitch(cap) + 64; }
+
+// MapRepMultiMap::matchData (:144-166) on every level, coarsest first, + the gate and the update parameters of
+// HectorSlamProcessor::update (:81-108), by ONE CTA for processor b.
+__device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned char *smem) {
+  HsState *st = P.state + b;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = HS_THREADS / 32;
+  const int n = C.n0 ? C.n0[b] : C.n0_uniform;
+  const bool exact = P.exact != 0, use_fma = P.use_fma != 0;
+  float2 *spts = reinterpret_cast<float2 *>(smem);
+  float *terms = reinterpret_cast<float *>(smem + sizeof(float2) * (size_t)P.cap);
+  const int pitch = hs_pitch(P.cap);
+  __shared__ float bc[8];    // estimate + trig published by the solving thread
+  __shared__ float tot[9];
+  __shared__ float s_world[3];
+  const unsigned long long t0 = hs_now_ns();
+  const float2 *gp = reinterpret_cast<const float2 *>(C.pts0) + (size_t)b * C.pts_stride;
+  for (int i = tid; i < n; i += HS_THREADS) {
+    const float2 p = gp[i];
+    spts[i] = p;
+    reinterpret_cast<float2 *>(P.l[0].pts)[(size_t)b * P.cap + i] = p;  // level-0 container for the update passes
+  }
+  if (tid == 0) {
+    const float *h = C.hints ? C.hints + 3 * b : st->last_match_pose;
+    s_world[0] = h[0]; s_world[1] = h[1]; s_world[2] = h[2];
+  }
+  __syncthreads();
+  float world0 = s_world[0], world1 = s_world[1], world2 = s_world[2];
+  bool any = false;
+  if (!C.map_without_matching && n > 0) {
+    float factor = 1.0f;
+    for (int l = 1; l < P.levels; l++) factor *= 0.5f;  // static_cast<float>(1.0 / pow(2.0, l)) is exactly 2^-l
+    for (int lv = P.levels - 1; lv >= 0; lv--, factor *= 2.0f) {
+      const HsLevel &m = P.l[lv];
+      const float *prob = m.prob + (size_t)b * m.sx * m.sy;
+      if (lv > 0)  // dataContainers[lv-1].setFrom(dataContainer, 2^-lv) (DataPointContainer.h:46-59): exact scaling
+        for (int i = tid; i < n; i += HS_THREADS)
+          reinterpret_cast<float2 *>(m.pts)[(size_t)b * P.cap + i] = make_float2(__fmul_rn(spts[i].x, factor), __fmul_rn(spts[i].y, factor));
+      // getMapCoordsPose (GridMapBase.h:238-242)
+      if (tid == 0) {
+        const float e0 = (m.tw_lin * world0 + 0.0f * world1) + m.tw_tx;
+        const float e1 = (0.0f * world0 + m.tw_lin * world1) + m.tw_ty;
+        const HsTrig tr = hs_trig(world2, exact, use_fma);
+        bc[0] = e0; bc[1] = e1; bc[2] = world2; bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
+      }
+      __syncthreads();
+      for (int it = 0; it < m.iterations; it++) {
+        const float e0 = bc[0], e1 = bc[1], c = bc[3], s = bc[4], sin_rot = bc[5], cos_rot = bc[6];
+        if (exact) {
+          for (int i = tid; i < n; i += HS_THREADS) {
+            float a[9];
+            const float2 p = make_float2(__fmul_rn(spts[i].x, factor), __fmul_rn(spts[i].y, factor));
+            hs_point_terms(prob, m.sx, m.sy, p, c, s, sin_rot, cos_rot, e0, e1, a);
+#pragma unroll
+            for (int q = 0; q < 9; q++) terms[q * pitch + i] = a[q];
+          }
+          __syncthreads();
+          if (warp == 0) {  // the reference's float32 sums, in point order: lane q owns sum q (9 dependent FADD chains)
+            float acc = 0.0f;
+            if (lane < 9) {
+              const float *col = terms + lane * pitch;
+              int i = 0;
+              for (; i + 8 <= n; i += 8) {
+                const float4 u = *reinterpret_cast<const float4 *>(col + i), v = *reinterpret_cast<const float4 *>(col + i + 4);
+                acc = __fadd_rn(acc, u.x); acc = __fadd_rn(acc, u.y); acc = __fadd_rn(acc, u.z); acc = __fadd_rn(acc, u.w);
+                acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+              }
+              for (; i < n; i++) acc = __fadd_rn(acc, col[i]);
+              tot[lane] = acc;
+            }
+          }
+        } else {
+          float a[9];
+#pragma unroll
+          for (int q = 0; q < 9; q++) a[q] = 0.0f;
+          for (int i = tid; i < n; i += HS_THREADS) {
+            float t[9];
+            const float2 p = make_float2(__fmul_rn(spts[i].x, factor), __fmul_rn(spts[i].y, factor));
+            hs_point_terms(prob, m.sx, m.sy, p, c, s, sin_rot, cos_rot, e0, e1, t);
+#pragma unroll
+            for (int q = 0; q < 9; q++) a[q] += t[q];
+          }
+#pragma unroll
+          for (int q = 0; q < 9; q++) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], d);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 9; q++) terms[q * NW + warp] = a[q];
+          }
+          __syncthreads();
+          if (warp == 0) {
+            float v = 0.0f;
+            if (lane < 9) {
+              for (int w = 0; w < NW; w++) v += terms[lane * NW + w];
+              tot[lane] = v;
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
+          const float dTr[3] = {tot[0], tot[1], tot[2]};
+          float Hm[9];
+          Hm[0] = tot[3]; Hm[4] = tot[4]; Hm[8] = tot[5];
+          Hm[1] = Hm[3] = tot[6]; Hm[2] = Hm[6] = tot[7]; Hm[5] = Hm[7] = tot[8];
+          float n0 = bc[0], n1 = bc[1], n2 = bc[2];
+          if (Hm[0] != 0.0f && Hm[4] != 0.0f) {
+            float dir[3];
+            hs_inv3_mul(Hm, dTr, dir);
+            if (dir[2] > 0.2f) dir[2] = 0.2f;
+            else if (dir[2] < -0.2f) dir[2] = -0.2f;
+            n0 += dir[0]; n1 += dir[1]; n2 += dir[2];
+          }
+          bc[0] = n0; bc[1] = n1; bc[2] = n2;
+          if (it + 1 < m.iterations) {
+            const HsTrig tr = hs_trig(n2, exact, use_fma);
+            bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
+          }
+        }
+        __syncthreads();
+      }
+      {
+        const float e0 = bc[0], e1 = bc[1], e2 = bc[2];
+        const double two_pi = 2.0f * 3.14159265358979323846;  // util::normalize_angle (UtilFunctions.h:36-48)
+        float a = (float)fmod(fmod((double)e2, two_pi) + two_pi, two_pi);
+        if ((double)a > 3.14159265358979323846) a = (float)((double)a - two_pi);
+        world0 = (m.wt_lin * e0 + (-0.0f) * e1) + m.wt_tx;  // getWorldCoordsPose (GridMapBase.h:229-233)
+        world1 = ((-0.0f) * e0 + m.wt_lin * e1) + m.wt_ty;
+        world2 = a;
+        any = true;
+      }
+      __syncthreads();  // bc / tot are rewritten by the next level
+    }
+  }
+  if (tid == 0) {
+    // ---- HectorSlamProcessor::update after the match (:88-107) ----
+    float est[3] = {world0, world1, world2};
+    if (any) {  // covMatrix = H of the last level matched (level 0)
+      st->last_cov[0] = tot[3]; st->last_cov[4] = tot[4]; st->last_cov[8] = tot[5];
+      st->last_cov[1] = st->last_cov[3] = tot[6]; st->last_cov[2] = st->last_cov[6] = tot[7];
+      st->last_cov[5] = st->last_cov[7] = tot[8];
+    }
+    if (!C.map_without_matching) {
+      st->n_matched += 1;
+      if (n > 0) {
+        float factor = 1.0f;
+        for (int l = 1; l < P.levels; l++) {
+          factor *= 0.5f;
+          st->n_pts[l] = n;
+          st->origo[l][0] = C.origo_x * factor; st->origo[l][1] = C.origo_y * factor;
+        }
+      } else {
+        for (int l = 1; l < P.levels; l++) st->n_pts[l] = 0;  // setFrom of an empty container
+      }
+    }
+    st->n_pts[0] = n;
+    st->origo[0][0] = C.origo_x; st->origo[0][1] = C.origo_y;
+    st->last_match_pose[0] = est[0]; st->last_match_pose[1] = est[1]; st->last_match_pose[2] = est[2];
+    const bool do_update = hs_pose_difference_larger_than(est, st->last_update_pose, P.min_dist, P.min_angle) ||
+                           C.map_without_matching;
+    st->do_update = do_update ? 1 : 0;
+    if (do_update) {
+      float uc, us;  // Rotation2Df of the update transform: glibc cosf / sinf -> the same cells as the CPU
+      if (exact) { uc = glibc_cosf(est[2], use_fma); us = glibc_sinf(est[2], use_fma); }
+      else { uc = cosf(est[2]); us = sinf(est[2]); }
+      for (int l = 0; l < P.levels; l++) {
+        const HsLevel &m = P.l[l];
+        const float mx = (m.tw_lin * est[0] + 0.0f * est[1]) + m.tw_tx;  // getMapCoordsPose (GridMapBase.h:238-242)
+        const float my = (0.0f * est[0] + m.tw_lin * est[1]) + m.tw_ty;
+        st->uc[l] = uc; st->us[l] = us; st->umx[l] = mx; st->umy[l] = my;
+        const float bxf = (uc * st->origo[l][0] + (-us) * st->origo[l][1]) + mx;
+        const float byf = (us * st->origo[l][0] + uc * st->origo[l][1]) + my;
+        st->bx[l] = (int)(bxf + 0.5f); st->by[l] = (int)(byf + 0.5f);  // Vector2i(float, float): truncation
+        st->epoch[l] += 1;
+        st->epoch_hi[l] = st->epoch[l] << 12;
+        st->mark_free[l] = st->curr_update_index[l] + 1;  // OccGridMapBase.h:120-121
+        st->mark_occ[l] = st->curr_update_index[l] + 2;
+        st->curr_update_index[l] += 3;                    // :167
+      }
+      st->last_update_pose[0] = est[0]; st->last_update_pose[1] = est[1]; st->last_update_pose[2] = est[2];
+      st->n_updated += 1;
+    }
+    float *o = C.out + 16 * (size_t)b;
+    o[0] = est[0]; o[1] = est[1]; o[2] = est[2];
+    for (int q = 0; q < 9; q++) o[3 + q] = st->last_cov[q];
+    o[12] = do_update ? 1.0f : 0.0f;
+    o[13] = any ? 1.0f : 0.0f;
+    if (C.mailbox && b == 0) {
+      for (int q = 0; q < 14; q++) C.mailbox[q] = o[q];
+      __threadfence_system();
+      reinterpret_cast<volatile unsigned int *>(C.mailbox)[15] = C.seq;
+      __threadfence_system();
+    }
+    st->t_match_ns = hs_now_ns() - t0;
+  }
+}
+
+struct HsLine {
+  bool ok;
+  int x0, y0, x1, y1;
+  unsigned int da, db;
+  int err0, off_a, off_b;
+};
+
+// endpoints (OccGridMapBase.h:127-154) + updateLineBresenhami set-up (:220-258)
+__device__ __forceinline__ HsLine hs_line(float c, float s, float mx, float my, int bx, int by, float px, float py, int sx,
+                                          int sy) {
+  HsLine L;
+  float ex = __fadd_rn(__fadd_rn(__fmul_rn(c, px), __fmul_rn(-s, py)), mx);
+  float ey = __fadd_rn(__fadd_rn(__fmul_rn(s, px), __fmul_rn(c, py)), my);
+  ex = __fadd_rn(ex, 0.5f);
+  ey = __fadd_rn(ey, 0.5f);
+  L.x0 = bx; L.y0 = by;
+  L.x1 = (int)ex; L.y1 = (int)ey;  // Vector2f::cast<int>(): truncation
+  L.ok = !(L.x0 == L.x1 && L.y0 == L.y1);
+  if ((L.x0 < 0) || (L.x0 >= sx) || (L.y0 < 0) || (L.y0 >= sy)) L.ok = false;
+  if ((L.x1 < 0) || (L.x1 >= sx) || (L.y1 < 0) || (L.y1 >= sy)) L.ok = false;
+  const int dx = L.x1 - L.x0, dy = L.y1 - L.y0;
+  const unsigned int adx = (unsigned int)abs(dx), ady = (unsigned int)abs(dy);
+  const int odx = dx > 0 ? 1 : -1, ody = (dy > 0 ? 1 : -1) * sx;  // util::sign: sign(0) = -1
+  if (adx >= ady) { L.da = adx; L.db = ady; L.err0 = (int)(adx / 2); L.off_a = odx; L.off_b = ody; }
+  else { L.da = ady; L.db = adx; L.err0 = (int)(ady / 2); L.off_a = ody; L.off_b = odx; }
+  return L;
+}
+
+// the update parameters of one level as the gate wrote them; L2 loads (other SMs wrote them during THIS launch)
+struct HsUpd {
+  int n;
+  float c, s, mx, my;
+  int bx, by;
+  uint32_t ehi;
+  int mark_free, mark_occ;
+};
+__device__ __forceinline__ HsUpd hs_load_upd(const HsState *st, int lv) {
+  HsUpd u;
+  u.n = __ldcg(&st->n_pts[lv]);
+  u.c = __ldcg(&st->uc[lv]); u.s = __ldcg(&st->us[lv]); u.mx = __ldcg(&st->umx[lv]); u.my = __ldcg(&st->umy[lv]);
+  u.bx = __ldcg(&st->bx[lv]); u.by = __ldcg(&st->by[lv]);
+  u.ehi = __ldcg(&st->epoch_hi[lv]);
+  u.mark_free = __ldcg(&st->mark_free[lv]); u.mark_occ = __ldcg(&st->mark_occ[lv]);
+  return u;
+}
+
+__device__ __forceinline__ float hs_prob_of(float lo, bool exact) {  // getGridProbability (GridMapLogOdds.h:136-140)
+  const float odds = exact ? (float)exp((double)lo) : expf(lo);  // unqualified exp(): the C library's double exp
+  return odds / (odds + 1.0f);
+}
+
+// MapRepMultiMap::updateByScan (:174-191) for processor b.  Work item = (level, beam), flattened over the levels, one
+// warp each; lanes over Bresenham steps in closed form.
+//   PASS 1 (mark) : every traversed cell records the LOWEST beam index that frees it / ends on it.
+//   PASS 2 (apply): the winner beam of each cell applies the reference's update exactly once: free-only cells get
+//                   += logOddsFree; end cells get the "(v + f) - f" un-free rounding iff a lower-indexed beam had freed them
+//                   first, then += logOddsOccupied if v < 50 — the floats of the sequential loop, whatever the execution order.
+template <int PASS>
+__device__ unsigned long long hs_update_pass(const HsBatch &P, int b, int w, int nw, int lane) {
+  const HsState *st = P.state + b;
+  const bool exact = P.exact != 0;
+  unsigned long long my_visits = 0;
+  int first[HS_L + 1];
+  first[0] = 0;
+  for (int lv = 0; lv < P.levels; lv++) first[lv + 1] = first[lv] + __ldcg(&st->n_pts[lv]);
+  int lv = 0;
+  HsUpd u = hs_load_upd(st, 0);
+  for (int j = w; j < first[P.levels]; j += nw) {
+    if (j >= first[lv + 1]) {
+      while (j >= first[lv + 1]) lv++;
+      u = hs_load_upd(st, lv);
+    }
+    const int i = j - first[lv];
+    const HsLevel &m = P.l[lv];
+    const size_t cells = (size_t)m.sx * m.sy;
+    uint32_t *fs = m.free_st + (size_t)b * cells, *os = m.occ_st + (size_t)b * cells;
+    const float2 pt = __ldcg(reinterpret_cast<const float2 *>(m.pts) + (size_t)b * P.cap + i);
+    const HsLine ln = hs_line(u.c, u.s, u.mx, u.my, u.bx, u.by, pt.x, pt.y, m.sx, m.sy);
+    if (!ln.ok) continue;
+    const uint32_t stamp = u.ehi | (uint32_t)(4095 - i);
+    const int start = ln.y0 * m.sx + ln.x0;
+    if (PASS == 1) {
+      for (unsigned int k = lane; k < ln.da; k += 32) {  // bresenham2D: da cells from the start, end excluded
+        const unsigned int inc = (unsigned int)(((unsigned long long)ln.err0 + (unsigned long long)k * ln.db) / ln.da);
+        atomicMax(fs + (start + (int)k * ln.off_a + (int)inc * ln.off_b), stamp);
+      }
+      if (lane == 0) atomicMax(os + (ln.y1 * m.sx + ln.x1), stamp);
+    } else {
+      float *lo = m.lo + (size_t)b * cells, *prob = m.prob + (size_t)b * cells;
+      int32_t *ui = m.ui + (size_t)b * cells;
+      for (unsigned int k = lane; k < ln.da; k += 32) {
+        const unsigned int inc = (unsigned int)(((unsigned long long)ln.err0 + (unsigned long long)k * ln.db) / ln.da);
+        const int off = start + (int)k * ln.off_a + (int)inc * ln.off_b;
+        my_visits++;
+        if (__ldcg(fs + off) == stamp && (__ldcg(os + off) >> 12) != (u.ehi >> 12)) {  // bresenhamCellFree (:302-312)
+          const float v = __fadd_rn(__ldcg(lo + off), P.lo_free);
+          lo[off] = v;
+          prob[off] = hs_prob_of(v, exact);
+          ui[off] = u.mark_free;
+        }
+      }
+      if (lane == 0) {
+        my_visits++;
+        const int off = ln.y1 * m.sx + ln.x1;
+        if (__ldcg(os + off) == stamp) {  // bresenhamCellOcc (:315-330), first beam ending here
+          float v = __ldcg(lo + off);
+          const uint32_t f = __ldcg(fs + off);
+          if ((f >> 12) == (u.ehi >> 12) && f > stamp) {  // a LOWER beam index freed it first: set free, then unset
+            v = __fadd_rn(v, P.lo_free);
+            v = __fsub_rn(v, P.lo_free);
+          }
+          if (v < 50.0f) v = __fadd_rn(v, P.lo_occ);
+          lo[off] = v;
+          prob[off] = hs_prob_of(v, exact);
+          ui[off] = u.mark_occ;
+        }
+      }
+    }
+  }
+  if (PASS == 2) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_visits += __shfl_xor_sync(0xffffffffu, my_visits, d);
+  }
+  return my_visits;
+}
+
+// ---- batch path: three launches per step over all B processors ----
+__global__ void __launch_bounds__(HS_THREADS) k_hs_match(HsBatch P, HsCall C) {
+  extern __shared__ __align__(16) unsigned char hs_smem[];
+  hs_match_cta(P, C, blockIdx.x, hs_smem);
+}
+__global__ void __launch_bounds__(256) k_hs_mark(HsBatch P) {
+  const int b = blockIdx.y;
+  if (!P.state[b].do_update) return;
+  hs_update_pass<1>(P, b, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(256) k_hs_apply(HsBatch P) {
+  const int b = blockIdx.y;
+  if (!P.state[b].do_update) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long v = hs_update_pass<2>(P, b, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, lane);
+  if (lane == 0 && v) atomicAdd(&P.state[b].visits, v);
+}
+
+// ---- single-processor path: ONE cooperative launch walks n_scans scans (n_scans = 1 for b2s_hector_slam_update) ----
+// CTA 0 matches while the other CTAs wait at the grid barrier; then every CTA takes beams of the update passes.
+__device__ __forceinline__ void hs_grid_barrier(unsigned int *counter, unsigned int &generation) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int target = (generation + 1) * gridDim.x;
+    atomicAdd(counter, 1u);
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      __nanosleep(40);
+    }
+    __threadfence();
+  }
+  generation++;
+  __syncthreads();
+}
+
+struct HsStream {
+  const float *pts;      // concatenated scans (device, or host-mapped for a single scan)
+  const int *offsets;    // [n_scans] first point of each scan, or NULL (single scan at 0)
+  const int *counts;     // [n_scans] or NULL -> count0
+  int count0, n_scans;
+  const float *hints;    // [n_scans][3] or NULL (chain through the processor's last scan-match pose)
+  const float *first_hint;  // device [3] or NULL
+  float origo_x, origo_y;
+  int map_without_matching;
+  float *out;            // [n_scans][16]
+  volatile float *mailbox;
+  unsigned int seq;
+  unsigned int *barrier;
+};
+
+__global__ void __launch_bounds__(HS_THREADS) k_hs_stream(HsBatch P, HsStream S) {
+  extern __shared__ __align__(16) unsigned char hs_smem[];
+  unsigned int generation = 0;
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * HS_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * HS_THREADS) >> 5;
+  HsState *st = P.state;
+  for (int i = 0; i < S.n_scans; i++) {
+    if (blockIdx.x == 0) {
+      HsCall C;
+      C.pts0 = S.pts + 2 * (size_t)(S.offsets ? S.offsets[i] : 0);
+      C.n0 = nullptr;
+      C.n0_uniform = S.counts ? S.counts[i] : S.count0;
+      C.pts_stride = 0;
+      C.hints = S.hints ? S.hints + 3 * (size_t)i : ((i == 0 && S.first_hint) ? S.first_hint : nullptr);
+      C.origo_x = S.origo_x; C.origo_y = S.origo_y;
+      C.map_without_matching = S.map_without_matching;
+      C.out = S.out + 16 * (size_t)i;
+      C.mailbox = S.mailbox;
+      C.seq = S.seq;
+      hs_match_cta(P, C, 0, hs_smem);
+    }
+    hs_grid_barrier(S.barrier, generation);
+    if (__ldcg(&st->do_update)) {
+      const unsigned long long t0 = hs_now_ns();
+      hs_update_pass<1>(P, 0, w, nw, lane);
+      hs_grid_barrier(S.barrier, generation);
+      const unsigned long long v = hs_update_pass<2>(P, 0, w, nw, lane);
+      if (lane == 0 && v) atomicAdd(&st->visits, v);
+      hs_grid_barrier(S.barrier, generation);  // the next match reads the refreshed probability planes
+      if (blockIdx.x == 0 && threadIdx.x == 0) st->t_update_ns = hs_now_ns() - t0;
+    }
+  }
+}
+
+__global__ void k_hs_fill(float *__restrict__ p, size_t n, float v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void k_hs_state_init(HsState *st, int batch, int reset_maps) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  HsState &s = st[b];
+  // HectorSlamProcessor::reset (:111-116)
+  s.last_update_pose[0] = s.last_update_pose[1] = s.last_update_pose[2] = 3.402823466e+38F;
+  s.last_match_pose[0] = s.last_match_pose[1] = s.last_match_pose[2] = 0.0f;
+  s.do_update = 0;
+  if (reset_maps == 2) {  // create
+    for (int q = 0; q < 9; q++) s.last_cov[q] = 0.0f;
+    for (int l = 0; l < HS_L; l++) { s.curr_update_index[l] = 0; s.epoch[l] = 0; s.n_pts[l] = 0; s.origo[l][0] = s.origo[l][1] = 0.0f; }
+    s.visits = s.n_matched = s.n_updated = 0;
+    s.t_match_ns = s.t_update_ns = 0;
+  }
+}
+
+__global__ void k_hs_epoch_reset(HsState *st, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  for (int l = 0; l < HS_L; l++) st[b].epoch[l] = 0;
+}
+
+__global__ void k_hs_ros(const float *__restrict__ lo, int n, int8_t *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = lo[i];
+  out[i] = v < 0.0f ? 0 : (v > 0.0f ? 100 : -1);  // HectorMappingRos::publishMap (hector_slam.cc:254-317)
+}
+
+static float hs_prob_to_log_odds(float prob) {  // GridMapLogOdds.h:153-157
+  float odds = prob / (1.0f - prob);
+  return (float)log((double)odds);
+}
+
+}  // namespace b2s
+
+struct b2s_hector_slam {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int levels = 0, batch = 1, cap = 0;
+  int sx[HS_L] = {}, sy[HS_L] = {};
+  float cell_length[HS_L] = {};
+  HsBatch P;
+  void *allocs[HS_L * 6 + 8] = {};
+  int n_allocs = 0;
+  HsState *d_state = nullptr;
+  float *d_out = nullptr;        // [batch][16] (per-scan / batch calls)
+  float *h_out = nullptr;        // pinned [batch][16]
+  float *h_pts = nullptr;        // host-mapped pinned staging of one scan (single-processor call)
+  float *h_pts_dev = nullptr;    // its device alias
+  volatile float *h_mail = nullptr;  // host-mapped mailbox [16]
+  float *h_mail_dev = nullptr;
+  float *h_hint = nullptr, *h_hint_dev = nullptr;  // host-mapped [3] pose hint of the per-scan call
+  unsigned int seq = 0;
+  unsigned int *d_barrier = nullptr;
+  unsigned long long host_updates = 0;  // upper bound of every level's device epoch
+  int stream_ctas = HS_STREAM_CTAS;
+  bool coop = true;
+  cudaEvent_t ev_done = nullptr;
+  bool launch_pending = false;  // a per-scan launch may still be running its update passes
+};
+
+static void hs_free_all(b2s_hector_slam *p) {
+  for (int i = 0; i < p->n_allocs; i++)
+    if (p->allocs[i]) cudaFree(p->allocs[i]);
+  p->n_allocs = 0;
+  if (p->d_state) cudaFree(p->d_state);
+  if (p->d_out) cudaFree(p->d_out);
+  if (p->d_barrier) cudaFree(p->d_barrier);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->h_pts) cudaFreeHost(p->h_pts);
+  if (p->h_mail) cudaFreeHost(const_cast<float *>(p->h_mail));
+  if (p->h_hint) cudaFreeHost(p->h_hint);
+  if (p->ev_done) cudaEventDestroy(p->ev_done);
+}
+
+extern "C" void b2s_hector_slam_destroy(b2s_hector_slam *p);
+
+static b2s_status hs_clear_maps(b2s_hector_slam *p) {  // GridMapBase::reset -> clear(): resetGridCell on every cell (:93-113)
+  for (int l = 0; l < p->levels; l++) {
+    const HsLevel &m = p->P.l[l];
+    const size_t cells = (size_t)m.sx * m.sy * p->batch;
+    B2S_CUDA_CHECK(cudaMemsetAsync(m.lo, 0, cells * 4, p->stream));       // logOdds 0
+    B2S_CUDA_CHECK(cudaMemsetAsync(m.ui, 0xff, cells * 4, p->stream));    // updateIndex -1
+    B2S_CUDA_CHECK(cudaMemsetAsync(m.free_st, 0, cells * 4, p->stream));
+    B2S_CUDA_CHECK(cudaMemsetAsync(m.occ_st, 0, cells * 4, p->stream));
+    k_hs_fill<<<ceil_div((long long)cells, 256), 256, 0, p->stream>>>(m.prob, cells, 0.5f);  // e^0 / (e^0 + 1)
+  }
+  B2S_CUDA_CHECK(cudaGetLastError());
+  return B2S_OK;
+}
+
+// stamps carry a 20-bit epoch: before any level's epoch could overflow, clear the stamps and restart the epochs.
+// host_updates counts calls (>= every device epoch), so the test needs no device read-back.
+static b2s_status hs_reserve_epochs(b2s_hector_slam *p, unsigned long long n_updates) {
+  if (p->host_updates + n_updates < HS_EPOCH_MAX) {
+    p->host_updates += n_updates;
+    return B2S_OK;
+  }
+  if (n_updates >= HS_EPOCH_MAX) B2S_FAIL(B2S_ERR_TOO_LARGE, "too many scans in one call (stamp epochs are 20 bits)");
+  for (int l = 0; l < p->levels; l++) {
+    const HsLevel &m = p->P.l[l];
+    const size_t cells = (size_t)m.sx * m.sy * p->batch;
+    B2S_CUDA_CHECK(cudaMemsetAsync(m.free_st, 0, cells * 4, p->stream));
+    B2S_CUDA_CHECK(cudaMemsetAsync(m.occ_st, 0, cells * 4, p->stream));
+  }
+  k_hs_epoch_reset<<<ceil_div(p->batch, 128), 128, 0, p->stream>>>(p->d_state, p->batch);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  p->host_updates = n_updates;
+  return B2S_OK;
+}
+
+static b2s_status hs_create(float map_resolution, int map_size_x, int map_size_y, float start_x, float start_y, int levels,
+                            int batch, int max_points, int device, void *cuda_stream, b2s_hector_slam **out) {
+  if (!out || levels < 1 || levels > B2S_HECTOR_MAX_LEVELS || !(map_resolution > 0.0f) || (map_size_x >> (levels - 1)) <= 2 ||
+      (map_size_y >> (levels - 1)) <= 2 || batch < 1 || max_points < 1)
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_hector_slam_create: bad levels / size / resolution / batch");
+  *out = nullptr;
+  if (max_points > HS_MAX_PTS) B2S_FAIL(B2S_ERR_TOO_LARGE, "at most 4096 points per scan");
+  if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
+  B2S_CUDA_CHECK(cudaSetDevice(device));
+  b2s_hector_slam *p = new (std::nothrow) b2s_hector_slam();
+  if (!p) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
+  p->device = device;
+  p->levels = levels;
+  p->batch = batch;
+  p->cap = max_points;
+#define HS_CHECK(expr) B2S_CUDA_CHECK_CLEAN(b2s_hector_slam_destroy(p), expr)
+  if (cuda_stream) {
+    p->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  } else {
+    HS_CHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    p->own_stream = true;
+  }
+  std::memset(&p->P, 0, sizeof(p->P));
+  p->P.levels = levels; p->P.batch = batch; p->P.cap = max_points;
+  p->P.lo_free = hs_prob_to_log_odds(0.4f);  // GridMapLogOdds.h:98-102
+  p->P.lo_occ = hs_prob_to_log_odds(0.6f);
+  p->P.min_dist = 0.4f; p->P.min_angle = 0.13f;  // HectorSlamProcessor.h:63-64
+  p->P.exact = 1;
+  const int variant = glibc_sincosf_variant_of_host();
+  p->P.use_fma = variant == 0 ? 0 : 1;
+  // MapRepMultiMap ctor (MapRepMultiMap.h:56-89): one offset for every level, dims halve, cell length doubles
+  const float total_x = map_resolution * static_cast<float>(map_size_x), total_y = map_resolution * static_cast<float>(map_size_y);
+  const float off_x = total_x * start_x, off_y = total_y * start_y;
+  int sx = map_size_x, sy = map_size_y;
+  float res = map_resolution;
+  for (int l = 0; l < levels; l++) {
+    HsLevel &m = p->P.l[l];
+    m.sx = sx; m.sy = sy;
+    p->sx[l] = sx; p->sy[l] = sy; p->cell_length[l] = res;
+    // GridMapBase::setMapTransformation (GridMapBase.h:270-286): AlignedScaling2f(s,s) * Translation2f(off)
+    const float scale_to_map = 1.0f / res;
+    m.tw_lin = scale_to_map;
+    m.tw_tx = scale_to_map * off_x; m.tw_ty = scale_to_map * off_y;
+    const float det = m.tw_lin * m.tw_lin - 0.0f * 0.0f, invdet = 1.0f / det, i01 = -0.0f * invdet;  // Affine inverse, cofactor form
+    m.wt_lin = m.tw_lin * invdet;
+    m.wt_tx = -(m.wt_lin * m.tw_tx + i01 * m.tw_ty);
+    m.wt_ty = -(i01 * m.tw_tx + m.wt_lin * m.tw_ty);
+    m.iterations = 1 + (l == 0 ? 5 : 3);
+    const size_t cells = (size_t)sx * sy * batch;
+    void **slots[5] = {(void **)&m.prob, (void **)&m.lo, (void **)&m.ui, (void **)&m.free_st, (void **)&m.occ_st};
+    for (void **s : slots) {
+      HS_CHECK(cudaMalloc(s, cells * 4));
+      p->allocs[p->n_allocs++] = *s;
+    }
+    HS_CHECK(cudaMalloc(reinterpret_cast<void **>(&m.pts), sizeof(float) * 2 * (size_t)max_points * batch));
+    p->allocs[p->n_allocs++] = m.pts;
+    sx /= 2; sy /= 2;
+    res *= 2.0f;
+  }
+  HS_CHECK(cudaMalloc(reinterpret_cast<void **>(&p->d_state), sizeof(HsState) * (size_t)batch));
+  p->P.state = p->d_state;
+  HS_CHECK(cudaMalloc(reinterpret_cast<void **>(&p->d_out), sizeof(float) * 16 * (size_t)batch));
+  HS_CHECK(cudaMalloc(reinterpret_cast<void **>(&p->d_barrier), sizeof(unsigned int)));
+  HS_CHECK(cudaMallocHost(reinterpret_cast<void **>(&p->h_out), sizeof(float) * 16 * (size_t)batch));
+  HS_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&p->h_pts), sizeof(float) * 2 * (size_t)max_points, cudaHostAllocMapped));
+  HS_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&p->h_pts_dev), p->h_pts, 0));
+  {
+    float *mail = nullptr;
+    HS_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&mail), sizeof(float) * 16, cudaHostAllocMapped));
+    std::memset(mail, 0, sizeof(float) * 16);
+    p->h_mail = mail;
+    HS_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&p->h_mail_dev), mail, 0));
+  }
+  HS_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&p->h_hint), sizeof(float) * 4, cudaHostAllocMapped));
+  HS_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&p->h_hint_dev), p->h_hint, 0));
+  HS_CHECK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+  const size_t smem = hs_smem_bytes(max_points);
+  HS_CHECK(raise_dyn_smem(k_hs_match, smem));
+  HS_CHECK(raise_dyn_smem(k_hs_stream, smem));
+  {
+    int coop = 0, sms = 0, per_sm = 0;
+    HS_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    HS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    HS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hs_stream, HS_THREADS, smem));
+    p->coop = coop != 0;
+    p->stream_ctas = std::max(1, std::min(HS_STREAM_CTAS, sms * std::max(per_sm, 0)));
+    if (!p->coop) p->stream_ctas = 1;  // without a co-residency guarantee a spinning grid barrier could deadlock
+  }
+  k_hs_state_init<<<ceil_div(batch, 128), 128, 0, p->stream>>>(p->d_state, batch, 2);
+  {
+    b2s_status st = hs_clear_maps(p);
+    if (st) { b2s_hector_slam_destroy(p); return st; }
+  }
+  HS_CHECK(cudaGetLastError());
+  HS_CHECK(cudaStreamSynchronize(p->stream));
+#undef HS_CHECK
+  *out = p;
+  return B2S_OK;
+}
+
+// wait until the previous per-scan launch (its update passes) has left the host-mapped staging buffers alone
+static b2s_status hs_wait_launch(b2s_hector_slam *p) {
+  if (p->launch_pending) {
+    B2S_CUDA_CHECK(cudaEventSynchronize(p->ev_done));
+    p->launch_pending = false;
+  }
+  return B2S_OK;
+}
+
+static b2s_status hs_launch_stream(b2s_hector_slam *p, const HsStream &S) {
+  B2S_CUDA_CHECK(cudaMemsetAsync(p->d_barrier, 0, sizeof(unsigned int), p->stream));
+  HsBatch P = p->P;
+  HsStream Sv = S;
+  Sv.barrier = p->d_barrier;
+  const size_t smem = hs_smem_bytes(p->cap);
+  if (p->coop) {
+    void *args[2] = {&P, &Sv};
+    B2S_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k_hs_stream), dim3(p->stream_ctas), dim3(HS_THREADS),
+                                               args, smem, p->stream));
+  } else {
+    k_hs_stream<<<1, HS_THREADS, smem, p->stream>>>(P, Sv);
+    B2S_CUDA_CHECK(cudaGetLastError());
+  }
+  return B2S_OK;
+}
+
+extern "C" {
+
+b2s_status b2s_hector_slam_create(float map_resolution, int map_size_x, int map_size_y, float start_x, float start_y,
+                                  int levels, int device, void *cuda_stream, b2s_hector_slam **out) {
+  return hs_create(map_resolution, map_size_x, map_size_y, start_x, start_y, levels, 1, 2048, device, cuda_stream, out);
+}
+
+b2s_status b2s_hector_slam_create_batch(int batch, int max_points, float map_resolution, int map_size_x, int map_size_y,
+                                        float start_x, float start_y, int levels, int device, void *cuda_stream,
+                                        b2s_hector_slam **out) {
+  return hs_create(map_resolution, map_size_x, map_size_y, start_x, start_y, levels, batch, max_points, device, cuda_stream, out);
+}
+
+void b2s_hector_slam_destroy(b2s_hector_slam *p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  hs_free_all(p);
+  if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+b2s_status b2s_hector_slam_set_update_factors(b2s_hector_slam *p, float update_free, float update_occupied) {
+  if (!p) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null handle");
+  p->P.lo_free = hs_prob_to_log_odds(update_free);
+  p->P.lo_occ = hs_prob_to_log_odds(update_occupied);
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_set_map_update_min_diff(b2s_hector_slam *p, float min_dist, float min_angle) {
+  if (!p) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null handle");
+  p->P.min_dist = min_dist;
+  p->P.min_angle = min_angle;
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_set_exact(b2s_hector_slam *p, int exact) {
+  if (!p) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null handle");
+  p->P.exact = exact ? 1 : 0;
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_reset(b2s_hector_slam *p) {
+  if (!p) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null handle");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  b2s_status st = hs_wait_launch(p);
+  if (st) return st;
+  k_hs_state_init<<<ceil_div(p->batch, 128), 128, 0, p->stream>>>(p->d_state, p->batch, 1);
+  return hs_clear_maps(p);
+}
+
+b2s_status b2s_hector_slam_update(b2s_hector_slam *p, const float *points, int n_points, const float origo[2],
+                                  const float pose_hint_world[3], int map_without_matching, float out_pose[3],
+                                  float out_cov[9], int *out_map_updated) {
+  if (!p || !origo || !pose_hint_world || !out_pose || n_points < 0 || (n_points > 0 && !points))
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (p->batch != 1) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_hector_slam_update serves single-processor handles; use b2s_hector_slam_update_batch");
+  if (n_points > p->cap) B2S_FAIL(B2S_ERR_TOO_LARGE, "more points than the handle's capacity (2048 for b2s_hector_slam_create)");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  b2s_status st = hs_wait_launch(p);  // the previous call's update passes still read nothing of ours, but its kernel reads h_hint / h_pts
+  if (st) return st;
+  if ((st = hs_reserve_epochs(p, 1))) return st;
+  if (n_points > 0) std::memcpy(p->h_pts, points, sizeof(float) * 2 * (size_t)n_points);
+  p->h_hint[0] = pose_hint_world[0]; p->h_hint[1] = pose_hint_world[1]; p->h_hint[2] = pose_hint_world[2];
+  p->seq += 1;
+  if (p->seq == 0) p->seq = 1;
+  HsStream S;
+  std::memset(&S, 0, sizeof(S));
+  S.pts = p->h_pts_dev;        // read over the host link by the matching CTA (8.6 KB for 1081 beams)
+  S.count0 = n_points;
+  S.n_scans = 1;
+  S.first_hint = p->h_hint_dev;
+  S.origo_x = origo[0]; S.origo_y = origo[1];
+  S.map_without_matching = map_without_matching;
+  S.out = p->d_out;
+  S.mailbox = p->h_mail_dev;
+  S.seq = p->seq;
+  if ((st = hs_launch_stream(p, S))) return st;
+  B2S_CUDA_CHECK(cudaEventRecord(p->ev_done, p->stream));
+  p->launch_pending = true;
+  // the pose arrives through the mailbox as soon as the match is done; the update passes keep running
+  const volatile unsigned int *flag = reinterpret_cast<const volatile unsigned int *>(p->h_mail) + 15;
+  for (unsigned long long spin = 0;; spin++) {
+    if (*flag == p->seq) break;
+    if ((spin & 0x3fff) == 0x3fff) {
+      const cudaError_t q = cudaEventQuery(p->ev_done);
+      if (q == cudaSuccess) {
+        if (*flag == p->seq) break;
+        B2S_FAIL(B2S_ERR_CUDA, "b2s_hector_slam_update: the kernel finished without posting its result");
+      }
+      if (q != cudaErrorNotReady) B2S_CUDA_CHECK(q);
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  float r[14];
+  for (int q = 0; q < 14; q++) r[q] = p->h_mail[q];
+  out_pose[0] = r[0]; out_pose[1] = r[1]; out_pose[2] = r[2];
+  if (out_cov && !map_without_matching) std::memcpy(out_cov, r + 3, 9 * sizeof(float));
+  if (out_map_updated) *out_map_updated = r[12] != 0.0f ? 1 : 0;
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_process_stream(b2s_hector_slam *p, int n_scans, const float *points, const int32_t *n_points,
+                                          const float origo[2], const float *first_pose_hint, const float *pose_hints,
+                                          int map_without_matching, float *out_poses, int32_t *out_map_updated,
+                                          float *out_last_cov) {
+  if (!p || n_scans < 0 || !origo || !out_poses || (n_scans > 0 && (!points || !n_points)))
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (map_without_matching && !pose_hints) B2S_FAIL(B2S_ERR_BAD_PARAMS, "map_without_matching needs a pose per scan (pose_hints)");
+  if (p->batch != 1) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_hector_slam_process_stream serves single-processor handles");
+  if (n_scans == 0) return B2S_OK;
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  b2s_status st = hs_wait_launch(p);
+  if (st) return st;
+  std::vector<int> offs((size_t)n_scans);
+  long long total = 0;
+  for (int i = 0; i < n_scans; i++) {
+    if (n_points[i] < 0 || n_points[i] > p->cap) B2S_FAIL(B2S_ERR_TOO_LARGE, "a scan has more points than the handle's capacity");
+    offs[i] = (int)total;
+    total += n_points[i];
+    if (total > 0x7fffffffLL / 2) B2S_FAIL(B2S_ERR_TOO_LARGE, "stream too long for one call");
+  }
+  if ((st = hs_reserve_epochs(p, (unsigned long long)n_scans))) return st;
+  float *d_pts = nullptr, *d_hints = nullptr, *d_first = nullptr, *d_out = nullptr;
+  int *d_offs = nullptr, *d_cnt = nullptr;
+  auto release = [&]() {
+    for (void *q : {(void *)d_pts, (void *)d_hints, (void *)d_first, (void *)d_out, (void *)d_offs, (void *)d_cnt})
+      if (q) cudaFreeAsync(q, p->stream);
+    cudaStreamSynchronize(p->stream);
+  };
+#define HS_CHECK(expr) B2S_CUDA_CHECK_CLEAN(release(), expr)
+  HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_pts), sizeof(float) * 2 * (size_t)std::max<long long>(total, 1), p->stream));
+  HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_out), sizeof(float) * 16 * (size_t)n_scans, p->stream));
+  HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_offs), sizeof(int) * (size_t)n_scans, p->stream));
+  HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_cnt), sizeof(int) * (size_t)n_scans, p->stream));
+  if (total > 0) HS_CHECK(cudaMemcpyAsync(d_pts, points, sizeof(float) * 2 * (size_t)total, cudaMemcpyHostToDevice, p->stream));
+  HS_CHECK(cudaMemcpyAsync(d_offs, offs.data(), sizeof(int) * (size_t)n_scans, cudaMemcpyHostToDevice, p->stream));
+  HS_CHECK(cudaMemcpyAsync(d_cnt, n_points, sizeof(int) * (size_t)n_scans, cudaMemcpyHostToDevice, p->stream));
+  if (pose_hints) {
+    HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_hints), sizeof(float) * 3 * (size_t)n_scans, p->stream));
+    HS_CHECK(cudaMemcpyAsync(d_hints, pose_hints, sizeof(float) * 3 * (size_t)n_scans, cudaMemcpyHostToDevice, p->stream));
+  } else if (first_pose_hint) {
+    HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_first), sizeof(float) * 3, p->stream));
+    HS_CHECK(cudaMemcpyAsync(d_first, first_pose_hint, sizeof(float) * 3, cudaMemcpyHostToDevice, p->stream));
+  }
+  HsStream S;
+  std::memset(&S, 0, sizeof(S));
+  S.pts = d_pts; S.offsets = d_offs; S.counts = d_cnt; S.n_scans = n_scans;
+  S.hints = d_hints; S.first_hint = d_first;
+  S.origo_x = origo[0]; S.origo_y = origo[1];
+  S.map_without_matching = map_without_matching;
+  S.out = d_out;
+  if ((st = hs_launch_stream(p, S))) { release(); return st; }
+  std::vector<float> host((size_t)n_scans * 16);
+  HS_CHECK(cudaMemcpyAsync(host.data(), d_out, sizeof(float) * 16 * (size_t)n_scans, cudaMemcpyDeviceToHost, p->stream));
+  HS_CHECK(cudaStreamSynchronize(p->stream));
+#undef HS_CHECK
+  release();
+  for (int i = 0; i < n_scans; i++) {
+    std::memcpy(out_poses + 3 * (size_t)i, host.data() + 16 * (size_t)i, 3 * sizeof(float));
+    if (out_map_updated) out_map_updated[i] = host[16 * (size_t)i + 12] != 0.0f ? 1 : 0;
+  }
+  if (out_last_cov && !map_without_matching) std::memcpy(out_last_cov, host.data() + 16 * (size_t)(n_scans - 1) + 3, 9 * sizeof(float));
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_update_batch(b2s_hector_slam *p, const float *points, const int32_t *n_points, const float origo[2],
+                                        const float *pose_hints, int map_without_matching, float *out_poses, float *out_covs,
+                                        int32_t *out_map_updated) {
+  if (!p || !points || !n_points || !origo || !out_poses) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (map_without_matching && !pose_hints) B2S_FAIL(B2S_ERR_BAD_PARAMS, "map_without_matching needs the poses (pose_hints)");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  b2s_status st = hs_wait_launch(p);
+  if (st) return st;
+  const int B = p->batch;
+  for (int b = 0; b < B; b++)
+    if (n_points[b] < 0 || n_points[b] > p->cap) B2S_FAIL(B2S_ERR_TOO_LARGE, "a scan has more points than the handle's capacity");
+  if ((st = hs_reserve_epochs(p, 1))) return st;
+  float *d_pts = nullptr, *d_hints = nullptr;
+  int *d_cnt = nullptr;
+  auto release = [&]() {
+    for (void *q : {(void *)d_pts, (void *)d_hints, (void *)d_cnt})
+      if (q) cudaFreeAsync(q, p->stream);
+  };
+#define HS_CHECK(expr) B2S_CUDA_CHECK_CLEAN((release(), cudaStreamSynchronize(p->stream)), expr)
+  HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_pts), sizeof(float) * 2 * (size_t)p->cap * B, p->stream));
+  HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_cnt), sizeof(int) * (size_t)B, p->stream));
+  HS_CHECK(cudaMemcpyAsync(d_pts, points, sizeof(float) * 2 * (size_t)p->cap * B, cudaMemcpyHostToDevice, p->stream));
+  HS_CHECK(cudaMemcpyAsync(d_cnt, n_points, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, p->stream));
+  if (pose_hints) {
+    HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_hints), sizeof(float) * 3 * (size_t)B, p->stream));
+    HS_CHECK(cudaMemcpyAsync(d_hints, pose_hints, sizeof(float) * 3 * (size_t)B, cudaMemcpyHostToDevice, p->stream));
+  }
+  HsCall C;
+  std::memset(&C, 0, sizeof(C));
+  C.pts0 = d_pts; C.n0 = d_cnt; C.pts_stride = p->cap;
+  C.hints = d_hints;
+  C.origo_x = origo[0]; C.origo_y = origo[1];
+  C.map_without_matching = map_without_matching;
+  C.out = p->d_out;
+  int max_n = 0;
+  for (int b = 0; b < B; b++) max_n = std::max(max_n, n_points[b]);
+  k_hs_match<<<B, HS_THREADS, hs_smem_bytes(p->cap), p->stream>>>(p->P, C);
+  // data containers of the coarse levels may hold more points than this step's scans (map_without_matching): size the
+  // update grid by the capacity bound
+  const dim3 grid(std::max(1, std::min(ceil_div(std::max(max_n, 1) * p->levels, 8), 148 * 8 / std::max(1, std::min(B, 8)))), B);
+  k_hs_mark<<<grid, 256, 0, p->stream>>>(p->P);
+  k_hs_apply<<<grid, 256, 0, p->stream>>>(p->P);
+  HS_CHECK(cudaGetLastError());
+  HS_CHECK(cudaMemcpyAsync(p->h_out, p->d_out, sizeof(float) * 16 * (size_t)B, cudaMemcpyDeviceToHost, p->stream));
+  release();
+  HS_CHECK(cudaStreamSynchronize(p->stream));
+#undef HS_CHECK
+  for (int b = 0; b < B; b++) {
+    std::memcpy(out_poses + 3 * (size_t)b, p->h_out + 16 * (size_t)b, 3 * sizeof(float));
+    if (out_covs && !map_without_matching) std::memcpy(out_covs + 9 * (size_t)b, p->h_out + 16 * (size_t)b + 3, 9 * sizeof(float));
+    if (out_map_updated) out_map_updated[b] = p->h_out[16 * (size_t)b + 12] != 0.0f ? 1 : 0;
+  }
+  return B2S_OK;
+}
+
+/* the same step with the scans ALREADY on the device (device pointers; nothing is copied, nothing is returned to the
+ * host): the resident-in-HBM form the throughput of the batched update is measured on */
+b2s_status b2s_hector_slam_update_batch_device(b2s_hector_slam *p, const float *d_points, const int32_t *d_n_points, int max_n,
+                                               const float origo[2], const float *d_pose_hints, int map_without_matching) {
+  if (!p || !d_points || !d_n_points || !origo) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (map_without_matching && !d_pose_hints) B2S_FAIL(B2S_ERR_BAD_PARAMS, "map_without_matching needs the poses");
+  if (max_n < 0 || max_n > p->cap) B2S_FAIL(B2S_ERR_TOO_LARGE, "more points than the handle's capacity");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  b2s_status st = hs_wait_launch(p);
+  if (st) return st;
+  if ((st = hs_reserve_epochs(p, 1))) return st;
+  const int B = p->batch;
+  HsCall C;
+  std::memset(&C, 0, sizeof(C));
+  C.pts0 = d_points; C.n0 = d_n_points; C.pts_stride = p->cap;
+  C.hints = d_pose_hints;
+  C.origo_x = origo[0]; C.origo_y = origo[1];
+  C.map_without_matching = map_without_matching;
+  C.out = p->d_out;
+  k_hs_match<<<B, HS_THREADS, hs_smem_bytes(p->cap), p->stream>>>(p->P, C);
+  const dim3 grid(std::max(1, std::min(ceil_div(std::max(max_n, 1) * p->levels, 8), 148 * 8 / std::max(1, std::min(B, 8)))), B);
+  k_hs_mark<<<grid, 256, 0, p->stream>>>(p->P);
+  k_hs_apply<<<grid, 256, 0, p->stream>>>(p->P);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_sync(b2s_hector_slam *p) {
+  if (!p) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null handle");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+  p->launch_pending = false;
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_level_dims(b2s_hector_slam *p, int level, int dims[2], float *cell_length) {
+  if (!p || !dims || level < 0 || level >= p->levels) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad level");
+  dims[0] = p->sx[level];
+  dims[1] = p->sy[level];
+  if (cell_length) *cell_length = p->cell_length[level];
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_copy_level_of(b2s_hector_slam *p, int b, int level, float *log_odds, int32_t *update_index) {
+  if (!p || level < 0 || level >= p->levels || b < 0 || b >= p->batch) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad level / processor");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  const HsLevel &m = p->P.l[level];
+  const size_t cells = (size_t)m.sx * m.sy;
+  if (log_odds) B2S_CUDA_CHECK(cudaMemcpyAsync(log_odds, m.lo + (size_t)b * cells, cells * 4, cudaMemcpyDeviceToHost, p->stream));
+  if (update_index) B2S_CUDA_CHECK(cudaMemcpyAsync(update_index, m.ui + (size_t)b * cells, cells * 4, cudaMemcpyDeviceToHost, p->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+  p->launch_pending = false;
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_copy_level(b2s_hector_slam *p, int level, float *log_odds, int32_t *update_index) {
+  return b2s_hector_slam_copy_level_of(p, 0, level, log_odds, update_index);
+}
+
+b2s_status b2s_hector_slam_copy_level_ros(b2s_hector_slam *p, int level, int8_t *out) {
+  if (!p || !out || level < 0 || level >= p->levels) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad level");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  const HsLevel &m = p->P.l[level];
+  const int n = m.sx * m.sy;
+  int8_t *d = nullptr;
+  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d), (size_t)n, p->stream));
+  k_hs_ros<<<ceil_div(n, 256), 256, 0, p->stream>>>(m.lo, n, d);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, (size_t)n, cudaMemcpyDeviceToHost, p->stream);
+  cudaFreeAsync(d, p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  B2S_CUDA_CHECK(e);
+  p->launch_pending = false;
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_stats(b2s_hector_slam *p, double out[5]) {
+  if (!p || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  std::vector<HsState> s((size_t)p->batch);
+  B2S_CUDA_CHECK(cudaMemcpyAsync(s.data(), p->d_state, sizeof(HsState) * (size_t)p->batch, cudaMemcpyDeviceToHost, p->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+  p->launch_pending = false;
+  out[0] = out[1] = out[2] = 0.0;
+  for (const HsState &x : s) { out[0] += (double)x.n_matched; out[1] += (double)x.n_updated; out[2] += (double)x.visits; }
+  out[3] = (double)s[0].t_match_ns * 1e-6;   // ms of processor 0's last match / update (device %globaltimer)
+  out[4] = (double)s[0].t_update_ns * 1e-6;
+  return B2S_OK;
+}
+
+/* the processor's own last poses (getLastScanMatchPose / getLastMapUpdatePose, HectorSlamProcessor.h:118-119) */
+b2s_status b2s_hector_slam_last_poses(b2s_hector_slam *p, int b, float last_scan_match_pose[3], float last_map_update_pose[3]) {
+  if (!p || b < 0 || b >= p->batch) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad processor");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  HsState s;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(&s, p->d_state + b, sizeof(HsState), cudaMemcpyDeviceToHost, p->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+  p->launch_pending = false;
+  if (last_scan_match_pose) std::memcpy(last_scan_match_pose, s.last_match_pose, 3 * sizeof(float));
+  if (last_map_update_pose) std::memcpy(last_map_update_pose, s.last_update_pose, 3 * sizeof(float));
+  return B2S_OK;
+}
+
+/* test hook: pretend `updates` map updates have already consumed stamp epochs (exercises the 20-bit epoch wrap) */
+b2s_status b2s_hector_slam_debug_set_epoch(b2s_hector_slam *p, unsigned int updates) {
+  if (!p || updates >= HS_EPOCH_MAX) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad epoch");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+  std::vector<HsState> s((size_t)p->batch);
+  B2S_CUDA_CHECK(cudaMemcpy(s.data(), p->d_state, sizeof(HsState) * (size_t)p->batch, cudaMemcpyDeviceToHost));
+  unsigned int have = 0;
+  for (const HsState &x : s)
+    for (int l = 0; l < p->levels; l++) have = std::max(have, x.epoch[l]);
+  if (updates < have) B2S_FAIL(B2S_ERR_BAD_PARAMS, "epochs only move forward");
+  for (HsState &x : s)
+    for (int l = 0; l < p->levels; l++) x.epoch[l] = updates;
+  B2S_CUDA_CHECK(cudaMemcpy(p->d_state, s.data(), sizeof(HsState) * (size_t)p->batch, cudaMemcpyHostToDevice));
+  p->host_updates = updates;
+  return B2S_OK;
+}
+
+}  // extern "C"

@@ -37,6 +37,17 @@ def _bind():
     L.b2s_hector_slam_copy_level.argtypes = [vp, C.c_int, fp, C.POINTER(C.c_int32)]
     L.b2s_hector_slam_copy_level_ros.argtypes = [vp, C.c_int, C.POINTER(C.c_int8)]
     L.b2s_hector_slam_stats.argtypes = [vp, C.POINTER(C.c_double)]
+    ip = C.POINTER(C.c_int32)
+    L.b2s_hector_slam_create_batch.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                               C.c_int, vp, C.POINTER(vp)]
+    L.b2s_hector_slam_set_exact.argtypes = [vp, C.c_int]
+    L.b2s_hector_slam_process_stream.argtypes = [vp, C.c_int, fp, ip, fp, fp, fp, C.c_int, fp, ip, fp]
+    L.b2s_hector_slam_update_batch.argtypes = [vp, fp, ip, fp, fp, C.c_int, fp, fp, ip]
+    L.b2s_hector_slam_update_batch_device.argtypes = [vp, vp, vp, C.c_int, fp, vp, C.c_int]
+    L.b2s_hector_slam_sync.argtypes = [vp]
+    L.b2s_hector_slam_copy_level_of.argtypes = [vp, C.c_int, C.c_int, fp, ip]
+    L.b2s_hector_slam_last_poses.argtypes = [vp, C.c_int, fp, fp]
+    L.b2s_hector_slam_debug_set_epoch.argtypes = [vp, C.c_uint]
     _bound = True
     return L
 
@@ -111,15 +122,81 @@ class HectorSlam:
     update() = multi-level matchData + gated updateByScan, one call per LaserScan."""
 
     def __init__(self, resolution=0.05, size_x=1024, size_y=1024, start=(0.5, 0.5), levels=3,
-                 update_free=0.4, update_occupied=0.9, min_dist=0.4, min_angle=0.13, device=0, stream=None):
+                 update_free=0.4, update_occupied=0.9, min_dist=0.4, min_angle=0.13, device=0, stream=None,
+                 batch=None, max_points=2048, exact=True):
         self.L = _bind()
         self.levels = levels
+        self.batch, self.cap = batch, max_points
         self.h = C.c_void_p()
-        check(self.L.b2s_hector_slam_create(resolution, size_x, size_y, start[0], start[1], levels, device,
-                                            C.c_void_p(stream) if stream else None, C.byref(self.h)))
+        if batch is None:
+            check(self.L.b2s_hector_slam_create(resolution, size_x, size_y, start[0], start[1], levels, device,
+                                                C.c_void_p(stream) if stream else None, C.byref(self.h)))
+            self.cap = 2048
+        else:  # B independent processors (robots / maps) behind one handle
+            check(self.L.b2s_hector_slam_create_batch(batch, max_points, resolution, size_x, size_y, start[0], start[1],
+                                                      levels, device, C.c_void_p(stream) if stream else None,
+                                                      C.byref(self.h)))
         check(self.L.b2s_hector_slam_set_update_factors(self.h, update_free, update_occupied))
         check(self.L.b2s_hector_slam_set_map_update_min_diff(self.h, min_dist, min_angle))
+        if not exact:
+            check(self.L.b2s_hector_slam_set_exact(self.h, 0))
         self.map_updated = False
+
+    def set_exact(self, exact):
+        check(self.L.b2s_hector_slam_set_exact(self.h, int(bool(exact))))
+
+    def process_stream(self, scans, origo, first_hint=None, pose_hints=None, map_without_matching=False):
+        """A whole stream of LaserScans in one call (hint of scan i = pose of scan i-1, as the node's loop chains them,
+        unless pose_hints gives one per scan).  Returns poses [n,3], updated flags [n], last covariance [3,3]."""
+        n = len(scans)
+        cnt = np.array([len(s) for s in scans], np.int32)
+        cat = f32(np.concatenate([f32(s).reshape(-1, 2) for s in scans], 0)) if n else np.zeros((0, 2), np.float32)
+        poses, upd, cov = np.zeros((n, 3), np.float32), np.zeros(n, np.int32), np.zeros(9, np.float32)
+        fh = f32(first_hint) if first_hint is not None else None
+        ph = f32(pose_hints) if pose_hints is not None else None
+        check(self.L.b2s_hector_slam_process_stream(self.h, n, _f(cat), cnt.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    _f(f32(origo)), _f(fh) if fh is not None else None,
+                                                    _f(ph) if ph is not None else None, int(map_without_matching),
+                                                    _f(poses), upd.ctypes.data_as(C.POINTER(C.c_int32)), _f(cov)))
+        return poses, upd.astype(bool), cov.reshape(3, 3)
+
+    def update_batch(self, scans, origo, pose_hints, map_without_matching=False):
+        """One scan per processor of a batched handle.  scans: list of B [n_b, 2] arrays."""
+        B = self.batch
+        pts = np.zeros((B, self.cap, 2), np.float32)
+        cnt = np.zeros(B, np.int32)
+        for b, s_ in enumerate(scans):
+            s_ = f32(s_).reshape(-1, 2)
+            pts[b, :len(s_)] = s_
+            cnt[b] = len(s_)
+        poses, covs, upd = np.zeros((B, 3), np.float32), np.zeros((B, 9), np.float32), np.zeros(B, np.int32)
+        ph = f32(pose_hints) if pose_hints is not None else None
+        check(self.L.b2s_hector_slam_update_batch(self.h, _f(pts), cnt.ctypes.data_as(C.POINTER(C.c_int32)), _f(f32(origo)),
+                                                  _f(ph) if ph is not None else None, int(map_without_matching), _f(poses),
+                                                  _f(covs), upd.ctypes.data_as(C.POINTER(C.c_int32))))
+        return poses, covs.reshape(B, 3, 3), upd.astype(bool)
+
+    def update_batch_device(self, d_points, d_counts, max_n, origo, d_hints, map_without_matching=False):
+        check(self.L.b2s_hector_slam_update_batch_device(self.h, C.c_void_p(d_points), C.c_void_p(d_counts), int(max_n),
+                                                         _f(f32(origo)), C.c_void_p(d_hints) if d_hints else None,
+                                                         int(map_without_matching)))
+
+    def sync(self):
+        check(self.L.b2s_hector_slam_sync(self.h))
+
+    def level_of(self, b, i):
+        sx, sy, _ = self.level_dims(i)
+        lo, ui = np.zeros(sx * sy, np.float32), np.zeros(sx * sy, np.int32)
+        check(self.L.b2s_hector_slam_copy_level_of(self.h, b, i, _f(lo), ui.ctypes.data_as(C.POINTER(C.c_int32))))
+        return lo.reshape(sy, sx), ui.reshape(sy, sx)
+
+    def last_poses(self, b=0):
+        a, u = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        check(self.L.b2s_hector_slam_last_poses(self.h, b, _f(a), _f(u)))
+        return a, u
+
+    def debug_set_epoch(self, updates):
+        check(self.L.b2s_hector_slam_debug_set_epoch(self.h, int(updates)))
 
     def update(self, points, origo, pose_hint, map_without_matching=False):
         p = f32(points).reshape(-1, 2)

@@ -377,9 +377,15 @@ b2s_status b2s_hector_map_copy_ros(b2s_hector_map *m, int8_t *out);
 b2s_status b2s_hector_map_last_timing(b2s_hector_map *m, double out[2]);
 
 /* ---------------------------------------------------------------- lesson4 front end: HectorSlamProcessor
- * One call per LaserScan = MapRepMultiMap::matchData (coarse-to-fine Gauss-Newton over all pyramid levels, one kernel
- * launch) + the map-update gate + MapRepMultiMap::updateByScan (all levels, two kernel launches).  The maps, the
- * per-level scaled copies of the scan and the running stamps stay resident on the device between calls. */
+ * One call per LaserScan = MapRepMultiMap::matchData (coarse-to-fine Gauss-Newton over all pyramid levels) + the
+ * map-update gate + MapRepMultiMap::updateByScan (all levels) — all on the device: the processor's state (last poses,
+ * update indices, the coarse levels' data containers) is device-resident, one cooperative launch does match + gate +
+ * update, and the pose returns through a host-mapped mailbox as soon as the match is done.  A whole stream of scans can
+ * be handed over at once (b2s_hector_slam_process_stream: no host round trip between scans), and a handle may hold B
+ * independent processors (b2s_hector_slam_create_batch).
+ * EXACT mode (default): bit-identical poses, Hessians and cells to the reference (sequential float32 sums in point
+ * order, glibc's sinf / cosf restated on the device); b2s_hector_slam_set_exact(p, 0) sums with a tree instead
+ * (faster; poses within 1e-4). */
 
 typedef struct b2s_hector_slam b2s_hector_slam; /* opaque: replaces hectorslam::HectorSlamProcessor
                                                    (slam_main/HectorSlamProcessor.h:50-150) */
@@ -413,9 +419,44 @@ b2s_status b2s_hector_slam_level_dims(b2s_hector_slam *p, int level, int dims[2]
 b2s_status b2s_hector_slam_copy_level(b2s_hector_slam *p, int level, float *log_odds, int32_t *update_index);
 /* nav_msgs/OccupancyGrid payload of one level as HectorMappingRos::publishMap fills it (hector_slam.cc:254-317) */
 b2s_status b2s_hector_slam_copy_level_ros(b2s_hector_slam *p, int level, int8_t *out);
-/* out[0] = scans matched, out[1] = scans let into the maps, out[2] = Bresenham cell visits so far (all levels),
- * out[3] / out[4] = ms of the last match / update kernels */
+/* out[0] = scans matched, out[1] = scans let into the maps, out[2] = Bresenham cell visits so far (all levels; summed
+ * over the processors of a batched handle), out[3] / out[4] = ms of processor 0's last match / update (device timer) */
 b2s_status b2s_hector_slam_stats(b2s_hector_slam *p, double out[5]);
+/* 1 (default) = the reference's arithmetic bit for bit; 0 = tree-summed Gauss-Newton terms + device sinf/cosf/expf */
+b2s_status b2s_hector_slam_set_exact(b2s_hector_slam *p, int exact);
+/* The node's loop over a recorded stream (hector_slam.cc:195-204: update(container, getLastScanMatchPose())) in ONE
+ * call: n_scans scans, points concatenated ([sum n_points][2], level-0 map-cell units), hint of scan i = pose of scan
+ * i-1 (first_pose_hint for scan 0; NULL = the processor's current last scan-match pose), or pose_hints[i] when given
+ * (required with map_without_matching).  out_poses [n_scans][3]; out_map_updated [n_scans] and out_last_cov[9] may be
+ * NULL.  Identical results to n_scans b2s_hector_slam_update calls. */
+b2s_status b2s_hector_slam_process_stream(b2s_hector_slam *p, int n_scans, const float *points, const int32_t *n_points,
+                                          const float origo[2], const float *first_pose_hint, const float *pose_hints,
+                                          int map_without_matching, float *out_poses, int32_t *out_map_updated,
+                                          float *out_last_cov);
+/* B independent HectorSlamProcessors (robots / maps) behind one handle (Hector maps shard over
+ * independent maps, not within one).  max_points = capacity of one scan (<= 4096). */
+b2s_status b2s_hector_slam_create_batch(int batch, int max_points, float map_resolution, int map_size_x, int map_size_y,
+                                        float start_x, float start_y, int levels, int device, void *cuda_stream,
+                                        b2s_hector_slam **out);
+/* update() of every processor with its own scan: points [B][max_points][2] (rows padded), n_points [B], pose_hints
+ * [B][3] (NULL = each processor's last scan-match pose); out_poses [B][3], out_covs [B][9] / out_map_updated [B] may
+ * be NULL. */
+b2s_status b2s_hector_slam_update_batch(b2s_hector_slam *p, const float *points, const int32_t *n_points,
+                                        const float origo[2], const float *pose_hints, int map_without_matching,
+                                        float *out_poses, float *out_covs, int32_t *out_map_updated);
+/* the same step on scans already in device memory (DEVICE pointers; asynchronous on the handle's stream, nothing
+ * returned to the host; max_n = upper bound of n_points): the resident-in-HBM form */
+b2s_status b2s_hector_slam_update_batch_device(b2s_hector_slam *p, const float *d_points, const int32_t *d_n_points,
+                                               int max_n, const float origo[2], const float *d_pose_hints,
+                                               int map_without_matching);
+b2s_status b2s_hector_slam_sync(b2s_hector_slam *p);
+b2s_status b2s_hector_slam_copy_level_of(b2s_hector_slam *p, int processor, int level, float *log_odds,
+                                         int32_t *update_index);
+/* getLastScanMatchPose / getLastMapUpdatePose (HectorSlamProcessor.h:118-119) of one processor; either may be NULL */
+b2s_status b2s_hector_slam_last_poses(b2s_hector_slam *p, int processor, float last_scan_match_pose[3],
+                                      float last_map_update_pose[3]);
+/* test hook: pretend `updates` map updates already consumed per-scan stamp epochs (exercises the 20-bit epoch wrap) */
+b2s_status b2s_hector_slam_debug_set_epoch(b2s_hector_slam *p, unsigned int updates);
 
 /* ---------------------------------------------------------------- ROS-shaped input adapters (host only)
  * The wire formats either side of the path: sensor_msgs/LaserScan in (here), nav_msgs/OccupancyGrid payloads out
