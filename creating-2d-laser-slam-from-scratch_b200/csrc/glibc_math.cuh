@@ -88,6 +88,33 @@ B2S_HD bool gm_sincosf_one(float y, int which, bool use_fma, float *out) {
   return false;
 }
 
+// sincosf(y): both values from one range reduction (glibc's sincosf shares it too and returns the same floats as
+// sinf / cosf — the host check compares all three)
+B2S_HD void glibc_sincosf(float y, bool use_fma, float *sp, float *cp) {
+  const uint32_t top = (gm_asuint(y) >> 20) & 0x7ffu;
+  double x = (double)y;
+  if (top < 0x3f4u) {
+    if (top < 0x398u) { *sp = y; *cp = 1.0f; return; }
+    const double x2 = x * x;
+    *sp = gm_sinf_poly(x, x2, false, 0, use_fma);
+    *cp = gm_sinf_poly(x, x2, false, 1, use_fma);
+    return;
+  }
+  if (top < 0x42fu) {
+    const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    const double r = x * hpi_inv;
+    const int n = (int)(((int32_t)r + 0x800000) >> 24);
+    x = gm_madd(-(double)n, hpi, x, use_fma);
+    const double sign = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    const double xs = x * sign, x2 = x * x;
+    *sp = gm_sinf_poly(xs, x2, (n & 2) != 0, n, use_fma);
+    *cp = gm_sinf_poly(xs, x2, (n & 2) != 0, n ^ 1, use_fma);
+    return;
+  }
+  *sp = sinf(y);
+  *cp = cosf(y);
+}
+
 B2S_HD float glibc_sinf(float y, bool use_fma) {
   float r;
   if (gm_sincosf_one(y, 0, use_fma, &r)) return r;

@@ -24,7 +24,9 @@
 // per sum), Rotation2Df's std::cos / std::sin(float) are glibc's sincosf restated (glibc_math.cuh), the unqualified
 // sin / cos / exp of the reference (C library DOUBLE functions rounded to float) are the device's double functions
 // rounded to float (both are within 2 ulp of the exact double, so the float agrees unless the exact value lies within
-// ~1e-16 relative of a float rounding boundary: ~5e-9 per evaluation).  FAST mode sums with a tree (poses within 1e-4).
+// ~1e-16 relative of a float rounding boundary: ~5e-9 per evaluation).  FAST mode differs in ONE thing: the nine sums are
+// tree-reduced (warp shuffles) instead of accumulated in point order, so its Hessians / poses differ in the last float bits
+// (~1e-6 m per scan, inside the 1e-4 contract) and a cell can move when a pose lands an ulp away.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -102,20 +104,33 @@ __device__ __forceinline__ unsigned long long hs_now_ns() {
   return t;
 }
 
-__device__ __forceinline__ void hs_interp(const float *__restrict__ prob, int sx, int sy, float x, float y, float out[3]) {
+// interpMapValueWithDerivatives (OccGridMapUtil.h:139-228) in two halves so that the four cell loads of SEVERAL points are
+// in flight together.  Plain loads (L1): within one launch the planes are only rewritten by the update passes, and every
+// CTA passes the grid barrier's gpu-scope acquire (which drops the SM's L1 lines) between an update and the next match.
+struct HsFetch {
+  float i0, i1, i2, i3, fx, fy;
+  bool inside;
+};
+__device__ __forceinline__ HsFetch hs_fetch(const float *__restrict__ prob, int sx, int sy, float x, float y) {
+  HsFetch f;
   const float lim_x = (float)sx - 2.0f, lim_y = (float)sy - 2.0f;  // setMapCellDims: dims - 2
-  if (x < 0.0f || x > lim_x || y < 0.0f || y > lim_y) { out[0] = out[1] = out[2] = 0.0f; return; }
-  const int ix = (int)x, iy = (int)y;
-  const float fx = x - (float)ix, fy = y - (float)iy;
-  const int index = iy * sx + ix;
-  // L2 loads: the planes are rewritten by other SMs between the scans of one persistent launch
-  const float i0 = __ldcg(prob + index), i1 = __ldcg(prob + index + 1), i2 = __ldcg(prob + index + sx),
-              i3 = __ldcg(prob + index + sx + 1);
-  const float dx1 = i0 - i1, dx2 = i2 - i3, dy1 = i0 - i2, dy2 = i1 - i3;
-  const float xfi = 1.0f - fx, yfi = 1.0f - fy;
-  out[0] = ((i0 * xfi + i1 * fx) * yfi) + ((i2 * xfi + i3 * fx) * fy);
-  out[1] = -((dx1 * yfi) + (dx2 * fy));
-  out[2] = -((dy1 * xfi) + (dy2 * fx));
+  f.inside = !(x < 0.0f || x > lim_x || y < 0.0f || y > lim_y);
+  f.i0 = f.i1 = f.i2 = f.i3 = 0.0f; f.fx = f.fy = 0.0f;
+  if (f.inside) {
+    const int ix = (int)x, iy = (int)y;
+    f.fx = x - (float)ix; f.fy = y - (float)iy;
+    const float *c = prob + (iy * sx + ix);
+    f.i0 = c[0]; f.i1 = c[1]; f.i2 = c[sx]; f.i3 = c[sx + 1];
+  }
+  return f;
+}
+__device__ __forceinline__ void hs_finish(const HsFetch &f, float out[3]) {
+  if (!f.inside) { out[0] = out[1] = out[2] = 0.0f; return; }
+  const float dx1 = f.i0 - f.i1, dx2 = f.i2 - f.i3, dy1 = f.i0 - f.i2, dy2 = f.i1 - f.i3;
+  const float xfi = 1.0f - f.fx, yfi = 1.0f - f.fy;
+  out[0] = ((f.i0 * xfi + f.i1 * f.fx) * yfi) + ((f.i2 * xfi + f.i3 * f.fx) * f.fy);
+  out[1] = -((dx1 * yfi) + (dx2 * f.fy));
+  out[2] = -((dy1 * xfi) + (dy2 * f.fx));
 }
 
 __device__ inline void hs_inv3_mul(const float m[9], const float v[3], float out[3]) {  // Matrix3f::inverse() * v
@@ -148,11 +163,14 @@ __device__ inline bool hs_pose_difference_larger_than(const float a[3], const fl
 }
 
 // terms of one point for getCompleteHessianDerivs (OccGridMapUtil.h:99-126)
-__device__ __forceinline__ void hs_point_terms(const float *__restrict__ prob, int sx, int sy, float2 p, float c, float s,
-                                               float sin_rot, float cos_rot, float e0, float e1, float a[9]) {
+__device__ __forceinline__ HsFetch hs_point_fetch(const float *__restrict__ prob, int sx, int sy, float2 p, float c, float s,
+                                                  float e0, float e1) {
   const float tx = (c * p.x + (-s) * p.y) + e0, ty = (s * p.x + c * p.y) + e1;
+  return hs_fetch(prob, sx, sy, tx, ty);
+}
+__device__ __forceinline__ void hs_point_terms(const HsFetch &f, float2 p, float sin_rot, float cos_rot, float a[9]) {
   float t[3];
-  hs_interp(prob, sx, sy, tx, ty, t);
+  hs_finish(f, t);
   const float rot = ((-sin_rot * p.x - cos_rot * p.y) * t[1] + (cos_rot * p.x - sin_rot * p.y) * t[2]);
   const float fun = 1.0f - t[0];
   a[0] = t[1] * fun; a[1] = t[2] * fun; a[2] = rot * fun;    // dTr
@@ -164,23 +182,20 @@ struct HsTrig {
   float c, s;              // Rotation2Df(angle): std::cos / std::sin(float) = glibc cosf / sinf
   float sin_rot, cos_rot;  // OccGridMapUtil.h:87-88: the C library's double sin / cos, rounded to float
 };
-__device__ inline HsTrig hs_trig(float angle, bool exact, bool use_fma) {
+__device__ inline HsTrig hs_trig(float angle, bool use_fma) {
   HsTrig t;
-  if (exact) {
-    t.c = glibc_cosf(angle, use_fma);
-    t.s = glibc_sinf(angle, use_fma);
-    t.sin_rot = (float)sin((double)angle);
-    t.cos_rot = (float)cos((double)angle);
-  } else {
-    t.c = cosf(angle); t.s = sinf(angle);
-    t.sin_rot = t.s; t.cos_rot = t.c;
-  }
+  glibc_sincosf(angle, use_fma, &t.s, &t.c);
+  double ds, dc;
+  sincos((double)angle, &ds, &dc);
+  t.sin_rot = (float)ds;
+  t.cos_rot = (float)dc;
   return t;
 }
 
 // shared memory of the match: [cap] float2 staged scan, then (EXACT) 9 term columns of `pitch` floats / (FAST) per-warp partials
 __host__ __device__ inline int hs_pitch(int cap) { return ((cap + 3) & ~3) + 4; }
-__host__ __device__ inline size_t hs_smem_bytes(int cap) { return sizeof(float2) * (size_t)cap + sizeof(float) * 9 * (size_t)hs_pitch(cap) + 64; }
+__host__ __device__ inline size_t hs_terms_offset(int cap) { return (sizeof(float2) * (size_t)cap + 15) & ~(size_t)15; }  // float4 reads of the columns
+__host__ __device__ inline size_t hs_smem_bytes(int cap) { return hs_terms_offset(cap) + sizeof(float) * 9 * (size_t)hs_pitch(cap) + 64; }
 
 // MapRepMultiMap::matchData (:144-166) on every level, coarsest first, + the gate and the update parameters of
 // HectorSlamProcessor::update (:81-108), by ONE CTA for processor b.
@@ -191,7 +206,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
   const int n = C.n0 ? C.n0[b] : C.n0_uniform;
   const bool exact = P.exact != 0, use_fma = P.use_fma != 0;
   float2 *spts = reinterpret_cast<float2 *>(smem);
-  float *terms = reinterpret_cast<float *>(smem + sizeof(float2) * (size_t)P.cap);
+  float *terms = reinterpret_cast<float *>(smem + hs_terms_offset(P.cap));
   const int pitch = hs_pitch(P.cap);
   __shared__ float bc[8];    // estimate + trig published by the solving thread
   __shared__ float tot[9];
@@ -223,82 +238,95 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
       if (tid == 0) {
         const float e0 = (m.tw_lin * world0 + 0.0f * world1) + m.tw_tx;
         const float e1 = (0.0f * world0 + m.tw_lin * world1) + m.tw_ty;
-        const HsTrig tr = hs_trig(world2, exact, use_fma);
+        const HsTrig tr = hs_trig(world2, use_fma);
         bc[0] = e0; bc[1] = e1; bc[2] = world2; bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
       }
       __syncthreads();
       for (int it = 0; it < m.iterations; it++) {
         const float e0 = bc[0], e1 = bc[1], c = bc[3], s = bc[4], sin_rot = bc[5], cos_rot = bc[6];
-        if (exact) {
-          for (int i = tid; i < n; i += HS_THREADS) {
-            float a[9];
-            const float2 p = make_float2(__fmul_rn(spts[i].x, factor), __fmul_rn(spts[i].y, factor));
-            hs_point_terms(prob, m.sx, m.sy, p, c, s, sin_rot, cos_rot, e0, e1, a);
+        float acc[9];
 #pragma unroll
-            for (int q = 0; q < 9; q++) terms[q * pitch + i] = a[q];
-          }
-          __syncthreads();
-          if (warp == 0) {  // the reference's float32 sums, in point order: lane q owns sum q (9 dependent FADD chains)
-            float acc = 0.0f;
-            if (lane < 9) {
-              const float *col = terms + lane * pitch;
-              int i = 0;
-              for (; i + 8 <= n; i += 8) {
-                const float4 u = *reinterpret_cast<const float4 *>(col + i), v = *reinterpret_cast<const float4 *>(col + i + 4);
-                acc = __fadd_rn(acc, u.x); acc = __fadd_rn(acc, u.y); acc = __fadd_rn(acc, u.z); acc = __fadd_rn(acc, u.w);
-                acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
-              }
-              for (; i < n; i++) acc = __fadd_rn(acc, col[i]);
-              tot[lane] = acc;
+        for (int q = 0; q < 9; q++) acc[q] = 0.0f;
+        for (int base = 0; base < n; base += 2 * HS_THREADS) {  // two points per thread, their eight cell loads in flight together
+          const int ia = base + tid, ib = base + tid + HS_THREADS;
+          float2 pa = make_float2(0.0f, 0.0f), pb = pa;
+          HsFetch fa, fb;
+          fa.inside = fb.inside = false;
+          if (ia < n) { pa = make_float2(__fmul_rn(spts[ia].x, factor), __fmul_rn(spts[ia].y, factor)); fa = hs_point_fetch(prob, m.sx, m.sy, pa, c, s, e0, e1); }
+          if (ib < n) { pb = make_float2(__fmul_rn(spts[ib].x, factor), __fmul_rn(spts[ib].y, factor)); fb = hs_point_fetch(prob, m.sx, m.sy, pb, c, s, e0, e1); }
+          float ta[9], tb[9];
+          if (ia < n) {
+            hs_point_terms(fa, pa, sin_rot, cos_rot, ta);
+            if (exact) {
+#pragma unroll
+              for (int q = 0; q < 9; q++) terms[q * pitch + ia] = ta[q];
+            } else {
+#pragma unroll
+              for (int q = 0; q < 9; q++) acc[q] += ta[q];
             }
           }
-        } else {
-          float a[9];
+          if (ib < n) {
+            hs_point_terms(fb, pb, sin_rot, cos_rot, tb);
+            if (exact) {
 #pragma unroll
-          for (int q = 0; q < 9; q++) a[q] = 0.0f;
-          for (int i = tid; i < n; i += HS_THREADS) {
-            float t[9];
-            const float2 p = make_float2(__fmul_rn(spts[i].x, factor), __fmul_rn(spts[i].y, factor));
-            hs_point_terms(prob, m.sx, m.sy, p, c, s, sin_rot, cos_rot, e0, e1, t);
+              for (int q = 0; q < 9; q++) terms[q * pitch + ib] = tb[q];
+            } else {
 #pragma unroll
-            for (int q = 0; q < 9; q++) a[q] += t[q];
-          }
-#pragma unroll
-          for (int q = 0; q < 9; q++) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], d);
-          }
-          if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < 9; q++) terms[q * NW + warp] = a[q];
-          }
-          __syncthreads();
-          if (warp == 0) {
-            float v = 0.0f;
-            if (lane < 9) {
-              for (int w = 0; w < NW; w++) v += terms[lane * NW + w];
-              tot[lane] = v;
+              for (int q = 0; q < 9; q++) acc[q] += tb[q];
             }
           }
         }
-        __syncthreads();
-        if (tid == 0) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
-          const float dTr[3] = {tot[0], tot[1], tot[2]};
-          float Hm[9];
-          Hm[0] = tot[3]; Hm[4] = tot[4]; Hm[8] = tot[5];
-          Hm[1] = Hm[3] = tot[6]; Hm[2] = Hm[6] = tot[7]; Hm[5] = Hm[7] = tot[8];
-          float n0 = bc[0], n1 = bc[1], n2 = bc[2];
-          if (Hm[0] != 0.0f && Hm[4] != 0.0f) {
-            float dir[3];
-            hs_inv3_mul(Hm, dTr, dir);
-            if (dir[2] > 0.2f) dir[2] = 0.2f;
-            else if (dir[2] < -0.2f) dir[2] = -0.2f;
-            n0 += dir[0]; n1 += dir[1]; n2 += dir[2];
+        if (!exact) {
+#pragma unroll
+          for (int q = 0; q < 9; q++) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], d);
           }
-          bc[0] = n0; bc[1] = n1; bc[2] = n2;
-          if (it + 1 < m.iterations) {
-            const HsTrig tr = hs_trig(n2, exact, use_fma);
-            bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
+          if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 9; q++) terms[q * NW + warp] = acc[q];
+          }
+        }
+        __syncthreads();
+        if (warp == 0) {
+          float v = 0.0f;
+          if (lane < 9) {
+            if (exact) {  // the reference's float32 sums, in point order: lane q owns sum q (nine dependent FADD chains)
+              const float *col = terms + lane * pitch;
+              int i = 0;
+              for (; i + 8 <= n; i += 8) {
+                const float4 u = *reinterpret_cast<const float4 *>(col + i), w = *reinterpret_cast<const float4 *>(col + i + 4);
+                v = __fadd_rn(v, u.x); v = __fadd_rn(v, u.y); v = __fadd_rn(v, u.z); v = __fadd_rn(v, u.w);
+                v = __fadd_rn(v, w.x); v = __fadd_rn(v, w.y); v = __fadd_rn(v, w.z); v = __fadd_rn(v, w.w);
+              }
+              for (; i < n; i++) v = __fadd_rn(v, col[i]);
+            } else {
+              for (int w = 0; w < NW; w++) v += terms[lane * NW + w];
+            }
+          }
+          float t9[9];
+#pragma unroll
+          for (int q = 0; q < 9; q++) t9[q] = __shfl_sync(0xffffffffu, v, q);
+          if (lane == 0) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
+#pragma unroll
+            for (int q = 0; q < 9; q++) tot[q] = t9[q];
+            const float dTr[3] = {t9[0], t9[1], t9[2]};
+            float Hm[9];
+            Hm[0] = t9[3]; Hm[4] = t9[4]; Hm[8] = t9[5];
+            Hm[1] = Hm[3] = t9[6]; Hm[2] = Hm[6] = t9[7]; Hm[5] = Hm[7] = t9[8];
+            float n0 = bc[0], n1 = bc[1], n2 = bc[2];
+            if (Hm[0] != 0.0f && Hm[4] != 0.0f) {
+              float dir[3];
+              hs_inv3_mul(Hm, dTr, dir);
+              if (dir[2] > 0.2f) dir[2] = 0.2f;
+              else if (dir[2] < -0.2f) dir[2] = -0.2f;
+              n0 += dir[0]; n1 += dir[1]; n2 += dir[2];
+            }
+            bc[0] = n0; bc[1] = n1; bc[2] = n2;
+            if (it + 1 < m.iterations) {
+              const HsTrig tr = hs_trig(n2, use_fma);
+              bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
+            }
           }
         }
         __syncthreads();
@@ -345,8 +373,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
     st->do_update = do_update ? 1 : 0;
     if (do_update) {
       float uc, us;  // Rotation2Df of the update transform: glibc cosf / sinf -> the same cells as the CPU
-      if (exact) { uc = glibc_cosf(est[2], use_fma); us = glibc_sinf(est[2], use_fma); }
-      else { uc = cosf(est[2]); us = sinf(est[2]); }
+      glibc_sincosf(est[2], use_fma, &us, &uc);
       for (int l = 0; l < P.levels; l++) {
         const HsLevel &m = P.l[l];
         const float mx = (m.tw_lin * est[0] + 0.0f * est[1]) + m.tw_tx;  // getMapCoordsPose (GridMapBase.h:238-242)
@@ -425,8 +452,8 @@ __device__ __forceinline__ HsUpd hs_load_upd(const HsState *st, int lv) {
   return u;
 }
 
-__device__ __forceinline__ float hs_prob_of(float lo, bool exact) {  // getGridProbability (GridMapLogOdds.h:136-140)
-  const float odds = exact ? (float)exp((double)lo) : expf(lo);  // unqualified exp(): the C library's double exp
+__device__ __forceinline__ float hs_prob_of(float lo) {  // getGridProbability (GridMapLogOdds.h:136-140)
+  const float odds = (float)exp((double)lo);  // unqualified exp(): the C library's double exp, rounded to float
   return odds / (odds + 1.0f);
 }
 
@@ -439,7 +466,6 @@ __device__ __forceinline__ float hs_prob_of(float lo, bool exact) {  // getGridP
 template <int PASS>
 __device__ unsigned long long hs_update_pass(const HsBatch &P, int b, int w, int nw, int lane) {
   const HsState *st = P.state + b;
-  const bool exact = P.exact != 0;
   unsigned long long my_visits = 0;
   int first[HS_L + 1];
   first[0] = 0;
@@ -476,7 +502,7 @@ __device__ unsigned long long hs_update_pass(const HsBatch &P, int b, int w, int
         if (__ldcg(fs + off) == stamp && (__ldcg(os + off) >> 12) != (u.ehi >> 12)) {  // bresenhamCellFree (:302-312)
           const float v = __fadd_rn(__ldcg(lo + off), P.lo_free);
           lo[off] = v;
-          prob[off] = hs_prob_of(v, exact);
+          prob[off] = hs_prob_of(v);
           ui[off] = u.mark_free;
         }
       }
@@ -492,7 +518,7 @@ __device__ unsigned long long hs_update_pass(const HsBatch &P, int b, int w, int
           }
           if (v < 50.0f) v = __fadd_rn(v, P.lo_occ);
           lo[off] = v;
-          prob[off] = hs_prob_of(v, exact);
+          prob[off] = hs_prob_of(v);
           ui[off] = u.mark_occ;
         }
       }
@@ -580,7 +606,9 @@ __global__ void __launch_bounds__(HS_THREADS) k_hs_stream(HsBatch P, HsStream S)
       hs_match_cta(P, C, 0, hs_smem);
     }
     hs_grid_barrier(S.barrier, generation);
-    if (__ldcg(&st->do_update)) {
+    // the gate's decision is read from this scan's own output row: without an update there is no further barrier, so CTA 0
+    // may already be matching scan i + 1 (and rewriting the state) while a slower CTA still looks at scan i's decision
+    if (__ldcg(S.out + 16 * (size_t)i + 12) != 0.0f) {
       const unsigned long long t0 = hs_now_ns();
       hs_update_pass<1>(P, 0, w, nw, lane);
       hs_grid_barrier(S.barrier, generation);

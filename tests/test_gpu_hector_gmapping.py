@@ -217,7 +217,7 @@ def test_hector_slam_self_driven_stream_bit_exact(pkg, mods):
     H, _ = mods
     poses, scans = _stream_case(pkg, H, 31, 120)
     kw = dict(resolution=0.05, size_x=1000, size_y=1000, start=(0.5, 0.5), levels=3, update_free=0.4, update_occupied=0.9,
-              min_dist=0.4, min_angle=0.9)
+              min_dist=0.08, min_angle=0.9)  # the synthetic walk drifts slowly: a low distance gate opens it a few times
     g, g2 = H.HectorSlam(**kw), H.HectorSlam(**kw)
     cpus = _processors(kw)
     est = poses[0].astype(np.float32)
