@@ -74,8 +74,10 @@ struct HsState {  // device-resident state of ONE processor
   int bx[HS_L], by[HS_L];
   unsigned int epoch_hi[HS_L];
   int mark_free[HS_L], mark_occ[HS_L];
+  int bb_x0[HS_L], bb_y0[HS_L], bb_x1[HS_L], bb_y1[HS_L];  // cells the update's rays can touch (inclusive; empty: x1 < x0)
   unsigned long long visits, n_matched, n_updated;
   unsigned long long t_match_ns, t_update_ns;
+  unsigned long long prof[8];  // SM cycles of processor 0's matching CTA: [0] staging, [1] point terms, [2] sums, [3] solve, [4] trig, [5] gate + bbox, [6] iterations
 };
 
 struct HsBatch {  // kernel parameter
@@ -182,14 +184,47 @@ struct HsTrig {
   float c, s;              // Rotation2Df(angle): std::cos / std::sin(float) = glibc cosf / sinf
   float sin_rot, cos_rot;  // OccGridMapUtil.h:87-88: the C library's double sin / cos, rounded to float
 };
-__device__ inline HsTrig hs_trig(float angle, bool use_fma) {
+__device__ inline HsTrig hs_trig(float angle, bool exact, bool use_fma) {
   HsTrig t;
   glibc_sincosf(angle, use_fma, &t.s, &t.c);
-  double ds, dc;
-  sincos((double)angle, &ds, &dc);
-  t.sin_rot = (float)ds;
-  t.cos_rot = (float)dc;
+  if (exact) {
+    double ds, dc;
+    sincos((double)angle, &ds, &dc);
+    t.sin_rot = (float)ds;
+    t.cos_rot = (float)dc;
+  } else {  // fast mode: the float sine / cosine stand in (they differ from the rounded double ones on ~1 % of angles, by one ulp)
+    t.sin_rot = t.s;
+    t.cos_rot = t.c;
+  }
   return t;
+}
+
+struct HsLine {
+  bool ok;
+  int x0, y0, x1, y1;
+  unsigned int da, db;
+  int err0, off_a, off_b;
+};
+
+// endpoints (OccGridMapBase.h:127-154) + updateLineBresenhami set-up (:220-258)
+__device__ __forceinline__ HsLine hs_line(float c, float s, float mx, float my, int bx, int by, float px, float py, int sx,
+                                          int sy) {
+  HsLine L;
+  float ex = __fadd_rn(__fadd_rn(__fmul_rn(c, px), __fmul_rn(-s, py)), mx);
+  float ey = __fadd_rn(__fadd_rn(__fmul_rn(s, px), __fmul_rn(c, py)), my);
+  ex = __fadd_rn(ex, 0.5f);
+  ey = __fadd_rn(ey, 0.5f);
+  L.x0 = bx; L.y0 = by;
+  L.x1 = (int)ex; L.y1 = (int)ey;  // Vector2f::cast<int>(): truncation
+  L.ok = !(L.x0 == L.x1 && L.y0 == L.y1);
+  if ((L.x0 < 0) || (L.x0 >= sx) || (L.y0 < 0) || (L.y0 >= sy)) L.ok = false;
+  if ((L.x1 < 0) || (L.x1 >= sx) || (L.y1 < 0) || (L.y1 >= sy)) L.ok = false;
+  const int dx = L.x1 - L.x0, dy = L.y1 - L.y0;
+  const unsigned int adx = (unsigned int)abs(dx), ady = (unsigned int)abs(dy);
+  const int odx = dx > 0 ? 1 : -1, ody = (dy > 0 ? 1 : -1) * sx;  // util::sign: sign(0) = -1
+  if (adx >= ady) { L.da = adx; L.db = ady; L.err0 = (int)(adx / 2); L.off_a = odx; L.off_b = ody; }
+  else { L.da = ady; L.db = adx; L.err0 = (int)(ady / 2); L.off_a = ody; L.off_b = odx; }
+  return L;
 }
 
 // shared memory of the match: [cap] float2 staged scan, then (EXACT) 9 term columns of `pitch` floats / (FAST) per-warp partials
@@ -211,7 +246,12 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
   __shared__ float bc[8];    // estimate + trig published by the solving thread
   __shared__ float tot[9];
   __shared__ float s_world[3];
+  __shared__ int s_do;
+  __shared__ int s_bb[HS_L][4];
   const unsigned long long t0 = hs_now_ns();
+  long long c_mark = clock64();
+  unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define HS_PROF(slot) do { if (tid == 0) { const long long c_now = clock64(); pf[slot] += (unsigned long long)(c_now - c_mark); c_mark = c_now; } } while (0)
   const float2 *gp = reinterpret_cast<const float2 *>(C.pts0) + (size_t)b * C.pts_stride;
   for (int i = tid; i < n; i += HS_THREADS) {
     const float2 p = gp[i];
@@ -223,6 +263,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
     s_world[0] = h[0]; s_world[1] = h[1]; s_world[2] = h[2];
   }
   __syncthreads();
+  HS_PROF(0);
   float world0 = s_world[0], world1 = s_world[1], world2 = s_world[2];
   bool any = false;
   if (!C.map_without_matching && n > 0) {
@@ -238,7 +279,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
       if (tid == 0) {
         const float e0 = (m.tw_lin * world0 + 0.0f * world1) + m.tw_tx;
         const float e1 = (0.0f * world0 + m.tw_lin * world1) + m.tw_ty;
-        const HsTrig tr = hs_trig(world2, use_fma);
+        const HsTrig tr = hs_trig(world2, exact, use_fma);
         bc[0] = e0; bc[1] = e1; bc[2] = world2; bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
       }
       __syncthreads();
@@ -288,6 +329,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
           }
         }
         __syncthreads();
+        HS_PROF(1);
         if (warp == 0) {
           float v = 0.0f;
           if (lane < 9) {
@@ -307,6 +349,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
           float t9[9];
 #pragma unroll
           for (int q = 0; q < 9; q++) t9[q] = __shfl_sync(0xffffffffu, v, q);
+          HS_PROF(2);
           if (lane == 0) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
 #pragma unroll
             for (int q = 0; q < 9; q++) tot[q] = t9[q];
@@ -323,10 +366,13 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
               n0 += dir[0]; n1 += dir[1]; n2 += dir[2];
             }
             bc[0] = n0; bc[1] = n1; bc[2] = n2;
+            HS_PROF(3);
             if (it + 1 < m.iterations) {
-              const HsTrig tr = hs_trig(n2, use_fma);
+              const HsTrig tr = hs_trig(n2, exact, use_fma);
               bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
             }
+            HS_PROF(4);
+            pf[6] += 1;
           }
         }
         __syncthreads();
@@ -402,36 +448,50 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
       reinterpret_cast<volatile unsigned int *>(C.mailbox)[15] = C.seq;
       __threadfence_system();
     }
+    s_do = do_update ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_do) {
+    // cells the rays of this update can touch, per level: the apply pass sweeps this box instead of re-walking the rays
+    if (tid < HS_L * 4) s_bb[tid >> 2][tid & 3] = (tid & 2) ? -2147483647 : 2147483647;  // {min x, min y, max x, max y}
+    __syncthreads();
+    for (int lv = 0; lv < P.levels; lv++) {
+      const HsLevel &m = P.l[lv];
+      const int nl = st->n_pts[lv];
+      const float c = st->uc[lv], s = st->us[lv], mx = st->umx[lv], my = st->umy[lv];
+      const int bx = st->bx[lv], by = st->by[lv];
+      const float2 *pp = reinterpret_cast<const float2 *>(m.pts) + (size_t)b * P.cap;
+      int lo_x = 2147483647, lo_y = 2147483647, hi_x = -2147483647, hi_y = -2147483647;
+      for (int i = tid; i < nl; i += HS_THREADS) {
+        const float2 pt = pp[i];
+        const HsLine ln = hs_line(c, s, mx, my, bx, by, pt.x, pt.y, m.sx, m.sy);
+        if (!ln.ok) continue;
+        lo_x = min(lo_x, min(ln.x0, ln.x1)); hi_x = max(hi_x, max(ln.x0, ln.x1));
+        lo_y = min(lo_y, min(ln.y0, ln.y1)); hi_y = max(hi_y, max(ln.y0, ln.y1));
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, d)); lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, d));
+        hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, d)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, d));
+      }
+      if (lane == 0) {
+        atomicMin(&s_bb[lv][0], lo_x); atomicMin(&s_bb[lv][1], lo_y);
+        atomicMax(&s_bb[lv][2], hi_x); atomicMax(&s_bb[lv][3], hi_y);
+      }
+    }
+    __syncthreads();
+    if (tid < P.levels) {
+      st->bb_x0[tid] = s_bb[tid][0]; st->bb_y0[tid] = s_bb[tid][1];
+      st->bb_x1[tid] = s_bb[tid][2]; st->bb_y1[tid] = s_bb[tid][3];  // no ray: max < min -> an empty box
+    }
+  }
+  HS_PROF(5);
+  if (tid == 0) {
+    if (b == 0)
+      for (int q = 0; q < 8; q++) st->prof[q] += pf[q];
     st->t_match_ns = hs_now_ns() - t0;
   }
-}
-
-struct HsLine {
-  bool ok;
-  int x0, y0, x1, y1;
-  unsigned int da, db;
-  int err0, off_a, off_b;
-};
-
-// endpoints (OccGridMapBase.h:127-154) + updateLineBresenhami set-up (:220-258)
-__device__ __forceinline__ HsLine hs_line(float c, float s, float mx, float my, int bx, int by, float px, float py, int sx,
-                                          int sy) {
-  HsLine L;
-  float ex = __fadd_rn(__fadd_rn(__fmul_rn(c, px), __fmul_rn(-s, py)), mx);
-  float ey = __fadd_rn(__fadd_rn(__fmul_rn(s, px), __fmul_rn(c, py)), my);
-  ex = __fadd_rn(ex, 0.5f);
-  ey = __fadd_rn(ey, 0.5f);
-  L.x0 = bx; L.y0 = by;
-  L.x1 = (int)ex; L.y1 = (int)ey;  // Vector2f::cast<int>(): truncation
-  L.ok = !(L.x0 == L.x1 && L.y0 == L.y1);
-  if ((L.x0 < 0) || (L.x0 >= sx) || (L.y0 < 0) || (L.y0 >= sy)) L.ok = false;
-  if ((L.x1 < 0) || (L.x1 >= sx) || (L.y1 < 0) || (L.y1 >= sy)) L.ok = false;
-  const int dx = L.x1 - L.x0, dy = L.y1 - L.y0;
-  const unsigned int adx = (unsigned int)abs(dx), ady = (unsigned int)abs(dy);
-  const int odx = dx > 0 ? 1 : -1, ody = (dy > 0 ? 1 : -1) * sx;  // util::sign: sign(0) = -1
-  if (adx >= ady) { L.da = adx; L.db = ady; L.err0 = (int)(adx / 2); L.off_a = odx; L.off_b = ody; }
-  else { L.da = ady; L.db = adx; L.err0 = (int)(ady / 2); L.off_a = ody; L.off_b = odx; }
-  return L;
+#undef HS_PROF
 }
 
 // the update parameters of one level as the gate wrote them; L2 loads (other SMs wrote them during THIS launch)
@@ -457,14 +517,10 @@ __device__ __forceinline__ float hs_prob_of(float lo) {  // getGridProbability (
   return odds / (odds + 1.0f);
 }
 
-// MapRepMultiMap::updateByScan (:174-191) for processor b.  Work item = (level, beam), flattened over the levels, one
-// warp each; lanes over Bresenham steps in closed form.
-//   PASS 1 (mark) : every traversed cell records the LOWEST beam index that frees it / ends on it.
-//   PASS 2 (apply): the winner beam of each cell applies the reference's update exactly once: free-only cells get
-//                   += logOddsFree; end cells get the "(v + f) - f" un-free rounding iff a lower-indexed beam had freed them
-//                   first, then += logOddsOccupied if v < 50 — the floats of the sequential loop, whatever the execution order.
-template <int PASS>
-__device__ unsigned long long hs_update_pass(const HsBatch &P, int b, int w, int nw, int lane) {
+// MapRepMultiMap::updateByScan (:174-191) for processor b, PASS 1 (mark): work item = (level, beam), flattened over
+// the levels, one warp each; lanes over Bresenham steps in closed form.  Every traversed cell records the LOWEST beam
+// index that frees it / ends on it (32-bit atomicMax of epoch | ~beam).  Returns this warp's cell visits.
+__device__ unsigned long long hs_mark_pass(const HsBatch &P, int b, int w, int nw, int lane) {
   const HsState *st = P.state + b;
   unsigned long long my_visits = 0;
   int first[HS_L + 1];
@@ -486,49 +542,80 @@ __device__ unsigned long long hs_update_pass(const HsBatch &P, int b, int w, int
     if (!ln.ok) continue;
     const uint32_t stamp = u.ehi | (uint32_t)(4095 - i);
     const int start = ln.y0 * m.sx + ln.x0;
-    if (PASS == 1) {
-      for (unsigned int k = lane; k < ln.da; k += 32) {  // bresenham2D: da cells from the start, end excluded
-        const unsigned int inc = (unsigned int)(((unsigned long long)ln.err0 + (unsigned long long)k * ln.db) / ln.da);
-        atomicMax(fs + (start + (int)k * ln.off_a + (int)inc * ln.off_b), stamp);
+    for (unsigned int k = lane; k < ln.da; k += 32) {  // bresenham2D: da cells from the start, end excluded
+      const unsigned int inc = (unsigned int)(((unsigned long long)ln.err0 + (unsigned long long)k * ln.db) / ln.da);
+      atomicMax(fs + (start + (int)k * ln.off_a + (int)inc * ln.off_b), stamp);
+    }
+    if (lane == 0) {
+      atomicMax(os + (ln.y1 * m.sx + ln.x1), stamp);
+      my_visits += (unsigned long long)ln.da + 1;
+    }
+  }
+  return my_visits;
+}
+
+// PASS 2 (apply): a dense, coalesced sweep over each level's bounding box of the rays (work item = 128 consecutive
+// cells of a row: four 128-byte loads per stamp plane per warp).  A cell stamped in this epoch gets the reference's
+// update exactly once: end cells (occ stamp of this epoch; the stamp's winner is the lowest beam ending there) take
+// bresenhamCellOcc — with the "(v + f) - f" un-free rounding iff a LOWER beam index had freed the cell first (its
+// free stamp, same epoch, is larger) — then += logOddsOccupied if v < 50; cells only freed take bresenhamCellFree.
+// The floats are those of the sequential loop (OccGridMapBase.h:302-330), whatever the execution order.
+__device__ void hs_apply_pass(const HsBatch &P, int b, int w, int nw, int lane) {
+  const HsState *st = P.state + b;
+  int first[HS_L + 1], x0[HS_L], y0[HS_L], x1[HS_L], chunks[HS_L];
+  first[0] = 0;
+  for (int lv = 0; lv < P.levels; lv++) {
+    x0[lv] = __ldcg(&st->bb_x0[lv]); y0[lv] = __ldcg(&st->bb_y0[lv]);
+    x1[lv] = __ldcg(&st->bb_x1[lv]);
+    const int y1 = __ldcg(&st->bb_y1[lv]);
+    const bool any = x1[lv] >= x0[lv] && y1 >= y0[lv];
+    chunks[lv] = any ? (x1[lv] - x0[lv] + 128) / 128 : 0;
+    first[lv + 1] = first[lv] + (any ? (y1 - y0[lv] + 1) * chunks[lv] : 0);
+  }
+  int lv = 0;
+  for (int j = w; j < first[P.levels]; j += nw) {
+    while (j >= first[lv + 1]) lv++;
+    const HsLevel &m = P.l[lv];
+    const size_t cells = (size_t)m.sx * m.sy;
+    const uint32_t *fs = m.free_st + (size_t)b * cells, *os = m.occ_st + (size_t)b * cells;
+    float *lo = m.lo + (size_t)b * cells, *prob = m.prob + (size_t)b * cells;
+    int32_t *ui = m.ui + (size_t)b * cells;
+    const uint32_t ep = __ldcg(&st->epoch_hi[lv]) >> 12;
+    const int mark_free = __ldcg(&st->mark_free[lv]), mark_occ = __ldcg(&st->mark_occ[lv]);
+    const int r = j - first[lv];
+    const int y = y0[lv] + r / chunks[lv];
+    const int xb = x0[lv] + (r % chunks[lv]) * 128 + lane;
+    uint32_t f[4], o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int x = xb + 32 * q;
+      f[q] = o[q] = 0;
+      if (x <= x1[lv]) {
+        f[q] = __ldcg(fs + (y * m.sx + x));
+        o[q] = __ldcg(os + (y * m.sx + x));
       }
-      if (lane == 0) atomicMax(os + (ln.y1 * m.sx + ln.x1), stamp);
-    } else {
-      float *lo = m.lo + (size_t)b * cells, *prob = m.prob + (size_t)b * cells;
-      int32_t *ui = m.ui + (size_t)b * cells;
-      for (unsigned int k = lane; k < ln.da; k += 32) {
-        const unsigned int inc = (unsigned int)(((unsigned long long)ln.err0 + (unsigned long long)k * ln.db) / ln.da);
-        const int off = start + (int)k * ln.off_a + (int)inc * ln.off_b;
-        my_visits++;
-        if (__ldcg(fs + off) == stamp && (__ldcg(os + off) >> 12) != (u.ehi >> 12)) {  // bresenhamCellFree (:302-312)
-          const float v = __fadd_rn(__ldcg(lo + off), P.lo_free);
-          lo[off] = v;
-          prob[off] = hs_prob_of(v);
-          ui[off] = u.mark_free;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int off = y * m.sx + xb + 32 * q;
+      if (o[q] != 0 && (o[q] >> 12) == ep) {  // bresenhamCellOcc (:315-330)
+        float v = __ldcg(lo + off);
+        if ((f[q] >> 12) == ep && f[q] > o[q]) {  // a lower beam index freed it first: set free, then unset
+          v = __fadd_rn(v, P.lo_free);
+          v = __fsub_rn(v, P.lo_free);
         }
-      }
-      if (lane == 0) {
-        my_visits++;
-        const int off = ln.y1 * m.sx + ln.x1;
-        if (__ldcg(os + off) == stamp) {  // bresenhamCellOcc (:315-330), first beam ending here
-          float v = __ldcg(lo + off);
-          const uint32_t f = __ldcg(fs + off);
-          if ((f >> 12) == (u.ehi >> 12) && f > stamp) {  // a LOWER beam index freed it first: set free, then unset
-            v = __fadd_rn(v, P.lo_free);
-            v = __fsub_rn(v, P.lo_free);
-          }
-          if (v < 50.0f) v = __fadd_rn(v, P.lo_occ);
-          lo[off] = v;
-          prob[off] = hs_prob_of(v);
-          ui[off] = u.mark_occ;
-        }
+        if (v < 50.0f) v = __fadd_rn(v, P.lo_occ);
+        lo[off] = v;
+        prob[off] = hs_prob_of(v);
+        ui[off] = mark_occ;
+      } else if (f[q] != 0 && (f[q] >> 12) == ep) {  // bresenhamCellFree (:302-312)
+        const float v = __fadd_rn(__ldcg(lo + off), P.lo_free);
+        lo[off] = v;
+        prob[off] = hs_prob_of(v);
+        ui[off] = mark_free;
       }
     }
   }
-  if (PASS == 2) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) my_visits += __shfl_xor_sync(0xffffffffu, my_visits, d);
-  }
-  return my_visits;
 }
 
 // ---- batch path: three launches per step over all B processors ----
@@ -539,14 +626,14 @@ __global__ void __launch_bounds__(HS_THREADS) k_hs_match(HsBatch P, HsCall C) {
 __global__ void __launch_bounds__(256) k_hs_mark(HsBatch P) {
   const int b = blockIdx.y;
   if (!P.state[b].do_update) return;
-  hs_update_pass<1>(P, b, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
+  const int lane = threadIdx.x & 31;
+  const unsigned long long v = hs_mark_pass(P, b, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, lane);
+  if (lane == 0 && v) atomicAdd(&P.state[b].visits, v);  // lane 0 carries the warp's count
 }
 __global__ void __launch_bounds__(256) k_hs_apply(HsBatch P) {
   const int b = blockIdx.y;
   if (!P.state[b].do_update) return;
-  const int lane = threadIdx.x & 31;
-  const unsigned long long v = hs_update_pass<2>(P, b, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, lane);
-  if (lane == 0 && v) atomicAdd(&P.state[b].visits, v);
+  hs_apply_pass(P, b, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
 }
 
 // ---- single-processor path: ONE cooperative launch walks n_scans scans (n_scans = 1 for b2s_hector_slam_update) ----
@@ -610,10 +697,10 @@ __global__ void __launch_bounds__(HS_THREADS) k_hs_stream(HsBatch P, HsStream S)
     // may already be matching scan i + 1 (and rewriting the state) while a slower CTA still looks at scan i's decision
     if (__ldcg(S.out + 16 * (size_t)i + 12) != 0.0f) {
       const unsigned long long t0 = hs_now_ns();
-      hs_update_pass<1>(P, 0, w, nw, lane);
-      hs_grid_barrier(S.barrier, generation);
-      const unsigned long long v = hs_update_pass<2>(P, 0, w, nw, lane);
+      const unsigned long long v = hs_mark_pass(P, 0, w, nw, lane);
       if (lane == 0 && v) atomicAdd(&st->visits, v);
+      hs_grid_barrier(S.barrier, generation);
+      hs_apply_pass(P, 0, w, nw, lane);
       hs_grid_barrier(S.barrier, generation);  // the next match reads the refreshed probability planes
       if (blockIdx.x == 0 && threadIdx.x == 0) st->t_update_ns = hs_now_ns() - t0;
     }
@@ -638,6 +725,8 @@ __global__ void k_hs_state_init(HsState *st, int batch, int reset_maps) {
     for (int l = 0; l < HS_L; l++) { s.curr_update_index[l] = 0; s.epoch[l] = 0; s.n_pts[l] = 0; s.origo[l][0] = s.origo[l][1] = 0.0f; }
     s.visits = s.n_matched = s.n_updated = 0;
     s.t_match_ns = s.t_update_ns = 0;
+    for (int q = 0; q < 8; q++) s.prof[q] = 0;
+    for (int l = 0; l < HS_L; l++) { s.bb_x0[l] = s.bb_y0[l] = 0; s.bb_x1[l] = s.bb_y1[l] = -1; }
   }
 }
 
@@ -1172,6 +1261,20 @@ b2s_status b2s_hector_slam_stats(b2s_hector_slam *p, double out[5]) {
   for (const HsState &x : s) { out[0] += (double)x.n_matched; out[1] += (double)x.n_updated; out[2] += (double)x.visits; }
   out[3] = (double)s[0].t_match_ns * 1e-6;   // ms of processor 0's last match / update (device %globaltimer)
   out[4] = (double)s[0].t_update_ns * 1e-6;
+  return B2S_OK;
+}
+
+/* SM cycles spent by processor 0's matching CTA since creation, by phase: [0] staging the scan, [1] per-point terms
+ * (cell loads + bilinear + products), [2] the nine sums, [3] 3x3 solve, [4] sine / cosine of the new heading,
+ * [5] gate + update parameters + ray bounding boxes, [6] Gauss-Newton iterations counted, [7] unused */
+b2s_status b2s_hector_slam_profile(b2s_hector_slam *p, double out[8]) {
+  if (!p || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  HsState s;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(&s, p->d_state, sizeof(HsState), cudaMemcpyDeviceToHost, p->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+  p->launch_pending = false;
+  for (int q = 0; q < 8; q++) out[q] = (double)s.prof[q];
   return B2S_OK;
 }
 

@@ -48,6 +48,7 @@ def _bind():
     L.b2s_hector_slam_copy_level_of.argtypes = [vp, C.c_int, C.c_int, fp, ip]
     L.b2s_hector_slam_last_poses.argtypes = [vp, C.c_int, fp, fp]
     L.b2s_hector_slam_debug_set_epoch.argtypes = [vp, C.c_uint]
+    L.b2s_hector_slam_profile.argtypes = [vp, C.POINTER(C.c_double)]
     _bound = True
     return L
 
@@ -194,6 +195,13 @@ class HectorSlam:
         a, u = np.zeros(3, np.float32), np.zeros(3, np.float32)
         check(self.L.b2s_hector_slam_last_poses(self.h, b, _f(a), _f(u)))
         return a, u
+
+    def profile(self):
+        out = np.zeros(8)
+        check(self.L.b2s_hector_slam_profile(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        it = max(out[6], 1.0)
+        return dict(staging=out[0], terms=out[1], sums=out[2], solve=out[3], trig=out[4], gate=out[5], iterations=out[6],
+                    cycles_per_iteration=dict(terms=out[1] / it, sums=out[2] / it, solve=out[3] / it, trig=out[4] / it))
 
     def debug_set_epoch(self, updates):
         check(self.L.b2s_hector_slam_debug_set_epoch(self.h, int(updates)))

@@ -456,6 +456,9 @@ b2s_status b2s_hector_slam_copy_level_of(b2s_hector_slam *p, int processor, int 
 /* getLastScanMatchPose / getLastMapUpdatePose (HectorSlamProcessor.h:118-119) of one processor; either may be NULL */
 b2s_status b2s_hector_slam_last_poses(b2s_hector_slam *p, int processor, float last_scan_match_pose[3],
                                       float last_map_update_pose[3]);
+/* SM cycles of processor 0's matching CTA since creation, by phase: staging, per-point terms, the nine sums, 3x3 solve,
+ * sine / cosine, gate + update parameters, iterations counted, (unused) */
+b2s_status b2s_hector_slam_profile(b2s_hector_slam *p, double out[8]);
 /* test hook: pretend `updates` map updates already consumed per-scan stamp epochs (exercises the 20-bit epoch wrap) */
 b2s_status b2s_hector_slam_debug_set_epoch(b2s_hector_slam *p, unsigned int updates);
 

@@ -40,6 +40,7 @@ for exact in (True, False):
     p, u, _ = hs.process_stream(pts, (0, 0), first_hint=poses[0].astype(np.float32))
     dt = time.perf_counter() - t0
     st = hs.stats()
+    out[f"profile_{tag}"] = hs.profile()
     out[f"stream_{tag}"] = {"scans_per_s": n / dt, "us_per_scan": 1e6 * dt / n, "updates": int(u.sum()),
                             "cell_visits": st["cell_visits"], "match_ms": st["match_ms"], "update_ms": st["update_ms"],
                             "xy_err": float(np.abs(p[-1][:2] - poses[-1][:2]).max())}
