@@ -431,9 +431,8 @@ __global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict
   if (f & 2) return;
   if (mode == 1 && (f & 1)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (c >= ncell) return;
   const uint8_t *grid = grids + (size_t)b * grid_pitch;
+  for (int c = blockIdx.x * (blockDim.x >> 5) + warp; c < ncell; c += gridDim.x * (blockDim.x >> 5)) {
   const int32_t base = bases[(size_t)b * ncell + c];
   for (int k = 0; k < na; k++) {
     const int32_t *offs = lut ? lut + ((size_t)b * na + k) * n : nullptr;
@@ -472,6 +471,7 @@ __global__ void __launch_bounds__(256) k_sweep_generic(const uint8_t *__restrict
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
     if (lane == 0) sums[((size_t)b * na + k) * ncell + c] = sum;
+  }
   }
 }
 
@@ -855,13 +855,36 @@ __device__ __forceinline__ void win_class_pair(const uint8_t *__restrict__ sgrid
   win_flush<SH, STRIDE, GEN>(lo, hi, acc, hi_half);
 }
 
+struct ReduceArgs {
+  const int32_t *sums;
+  const double *centers;
+  int32_t *flags;
+  b2s_matcher_params p;
+  b2s_search s;
+  b2s_grid_info g;
+  double scale;
+  int n, nx, ny, na;
+  double *probs_all;
+  b2s_match_result *results;
+  int k_first, mode;
+  double *part_best;
+  const double *glob_best;
+  double *tie_out;
+  const double *tie_in;
+};
+
+// flags bit 2 (value 4): this match's tail already ran inside the sweep kernel (fused path)
+constexpr int32_t FLAG_REDUCED = 4;
+
+__device__ void reduce_match(const int b, const ReduceArgs &A);
+
 template <int STRIDE, bool GEN>
 __global__ void __launch_bounds__(WIN_THREADS, 1)
     k_sweep_window(const uint8_t *__restrict__ grids, size_t grid_pitch, int data_size, int copy_bytes,
                    const int32_t *__restrict__ lists, const int32_t *__restrict__ counts,
                    const int32_t *__restrict__ starts, const int32_t *__restrict__ flags, int batch, int n, int na,
                    int nx, int ny, int width_step, int32_t *__restrict__ sums, int *__restrict__ work_counter,
-                   int band_rows, int nbands, int band_bytes, int neg_bands) {
+                   int band_rows, int nbands, int band_bytes, int neg_bands, int fuse_tail, ReduceArgs RA) {
   // Grids larger than shared memory are swept in `nbands` row bands: a work unit is (match, band, 32-row candidate
   // tile); the image holds the rows that tile of a window whose ORIGIN lies in the band can touch (band_rows +
   // STRIDE * 31 + 2), k_offsets_sorted grouped the beams by the band of their origin (bands [0, neg_bands) hold origins
@@ -989,6 +1012,13 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
       }
     }
     __syncthreads();  // everyone is done with sgrid before the next unit's copy is issued
+    if (fuse_tail) {
+      // The fp64 tail of CorrelateScan for THIS match, while its response volume (just written by this CTA) is still
+      // in L2: no separate k_reduce launch re-reads 700 MB from DRAM after the sweep.  (nbands == 1: a unit is a match.)
+      reduce_match(b, RA);
+      __syncthreads();
+      if (threadIdx.x == 0) RA.flags[b] = f | FLAG_REDUCED;
+    }
   }
 }
 
@@ -998,7 +1028,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
 // (iy, ix, k) with linear index (iy*nx + ix)*na + k; ties are summed sequentially in that order when there are
 // at most RED_MAX_TIES of them (bit-identical to the reference), otherwise by a fixed-order tree.
 // ----------------------------------------------------------------------------------------------
-constexpr int RED_THREADS = 512;   // 60 registers: two CTAs per SM, so one match's serial tail overlaps another's streaming pass
+constexpr int RED_THREADS = 512;   // == WIN_THREADS: the sweep kernel's CTAs run the tail themselves (fused path)
+static_assert(RED_THREADS == WIN_THREADS, "the fused tail runs on the sweep kernel's CTA");
+// (stand-alone k_reduce: 60 registers, two CTAs per SM, so one match's serial tail overlaps another's streaming pass)
 constexpr int RED_MAX_TIES = 512;
 constexpr int RED_UNROLL = 8;
 
@@ -1026,16 +1058,22 @@ __device__ __forceinline__ float red_fscore(int32_t isum, float apf_k, float dpf
   return (float)isum * apf_k * dpf;
 }
 
-__global__ void __launch_bounds__(RED_THREADS)
-    k_reduce(const int32_t *__restrict__ sums, const double *__restrict__ centers, const int32_t *__restrict__ flags,
-             b2s_matcher_params p, b2s_search s, b2s_grid_info g, double scale, int n, int nx, int ny, int na,
-             double *__restrict__ probs_all, b2s_match_result *__restrict__ results, int k_first, int mode,
-             double *__restrict__ part_best, const double *__restrict__ glob_best, double *__restrict__ tie_out,
-             const double *__restrict__ tie_in) {
-  // mode 0: the whole tail.  Modes 1-3 are the phases of a sweep whose ANGLES are split over several GPUs
-  // (SURVEY.md §8(e)(ii)); between them the host all-reduces: 1 = best + per-cell maxima of this angle subset;
-  // 2 = tie sums of this subset against the global best; 3 = mean pose + covariance from the global sums / plane.
-  const int b = blockIdx.x;
+__device__ __noinline__ void reduce_match(const int b, const ReduceArgs &A) {
+  const int32_t *sums = A.sums;  // no __restrict__ / no read-only path: the fused sweep wrote them in this very launch
+  const double *__restrict__ centers = A.centers;
+  const int32_t *__restrict__ flags = A.flags;
+  const b2s_matcher_params &p = A.p;
+  const b2s_search &s = A.s;
+  const b2s_grid_info &g = A.g;
+  const double scale = A.scale;
+  const int n = A.n, nx = A.nx, ny = A.ny, na = A.na;
+  double *__restrict__ probs_all = A.probs_all;
+  b2s_match_result *__restrict__ results = A.results;
+  const int k_first = A.k_first, mode = A.mode;
+  double *__restrict__ part_best = A.part_best;
+  const double *__restrict__ glob_best = A.glob_best;
+  double *__restrict__ tie_out = A.tie_out;
+  const double *__restrict__ tie_in = A.tie_in;
   const int tid = threadIdx.x;
   const int ncell = nx * ny;
   b2s_match_result *res = results + b;
@@ -1103,7 +1141,7 @@ __global__ void __launch_bounds__(RED_THREADS)
       for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
         int32_t v[RED_UNROLL];
 #pragma unroll
-        for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldg(bs + (size_t)(k0 + u) * ncell + c) : 0;
+        for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldcg(bs + (size_t)(k0 + u) * ncell + c) : 0;
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; u++) {
           if (k0 + u >= na) continue;
@@ -1130,7 +1168,7 @@ __global__ void __launch_bounds__(RED_THREADS)
         for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
           int32_t v[RED_UNROLL];
 #pragma unroll
-          for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldg(bs + (size_t)(k0 + u) * ncell + c) : 0;
+          for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldcg(bs + (size_t)(k0 + u) * ncell + c) : 0;
 #pragma unroll
           for (int u = 0; u < RED_UNROLL; u++) {
             if (k0 + u >= na) continue;
@@ -1146,7 +1184,7 @@ __global__ void __launch_bounds__(RED_THREADS)
     } else {
       for (int k = 0; k < na; k++) {
         const double angle = start_a + (double)(uint32_t)(k_first + k) * s.angle_res;
-        cell_best = dmax(cell_best, candidate_response(bs[(size_t)k * ncell + c], n, pen, sq, angle, ch, p));
+        cell_best = dmax(cell_best, candidate_response(__ldcg(bs + (size_t)k * ncell + c), n, pen, sq, angle, ch, p));
       }
     }
     best = dmax(best, cell_best);
@@ -1192,7 +1230,7 @@ __global__ void __launch_bounds__(RED_THREADS)
     for (int k0 = 0; k0 < na; k0 += RED_UNROLL) {
       int32_t v[RED_UNROLL];
 #pragma unroll
-      for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldg(bs + (size_t)(k0 + u) * ncell + c) : 0;
+      for (int u = 0; u < RED_UNROLL; u++) v[u] = (k0 + u < na) ? __ldcg(bs + (size_t)(k0 + u) * ncell + c) : 0;
 #pragma unroll
       for (int u = 0; u < RED_UNROLL; u++) {
         const int k = k0 + u;
@@ -1345,6 +1383,11 @@ __global__ void __launch_bounds__(RED_THREADS)
   res->response = s.fine ? best : (best > 1.0 ? 1.0 : best);  // Mapper.cpp:514-517
   res->status = B2S_OK;
   res->tie_count = total;
+}
+
+__global__ void __launch_bounds__(RED_THREADS, 2) k_reduce(ReduceArgs A) {
+  if (A.flags[blockIdx.x] & FLAG_REDUCED) return;  // the sweep kernel already ran this match's tail
+  reduce_match(blockIdx.x, A);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1978,11 +2021,19 @@ b2s_status b2s_matcher_correlate_split_begin(b2s_matcher *m, const double *cente
   return B2S_OK;
 }
 
+static ReduceArgs reduce_args(b2s_matcher *m, const b2s_search &s, int nx, int ny, int na, int k_first, int mode) {
+  ReduceArgs A;
+  A.sums = m->d_sums; A.centers = m->d_centers; A.flags = m->d_flags;
+  A.p = m->p; A.s = s; A.g = m->g; A.scale = 1.0 / m->p.resolution;
+  A.n = m->n; A.nx = nx; A.ny = ny; A.na = na;
+  A.probs_all = m->d_probs; A.results = m->d_results;
+  A.k_first = k_first; A.mode = mode;
+  A.part_best = m->d_part_best; A.glob_best = m->d_glob_best; A.tie_out = m->d_tie; A.tie_in = m->d_tie;
+  return A;
+}
+
 static b2s_status split_phase(b2s_matcher *m, int mode) {
-  const b2s_search &s = m->last_search;
-  k_reduce<<<m->batch, RED_THREADS, 0, m->stream>>>(m->d_sums, m->d_centers, m->d_flags, m->p, s, m->g, 1.0 / m->p.resolution,
-                                                    m->n, m->last.nx, m->last.ny, m->last.na, m->d_probs, m->d_results,
-                                                    m->last_k_first, mode, m->d_part_best, m->d_glob_best, m->d_tie, m->d_tie);
+  k_reduce<<<m->batch, RED_THREADS, 0, m->stream>>>(reduce_args(m, m->last_search, m->last.nx, m->last.ny, m->last.na, m->last_k_first, mode));
   B2S_CUDA_CHECK(cudaGetLastError());
   return B2S_OK;
 }
@@ -2087,7 +2138,14 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   const int tiles_x_w = (nx + cpt - 1) / cpt, tiles_y_w = (ny + 31) / 32;
   const int rows_total = tiles_y_w * 32;
   const int halo_rows = std::max(stride, 1) * 31 + 2;  // rows below the first row of a 32-row candidate tile that a lane may touch
-  const long long smem_limit = (long long)m->smem_optin - 4096;  // static shared memory of the kernel + margin
+  // static shared memory of the sweep kernel (its own + the fused tail's scratch) comes out of the opt-in budget
+  static size_t win_static = 0;
+  if (!win_static) {
+    cudaFuncAttributes fa;
+    B2S_CUDA_CHECK(cudaFuncGetAttributes(&fa, k_sweep_window<1, false>));
+    win_static = fa.sharedSizeBytes;
+  }
+  const long long smem_limit = (long long)m->smem_optin - (long long)win_static - 512;
   int band_rows = std::max(m->g.height, 1), nbands = 1, band_bytes = copy_bytes, neg_bands = 0;
   bool bands_ok = true;
   if ((long long)copy_bytes + 2 * WIN_GUARD > smem_limit) {
@@ -2149,6 +2207,9 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     if (nbands > 1)  // bands accumulate with RED.ADD
       B2S_CUDA_CHECK(cudaMemsetAsync(m->d_sums, 0, sizeof(int32_t) * (size_t)B * na * ncell, m->stream));
     const int ctas = (int)std::min<long long>((long long)B * nbands * (nbands > 1 ? tiles_y_w : 1), m->num_sms);
+    // whole matches per CTA (one band) and an unsplit sweep: the CTA runs the match's fp64 tail itself right after its
+    // last tile, reading the volume back from L2; k_reduce then only serves matches the window kernel skipped
+    const bool fuse_tail = nbands == 1 && mode == 0 && m->force_kernel != 2;
     // the GEN = false instantiation assumes exactly two lanes per row-start bank (see win_load)
     const int bank_step = ((m->g.width_step >> 2) * std::max(stride, 1)) & 31;
     const bool gen = (bank_step & 3) != 2;
@@ -2157,7 +2218,8 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
       kern<<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes, m->d_lists,
                                                        m->d_counts, m->d_starts, m->d_flags, B, n, na, nx, ny,
                                                        m->g.width_step, m->d_sums, m->d_work, band_rows, nbands,
-                                                       band_bytes, neg_bands);
+                                                       band_bytes, neg_bands, fuse_tail ? 1 : 0,
+                                                       reduce_args(m, *s, nx, ny, na, k_first, mode));
       return B2S_OK;
     };
     if (stride == 2) st = gen ? launch(k_sweep_window<2, true>) : launch(k_sweep_window<2, false>);
@@ -2165,7 +2227,8 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     if (st) return st;
     // matches whose lattice is not the regular raster (a centre exactly on a rounding tie) fall through;
     // they compute their lookup values on the fly (no table was materialised for them)
-    k_sweep_generic<<<ggrid, 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, nullptr, m->d_bases,
+    // (a few CTAs per match that exit at once unless the lattice is irregular: the kernel loops over the cells)
+    k_sweep_generic<<<dim3(4, (unsigned)B), 256, 0, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, nullptr, m->d_bases,
                                                   m->d_flags, 1, n, na, ncell, m->d_sums, m->d_ranges, m->d_local,
                                                   m->d_grid_off, m->d_centers, s->angle_offset, s->angle_res,
                                                   m->g.width_step, scale, k_first);
@@ -2181,9 +2244,7 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   B2S_CUDA_CHECK(cudaEventRecord(m->ev[2], m->stream));
 
   // ---- fp64 tail ----
-  k_reduce<<<B, RED_THREADS, 0, m->stream>>>(m->d_sums, m->d_centers, m->d_flags, m->p, *s, m->g, scale, n, nx, ny, na,
-                                             m->d_probs, m->d_results, k_first, mode, m->d_part_best, m->d_glob_best,
-                                             m->d_tie, m->d_tie);
+  k_reduce<<<B, RED_THREADS, 0, m->stream>>>(reduce_args(m, *s, nx, ny, na, k_first, mode));
   if (s->fine) {
     size_t sm = sizeof(double) * (size_t)na;
     if (sm > 48 * 1024) B2S_FAIL(B2S_ERR_TOO_LARGE, "too many angles for the angular-covariance kernel");
