@@ -5,11 +5,18 @@
 // solver is plugged into the reference Mapper and into ours in tests.
 //
 // Error of constraint (i -> j, mean d, information L):  e = [ R(th_i)^T (t_j - t_i) - d_xy ;  wrap(th_j - th_i - d_th) ],
-// cost = sum e^T L e.  Levenberg-Marquardt on the normal equations H dx = -g (3x3 blocks), solved by conjugate
-// gradients with a block-Jacobi preconditioner; the first node is held fixed.
+// cost = sum e^T L e.  Levenberg-Marquardt on the normal equations (H + lambda diag H) dx = -g, 3x3 blocks, solved
+// DIRECTLY by a sparse block L D L^T factorisation (what sba's doSPA does with CHOLMOD / CSparse): a greedy
+// minimum-degree elimination order computed once per solve on the graph of the constraints — which also yields every
+// column's fill pattern — then a right-looking numeric factorisation per LM trial and two triangular sweeps.  A
+// trajectory graph (chain + near links + loop closures) keeps its fill near-linear under that ordering: the
+// 5 000-node / 10 747-constraint bench graph solves in tens of milliseconds (the earlier block-Jacobi PCG took 3.5 s).
+// The first node is held fixed.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <queue>
 #include <new>
 #include <vector>
 
@@ -75,6 +82,133 @@ void mat3_AB(const double A[9], const double B[9], double out[9]) {
     for (int j = 0; j < 3; j++) out[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 
+// ---- sparse block L D L^T ----------------------------------------------------------------------------------------
+struct Factor {
+  int n = 0;
+  std::vector<int> order, pos;               // elimination order / its inverse
+  std::vector<std::vector<int>> rows;        // rows[k]: nodes of column order[k] below the diagonal, sorted by pos
+  std::vector<std::vector<double>> blk;      // blk[k]: 9 doubles per entry of rows[k] (block (row, order[k]))
+  std::vector<double> D, Dinv;               // diagonal blocks by elimination position
+};
+
+// greedy minimum degree on the elimination graph; the neighbours a node has when it is eliminated ARE its column's rows
+void symbolic(Factor &F, int n, const std::vector<std::pair<int, int>> &edges) {
+  F.n = n;
+  std::vector<std::vector<int>> adj((size_t)n);
+  for (const auto &e : edges)
+    if (e.first != e.second) { adj[e.first].push_back(e.second); adj[e.second].push_back(e.first); }
+  for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+  std::vector<char> dead((size_t)n, 0);
+  typedef std::pair<int, int> DI;  // (degree, node), stale entries skipped
+  std::priority_queue<DI, std::vector<DI>, std::greater<DI>> pq;
+  for (int i = 0; i < n; i++) pq.push(DI((int)adj[i].size(), i));
+  F.order.clear(); F.pos.assign((size_t)n, -1); F.rows.assign((size_t)n, {});
+  std::vector<int> merged;
+  while (!pq.empty()) {
+    const DI top = pq.top();
+    pq.pop();
+    const int v = top.second;
+    if (dead[v] || top.first != (int)adj[v].size()) continue;
+    dead[v] = 1;
+    const int k = (int)F.order.size();
+    F.pos[v] = k;
+    F.order.push_back(v);
+    const std::vector<int> N = adj[v];  // all alive: dead nodes are removed from their neighbours' lists below
+    F.rows[k] = N;
+    for (int u : N) {  // clique among the neighbours, v removed
+      merged.clear();
+      std::set_union(adj[u].begin(), adj[u].end(), N.begin(), N.end(), std::back_inserter(merged));
+      merged.erase(std::remove_if(merged.begin(), merged.end(), [&](int w) { return w == u || w == v; }), merged.end());
+      adj[u].swap(merged);
+      pq.push(DI((int)adj[u].size(), u));
+    }
+    std::vector<int>().swap(adj[v]);
+  }
+  for (int k = 0; k < n; k++) std::sort(F.rows[k].begin(), F.rows[k].end(), [&](int a, int b) { return F.pos[a] < F.pos[b]; });
+  F.blk.assign((size_t)n, {});
+  for (int k = 0; k < n; k++) F.blk[k].assign(9 * F.rows[k].size(), 0.0);
+  F.D.assign(9 * (size_t)n, 0.0);
+  F.Dinv.assign(9 * (size_t)n, 0.0);
+}
+
+inline double *find_block(Factor &F, int col_pos, int row_node) {  // block (row_node, order[col_pos]); must exist
+  const std::vector<int> &r = F.rows[col_pos];
+  const int target = F.pos[row_node];
+  size_t lo = 0, hi = r.size();
+  while (lo < hi) {
+    const size_t mid = (lo + hi) / 2;
+    if (F.pos[r[mid]] < target) lo = mid + 1; else hi = mid;
+  }
+  return (lo < r.size() && r[lo] == row_node) ? &F.blk[col_pos][9 * lo] : nullptr;
+}
+
+// numeric right-looking factorisation of the matrix held in F.D / F.blk (lower part); false = not positive definite
+bool factorise(Factor &F) {
+  const int n = F.n;
+  std::vector<double> W;
+  for (int k = 0; k < n; k++) {
+    double *Dk = &F.D[9 * (size_t)k];
+    if (!(Dk[0] > 0.0) || !inv3(Dk, &F.Dinv[9 * (size_t)k])) return false;
+    const double *Di = &F.Dinv[9 * (size_t)k];
+    const std::vector<int> &R = F.rows[k];
+    const size_t m = R.size();
+    W.assign(F.blk[k].begin(), F.blk[k].end());  // B_ik before scaling
+    for (size_t t = 0; t < m; t++) {             // L_ik = B_ik D^-1
+      double *B = &F.blk[k][9 * t], L[9];
+      mat3_AB(B, Di, L);
+      std::memcpy(B, L, sizeof(L));
+    }
+    for (size_t tj = 0; tj < m; tj++) {          // A_ij -= L_ik B_jk^T for i >= j among the rows of column k
+      const int j = R[tj], pj = F.pos[j];
+      const double *Wj = &W[9 * tj];
+      {
+        const double *Li = &F.blk[k][9 * tj];
+        double *T = &F.D[9 * (size_t)pj];
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++) T[3 * a + b] -= Li[3 * a] * Wj[3 * b] + Li[3 * a + 1] * Wj[3 * b + 1] + Li[3 * a + 2] * Wj[3 * b + 2];
+      }
+      size_t cursor = 0;
+      const std::vector<int> &Rj = F.rows[pj];
+      for (size_t ti = tj + 1; ti < m; ti++) {
+        const int i = R[ti];
+        while (cursor < Rj.size() && Rj[cursor] != i) cursor++;  // both lists are sorted by pos: one merge walk
+        if (cursor == Rj.size()) return false;                   // (cannot happen: fill pattern of the elimination)
+        const double *Li = &F.blk[k][9 * ti];
+        double *T = &F.blk[pj][9 * cursor];
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++) T[3 * a + b] -= Li[3 * a] * Wj[3 * b] + Li[3 * a + 1] * Wj[3 * b + 1] + Li[3 * a + 2] * Wj[3 * b + 2];
+      }
+    }
+  }
+  return true;
+}
+
+void solve_factored(const Factor &F, std::vector<double> &b) {  // b indexed by node, overwritten with the solution
+  const int n = F.n;
+  for (int k = 0; k < n; k++) {  // L y = b
+    const double *bk = &b[3 * (size_t)F.order[k]];
+    for (size_t t = 0; t < F.rows[k].size(); t++) {
+      const double *L = &F.blk[k][9 * t];
+      double *bi = &b[3 * (size_t)F.rows[k][t]];
+      for (int a = 0; a < 3; a++) bi[a] -= L[3 * a] * bk[0] + L[3 * a + 1] * bk[1] + L[3 * a + 2] * bk[2];
+    }
+  }
+  for (int k = 0; k < n; k++) {  // D z = y
+    double *bk = &b[3 * (size_t)F.order[k]];
+    const double *Di = &F.Dinv[9 * (size_t)k];
+    const double t0 = bk[0], t1 = bk[1], t2 = bk[2];
+    for (int a = 0; a < 3; a++) bk[a] = Di[3 * a] * t0 + Di[3 * a + 1] * t1 + Di[3 * a + 2] * t2;
+  }
+  for (int k = n - 1; k >= 0; k--) {  // L^T x = z
+    double *bk = &b[3 * (size_t)F.order[k]];
+    for (size_t t = 0; t < F.rows[k].size(); t++) {
+      const double *L = &F.blk[k][9 * t];
+      const double *bi = &b[3 * (size_t)F.rows[k][t]];
+      for (int a = 0; a < 3; a++) bk[a] -= L[a] * bi[0] + L[3 + a] * bi[1] + L[6 + a] * bi[2];
+    }
+  }
+}
+
 int solve(G *g) {
   const int n = (int)g->nodes.size();
   if (n < 2 || g->cons.empty()) return 0;
@@ -83,8 +217,15 @@ int solve(G *g) {
   double lambda = 1e-4, cur = chi2(g, x);
   g->chi_before = cur;
   g->lm_steps = 0;
+  Factor F;
+  {
+    std::vector<std::pair<int, int>> edges;
+    edges.reserve(g->cons.size());
+    for (const auto &c : g->cons) edges.push_back(std::make_pair(c.a, c.b));
+    symbolic(F, n, edges);
+  }
   std::vector<Lin> lin(g->cons.size());
-  std::vector<double> grad(3 * (size_t)n), diag(9 * (size_t)n), dinv(9 * (size_t)n), dx(3 * (size_t)n), r, z, p, Ap;
+  std::vector<double> grad(3 * (size_t)n), diag(9 * (size_t)n), dx(3 * (size_t)n);
   for (int it = 0; it < g->lm_iterations; it++) {
     std::fill(grad.begin(), grad.end(), 0.0);
     std::fill(diag.begin(), diag.end(), 0.0);
@@ -111,59 +252,35 @@ int solve(G *g) {
     }
     bool improved = false;
     for (int tries = 0; tries < 8 && !improved; tries++) {
-      // (H + lambda * diag(H)) dx = -grad with node 0 fixed, PCG with the inverse 3x3 diagonal blocks
-      for (int i = 0; i < n; i++) {
-        double blk[9];
-        std::memcpy(blk, &diag[9 * i], sizeof(blk));
-        for (int q = 0; q < 3; q++) blk[4 * q] = blk[4 * q] * (1.0 + lambda) + 1e-12;
-        if (!inv3(blk, &dinv[9 * i])) std::memset(&dinv[9 * i], 0, sizeof(blk));
-      }
-      auto apply = [&](const std::vector<double> &v, std::vector<double> &out) {
-        out.assign(v.size(), 0.0);
-        for (int i = 1; i < n; i++)
-          for (int a = 0; a < 3; a++) {
-            double s = 0;
-            for (int b = 0; b < 3; b++) s += diag[9 * i + 3 * a + b] * v[3 * i + b];
-            out[3 * i + a] = s + lambda * diag[9 * i + 4 * a] * v[3 * i + a];
-          }
-        for (size_t k = 0; k < g->cons.size(); k++) {
-          const int a = g->cons[k].a, b = g->cons[k].b;
-          for (int i = 0; i < 3; i++) {
-            double sab = 0, sba = 0;
-            for (int j = 0; j < 3; j++) { sab += lin[k].Hab[3 * i + j] * v[3 * b + j]; sba += lin[k].Hab[3 * j + i] * v[3 * a + j]; }
-            if (a != 0) out[3 * a + i] += (b != 0 ? sab : 0.0);
-            if (b != 0) out[3 * b + i] += (a != 0 ? sba : 0.0);
-          }
+      // assemble the lower part of (H + lambda diag H) in elimination order; node 0 is fixed: identity row / column
+      for (int k = 0; k < n; k++) {
+        const int v = F.order[k];
+        double *Dk = &F.D[9 * (size_t)k];
+        if (v == 0) {
+          const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+          std::memcpy(Dk, I, sizeof(I));
+        } else {
+          std::memcpy(Dk, &diag[9 * (size_t)v], 9 * sizeof(double));
+          for (int q = 0; q < 3; q++) Dk[4 * q] = Dk[4 * q] * (1.0 + lambda) + 1e-12;
         }
-      };
-      auto precond = [&](const std::vector<double> &v, std::vector<double> &out) {
-        out.assign(v.size(), 0.0);
-        for (int i = 1; i < n; i++)
-          for (int a = 0; a < 3; a++) out[3 * i + a] = dinv[9 * i + 3 * a] * v[3 * i] + dinv[9 * i + 3 * a + 1] * v[3 * i + 1] + dinv[9 * i + 3 * a + 2] * v[3 * i + 2];
-      };
-      std::fill(dx.begin(), dx.end(), 0.0);
-      r.assign(grad.size(), 0.0);
-      for (size_t i = 3; i < grad.size(); i++) r[i] = -grad[i];
-      precond(r, z);
-      p = z;
-      double rz = 0, r0 = 0;
-      for (size_t i = 0; i < r.size(); i++) { rz += r[i] * z[i]; r0 += r[i] * r[i]; }
-      for (int cg = 0; cg < g->cg_iterations && rz > 0; cg++) {
-        apply(p, Ap);
-        double pAp = 0;
-        for (size_t i = 0; i < p.size(); i++) pAp += p[i] * Ap[i];
-        if (!(pAp > 0)) break;
-        const double alpha = rz / pAp;
-        double rr = 0;
-        for (size_t i = 0; i < p.size(); i++) { dx[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rr += r[i] * r[i]; }
-        if (rr <= 1e-20 * (r0 + 1e-300)) break;
-        precond(r, z);
-        double rz2 = 0;
-        for (size_t i = 0; i < r.size(); i++) rz2 += r[i] * z[i];
-        const double beta = rz2 / rz;
-        rz = rz2;
-        for (size_t i = 0; i < p.size(); i++) p[i] = z[i] + beta * p[i];
+        std::fill(F.blk[k].begin(), F.blk[k].end(), 0.0);
       }
+      for (size_t k = 0; k < g->cons.size(); k++) {
+        const int a = g->cons[k].a, b = g->cons[k].b;
+        if (a == 0 || b == 0 || a == b) continue;
+        // H_ab = Hab (rows a, cols b); the lower-part block sits in the column of whichever node is eliminated first
+        if (F.pos[a] < F.pos[b]) {  // block (b, a) = Hab^T
+          double *T = find_block(F, F.pos[a], b);
+          if (T) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[3 * i + j] += lin[k].Hab[3 * j + i];
+        } else {                    // block (a, b) = Hab
+          double *T = find_block(F, F.pos[b], a);
+          if (T) for (int q = 0; q < 9; q++) T[q] += lin[k].Hab[q];
+        }
+      }
+      if (!factorise(F)) { lambda *= 10.0; continue; }
+      for (size_t i = 0; i < grad.size(); i++) dx[i] = i < 3 ? 0.0 : -grad[i];
+      solve_factored(F, dx);
+      dx[0] = dx[1] = dx[2] = 0.0;
       std::vector<double> xn(x);
       for (int i = 1; i < n; i++) { xn[3 * i] += dx[3 * i]; xn[3 * i + 1] += dx[3 * i + 1]; xn[3 * i + 2] = wrap(xn[3 * i + 2] + dx[3 * i + 2]); }
       const double nxt = chi2(g, xn);
