@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -85,6 +86,7 @@ struct HsBatch {  // kernel parameter
   int levels, batch, cap;
   float lo_free, lo_occ, min_dist, min_angle;
   int exact, use_fma;
+  int l2_loads;    // 1: the match reads the probability planes with ld.global.cg (tuning switch B2S_HS_L2_LOADS)
   HsState *state;  // [batch]
 };
 
@@ -113,7 +115,7 @@ struct HsFetch {
   float i0, i1, i2, i3, fx, fy;
   bool inside;
 };
-__device__ __forceinline__ HsFetch hs_fetch(const float *__restrict__ prob, int sx, int sy, float x, float y) {
+__device__ __forceinline__ HsFetch hs_fetch(const float *__restrict__ prob, int sx, int sy, float x, float y, bool l2) {
   HsFetch f;
   const float lim_x = (float)sx - 2.0f, lim_y = (float)sy - 2.0f;  // setMapCellDims: dims - 2
   f.inside = !(x < 0.0f || x > lim_x || y < 0.0f || y > lim_y);
@@ -122,7 +124,8 @@ __device__ __forceinline__ HsFetch hs_fetch(const float *__restrict__ prob, int 
     const int ix = (int)x, iy = (int)y;
     f.fx = x - (float)ix; f.fy = y - (float)iy;
     const float *c = prob + (iy * sx + ix);
-    f.i0 = c[0]; f.i1 = c[1]; f.i2 = c[sx]; f.i3 = c[sx + 1];
+    if (l2) { f.i0 = __ldcg(c); f.i1 = __ldcg(c + 1); f.i2 = __ldcg(c + sx); f.i3 = __ldcg(c + sx + 1); }
+    else { f.i0 = c[0]; f.i1 = c[1]; f.i2 = c[sx]; f.i3 = c[sx + 1]; }
   }
   return f;
 }
@@ -166,9 +169,9 @@ __device__ inline bool hs_pose_difference_larger_than(const float a[3], const fl
 
 // terms of one point for getCompleteHessianDerivs (OccGridMapUtil.h:99-126)
 __device__ __forceinline__ HsFetch hs_point_fetch(const float *__restrict__ prob, int sx, int sy, float2 p, float c, float s,
-                                                  float e0, float e1) {
+                                                  float e0, float e1, bool l2) {
   const float tx = (c * p.x + (-s) * p.y) + e0, ty = (s * p.x + c * p.y) + e1;
-  return hs_fetch(prob, sx, sy, tx, ty);
+  return hs_fetch(prob, sx, sy, tx, ty, l2);
 }
 __device__ __forceinline__ void hs_point_terms(const HsFetch &f, float2 p, float sin_rot, float cos_rot, float a[9]) {
   float t[3];
@@ -239,7 +242,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = HS_THREADS / 32;
   const int n = C.n0 ? C.n0[b] : C.n0_uniform;
-  const bool exact = P.exact != 0, use_fma = P.use_fma != 0;
+  const bool exact = P.exact != 0, use_fma = P.use_fma != 0, l2 = P.l2_loads != 0;
   float2 *spts = reinterpret_cast<float2 *>(smem);
   float *terms = reinterpret_cast<float *>(smem + hs_terms_offset(P.cap));
   const int pitch = hs_pitch(P.cap);
@@ -293,8 +296,8 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
           float2 pa = make_float2(0.0f, 0.0f), pb = pa;
           HsFetch fa, fb;
           fa.inside = fb.inside = false;
-          if (ia < n) { pa = make_float2(__fmul_rn(spts[ia].x, factor), __fmul_rn(spts[ia].y, factor)); fa = hs_point_fetch(prob, m.sx, m.sy, pa, c, s, e0, e1); }
-          if (ib < n) { pb = make_float2(__fmul_rn(spts[ib].x, factor), __fmul_rn(spts[ib].y, factor)); fb = hs_point_fetch(prob, m.sx, m.sy, pb, c, s, e0, e1); }
+          if (ia < n) { pa = make_float2(__fmul_rn(spts[ia].x, factor), __fmul_rn(spts[ia].y, factor)); fa = hs_point_fetch(prob, m.sx, m.sy, pa, c, s, e0, e1, l2); }
+          if (ib < n) { pb = make_float2(__fmul_rn(spts[ib].x, factor), __fmul_rn(spts[ib].y, factor)); fb = hs_point_fetch(prob, m.sx, m.sy, pb, c, s, e0, e1, l2); }
           float ta[9], tb[9];
           if (ia < n) {
             hs_point_terms(fa, pa, sin_rot, cos_rot, ta);
@@ -334,14 +337,22 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
           float v = 0.0f;
           if (lane < 9) {
             if (exact) {  // the reference's float32 sums, in point order: lane q owns sum q (nine dependent FADD chains)
+              // software-pipelined: the next 16 terms are loaded while the current 16 are added (the chain itself is
+              // the floor: one dependent FADD per point)
               const float *col = terms + lane * pitch;
-              int i = 0;
-              for (; i + 8 <= n; i += 8) {
-                const float4 u = *reinterpret_cast<const float4 *>(col + i), w = *reinterpret_cast<const float4 *>(col + i + 4);
-                v = __fadd_rn(v, u.x); v = __fadd_rn(v, u.y); v = __fadd_rn(v, u.z); v = __fadd_rn(v, u.w);
-                v = __fadd_rn(v, w.x); v = __fadd_rn(v, w.y); v = __fadd_rn(v, w.z); v = __fadd_rn(v, w.w);
+              const float4 *c4 = reinterpret_cast<const float4 *>(col);
+              const int blocks = n >> 4;
+              float4 a0, a1, a2, a3;
+              if (blocks > 0) { a0 = c4[0]; a1 = c4[1]; a2 = c4[2]; a3 = c4[3]; }
+              for (int bk = 0; bk < blocks; bk++) {
+                float4 b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+                if (bk + 1 < blocks) { a0 = c4[4 * bk + 4]; a1 = c4[4 * bk + 5]; a2 = c4[4 * bk + 6]; a3 = c4[4 * bk + 7]; }
+                v = __fadd_rn(v, b0.x); v = __fadd_rn(v, b0.y); v = __fadd_rn(v, b0.z); v = __fadd_rn(v, b0.w);
+                v = __fadd_rn(v, b1.x); v = __fadd_rn(v, b1.y); v = __fadd_rn(v, b1.z); v = __fadd_rn(v, b1.w);
+                v = __fadd_rn(v, b2.x); v = __fadd_rn(v, b2.y); v = __fadd_rn(v, b2.z); v = __fadd_rn(v, b2.w);
+                v = __fadd_rn(v, b3.x); v = __fadd_rn(v, b3.y); v = __fadd_rn(v, b3.z); v = __fadd_rn(v, b3.w);
               }
-              for (; i < n; i++) v = __fadd_rn(v, col[i]);
+              for (int i = blocks << 4; i < n; i++) v = __fadd_rn(v, col[i]);
             } else {
               for (int w = 0; w < NW; w++) v += terms[lane * NW + w];
             }
@@ -855,6 +866,7 @@ static b2s_status hs_create(float map_resolution, int map_size_x, int map_size_y
   p->P.lo_occ = hs_prob_to_log_odds(0.6f);
   p->P.min_dist = 0.4f; p->P.min_angle = 0.13f;  // HectorSlamProcessor.h:63-64
   p->P.exact = 1;
+  { const char *e = getenv("B2S_HS_L2_LOADS"); p->P.l2_loads = (e && e[0] == '1') ? 1 : 0; }
   const int variant = glibc_sincosf_variant_of_host();
   p->P.use_fma = variant == 0 ? 0 : 1;
   // MapRepMultiMap ctor (MapRepMultiMap.h:56-89): one offset for every level, dims halve, cell length doubles

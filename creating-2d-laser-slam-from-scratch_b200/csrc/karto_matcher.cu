@@ -1658,7 +1658,7 @@ b2s_status b2s_matcher_grid_info(const b2s_matcher *m, b2s_grid_info *out) {
 }
 
 b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which) {
-  if (!m || which < 0 || which > 3) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad kernel selector");
+  if (!m || which < 0 || which > 4) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad kernel selector");
   m->force_kernel = which;
   return B2S_OK;
 }
@@ -2166,9 +2166,9 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
                         (size_t)n * OFF_SMEM_PER_BEAM + 64 <= 200 * 1024 && !m->grid_high_bytes;
   bool use_window = win_fits;
   if (m->force_kernel == 1) use_window = false;
-  if (m->force_kernel >= 2 && !win_fits)
+  if (m->force_kernel >= 2 && m->force_kernel != 4 && !win_fits)
     B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but not applicable to this lattice / grid / beam count");
-  if (m->force_kernel >= 2) use_window = true;
+  if (m->force_kernel >= 2 && m->force_kernel != 4) use_window = true;
   const bool need_plain_lut = !use_window || s->fine;  // generic sweep and the angular covariance read the plain table
   if (need_plain_lut && (st = ensure_cap(&m->d_lut, &m->lut_cap, (size_t)B * na * std::max(n, 1)))) return st;
 
@@ -2207,9 +2207,11 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     if (nbands > 1)  // bands accumulate with RED.ADD
       B2S_CUDA_CHECK(cudaMemsetAsync(m->d_sums, 0, sizeof(int32_t) * (size_t)B * na * ncell, m->stream));
     const int ctas = (int)std::min<long long>((long long)B * nbands * (nbands > 1 ? tiles_y_w : 1), m->num_sms);
-    // whole matches per CTA (one band) and an unsplit sweep: the CTA runs the match's fp64 tail itself right after its
-    // last tile, reading the volume back from L2; k_reduce then only serves matches the window kernel skipped
-    const bool fuse_tail = nbands == 1 && mode == 0 && m->force_kernel != 2;
+    // b2s_matcher_set_kernel(m, 4): the sweep CTA runs each match's fp64 tail itself right after its last tile (volume read
+    // back from L2, no k_reduce pass over DRAM).  Measured SLOWER on cfg 2 (8.80 -> 9.06 ms per 1024 matches): the
+    // sweep kernel owns its SM (127 registers x 512 threads), so the tail's serial stretches are no longer hidden by a
+    // second resident CTA as they are in the stand-alone k_reduce (two 512-thread CTAs per SM).  Kept as an option.
+    const bool fuse_tail = nbands == 1 && mode == 0 && m->force_kernel == 4;
     // the GEN = false instantiation assumes exactly two lanes per row-start bank (see win_load)
     const int bank_step = ((m->g.width_step >> 2) * std::max(stride, 1)) & 31;
     const bool gen = (bank_step & 3) != 2;

@@ -19,8 +19,9 @@ pts = [H.scan_to_data_container(ranges[i], laser, 0.05, max_dist=30.0, min_dist=
 kw = dict(resolution=0.05, size_x=1000, size_y=1000, start=(0.5, 0.5), levels=3, update_free=0.4, update_occupied=0.9,
           min_dist=0.4, min_angle=0.9)
 out = {"scans": n}
-for exact in (True, False):
-    tag = "exact" if exact else "fast"
+for exact, l2 in ((True, "0"), (False, "0"), (True, "1"), (False, "1")):
+    os.environ["B2S_HS_L2_LOADS"] = l2
+    tag = ("exact" if exact else "fast") + ("_l2loads" if l2 == "1" else "")
     hs = H.HectorSlam(exact=exact, **kw)
     est = poses[0].astype(np.float32)
     est, _ = hs.update(pts[0], (0, 0), est)
@@ -45,6 +46,7 @@ for exact in (True, False):
                             "cell_visits": st["cell_visits"], "match_ms": st["match_ms"], "update_ms": st["update_ms"],
                             "xy_err": float(np.abs(p[-1][:2] - poses[-1][:2]).max())}
     hs.close()
+os.environ["B2S_HS_L2_LOADS"] = "0"
 # batched mapping (map_without_matching): B independent 1000^2 maps, one scan each per step, scans resident on the device
 import torch
 cap = max(len(p) for p in pts)
