@@ -333,26 +333,32 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
         }
         __syncthreads();
         HS_PROF(1);
+        if (exact && warp < 9) {
+          // The reference's float32 sums, in point order (OccGridMapUtil.h:99-126): warp q owns sum q.  Its lanes load 32
+          // consecutive terms with one conflict-free instruction (the next 32 are fetched before the current ones are
+          // consumed); every lane then runs the same chain of dependent FADDs over the 32 values broadcast by shuffles
+          // (independent of the chain, so they run ahead of it).  One dependent add per point is the floor of this mode.
+          const float *col = terms + warp * pitch;
+          const int full = n & ~31;
+          float v = 0.0f;
+          float x = full > 0 ? col[lane] : 0.0f;
+          for (int base = 0; base < full; base += 32) {
+            const float cur = x;
+            if (base + 32 < full) x = col[base + 32 + lane];
+#pragma unroll
+            for (int j = 0; j < 32; j++) v = __fadd_rn(v, __shfl_sync(0xffffffffu, cur, j));
+          }
+          const int rem = n - full;
+          const float xt = lane < rem ? col[full + lane] : 0.0f;
+          for (int j = 0; j < rem; j++) v = __fadd_rn(v, __shfl_sync(0xffffffffu, xt, j));
+          if (lane == 0) tot[warp] = v;
+          asm volatile("bar.sync 1, 288;" ::: "memory");  // the nine summing warps only
+        }
         if (warp == 0) {
           float v = 0.0f;
           if (lane < 9) {
-            if (exact) {  // the reference's float32 sums, in point order: lane q owns sum q (nine dependent FADD chains)
-              // software-pipelined: the next 16 terms are loaded while the current 16 are added (the chain itself is
-              // the floor: one dependent FADD per point)
-              const float *col = terms + lane * pitch;
-              const float4 *c4 = reinterpret_cast<const float4 *>(col);
-              const int blocks = n >> 4;
-              float4 a0, a1, a2, a3;
-              if (blocks > 0) { a0 = c4[0]; a1 = c4[1]; a2 = c4[2]; a3 = c4[3]; }
-              for (int bk = 0; bk < blocks; bk++) {
-                float4 b0 = a0, b1 = a1, b2 = a2, b3 = a3;
-                if (bk + 1 < blocks) { a0 = c4[4 * bk + 4]; a1 = c4[4 * bk + 5]; a2 = c4[4 * bk + 6]; a3 = c4[4 * bk + 7]; }
-                v = __fadd_rn(v, b0.x); v = __fadd_rn(v, b0.y); v = __fadd_rn(v, b0.z); v = __fadd_rn(v, b0.w);
-                v = __fadd_rn(v, b1.x); v = __fadd_rn(v, b1.y); v = __fadd_rn(v, b1.z); v = __fadd_rn(v, b1.w);
-                v = __fadd_rn(v, b2.x); v = __fadd_rn(v, b2.y); v = __fadd_rn(v, b2.z); v = __fadd_rn(v, b2.w);
-                v = __fadd_rn(v, b3.x); v = __fadd_rn(v, b3.y); v = __fadd_rn(v, b3.z); v = __fadd_rn(v, b3.w);
-              }
-              for (int i = blocks << 4; i < n; i++) v = __fadd_rn(v, col[i]);
+            if (exact) {
+              v = tot[lane];
             } else {
               for (int w = 0; w < NW; w++) v += terms[lane * NW + w];
             }
