@@ -333,64 +333,52 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
         }
         __syncthreads();
         HS_PROF(1);
-        if (exact && warp < 9) {
-          // The reference's float32 sums, in point order (OccGridMapUtil.h:99-126): warp q owns sum q.  Its lanes load 32
-          // consecutive terms with one conflict-free instruction (the next 32 are fetched before the current ones are
-          // consumed); every lane then runs the same chain of dependent FADDs over the 32 values broadcast by shuffles
-          // (independent of the chain, so they run ahead of it).  One dependent add per point is the floor of this mode.
-          const float *col = terms + warp * pitch;
-          const int full = n & ~31;
-          float v = 0.0f;
-          float x = full > 0 ? col[lane] : 0.0f;
-          for (int base = 0; base < full; base += 32) {
-            const float cur = x;
-            if (base + 32 < full) x = col[base + 32 + lane];
-#pragma unroll
-            for (int j = 0; j < 32; j++) v = __fadd_rn(v, __shfl_sync(0xffffffffu, cur, j));
+        if (exact) {
+          // The reference's float32 sums, in point order (OccGridMapUtil.h:99-126): ONE warp instruction advances all nine
+          // chains (lane q owns sum q), so the floor is one dependent FADD per point.  (Nine warps with one chain each
+          // share four schedulers and measured 2.5x slower.)
+          if (warp == 0 && lane < 9) {
+            float acc = 0.0f;
+            const float *col = terms + lane * pitch;
+            int i = 0;
+            for (; i + 8 <= n; i += 8) {
+              const float4 u = *reinterpret_cast<const float4 *>(col + i), w = *reinterpret_cast<const float4 *>(col + i + 4);
+              acc = __fadd_rn(acc, u.x); acc = __fadd_rn(acc, u.y); acc = __fadd_rn(acc, u.z); acc = __fadd_rn(acc, u.w);
+              acc = __fadd_rn(acc, w.x); acc = __fadd_rn(acc, w.y); acc = __fadd_rn(acc, w.z); acc = __fadd_rn(acc, w.w);
+            }
+            for (; i < n; i++) acc = __fadd_rn(acc, col[i]);
+            tot[lane] = acc;
           }
-          const int rem = n - full;
-          const float xt = lane < rem ? col[full + lane] : 0.0f;
-          for (int j = 0; j < rem; j++) v = __fadd_rn(v, __shfl_sync(0xffffffffu, xt, j));
-          if (lane == 0) tot[warp] = v;
-          asm volatile("bar.sync 1, 288;" ::: "memory");  // the nine summing warps only
+          __syncthreads();
+        } else if (warp == 0) {
+          float v = 0.0f;
+          if (lane < 9)
+            for (int w = 0; w < NW; w++) v += terms[lane * NW + w];
+          if (lane < 9) tot[lane] = v;
+          __syncwarp();
         }
-        if (warp == 0) {
-          float v = 0.0f;
-          if (lane < 9) {
-            if (exact) {
-              v = tot[lane];
-            } else {
-              for (int w = 0; w < NW; w++) v += terms[lane * NW + w];
-            }
+        HS_PROF(2);
+        if (tid == 0) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
+          const float dTr[3] = {tot[0], tot[1], tot[2]};
+          float Hm[9];
+          Hm[0] = tot[3]; Hm[4] = tot[4]; Hm[8] = tot[5];
+          Hm[1] = Hm[3] = tot[6]; Hm[2] = Hm[6] = tot[7]; Hm[5] = Hm[7] = tot[8];
+          float n0 = bc[0], n1 = bc[1], n2 = bc[2];
+          if (Hm[0] != 0.0f && Hm[4] != 0.0f) {
+            float dir[3];
+            hs_inv3_mul(Hm, dTr, dir);
+            if (dir[2] > 0.2f) dir[2] = 0.2f;
+            else if (dir[2] < -0.2f) dir[2] = -0.2f;
+            n0 += dir[0]; n1 += dir[1]; n2 += dir[2];
           }
-          float t9[9];
-#pragma unroll
-          for (int q = 0; q < 9; q++) t9[q] = __shfl_sync(0xffffffffu, v, q);
-          HS_PROF(2);
-          if (lane == 0) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
-#pragma unroll
-            for (int q = 0; q < 9; q++) tot[q] = t9[q];
-            const float dTr[3] = {t9[0], t9[1], t9[2]};
-            float Hm[9];
-            Hm[0] = t9[3]; Hm[4] = t9[4]; Hm[8] = t9[5];
-            Hm[1] = Hm[3] = t9[6]; Hm[2] = Hm[6] = t9[7]; Hm[5] = Hm[7] = t9[8];
-            float n0 = bc[0], n1 = bc[1], n2 = bc[2];
-            if (Hm[0] != 0.0f && Hm[4] != 0.0f) {
-              float dir[3];
-              hs_inv3_mul(Hm, dTr, dir);
-              if (dir[2] > 0.2f) dir[2] = 0.2f;
-              else if (dir[2] < -0.2f) dir[2] = -0.2f;
-              n0 += dir[0]; n1 += dir[1]; n2 += dir[2];
-            }
-            bc[0] = n0; bc[1] = n1; bc[2] = n2;
-            HS_PROF(3);
-            if (it + 1 < m.iterations) {
-              const HsTrig tr = hs_trig(n2, exact, use_fma);
-              bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
-            }
-            HS_PROF(4);
-            pf[6] += 1;
+          bc[0] = n0; bc[1] = n1; bc[2] = n2;
+          HS_PROF(3);
+          if (it + 1 < m.iterations) {
+            const HsTrig tr = hs_trig(n2, exact, use_fma);
+            bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
           }
+          HS_PROF(4);
+          pf[6] += 1;
         }
         __syncthreads();
       }
