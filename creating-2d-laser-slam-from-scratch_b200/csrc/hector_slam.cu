@@ -138,7 +138,7 @@ __device__ __forceinline__ void hs_finish(const HsFetch &f, float out[3]) {
   out[2] = -((dy1 * xfi) + (dy2 * f.fx));
 }
 
-__device__ inline void hs_inv3_mul(const float m[9], const float v[3], float out[3]) {  // Matrix3f::inverse() * v
+__device__ __noinline__ void hs_inv3_mul(const float m[9], const float v[3], float out[3]) {  // Matrix3f::inverse() * v
   const float c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
   const float det = c00 * m[0] + (c10 * m[1] + c20 * m[2]);  /* Eigen's unrolled 3-term redux: a0 + (a1 + a2) */
   const float invdet = 1.0f / det;
@@ -183,11 +183,21 @@ __device__ __forceinline__ void hs_point_terms(const HsFetch &f, float2 p, float
   a[6] = t[1] * t[2]; a[7] = t[1] * rot; a[8] = t[2] * rot;  // H01 H02 H12
 }
 
+// util::normalize_angle (UtilFunctions.h:36-48): double fmod, float result
+__device__ __noinline__ float hs_normalize_angle(float e2) {
+  const double two_pi = 2.0f * 3.14159265358979323846;
+  float a = (float)fmod(fmod((double)e2, two_pi) + two_pi, two_pi);
+  if ((double)a > 3.14159265358979323846) a = (float)((double)a - two_pi);  // `a -= 2.0f*M_PI` promotes to double
+  return a;
+}
+
 struct HsTrig {
   float c, s;              // Rotation2Df(angle): std::cos / std::sin(float) = glibc cosf / sinf
   float sin_rot, cos_rot;  // OccGridMapUtil.h:87-88: the C library's double sin / cos, rounded to float
 };
-__device__ inline HsTrig hs_trig(float angle, bool exact, bool use_fma) {
+// (out of line on purpose: the Gauss-Newton loop is executed by few warps, so its code must stay inside the instruction
+// cache — 60-90 KB kernels with the double-precision sincos / fmod expansions inlined at every use ran 2x slower)
+__device__ __noinline__ HsTrig hs_trig(float angle, bool exact, bool use_fma) {
   HsTrig t;
   glibc_sincosf(angle, use_fma, &t.s, &t.c);
   if (exact) {
@@ -237,12 +247,14 @@ __host__ __device__ inline size_t hs_smem_bytes(int cap) { return hs_terms_offse
 
 // MapRepMultiMap::matchData (:144-166) on every level, coarsest first, + the gate and the update parameters of
 // HectorSlamProcessor::update (:81-108), by ONE CTA for processor b.
+template <bool EXACT>
 __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned char *smem) {
   HsState *st = P.state + b;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = HS_THREADS / 32;
   const int n = C.n0 ? C.n0[b] : C.n0_uniform;
-  const bool exact = P.exact != 0, use_fma = P.use_fma != 0, l2 = P.l2_loads != 0;
+  constexpr bool exact = EXACT;  // compile-time: each mode's kernel carries only its own code
+  const bool use_fma = P.use_fma != 0, l2 = P.l2_loads != 0;
   float2 *spts = reinterpret_cast<float2 *>(smem);
   float *terms = reinterpret_cast<float *>(smem + hs_terms_offset(P.cap));
   const int pitch = hs_pitch(P.cap);
@@ -384,9 +396,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
       }
       {
         const float e0 = bc[0], e1 = bc[1], e2 = bc[2];
-        const double two_pi = 2.0f * 3.14159265358979323846;  // util::normalize_angle (UtilFunctions.h:36-48)
-        float a = (float)fmod(fmod((double)e2, two_pi) + two_pi, two_pi);
-        if ((double)a > 3.14159265358979323846) a = (float)((double)a - two_pi);
+        const float a = hs_normalize_angle(e2);
         world0 = (m.wt_lin * e0 + (-0.0f) * e1) + m.wt_tx;  // getWorldCoordsPose (GridMapBase.h:229-233)
         world1 = ((-0.0f) * e0 + m.wt_lin * e1) + m.wt_ty;
         world2 = a;
@@ -624,9 +634,10 @@ __device__ void hs_apply_pass(const HsBatch &P, int b, int w, int nw, int lane) 
 }
 
 // ---- batch path: three launches per step over all B processors ----
+template <bool EXACT>
 __global__ void __launch_bounds__(HS_THREADS) k_hs_match(HsBatch P, HsCall C) {
   extern __shared__ __align__(16) unsigned char hs_smem[];
-  hs_match_cta(P, C, blockIdx.x, hs_smem);
+  hs_match_cta<EXACT>(P, C, blockIdx.x, hs_smem);
 }
 __global__ void __launch_bounds__(256) k_hs_mark(HsBatch P) {
   const int b = blockIdx.y;
@@ -676,6 +687,7 @@ struct HsStream {
   unsigned int *barrier;
 };
 
+template <bool EXACT>
 __global__ void __launch_bounds__(HS_THREADS) k_hs_stream(HsBatch P, HsStream S) {
   extern __shared__ __align__(16) unsigned char hs_smem[];
   unsigned int generation = 0;
@@ -695,7 +707,7 @@ __global__ void __launch_bounds__(HS_THREADS) k_hs_stream(HsBatch P, HsStream S)
       C.out = S.out + 16 * (size_t)i;
       C.mailbox = S.mailbox;
       C.seq = S.seq;
-      hs_match_cta(P, C, 0, hs_smem);
+      hs_match_cta<EXACT>(P, C, 0, hs_smem);
     }
     hs_grid_barrier(S.barrier, generation);
     // the gate's decision is read from this scan's own output row: without an update there is no further barrier, so CTA 0
@@ -910,13 +922,15 @@ static b2s_status hs_create(float map_resolution, int map_size_x, int map_size_y
   HS_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&p->h_hint_dev), p->h_hint, 0));
   HS_CHECK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
   const size_t smem = hs_smem_bytes(max_points);
-  HS_CHECK(raise_dyn_smem(k_hs_match, smem));
-  HS_CHECK(raise_dyn_smem(k_hs_stream, smem));
+  HS_CHECK(raise_dyn_smem(k_hs_match<true>, smem));
+  HS_CHECK(raise_dyn_smem(k_hs_match<false>, smem));
+  HS_CHECK(raise_dyn_smem(k_hs_stream<true>, smem));
+  HS_CHECK(raise_dyn_smem(k_hs_stream<false>, smem));
   {
     int coop = 0, sms = 0, per_sm = 0;
     HS_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     HS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    HS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hs_stream, HS_THREADS, smem));
+    HS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hs_stream<true>, HS_THREADS, smem));
     p->coop = coop != 0;
     p->stream_ctas = std::max(1, std::min(HS_STREAM_CTAS, sms * std::max(per_sm, 0)));
     if (!p->coop) p->stream_ctas = 1;  // without a co-residency guarantee a spinning grid barrier could deadlock
@@ -950,10 +964,11 @@ static b2s_status hs_launch_stream(b2s_hector_slam *p, const HsStream &S) {
   const size_t smem = hs_smem_bytes(p->cap);
   if (p->coop) {
     void *args[2] = {&P, &Sv};
-    B2S_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k_hs_stream), dim3(p->stream_ctas), dim3(HS_THREADS),
-                                               args, smem, p->stream));
+    const void *kern = P.exact ? reinterpret_cast<const void *>(k_hs_stream<true>) : reinterpret_cast<const void *>(k_hs_stream<false>);
+    B2S_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(p->stream_ctas), dim3(HS_THREADS), args, smem, p->stream));
   } else {
-    k_hs_stream<<<1, HS_THREADS, smem, p->stream>>>(P, Sv);
+    if (P.exact) k_hs_stream<true><<<1, HS_THREADS, smem, p->stream>>>(P, Sv);
+    else k_hs_stream<false><<<1, HS_THREADS, smem, p->stream>>>(P, Sv);
     B2S_CUDA_CHECK(cudaGetLastError());
   }
   return B2S_OK;
@@ -1161,7 +1176,8 @@ b2s_status b2s_hector_slam_update_batch(b2s_hector_slam *p, const float *points,
   C.out = p->d_out;
   int max_n = 0;
   for (int b = 0; b < B; b++) max_n = std::max(max_n, n_points[b]);
-  k_hs_match<<<B, HS_THREADS, hs_smem_bytes(p->cap), p->stream>>>(p->P, C);
+  if (p->P.exact) k_hs_match<true><<<B, HS_THREADS, hs_smem_bytes(p->cap), p->stream>>>(p->P, C);
+  else k_hs_match<false><<<B, HS_THREADS, hs_smem_bytes(p->cap), p->stream>>>(p->P, C);
   // data containers of the coarse levels may hold more points than this step's scans (map_without_matching): size the
   // update grid by the capacity bound
   const dim3 grid(std::max(1, std::min(ceil_div(std::max(max_n, 1) * p->levels, 8), 148 * 8 / std::max(1, std::min(B, 8)))), B);
@@ -1199,7 +1215,8 @@ b2s_status b2s_hector_slam_update_batch_device(b2s_hector_slam *p, const float *
   C.origo_x = origo[0]; C.origo_y = origo[1];
   C.map_without_matching = map_without_matching;
   C.out = p->d_out;
-  k_hs_match<<<B, HS_THREADS, hs_smem_bytes(p->cap), p->stream>>>(p->P, C);
+  if (p->P.exact) k_hs_match<true><<<B, HS_THREADS, hs_smem_bytes(p->cap), p->stream>>>(p->P, C);
+  else k_hs_match<false><<<B, HS_THREADS, hs_smem_bytes(p->cap), p->stream>>>(p->P, C);
   const dim3 grid(std::max(1, std::min(ceil_div(std::max(max_n, 1) * p->levels, 8), 148 * 8 / std::max(1, std::min(B, 8)))), B);
   k_hs_mark<<<grid, 256, 0, p->stream>>>(p->P);
   k_hs_apply<<<grid, 256, 0, p->stream>>>(p->P);
