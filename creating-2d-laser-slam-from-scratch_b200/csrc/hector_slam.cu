@@ -138,7 +138,7 @@ __device__ __forceinline__ void hs_finish(const HsFetch &f, float out[3]) {
   out[2] = -((dy1 * xfi) + (dy2 * f.fx));
 }
 
-__device__ __noinline__ void hs_inv3_mul(const float m[9], const float v[3], float out[3]) {  // Matrix3f::inverse() * v
+__device__ __forceinline__ void hs_inv3_mul(const float m[9], const float v[3], float out[3]) {  // Matrix3f::inverse() * v
   const float c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
   const float det = c00 * m[0] + (c10 * m[1] + c20 * m[2]);  /* Eigen's unrolled 3-term redux: a0 + (a1 + a2) */
   const float invdet = 1.0f / det;
