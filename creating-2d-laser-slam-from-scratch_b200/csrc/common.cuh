@@ -170,6 +170,23 @@ inline cudaError_t raise_dyn_smem(K kern, size_t bytes) {
   return e;
 }
 
+// Calls that stage through cudaMallocAsync / cudaFreeAsync and then synchronise would hand their memory back to the driver
+// every time (the default pool's release threshold is 0) and pay a fresh allocation on the next call (~1 ms).  The
+// library's create functions raise the threshold of the device's default pool once, so freed blocks stay cached.
+inline void keep_pool_memory(int device) {
+  static std::mutex mu;
+  static std::map<int, bool> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = 1ull << 32;  // up to 4 GiB of freed staging blocks stay in the pool
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done[device] = true;
+}
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace b2s

@@ -32,6 +32,10 @@ struct b2s_gmap {
   int32_t *d_n = nullptr, *d_visits = nullptr;
   float *d_accx = nullptr, *d_accy = nullptr;
   int *d_flag = nullptr;
+  double *d_in = nullptr;   // [2][in_cap]: ranges, angles of the current scan
+  int in_cap = 0;
+  double *h_in = nullptr;   // pinned staging of the same
+  int *h_flag = nullptr;    // pinned
 };
 
 namespace b2s {
@@ -75,7 +79,8 @@ __global__ void __launch_bounds__(256)
     k_gm_update(const double *__restrict__ ranges, const double *__restrict__ angles, int nb, double lx, double ly,
                 double cx, double cy, double delta, int sx2, int sy2, int msx, double max_range, double max_use,
                 int32_t *__restrict__ n, int32_t *__restrict__ visits, float *__restrict__ accx,
-                float *__restrict__ accy) {
+                float *__restrict__ accy, const int *__restrict__ leaves_map) {
+  if (*leaves_map) return;  // k_gm_check found a beam leaving the map: the reference asserts, nothing may be updated
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int p0x = gm_world2map(lx, cx, delta, sx2), p0y = gm_world2map(ly, cy, delta, sy2);
@@ -134,6 +139,7 @@ b2s_status b2s_gmap_create(double center_x, double center_y, double xmin, double
   *out = nullptr;
   if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
   B2S_CUDA_CHECK(cudaSetDevice(device));
+  keep_pool_memory(device);
   b2s_gmap *g = new (std::nothrow) b2s_gmap();
   if (!g) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
   g->device = device;
@@ -171,8 +177,10 @@ void b2s_gmap_destroy(b2s_gmap *g) {
   if (!g) return;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  for (void *p : {(void *)g->d_n, (void *)g->d_visits, (void *)g->d_accx, (void *)g->d_accy, (void *)g->d_flag})
+  for (void *p : {(void *)g->d_n, (void *)g->d_visits, (void *)g->d_accx, (void *)g->d_accy, (void *)g->d_flag, (void *)g->d_in})
     if (p) cudaFree(p);
+  if (g->h_in) cudaFreeHost(g->h_in);
+  if (g->h_flag) cudaFreeHost(g->h_flag);
   if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -193,31 +201,35 @@ b2s_status b2s_gmap_compute_map(b2s_gmap *g, const double *ranges, const double 
   const double lx = laser_pose[0], ly = laser_pose[1];  // ComputeMap uses lp = (x, y, 0): beam angles are absolute
   const int p0x = cast_i32(round((lx - g->cx) / g->delta)) + g->sx2, p0y = cast_i32(round((ly - g->cy) / g->delta)) + g->sy2;
   if (p0x < 0 || p0y < 0 || p0x >= g->msx || p0y >= g->msy) B2S_FAIL(B2S_ERR_OUT_OF_RANGE, "laser position outside the map");
-  double *d_r = nullptr, *d_a = nullptr;
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_r), sizeof(double) * n, st));
-  B2S_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_a), sizeof(double) * n, st));
-  B2S_CUDA_CHECK(cudaMemcpyAsync(d_r, ranges, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  B2S_CUDA_CHECK(cudaMemcpyAsync(d_a, angles, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  if (n > g->in_cap) {  // scan buffers live in the handle: no per-call allocation
+    if (g->d_in) B2S_CUDA_CHECK(cudaFree(g->d_in));
+    if (g->h_in) B2S_CUDA_CHECK(cudaFreeHost(g->h_in));
+    g->d_in = nullptr; g->h_in = nullptr; g->in_cap = 0;
+    const int cap = std::max(n, 2048);
+    B2S_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&g->d_in), sizeof(double) * 2 * (size_t)cap));
+    B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&g->h_in), sizeof(double) * 2 * (size_t)cap));
+    g->in_cap = cap;
+  }
+  if (!g->h_flag) B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&g->h_flag), sizeof(int)));
+  std::memcpy(g->h_in, ranges, sizeof(double) * n);
+  std::memcpy(g->h_in + n, angles, sizeof(double) * n);
+  double *d_r = g->d_in, *d_a = g->d_in + n;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(g->d_in, g->h_in, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, st));
   B2S_CUDA_CHECK(cudaMemsetAsync(g->d_flag, 0, sizeof(int), st));
   k_gm_check<<<ceil_div(n, 256), 256, 0, st>>>(d_r, d_a, n, lx, ly, g->cx, g->cy, g->delta, g->sx2, g->sy2, g->msx,
                                                g->msy, max_range, max_urange, g->d_flag);
-  int flag = 0;
-  B2S_CUDA_CHECK(cudaMemcpyAsync(&flag, g->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  // the update reads the verdict on the device (no host round trip between check and update)
+  k_gm_update<<<std::min(ceil_div(n, 8), 148 * 8), 256, 0, st>>>(d_r, d_a, n, lx, ly, g->cx, g->cy, g->delta, g->sx2,
+                                                                g->sy2, g->msx, max_range, max_urange, g->d_n,
+                                                                g->d_visits, g->d_accx, g->d_accy, g->d_flag);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK(cudaMemcpyAsync(g->h_flag, g->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2S_CUDA_CHECK(cudaStreamSynchronize(st));
-  b2s_status rc = B2S_OK;
-  if (flag) {
+  if (*g->h_flag) {
     set_last_error("a beam leaves the map (the reference asserts here, map.h:186-191); nothing was updated");
-    rc = B2S_ERR_OUT_OF_RANGE;
-  } else {
-    k_gm_update<<<std::min(ceil_div(n, 8), 148 * 8), 256, 0, st>>>(d_r, d_a, n, lx, ly, g->cx, g->cy, g->delta, g->sx2,
-                                                                  g->sy2, g->msx, max_range, max_urange, g->d_n,
-                                                                  g->d_visits, g->d_accx, g->d_accy);
-    B2S_CUDA_CHECK(cudaGetLastError());
+    return B2S_ERR_OUT_OF_RANGE;
   }
-  B2S_CUDA_CHECK(cudaFreeAsync(d_r, st));
-  B2S_CUDA_CHECK(cudaFreeAsync(d_a, st));
-  B2S_CUDA_CHECK(cudaStreamSynchronize(st));
-  return rc;
+  return B2S_OK;
 }
 
 b2s_status b2s_gmap_copy(b2s_gmap *g, int32_t *n, int32_t *visits, float *acc_x, float *acc_y) {

@@ -296,6 +296,7 @@ b2s_status b2s_hector_map_create(int size_x, int size_y, float resolution, float
   *out = nullptr;
   if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
   B2S_CUDA_CHECK(cudaSetDevice(device));
+  keep_pool_memory(device);
   b2s_hector_map *m = new (std::nothrow) b2s_hector_map();
   if (!m) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
   m->device = device;

@@ -853,6 +853,7 @@ static b2s_status hs_create(float map_resolution, int map_size_x, int map_size_y
   if (max_points > HS_MAX_PTS) B2S_FAIL(B2S_ERR_TOO_LARGE, "at most 4096 points per scan");
   if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
   B2S_CUDA_CHECK(cudaSetDevice(device));
+  keep_pool_memory(device);
   b2s_hector_slam *p = new (std::nothrow) b2s_hector_slam();
   if (!p) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
   p->device = device;

@@ -876,7 +876,7 @@ struct ReduceArgs {
 // flags bit 2 (value 4): this match's tail already ran inside the sweep kernel (fused path)
 constexpr int32_t FLAG_REDUCED = 4;
 
-__device__ void reduce_match(const int b, const ReduceArgs &A);
+__device__ void reduce_match(const int b, const ReduceArgs &A);  // out-of-line copy of the tail for the fused option
 
 template <int STRIDE, bool GEN>
 __global__ void __launch_bounds__(WIN_THREADS, 1)
@@ -1058,7 +1058,7 @@ __device__ __forceinline__ float red_fscore(int32_t isum, float apf_k, float dpf
   return (float)isum * apf_k * dpf;
 }
 
-__device__ __noinline__ void reduce_match(const int b, const ReduceArgs &A) {
+__device__ __forceinline__ void reduce_match_body(const int b, const ReduceArgs &A) {
   const int32_t *sums = A.sums;  // no __restrict__ / no read-only path: the fused sweep wrote them in this very launch
   const double *__restrict__ centers = A.centers;
   const int32_t *__restrict__ flags = A.flags;
@@ -1385,9 +1385,11 @@ __device__ __noinline__ void reduce_match(const int b, const ReduceArgs &A) {
   res->tie_count = total;
 }
 
+__device__ __noinline__ void reduce_match(const int b, const ReduceArgs &A) { reduce_match_body(b, A); }
+
 __global__ void __launch_bounds__(RED_THREADS, 2) k_reduce(ReduceArgs A) {
   if (A.flags[blockIdx.x] & FLAG_REDUCED) return;  // the sweep kernel already ran this match's tail
-  reduce_match(blockIdx.x, A);
+  reduce_match_body(blockIdx.x, A);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1621,6 +1623,7 @@ b2s_status b2s_matcher_create(const b2s_matcher_params *params, const b2s_laser 
   if (st) return st;
   if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
   B2S_CUDA_CHECK(cudaSetDevice(device));
+  keep_pool_memory(device);
   b2s_matcher *m = new (std::nothrow) b2s_matcher();
   if (!m) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
   st = matcher_create_impl(params, laser, device, max_batch, max_base_scans, cuda_stream, m, g);

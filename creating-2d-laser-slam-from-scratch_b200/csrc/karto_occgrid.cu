@@ -156,93 +156,6 @@ __global__ void __launch_bounds__(256)
   if (lane == 0 && my_visits) atomicAdd(visits, my_visits);
 }
 
-// The same ray trace with the pass counters PRIVATISED IN SHARED MEMORY.  A whole-map rebuild funnels hundreds of
-// millions of increments into a map of ~10^5 cells (every beam of a scan crosses the sensor's cell), so global RED.ADD
-// is bound by the L2 atomic units (ncu: DRAM 0.3 %, L2 42 %).  Here the map is cut into `nbands` bands of whole rows that
-// fit a CTA's shared memory as uint32 counters; CTA (band, chunk) walks its chunk of the beams, clips every line to the
-// band in closed form (the minor-axis step count floor((2k dy + dx) / (2 dx)) is monotone in k), counts into shared
-// memory (ATOMS) and adds its band to the global counters once at the end (coalesced RED, non-zero cells only).
-// Integer sums commute: counters are bit-identical to k_raytrace's.  Hits (one per beam) stay global.
-__global__ void __launch_bounds__(512)
-    k_raytrace_banded(const double *__restrict__ ranges, const double *__restrict__ sensor, const double *__restrict__ pts,
-                      b2s_laser l, long long n_beams, int w, int h, int step, double off_x, double off_y, double scale,
-                      uint32_t *__restrict__ pass, uint32_t *__restrict__ hit, unsigned long long *__restrict__ visits,
-                      int band_rows, int nbands, long long beams_per_chunk) {
-  extern __shared__ uint32_t s_pass[];  // [band_rows][step]
-  const int band = blockIdx.x % nbands;
-  const long long chunk = blockIdx.x / nbands;
-  const int y_lo = band * band_rows, y_hi = min(h, y_lo + band_rows) - 1;
-  const int band_cells = (y_hi - y_lo + 1) * step;
-  for (int i = threadIdx.x; i < band_cells; i += blockDim.x) s_pass[i] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int n = l.n_readings;
-  const long long b_end = min(n_beams, (chunk + 1) * beams_per_chunk);
-  unsigned long long my_visits = 0;
-  for (long long beam = chunk * beams_per_chunk + warp; beam < b_end; beam += nw) {
-    const int s = (int)(beam / n);
-    const double rr = ranges[beam];
-    if (rr <= l.min_range || rr >= l.max_range || isnan(rr)) continue;  // Karto.h:5873-5878
-    const bool end_valid = rr < (l.range_threshold - KT_TOLERANCE);     // Karto.h:5871
-    const double sx = sensor[3 * s], sy = sensor[3 * s + 1];
-    double px = pts[beam * 2], py = pts[beam * 2 + 1];
-    if (rr >= l.range_threshold) {  // Karto.h:5879-5887: clip to the range threshold, no hit
-      const double ratio = l.range_threshold / rr;
-      const double dx = px - sx, dy = py - sy;
-      px = __dadd_rn(sx, __dmul_rn(ratio, dx));
-      py = __dadd_rn(sy, __dmul_rn(ratio, dy));
-    }
-    int x0 = world_to_grid_1(sx, off_x, scale), y0 = world_to_grid_1(sy, off_y, scale);
-    int x1 = world_to_grid_1(px, off_x, scale), y1 = world_to_grid_1(py, off_y, scale);
-    const int tx = x1, ty = y1;
-    // TraceLine canonicalisation (Karto.h:4682-4692)
-    const bool steep = abs(y1 - y0) > abs(x1 - x0);
-    if (steep) { int t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
-    if (x0 > x1) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
-    const long long dx = (long long)x1 - x0, dy = llabs((long long)y1 - y0);
-    const int ystep = (y0 < y1) ? 1 : -1;
-    // steps k in [0, dx] whose cell lies in rows [y_lo, y_hi]
-    long long ka = 0, kb = dx;
-    if (steep) {  // the dominant coordinate x0 + k IS the row
-      ka = max(ka, (long long)y_lo - x0);
-      kb = min(kb, (long long)y_hi - x0);
-    } else if (dy == 0) {
-      if (y0 < y_lo || y0 > y_hi) kb = -1;
-    } else {  // row = y0 + ystep * inc(k), inc(k) = floor((2 k dy + dx) / (2 dx)) non-decreasing in k
-      const long long ia = ystep > 0 ? (long long)y_lo - y0 : (long long)y0 - y_hi;  // inc(k) in [ia, ib]
-      const long long ib = ystep > 0 ? (long long)y_hi - y0 : (long long)y0 - y_lo;
-      if (ib < 0) kb = -1;
-      else {
-        if (ia > 0) ka = max(ka, (2 * dx * ia - dx + 2 * dy - 1) / (2 * dy));  // smallest k with inc(k) >= ia
-        kb = min(kb, (2 * dx * (ib + 1) - dx - 1) / (2 * dy));                 // largest k with inc(k) <= ib
-      }
-    }
-    for (long long k = ka + lane; k <= kb; k += 32) {
-      const long long inc = dx > 0 ? (2 * k * dy + dx) / (2 * dx) : 0;
-      const int x = x0 + (int)k, y = y0 + ystep * (int)inc;
-      const int cx = steep ? y : x, cy = steep ? x : y;
-      if (cx >= 0 && cx < w && cy >= y_lo && cy <= y_hi) {
-        atomicAdd(&s_pass[(cy - y_lo) * step + cx], 1u);
-        my_visits++;
-      }
-    }
-    if (lane == 0 && end_valid && tx >= 0 && tx < w && ty >= y_lo && ty <= y_hi) {  // Karto.h:5924-5942
-      atomicAdd(&s_pass[(ty - y_lo) * step + tx], 1u);
-      atomicAdd(hit + tx + (size_t)ty * step, 1u);
-      my_visits += 2;
-    }
-  }
-  __syncthreads();
-  uint32_t *gband = pass + (size_t)y_lo * step;
-  for (int i = threadIdx.x; i < band_cells; i += blockDim.x) {
-    const uint32_t v = s_pass[i];
-    if (v) atomicAdd(gband + i, v);
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) my_visits += __shfl_xor_sync(0xffffffffu, my_visits, d);
-  if (lane == 0 && my_visits) atomicAdd(visits, my_visits);
-}
-
 // OccupancyGrid::Update / UpdateCell (Karto.h:5953-5990): MinPassThrough = 2, OccupancyThreshold = 0.1
 __global__ void k_occ_threshold(const uint32_t *__restrict__ pass, const uint32_t *__restrict__ hit, int n,
                                 uint8_t *__restrict__ cells) {
@@ -289,6 +202,7 @@ static b2s_status occ_create_impl(const b2s_laser *laser, int n_scans, const dou
   if (double_equal(resolution, 0.0)) B2S_FAIL(B2S_ERR_BAD_PARAMS, "Resolution cannot be 0");  // Karto.h:5627-5630
   if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
   B2S_CUDA_CHECK(cudaSetDevice(device));
+  keep_pool_memory(device);
   b2s_occ_grid *g = new (std::nothrow) b2s_occ_grid();
   if (!g) B2S_FAIL(B2S_ERR_CUDA, "out of host memory");
   g->device = device;
@@ -358,30 +272,12 @@ static b2s_status occ_create_impl(const b2s_laser *laser, int n_scans, const dou
     const long long n_beams = (long long)M * (long long)n;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    // shared-memory privatised counters when the map fits a few row bands and there are enough beams to amortise the
-    // per-CTA band flush; otherwise (large maps: increments are spread, contention is low) global atomics
-    int optin = 0;
-    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    const long long band_budget = ((long long)optin - 2048) / 4;  // uint32 counters per band
-    const int band_rows = (int)std::min<long long>(I.height, band_budget / std::max(I.width_step, 1));
-    const int nbands = band_rows > 0 ? (I.height + band_rows - 1) / band_rows : 0;
-    const char *force = getenv("B2S_OCC_RAYTRACE");  // "global" / "banded": pin the kernel (tests, profiling)
-    bool banded = nbands >= 1 && nbands <= 8 && n_beams >= 64LL * 1024;
-    if (force && !strcmp(force, "global")) banded = false;
-    if (force && !strcmp(force, "banded") && nbands >= 1 && nbands <= 64) banded = true;
-    if (banded) {
-      const int chunks = std::max(1, sms / nbands);
-      const long long per = (n_beams + chunks - 1) / chunks;
-      const size_t smem = sizeof(uint32_t) * (size_t)band_rows * I.width_step;
-      B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), raise_dyn_smem(k_raytrace_banded, smem));
-      k_raytrace_banded<<<nbands * chunks, 512, smem, st>>>(d_ranges, d_sensor, d_pts, *laser, n_beams, I.width, I.height,
-                                                            I.width_step, I.offset[0], I.offset[1], scale, g->d_pass,
-                                                            g->d_hit, d_visits, band_rows, nbands, per);
-    } else {
-      const int blocks = (int)std::min<long long>((n_beams + 7) / 8, (long long)sms * 16);
-      k_raytrace<<<blocks, 256, 0, st>>>(d_ranges, d_sensor, d_pts, *laser, n_beams, I.width, I.height, I.width_step,
-                                         I.offset[0], I.offset[1], scale, g->d_pass, g->d_hit, d_visits);
-    }
+    // Global RED.ADD.  (A shared-memory privatised variant — row bands of the map as per-CTA uint32 tiles, lines clipped
+    // to a band in closed form — was built and measured at 79 G cell visits/s against 151 G here: on this part ATOMS
+    // retires ~0.5 lane/clk/SM, no better than the L2 atomic units, and one 200 KB tile per SM leaves 16 warps to hide it.)
+    const int blocks = (int)std::min<long long>((n_beams + 7) / 8, (long long)sms * 16);
+    k_raytrace<<<blocks, 256, 0, st>>>(d_ranges, d_sensor, d_pts, *laser, n_beams, I.width, I.height, I.width_step,
+                                       I.offset[0], I.offset[1], scale, g->d_pass, g->d_hit, d_visits);
   }
   B2S_CUDA_CHECK_CLEAN(b2s_occ_grid_destroy(g), cudaEventRecord(ev[1], st));
   if (I.data_size > 0) k_occ_threshold<<<ceil_div(I.data_size, 256), 256, 0, st>>>(g->d_pass, g->d_hit, I.data_size, g->d_cells);

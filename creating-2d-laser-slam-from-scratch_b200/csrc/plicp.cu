@@ -303,6 +303,7 @@ extern "C" b2s_status b2s_plicp_match(const b2s_icp_params *params, int batch, i
     B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_plicp_match: null/invalid argument");
   if (b2s_device_count() <= device) B2S_FAIL(B2S_ERR_NO_DEVICE, "no usable CUDA device (the product path has no CPU fallback)");
   B2S_CUDA_CHECK(cudaSetDevice(device));
+  keep_pool_memory(device);
   // shared memory: the kernel's static arrays + the per-beam dynamic part must fit the opt-in limit of the device
   cudaFuncAttributes fa;
   B2S_CUDA_CHECK(cudaFuncGetAttributes(&fa, k_plicp));

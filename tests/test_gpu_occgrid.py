@@ -144,25 +144,3 @@ def test_sharded_scan_list_equals_whole(pkg, O, world):
     g1 = par.occupancy_grid_sharded(O, al, ranges, poses, 0.05)
     same(g1.arrays(), O.OccupancyGrid(al, ranges, poses, 0.05).arrays())
 
-
-def test_banded_shared_memory_raytrace_equals_global(pkg, O, monkeypatch):
-    """The shared-memory privatised ray trace (row bands of the map, closed-form clipping of every line to a band) and
-    the global-atomic one give identical counters; several bands are forced with a finer map (0.02 m: ~10 bands)."""
-    abi, synth = pkg.abi, pkg.synth
-    laser = synth.Laser()
-    _, poses, ranges = synth.make_trajectory(5, 40, laser, step_xy=0.3, step_th_deg=8)
-    ranges[3, ::41] = np.nan
-    ranges[9, ::17] = 40.0
-    al = abi.laser_from(laser)
-    for res in (0.05, 0.02):
-        got = {}
-        for mode in ("global", "banded"):
-            monkeypatch.setenv("B2S_OCC_RAYTRACE", mode)
-            g = O.OccupancyGrid(al, ranges, poses, res)
-            got[mode] = g.arrays()
-            g.close()
-        monkeypatch.delenv("B2S_OCC_RAYTRACE")
-        same(got["global"], got["banded"])
-        assert got["global"]["cell_visits"] == got["banded"]["cell_visits"]
-        if res == 0.05:
-            same(got["banded"], port.occupancy_grid(al, ranges, poses, res))

@@ -75,3 +75,17 @@ v = hb.stats()["cell_visits"] - v0
 out["batched_mapping"] = {"batch": B, "steps": steps - 3, "scans_per_s": B * (steps - 3) / dt, "cell_visits": v,
                           "cells_per_s": v / dt, "A2_GBps": 2 * 8 * v / dt / 1e9, "ms_per_step": 1e3 * dt / (steps - 3)}
 print(json.dumps(out, indent=1))
+# mapping-only stream (one map, every scan updates) at two lengths: fixed or per-scan cost?
+for n_m in (100, 1000):
+    hs = H.HectorSlam(**dict(kw, min_dist=0.0, min_angle=0.0))
+    hs.process_stream(pts[:4], (0, 0), pose_hints=poses[:4].astype(np.float32), map_without_matching=True)
+    hs.reset()
+    hs.sync()
+    ph = poses[:n_m].astype(np.float32)
+    t0 = time.perf_counter()
+    hs.process_stream(pts[:n_m], (0, 0), pose_hints=ph, map_without_matching=True)
+    dt = time.perf_counter() - t0
+    st = hs.stats()
+    print(json.dumps({"mapping_only_stream": n_m, "ms": dt * 1e3, "us_per_scan": 1e6 * dt / n_m, "update_ms": st["update_ms"],
+                      "match_ms": st["match_ms"], "visits": st["cell_visits"], "profile": hs.profile()}))
+    hs.close()
