@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -186,6 +187,16 @@ inline void keep_pool_memory(int device) {
   cudaGetLastError();
   done[device] = true;
 }
+
+// NVTX range around a host entry point (SURVEY.md §5 tracing): shows up as "b2s:<name>" in Nsight timelines; nvtx3 is
+// header-only and costs a predictable branch when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define B2S_NVTX(name) ::b2s::NvtxRange _b2s_nvtx_range("b2s:" name)
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

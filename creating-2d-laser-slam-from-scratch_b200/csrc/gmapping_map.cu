@@ -194,6 +194,7 @@ b2s_status b2s_gmap_size(const b2s_gmap *g, int32_t size_xy[2]) {
 
 b2s_status b2s_gmap_compute_map(b2s_gmap *g, const double *ranges, const double *angles, int n,
                                 const double laser_pose[3], double max_range, double max_urange) {
+  B2S_NVTX("K2b ComputeMap");
   if (!g || !ranges || !angles || !laser_pose || n < 0) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (n == 0) return B2S_OK;
   B2S_CUDA_CHECK(cudaSetDevice(g->device));

@@ -375,6 +375,7 @@ static b2s_status hc_upload_points(b2s_hector_map *m, const float *points, int n
 
 static b2s_status hc_update(b2s_hector_map *m, const float *points, int n_points, const float origo[2],
                             const float world_pose[3], bool just_once) {
+  B2S_NVTX("K2a updateByScan");
   if (!m || !origo || !world_pose || n_points < 0 || (n_points > 0 && !points)) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   B2S_CUDA_CHECK(cudaSetDevice(m->device));
   const int mark_free = m->curr_update_index + 1, mark_occ = m->curr_update_index + 2;  // OccGridMapBase.h:120-121

@@ -1029,6 +1029,7 @@ b2s_status b2s_hector_slam_reset(b2s_hector_slam *p) {
 b2s_status b2s_hector_slam_update(b2s_hector_slam *p, const float *points, int n_points, const float origo[2],
                                   const float pose_hint_world[3], int map_without_matching, float out_pose[3],
                                   float out_cov[9], int *out_map_updated) {
+  B2S_NVTX("Hector update (match + gate + map update)");
   if (!p || !origo || !pose_hint_world || !out_pose || n_points < 0 || (n_points > 0 && !points))
     B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (p->batch != 1) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_hector_slam_update serves single-processor handles; use b2s_hector_slam_update_batch");
@@ -1081,6 +1082,7 @@ b2s_status b2s_hector_slam_process_stream(b2s_hector_slam *p, int n_scans, const
                                           const float origo[2], const float *first_pose_hint, const float *pose_hints,
                                           int map_without_matching, float *out_poses, int32_t *out_map_updated,
                                           float *out_last_cov) {
+  B2S_NVTX("Hector stream");
   if (!p || n_scans < 0 || !origo || !out_poses || (n_scans > 0 && (!points || !n_points)))
     B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (map_without_matching && !pose_hints) B2S_FAIL(B2S_ERR_BAD_PARAMS, "map_without_matching needs a pose per scan (pose_hints)");
@@ -1201,6 +1203,7 @@ b2s_status b2s_hector_slam_update_batch(b2s_hector_slam *p, const float *points,
  * host): the resident-in-HBM form the throughput of the batched update is measured on */
 b2s_status b2s_hector_slam_update_batch_device(b2s_hector_slam *p, const float *d_points, const int32_t *d_n_points, int max_n,
                                                const float origo[2], const float *d_pose_hints, int map_without_matching) {
+  B2S_NVTX("Hector batch step");
   if (!p || !d_points || !d_n_points || !origo) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (map_without_matching && !d_pose_hints) B2S_FAIL(B2S_ERR_BAD_PARAMS, "map_without_matching needs the poses");
   if (max_n < 0 || max_n > p->cap) B2S_FAIL(B2S_ERR_TOO_LARGE, "more points than the handle's capacity");

@@ -793,6 +793,7 @@ b2s_status b2s_mapper_set_scan_solver(b2s_mapper *m, const b2s_scan_solver *solv
 
 b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double odometric_pose[3], double time,
                               int32_t *out_processed, double out_corrected_pose[3]) {
+  B2S_NVTX("Mapper::Process");
   if (!m || !ranges || !odometric_pose) B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_mapper_process: null argument");
   if (out_processed) *out_processed = 0;
   if (m->failed)

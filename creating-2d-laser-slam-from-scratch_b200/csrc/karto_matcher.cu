@@ -34,6 +34,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "nccl_dl.cuh"
 #include "scan_kernels.cuh"
 
 namespace b2s {
@@ -145,6 +146,9 @@ struct b2s_matcher {
   int32_t *d_lists = nullptr, *d_counts = nullptr, *d_starts = nullptr;  // window kernel: per-(match, angle) grouped window origins
   size_t lists_cap = 0, counts_cap = 0, starts_cap = 0;
   double *d_part_best = nullptr, *d_glob_best = nullptr, *d_tie = nullptr;  // split-sweep phases: [B], [B], [B][5]
+  int32_t *d_status = nullptr;                                              // [B] statuses of a split sweep
+  cudaEvent_t ev_split[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double last_split_ms[4] = {0, 0, 0, 0};
   int last_k_first = 0;
   uint16_t *d_sat = nullptr;  // [B][(sby+1)(sbx+1)] block summed-area tables of the grids
   int sbx = 0, sby = 0;
@@ -1472,6 +1476,16 @@ __global__ void k_results_to_centers(const b2s_match_result *__restrict__ result
   centers[3 * b + 2] = results[b].pose[2];
 }
 
+// split sweep: per-match status out of / back into the result records (all-reduced with MAX between the phases)
+__global__ void k_status_pack(const b2s_match_result *__restrict__ results, int32_t *__restrict__ st, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch) st[b] = results[b].status;
+}
+__global__ void k_status_apply(b2s_match_result *__restrict__ results, const int32_t *__restrict__ st, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch && st[b] != 0) results[b].status = st[b];  // a rank saw an out-of-range candidate: the reference throws
+}
+
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
@@ -1604,6 +1618,7 @@ static b2s_status matcher_create_impl(const b2s_matcher_params *params, const b2
   if ((st = dev_alloc(&m->d_part_best, B))) return st;
   if ((st = dev_alloc(&m->d_glob_best, B))) return st;
   if ((st = dev_alloc(&m->d_tie, B * 5))) return st;
+  if ((st = dev_alloc(&m->d_status, B))) return st;
   B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m->h_results), B * sizeof(b2s_match_result)));
   B2S_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&m->h_stats), sizeof(unsigned long long)));
   *m->h_stats = 0;
@@ -1642,13 +1657,15 @@ void b2s_matcher_destroy(b2s_matcher *m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   void *ptrs[] = {m->d_kernel, m->d_ranges, m->d_poses, m->d_sensor, m->d_pts, m->d_local, m->d_grids,
-                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_pool, m->d_base_src, m->d_lut, m->d_lists, m->d_counts, m->d_starts, m->d_sat, m->d_stats, m->d_part_best, m->d_glob_best, m->d_tie, m->d_sums, m->d_bases,
+                  m->d_grid_off, m->d_base_ranges, m->d_base_poses, m->d_base_pts, m->d_pool, m->d_base_src, m->d_lut, m->d_lists, m->d_counts, m->d_starts, m->d_sat, m->d_stats, m->d_part_best, m->d_glob_best, m->d_tie, m->d_status, m->d_sums, m->d_bases,
                   m->d_flags, m->d_probs, m->d_centers, m->d_results, m->d_work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (m->h_results) cudaFreeHost(m->h_results);
   if (m->h_stats) cudaFreeHost(m->h_stats);
   for (auto &e : m->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto &e : m->ev_split)
     if (e) cudaEventDestroy(e);
   if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -1693,6 +1710,7 @@ b2s_status b2s_matcher_set_scans(b2s_matcher *m, int batch, const double *ranges
 // rows of the handle's device-resident scan pool
 static b2s_status add_scans_impl(b2s_matcher *m, int n_base, const double *base_ranges, const int32_t *pool_rows,
                                  const double *base_poses) {
+  B2S_NVTX("K1 add_scans (rasterise + smear)");
   if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || n_base < 0 || (n_base > 0 && ((!base_ranges && !pool_rows) || !base_poses))) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->scans_set) B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_matcher_set_scans must precede b2s_matcher_add_scans");
@@ -1908,6 +1926,7 @@ b2s_status b2s_matcher_correlate_scan(b2s_matcher *m, const double *centers, con
 }
 
 b2s_status b2s_matcher_match_scan(b2s_matcher *m, int do_penalize, int do_refine, b2s_match_result *results) {
+  B2S_NVTX("K1 MatchScan (coarse + fine)");
   if (m && m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end: the handle cannot change state in between");
   if (!m || !results) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
@@ -2075,6 +2094,72 @@ b2s_status b2s_matcher_correlate_split_finish(b2s_matcher *m, const double *glob
   return B2S_OK;
 }
 
+/* The same angle-split CorrelateScan with the collectives INSIDE the library (north_star: "a single
+ * NCCL all-reduce on the per-scan best-score"): every rank holds the same scans + grids and calls this with its rank; the
+ * angle steps are partitioned by rank, and between the three phases the library all-reduces device buffers on the
+ * handle's stream through the caller's NCCL communicator — best response (MAX, B doubles), per-cell maxima plane (MAX,
+ * B x probs_len doubles), status (MAX), tie sums (SUM, 5B doubles).  No host staging; results equal the single-GPU
+ * b2s_matcher_correlate_scan on every rank. */
+b2s_status b2s_matcher_correlate_scan_split(b2s_matcher *m, void *nccl_comm, int rank, int world, const double *centers,
+                                            const b2s_search *search, b2s_match_result *results) {
+  if (!m || !nccl_comm || !centers || !search || !results || world < 1 || rank < 0 || rank >= world)
+    B2S_FAIL(B2S_ERR_BAD_PARAMS, "null / bad argument");
+  if (m->pending) B2S_FAIL(B2S_ERR_BAD_STATE, "a b2s_matcher_correlate_scan_begin awaits its _end");
+  if (search->fine) B2S_FAIL(B2S_ERR_BAD_PARAMS, "only the coarse stage (doingFineMatch = false) can be split");
+  if (!m->scans_set || !m->grids_set) B2S_FAIL(B2S_ERR_BAD_STATE, "scans and grids must be set first");
+  const NcclApi &nc = nccl_api();
+  if (!nc.ok) B2S_FAIL(B2S_ERR_BAD_STATE, "libnccl.so.2 could not be loaded (dlopen)");
+  B2S_CUDA_CHECK(cudaSetDevice(m->device));
+  for (auto &e : m->ev_split)
+    if (!e) B2S_CUDA_CHECK(cudaEventCreate(&e));
+  const int B = m->batch;
+  const size_t plen = (size_t)((m->g.search_side + 7) & ~7) * m->g.search_side;
+  const int na_full = n_steps(search->angle_offset, search->angle_res);
+  const int base = na_full / world, extra = na_full % world;  // contiguous, balanced (parallel.shard_bounds)
+  const int k_first = rank * base + std::min(rank, extra), k_count = base + (rank < extra ? 1 : 0);
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->d_centers, centers, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, m->stream));
+  b2s_status st = run_correlate(m, search, true, k_first, k_count, 1);
+  if (st) return st;
+  k_status_pack<<<ceil_div(B, 128), 128, 0, m->stream>>>(m->d_results, m->d_status, B);
+  auto check_nccl = [&](int rc, const char *what) -> b2s_status {
+    if (rc == 0) return B2S_OK;
+    set_last_error(std::string(what) + " failed: " + (nc.error_string ? nc.error_string(rc) : "NCCL error"));
+    return B2S_ERR_CUDA;
+  };
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev_split[0], m->stream));
+  if ((st = check_nccl(nc.all_reduce(m->d_part_best, m->d_glob_best, (size_t)B, NCCL_FLOAT64, NCCL_MAX, nccl_comm, m->stream), "ncclAllReduce(best)"))) return st;
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev_split[1], m->stream));
+  if ((st = check_nccl(nc.all_reduce(m->d_probs, m->d_probs, plen * B, NCCL_FLOAT64, NCCL_MAX, nccl_comm, m->stream), "ncclAllReduce(plane)"))) return st;
+  if ((st = check_nccl(nc.all_reduce(m->d_status, m->d_status, (size_t)B, NCCL_INT32, NCCL_MAX, nccl_comm, m->stream), "ncclAllReduce(status)"))) return st;
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev_split[2], m->stream));
+  B2S_CUDA_CHECK(cudaMemsetAsync(m->d_tie, 0, sizeof(double) * 5 * B, m->stream));
+  if ((st = split_phase(m, 2))) return st;
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev_split[3], m->stream));
+  if ((st = check_nccl(nc.all_reduce(m->d_tie, m->d_tie, (size_t)5 * B, NCCL_FLOAT64, NCCL_SUM, nccl_comm, m->stream), "ncclAllReduce(ties)"))) return st;
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev_split[4], m->stream));
+  if ((st = split_phase(m, 3))) return st;
+  k_status_apply<<<ceil_div(B, 128), 128, 0, m->stream>>>(m->d_results, m->d_status, B);
+  B2S_CUDA_CHECK(cudaGetLastError());
+  B2S_CUDA_CHECK(cudaEventRecord(m->ev_split[5], m->stream));
+  B2S_CUDA_CHECK(cudaMemcpyAsync(m->h_results, m->d_results, sizeof(b2s_match_result) * B, cudaMemcpyDeviceToHost, m->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  std::memcpy(results, m->h_results, sizeof(b2s_match_result) * B);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, m->ev_split[0], m->ev_split[1]) == cudaSuccess) m->last_split_ms[0] = ms;  // best
+  if (cudaEventElapsedTime(&ms, m->ev_split[1], m->ev_split[2]) == cudaSuccess) m->last_split_ms[1] = ms;  // plane + status
+  if (cudaEventElapsedTime(&ms, m->ev_split[3], m->ev_split[4]) == cudaSuccess) m->last_split_ms[2] = ms;  // tie sums
+  if (cudaEventElapsedTime(&ms, m->ev_split[0], m->ev_split[5]) == cudaSuccess) m->last_split_ms[3] = ms;  // all phases after the sweep
+  return B2S_OK;
+}
+
+/* ms of the last b2s_matcher_correlate_scan_split: all-reduce(best), all-reduce(plane + status), all-reduce(tie sums),
+ * everything between the end of the local sweep and the final results */
+b2s_status b2s_matcher_last_split_timing(b2s_matcher *m, double out[4]) {
+  if (!m || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  for (int i = 0; i < 4; i++) out[i] = m->last_split_ms[i];
+  return B2S_OK;
+}
+
 b2s_status b2s_matcher_get_response_sums(b2s_matcher *m, int b, int32_t *out, int32_t dims[3]) {
   if (!m || !out || b < 0 || b >= m->batch) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad argument");
   if (!m->have_sweep) B2S_FAIL(B2S_ERR_BAD_STATE, "no sweep has been run");
@@ -2113,6 +2198,7 @@ namespace b2s {
 // One CorrelateScan over the batch with centres already in d_centers.  Results stay in d_results.
 static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*centers_on_device*/, int k_first, int na_override,
                                 int mode) {
+  B2S_NVTX("K1 correlate (lists + sweep + tail)");
   if (s->angle_res == 0.0 || s->res_x == 0.0 || s->res_y == 0.0)
     B2S_FAIL(B2S_ERR_BAD_PARAMS, "search resolutions must be non-zero");  // assert at Mapper.cpp:319
   const int B = m->batch, n = m->n;

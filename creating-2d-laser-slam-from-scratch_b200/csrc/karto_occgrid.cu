@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "nccl_dl.cuh"
 #include "scan_kernels.cuh"
 
 using namespace b2s;
@@ -190,6 +191,7 @@ extern "C" {
 static b2s_status occ_create_impl(const b2s_laser *laser, int n_scans, const double *ranges, const double *poses,
                                   double resolution, const double *given_bbox, double *bbox_out, int device,
                                   void *cuda_stream, b2s_occ_grid **out) {
+  B2S_NVTX("K2c OccupancyGrid::CreateFromScans");
   if (!laser || n_scans < 0 || (n_scans > 0 && (!ranges || !poses)) || (!out && !bbox_out))
     B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_occ_grid: null/negative argument");
   if (out) *out = nullptr;
@@ -323,6 +325,23 @@ b2s_status b2s_occ_grid_device_counters(b2s_occ_grid *g, uint32_t **d_pass, uint
   B2S_CUDA_CHECK(cudaStreamSynchronize(g->stream));  // the caller's collective runs on its own stream
   *d_pass = g->d_pass;
   *d_hit = g->d_hit;
+  return B2S_OK;
+}
+
+/* step 3 of the sharded build with the collective inside the library: pass / hit counters summed over the ranks in place
+ * on the device (two ncclAllReduce(SUM, uint32) on the grid's stream through the caller's communicator) */
+b2s_status b2s_occ_grid_allreduce_counters(b2s_occ_grid *g, void *nccl_comm) {
+  if (!g || !nccl_comm) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  const NcclApi &nc = nccl_api();
+  if (!nc.ok) B2S_FAIL(B2S_ERR_BAD_STATE, "libnccl.so.2 could not be loaded (dlopen)");
+  B2S_CUDA_CHECK(cudaSetDevice(g->device));
+  const size_t cells = (size_t)std::max(g->info.data_size, 0);
+  if (cells == 0) return B2S_OK;
+  for (uint32_t *buf : {g->d_pass, g->d_hit}) {
+    const int rc = nc.all_reduce(buf, buf, cells, NCCL_UINT32, NCCL_SUM, nccl_comm, g->stream);
+    if (rc != 0) B2S_FAIL(B2S_ERR_CUDA, std::string("ncclAllReduce(counters) failed: ") + (nc.error_string ? nc.error_string(rc) : "NCCL error"));
+  }
+  B2S_CUDA_CHECK(cudaStreamSynchronize(g->stream));
   return B2S_OK;
 }
 

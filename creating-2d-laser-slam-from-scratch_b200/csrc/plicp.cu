@@ -298,6 +298,7 @@ extern "C" b2s_status b2s_plicp_match(const b2s_icp_params *params, int batch, i
                                       const double *sens_ranges, const double *theta, double range_min,
                                       double range_max, const double *first_guess, int device, void *cuda_stream,
                                       b2s_icp_result *results) {
+  B2S_NVTX("K3 PL-ICP batch");
   if (!params || !ref_ranges || !sens_ranges || !theta || !first_guess || !results || batch <= 0 || n < 3 ||
       params->max_iterations < 1)
     B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_plicp_match: null/invalid argument");

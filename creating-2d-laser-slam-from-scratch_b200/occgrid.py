@@ -100,6 +100,11 @@ class OccupancyGrid:
         return (_DeviceArray(C.cast(dp_, C.c_void_p).value or 0, n, self),
                 _DeviceArray(C.cast(dh_, C.c_void_p).value or 0, n, self))
 
+    def allreduce_counters(self, nccl_comm):
+        """b2s_occ_grid_allreduce_counters: both counter planes summed over the ranks in place by the library (NCCL)."""
+        self.L.b2s_occ_grid_allreduce_counters.argtypes = [C.c_void_p, C.c_void_p]
+        check(self.L.b2s_occ_grid_allreduce_counters(self.h, nccl_comm.comm))
+
     def set_counters(self, passes, hits):
         pa = np.ascontiguousarray(passes, np.uint32).reshape(-1)
         hi = np.ascontiguousarray(hits, np.uint32).reshape(-1)

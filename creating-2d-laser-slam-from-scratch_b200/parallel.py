@@ -92,7 +92,8 @@ def correlate_scan_angle_split(matcher, centers, search, n_angles: int, group=No
     return out
 
 
-def occupancy_grid_sharded(occgrid_mod, laser, ranges_shard, poses_shard, resolution: float, device: int = 0, group=None):
+def occupancy_grid_sharded(occgrid_mod, laser, ranges_shard, poses_shard, resolution: float, device: int = 0, group=None,
+                           nccl_comm=None):
     """karto::OccupancyGrid::CreateFromScans (Karto.h:5659-5673) over a scan list SHARDED across the ranks
     (SURVEY.md §8(e)(iii)): bounding boxes are reduced (MIN/MAX), each rank ray-traces its shard into the globally
     dimensioned grid, the uint32 pass/hit counters are summed with one all-reduce each (in place on the device with
@@ -108,7 +109,9 @@ def occupancy_grid_sharded(occgrid_mod, laser, ranges_shard, poses_shard, resolu
         bbox = np.concatenate([-lo, hi])
     g = occgrid_mod.OccupancyGrid(laser, ranges_shard, poses_shard, resolution, device=device, bbox=bbox)
     if live and g.info.data_size > 0:
-        if dist.get_backend(group) == "nccl":
+        if nccl_comm is not None:  # the collective inside the library: ncclAllReduce(SUM) on the device counters
+            g.allreduce_counters(nccl_comm)
+        elif dist.get_backend(group) == "nccl":
             for arr in g.device_counters():
                 t = torch.as_tensor(arr, device=torch.device("cuda", device))
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -120,3 +123,61 @@ def occupancy_grid_sharded(occgrid_mod, laser, ranges_shard, poses_shard, resolu
             g.set_counters(pa, hi_)
     g.update()
     return g
+
+
+# ---- a raw NCCL communicator for the in-library collectives (b2s_matcher_correlate_scan_split, b2s_occ_grid_allreduce_counters)
+class NcclComm:
+    """ncclComm_t created with ncclGetUniqueId / ncclCommInitRank through ctypes; the 128-byte id travels over the
+    already-initialised torch.distributed group.  A C++ host does the same with its own bootstrap."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+
+        self.C = C
+        self.lib = C.CDLL("libnccl.so.2", mode=C.RTLD_GLOBAL)
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_char * 128)]
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = UniqueId()
+        if self.rank == 0:
+            rc = self.lib.ncclGetUniqueId(C.byref(uid))
+            assert rc == 0, rc
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).clone().to(dev)
+        dist.broadcast(t, 0, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        C.memmove(C.byref(uid), raw, 128)
+        self.comm = C.c_void_p()
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        rc = self.lib.ncclCommInitRank(C.byref(self.comm), self.world, uid, self.rank)
+        assert rc == 0, rc
+
+    def close(self):
+        if getattr(self, "comm", None) and self.comm.value:
+            self.lib.ncclCommDestroy.argtypes = [self.C.c_void_p]
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = self.C.c_void_p()
+
+
+def correlate_scan_split_in_library(matcher, centers, search, comm: "NcclComm"):
+    """b2s_matcher_correlate_scan_split: the same angle-split sweep with the all-reduces issued by the library itself on
+    device buffers (no host staging).  Returns (results tuple, collective timings in ms)."""
+    import ctypes as C
+    from . import abi
+    from .matcher import check, results_to_arrays
+
+    L = matcher.L
+    L.b2s_matcher_correlate_scan_split.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                                   C.POINTER(abi.Search), C.POINTER(abi.MatchResult)]
+    L.b2s_matcher_last_split_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    c = np.ascontiguousarray(centers, np.float64).reshape(matcher.batch, 3)
+    res = (abi.MatchResult * matcher.batch)()
+    check(L.b2s_matcher_correlate_scan_split(matcher.h, comm.comm, comm.rank, comm.world, c.ctypes.data_as(C.POINTER(C.c_double)),
+                                             C.byref(search), res))
+    t = np.zeros(4)
+    check(L.b2s_matcher_last_split_timing(matcher.h, t.ctypes.data_as(C.POINTER(C.c_double))))
+    return results_to_arrays(res, matcher.batch), dict(allreduce_best_ms=t[0], allreduce_plane_ms=t[1], allreduce_ties_ms=t[2],
+                                                        after_sweep_ms=t[3])

@@ -189,6 +189,15 @@ b2s_status b2s_matcher_compute_offsets(b2s_matcher *m, int b, double angle_cente
                                        double angle_res, int32_t *out, int32_t *out_n_angles);
 /* integer numerators of GetResponse (Mapper.cpp:819-856) of the LAST correlate_scan sweep for match b,
  * in the reference's loop order out[nY][nX][nAngles] (Mapper.cpp:373-424). */
+/* The angle-split sweep with the collectives INSIDE the library: nccl_comm is the caller's ncclComm_t (the library
+ * dlopens libnccl.so.2 and calls ncclAllReduce on the handle's stream; no host staging, no Python).  Every rank calls
+ * it with the same scans / grids / centres and its own rank; results are those of b2s_matcher_correlate_scan on
+ * every rank.  Collectives: best response MAX (B doubles), per-cell plane MAX (B x probs_len doubles), status MAX,
+ * tie sums SUM (5B doubles). */
+b2s_status b2s_matcher_correlate_scan_split(b2s_matcher *m, void *nccl_comm, int rank, int world, const double *centers,
+                                            const b2s_search *search, b2s_match_result *results);
+/* ms of its last call: all-reduce(best), all-reduce(plane + status), all-reduce(tie sums), sweep end -> results */
+b2s_status b2s_matcher_last_split_timing(b2s_matcher *m, double out[4]);
 b2s_status b2s_matcher_get_response_sums(b2s_matcher *m, int b, int32_t *out, int32_t dims[3]);
 
 /* Device time (ms, CUDA events on the handle's stream) of the stages of the LAST correlate_scan call:
@@ -335,6 +344,9 @@ b2s_status b2s_occ_grid_create_shard(const b2s_laser *laser, int n_scans, const 
                                      b2s_occ_grid **out);
 b2s_status b2s_occ_grid_device_counters(b2s_occ_grid *g, uint32_t **d_pass, uint32_t **d_hit);
 b2s_status b2s_occ_grid_set_counters(b2s_occ_grid *g, const uint32_t *pass, const uint32_t *hit);
+/* step 3 with the collective inside the library: ncclAllReduce(SUM) of both counter planes in place through the caller's
+ * ncclComm_t (dlopened libnccl.so.2), on the grid's stream */
+b2s_status b2s_occ_grid_allreduce_counters(b2s_occ_grid *g, void *nccl_comm);
 b2s_status b2s_occ_grid_update(b2s_occ_grid *g);
 b2s_status b2s_occ_grid_info_get(const b2s_occ_grid *g, b2s_occ_grid_info *out);
 /* cells: uint8 {0 unknown, 100 occupied, 255 free}; pass/hit: uint32 counters; any pointer may be NULL */
