@@ -298,6 +298,8 @@ class Ctx:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
         torch.cuda.set_device(self.local)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (VERSION prints a banner there)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         self.pkg = importlib.import_module(PKG)

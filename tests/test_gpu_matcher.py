@@ -587,3 +587,27 @@ def test_scan_pool_base_sets(pkg):
         b.add_scans_pool([[0, 1, 2, 9]] * 3, np.stack([poses[c] for c in chains]))
     assert e.value.status == abi.B2S_ERR_OUT_OF_RANGE
     a.close(), b.close()
+
+
+def test_cfg4_largest_window_full_size(pkg, M):
+    """BASELINE cfg 4's largest shape at FULL size: one match, 61 x 61 x 361 candidates (+-0.75 m @0.025 m, +-45 deg @0.25
+    deg) on the 807 x 807 grid: all 1 343 281 integer response sums bit-exact vs the restatement, response / pose /
+    covariance within 1e-9 (the oracle takes a few seconds for its 1.45 G lookups)."""
+    abi, synth = pkg.abi, pkg.synth
+    l4 = synth.Laser(range_threshold=9.25)
+    params, laser = abi.matcher_params(1.5, 0.025, 0.03, 9.25), abi.laser_from(l4)
+    c = synth.make_match_case(4_100_001, l4)
+    m = M.ScanMatcher(params, laser, max_batch=1, max_base_scans=1)
+    m.set_scans(c.ranges[None], c.odom_pose[None])
+    m.add_scans(c.base_ranges[None, None], c.base_pose[None, None])
+    se = abi.Search(0.75, 0.75, 0.025, 0.025, 45 * D, 0.25 * D, 1, 0)
+    assert (abi.n_steps(0.75, 0.025), abi.n_steps(45 * D, 0.25 * D)) == (61, 361)
+    gpu = m.correlate_scan(c.odom_pose[None], se)
+    assert m.last_timing()["path"] == 2
+    pm = port_case(abi, params, laser, c.ranges, c.odom_pose, c.base_ranges[None], c.base_pose[None])
+    rc, r = pm.correlate_scan(pm.sp, se, want_sums=True)
+    assert rc == 0
+    assert np.array_equal(m.response_sums(0, (61, 61, 361)), pm.last_sums)
+    gpu = m.correlate_scan(pm.sp[None], se)
+    assert_result(gpu, 0, r)
+    m.close()
