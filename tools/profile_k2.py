@@ -53,6 +53,22 @@ for s in range(steps):
     hb.update_batch_device(dp[s].data_ptr(), dn[s].data_ptr(), cap, (0, 0), dh[s].data_ptr(), True)
 hb.sync()
 hb.close()
+# the hall case (maps stream through HBM)
+_, hp2, hr2 = synth.make_trajectory(29, 48, laser, half_w=22.0, half_h=22.0, step_xy=0.3, step_th_deg=8, n_boxes=24)
+pts2 = [H.scan_to_data_container(hr2[i], laser, 0.05, max_dist=30.0, min_dist=0.2) for i in range(len(hp2))]
+cap2 = max(len(p) for p in pts2)
+hb = H.HectorSlam(batch=B, max_points=cap2, **dict(kw, min_dist=0.0, min_angle=0.0))
+hq = np.zeros((steps, B, cap2, 2), np.float32); hm = np.zeros((steps, B), np.int32); hg = np.zeros((steps, B, 3), np.float32)
+for s in range(steps):
+    for b in range(B):
+        i = (s * 5 + b * 11) % len(pts2)
+        hq[s, b, :len(pts2[i])] = pts2[i]; hm[s, b] = len(pts2[i]); hg[s, b] = hp2[i]
+dq, dm, dg = torch.from_numpy(hq).cuda(), torch.from_numpy(hm).cuda(), torch.from_numpy(hg).cuda()
+torch.cuda.synchronize()
+for s in range(steps):
+    hb.update_batch_device(dq[s].data_ptr(), dm[s].data_ptr(), cap2, (0, 0), dg[s].data_ptr(), True)
+hb.sync()
+hb.close()
 hb = H.HectorSlam(batch=B, max_points=cap, **kw)  # B SLAM processors: k_hs_match at B CTAs
 for s in range(2):
     hb.update_batch_device(dp[s].data_ptr(), dn[s].data_ptr(), cap, (0, 0), dh[s].data_ptr(), False)
