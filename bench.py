@@ -820,6 +820,7 @@ def base_line(ctx, args, value, ms_max, steps, config, e2e, roofline, launches, 
 def k1_roofline(sweep_ms, matches_per_launch, a1_bytes, clocks, traffic_key, batch):
     peak, peak_src = hbm_peak()
     traffic, traffic_src = committed_traffic(traffic_key, batch)
+    sweep_ms = max(float(sweep_ms), 1e-6)
     achieved = a1_bytes * matches_per_launch / (sweep_ms * 1e-3) / 1e9
     sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
     smem_ceiling = 148 * 32 * sm_clk  # 4-byte bank accesses / s

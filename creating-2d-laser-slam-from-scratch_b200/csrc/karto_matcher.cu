@@ -2187,6 +2187,14 @@ b2s_status b2s_matcher_last_stats(b2s_matcher *m, double out[4]) {
 
 b2s_status b2s_matcher_last_timing(b2s_matcher *m, double out[4]) {
   if (!m || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  if (m->have_sweep && !m->pending && cudaSetDevice(m->device) == cudaSuccess && cudaStreamSynchronize(m->stream) == cudaSuccess) {
+    // the events of the LAST sweep (whichever entry point ran it: correlate_scan, match_scan's last stage, a split phase)
+    for (int i = 0; i < 3; i++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]) == cudaSuccess) m->last_ms[i] = ms;
+    }
+    cudaGetLastError();
+  }
   out[0] = m->last_ms[0]; out[1] = m->last_ms[1]; out[2] = m->last_ms[2]; out[3] = (double)m->last_path;
   return B2S_OK;
 }
