@@ -13,11 +13,12 @@ prof = os.path.join(root, "profiles")
 traffic = {}
 for name in ("k1", "k2"):
     rep = os.path.join(src, name + ".ncu-rep")
-    if not os.path.exists(rep):
-        continue
     raw = os.path.join(src, name + "_raw.csv")
-    with open(raw, "w") as f:
-        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=f, stderr=subprocess.DEVNULL, check=True)
+    if not os.path.exists(raw):
+        if not os.path.exists(rep):
+            continue
+        with open(raw, "w") as f:
+            subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=f, stderr=subprocess.DEVNULL, check=True)
     out = os.path.join(prof, f"{tag}_ncu_{name}_summary.json")
     subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), raw, out], check=True)
     rows = json.load(open(out))
