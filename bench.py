@@ -659,8 +659,12 @@ def bench_k2(pkg, local, quick=False):
     try:
         MPm = pkg.load("mapper")
         lm = synth.Laser(range_threshold=12.0)
-        n_map = 120 if quick else 400
-        _, tru, odo, rng_m = synth.make_loop_trajectory(17, n_map, lm, radius=2.0, step=0.25)
+        n_map = 120 if quick else 520
+        # a 9 m-radius lap in a 28 m x 24 m hall (226 key frames per lap): the second lap meets the first one's scans as
+        # loop-closure candidates (not near-linked: link distance 1.5 m), so TryCloseLoop runs its batched matches
+        _, tru, odo, rng_m = synth.make_loop_trajectory(17, n_map, lm, radius=2.0 if quick else 9.0, step=0.25,
+                                                        half_w=8.0 if quick else 14.0, half_h=6.0 if quick else 12.0,
+                                                        n_boxes=6 if quick else 12)
         yaml = dict(scan_buffer_size=110, scan_buffer_maximum_scan_distance=100.0, link_match_minimum_response_fine=0.1,
                     link_scan_maximum_distance=1.5, loop_search_maximum_distance=10.0, loop_match_minimum_chain_size=5,
                     loop_match_maximum_variance_coarse=9.0, loop_match_minimum_response_coarse=0.35,
