@@ -527,7 +527,7 @@ def bench_k2(pkg, local, quick=False):
         v = hb.stats()["cell_visits"] - v0
         out["hector_batched_maps"] = {"maps": Bm, "steps": steps - 3, "scans_per_s": Bm * (steps - 3) / dt, "cell_visits": v,
                                       "cells_per_s": v / dt, "ms_per_step": 1e3 * dt / (steps - 3),
-                                      "map_state_MB": Bm * 1000 * 1000 * 20 * (1 + 0.25 + 0.0625) / 1e6,
+                                      "map_state_MB": Bm * 1000 * 1000 * 32 * (1 + 0.25 + 0.0625) / 1e6,
                                       "note": "mapping only, given poses; scans already in HBM (b2s_hector_slam_update_batch_device)"}
         roof_row("hector_batched_maps", 2 * 8 * v, dt, "k_hs_mark + k_hs_apply", traffic_key="k_hs_batched_update", batch=Bm)
         hb.close()

@@ -52,8 +52,10 @@ constexpr unsigned HS_EPOCH_MAX = (1u << HS_EPOCH_BITS) - 1;
 constexpr int HS_STREAM_CTAS = 48;       // cooperative grid of the stream kernel (one CTA per SM, all co-resident)
 
 struct HsLevel {  // one MapRepMultiMap level, all B processors ([b][cells] planes)
-  float *prob;    // getGridProbability(cell), refreshed whenever a cell's log-odds changes: the device-side form of the
-                  // reference's per-scan GridMapCacheArray
+  float4 *quad;   // per cell (x, y): getGridProbability of the four cells (x, y), (x+1, y), (x, y+1), (x+1, y+1) — what one
+                  // bilinear look-up of the matcher reads — refreshed whenever a cell's log-odds changes (the device-side
+                  // form of the reference's per-scan GridMapCacheArray).  ONE 16-byte load per scan point instead of four
+                  // scattered 4-byte ones: the match's per-point phase was bound by L1 tag throughput (gathers)
   float *lo;
   int32_t *ui;
   uint32_t *free_st, *occ_st;  // per-scan stamps: (epoch << 12) | (4095 - beam)
@@ -115,7 +117,7 @@ struct HsFetch {
   float i0, i1, i2, i3, fx, fy;
   bool inside;
 };
-__device__ __forceinline__ HsFetch hs_fetch(const float *__restrict__ prob, int sx, int sy, float x, float y, bool l2) {
+__device__ __forceinline__ HsFetch hs_fetch(const float4 *__restrict__ quad, int sx, int sy, float x, float y, bool l2) {
   HsFetch f;
   const float lim_x = (float)sx - 2.0f, lim_y = (float)sy - 2.0f;  // setMapCellDims: dims - 2
   f.inside = !(x < 0.0f || x > lim_x || y < 0.0f || y > lim_y);
@@ -123,9 +125,9 @@ __device__ __forceinline__ HsFetch hs_fetch(const float *__restrict__ prob, int 
   if (f.inside) {
     const int ix = (int)x, iy = (int)y;
     f.fx = x - (float)ix; f.fy = y - (float)iy;
-    const float *c = prob + (iy * sx + ix);
-    if (l2) { f.i0 = __ldcg(c); f.i1 = __ldcg(c + 1); f.i2 = __ldcg(c + sx); f.i3 = __ldcg(c + sx + 1); }
-    else { f.i0 = c[0]; f.i1 = c[1]; f.i2 = c[sx]; f.i3 = c[sx + 1]; }
+    const float4 *c = quad + (iy * sx + ix);
+    const float4 q = l2 ? __ldcg(c) : *c;
+    f.i0 = q.x; f.i1 = q.y; f.i2 = q.z; f.i3 = q.w;
   }
   return f;
 }
@@ -168,7 +170,7 @@ __device__ inline bool hs_pose_difference_larger_than(const float a[3], const fl
 }
 
 // terms of one point for getCompleteHessianDerivs (OccGridMapUtil.h:99-126)
-__device__ __forceinline__ HsFetch hs_point_fetch(const float *__restrict__ prob, int sx, int sy, float2 p, float c, float s,
+__device__ __forceinline__ HsFetch hs_point_fetch(const float4 *__restrict__ prob, int sx, int sy, float2 p, float c, float s,
                                                   float e0, float e1, bool l2) {
   const float tx = (c * p.x + (-s) * p.y) + e0, ty = (s * p.x + c * p.y) + e1;
   return hs_fetch(prob, sx, sy, tx, ty, l2);
@@ -286,7 +288,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
     for (int l = 1; l < P.levels; l++) factor *= 0.5f;  // static_cast<float>(1.0 / pow(2.0, l)) is exactly 2^-l
     for (int lv = P.levels - 1; lv >= 0; lv--, factor *= 2.0f) {
       const HsLevel &m = P.l[lv];
-      const float *prob = m.prob + (size_t)b * m.sx * m.sy;
+      const float4 *prob = m.quad + (size_t)b * m.sx * m.sy;
       if (lv > 0)  // dataContainers[lv-1].setFrom(dataContainer, 2^-lv) (DataPointContainer.h:46-59): exact scaling
         for (int i = tid; i < n; i += HS_THREADS)
           reinterpret_cast<float2 *>(m.pts)[(size_t)b * P.cap + i] = make_float2(__fmul_rn(spts[i].x, factor), __fmul_rn(spts[i].y, factor));
@@ -569,6 +571,17 @@ __device__ unsigned long long hs_mark_pass(const HsBatch &P, int b, int w, int n
   return my_visits;
 }
 
+// the probability of cell (x, y) enters the quads of (x, y), (x-1, y), (x, y-1), (x-1, y-1)
+__device__ __forceinline__ void hs_publish_prob(float4 *__restrict__ quad, int sx, int x, int y, float p) {
+  float *q = reinterpret_cast<float *>(quad + (y * sx + x));
+  q[0] = p;
+  if (x > 0) q[-4 + 1] = p;
+  if (y > 0) {
+    q[-4 * sx + 2] = p;
+    if (x > 0) q[-4 * sx - 4 + 3] = p;
+  }
+}
+
 // PASS 2 (apply): a dense, coalesced sweep over each level's bounding box of the rays (work item = 128 consecutive
 // cells of a row: four 128-byte loads per stamp plane per warp).  A cell stamped in this epoch gets the reference's
 // update exactly once: end cells (occ stamp of this epoch; the stamp's winner is the lowest beam ending there) take
@@ -593,7 +606,8 @@ __device__ void hs_apply_pass(const HsBatch &P, int b, int w, int nw, int lane) 
     const HsLevel &m = P.l[lv];
     const size_t cells = (size_t)m.sx * m.sy;
     const uint32_t *fs = m.free_st + (size_t)b * cells, *os = m.occ_st + (size_t)b * cells;
-    float *lo = m.lo + (size_t)b * cells, *prob = m.prob + (size_t)b * cells;
+    float *lo = m.lo + (size_t)b * cells;
+    float4 *quad = m.quad + (size_t)b * cells;
     int32_t *ui = m.ui + (size_t)b * cells;
     const uint32_t ep = __ldcg(&st->epoch_hi[lv]) >> 12;
     const int mark_free = __ldcg(&st->mark_free[lv]), mark_occ = __ldcg(&st->mark_occ[lv]);
@@ -621,12 +635,12 @@ __device__ void hs_apply_pass(const HsBatch &P, int b, int w, int nw, int lane) 
         }
         if (v < 50.0f) v = __fadd_rn(v, P.lo_occ);
         lo[off] = v;
-        prob[off] = hs_prob_of(v);
+        hs_publish_prob(quad, m.sx, xb + 32 * q, y, hs_prob_of(v));
         ui[off] = mark_occ;
       } else if (f[q] != 0 && (f[q] >> 12) == ep) {  // bresenhamCellFree (:302-312)
         const float v = __fadd_rn(__ldcg(lo + off), P.lo_free);
         lo[off] = v;
-        prob[off] = hs_prob_of(v);
+        hs_publish_prob(quad, m.sx, xb + 32 * q, y, hs_prob_of(v));
         ui[off] = mark_free;
       }
     }
@@ -818,7 +832,7 @@ static b2s_status hs_clear_maps(b2s_hector_slam *p) {  // GridMapBase::reset -> 
     B2S_CUDA_CHECK(cudaMemsetAsync(m.ui, 0xff, cells * 4, p->stream));    // updateIndex -1
     B2S_CUDA_CHECK(cudaMemsetAsync(m.free_st, 0, cells * 4, p->stream));
     B2S_CUDA_CHECK(cudaMemsetAsync(m.occ_st, 0, cells * 4, p->stream));
-    k_hs_fill<<<ceil_div((long long)cells, 256), 256, 0, p->stream>>>(m.prob, cells, 0.5f);  // e^0 / (e^0 + 1)
+    k_hs_fill<<<ceil_div((long long)cells * 4, 256), 256, 0, p->stream>>>(reinterpret_cast<float *>(m.quad), cells * 4, 0.5f);  // e^0 / (e^0 + 1)
   }
   B2S_CUDA_CHECK(cudaGetLastError());
   return B2S_OK;
@@ -895,11 +909,13 @@ static b2s_status hs_create(float map_resolution, int map_size_x, int map_size_y
     m.wt_ty = -(i01 * m.tw_tx + m.wt_lin * m.tw_ty);
     m.iterations = 1 + (l == 0 ? 5 : 3);
     const size_t cells = (size_t)sx * sy * batch;
-    void **slots[5] = {(void **)&m.prob, (void **)&m.lo, (void **)&m.ui, (void **)&m.free_st, (void **)&m.occ_st};
+    void **slots[4] = {(void **)&m.lo, (void **)&m.ui, (void **)&m.free_st, (void **)&m.occ_st};
     for (void **s : slots) {
       HS_CHECK(cudaMalloc(s, cells * 4));
       p->allocs[p->n_allocs++] = *s;
     }
+    HS_CHECK(cudaMalloc(reinterpret_cast<void **>(&m.quad), cells * 16));
+    p->allocs[p->n_allocs++] = m.quad;
     HS_CHECK(cudaMalloc(reinterpret_cast<void **>(&m.pts), sizeof(float) * 2 * (size_t)max_points * batch));
     p->allocs[p->n_allocs++] = m.pts;
     sx /= 2; sy /= 2;
