@@ -201,13 +201,17 @@ struct HsTrig {
 // cache — 60-90 KB kernels with the double-precision sincos / fmod expansions inlined at every use ran 2x slower)
 __device__ __noinline__ HsTrig hs_trig(float angle, bool exact, bool use_fma) {
   HsTrig t;
-  glibc_sincosf(angle, use_fma, &t.s, &t.c);
   if (exact) {
+    glibc_sincosf(angle, use_fma, &t.s, &t.c);
     double ds, dc;
     sincos((double)angle, &ds, &dc);
     t.sin_rot = (float)ds;
     t.cos_rot = (float)dc;
-  } else {  // fast mode: the float sine / cosine stand in (they differ from the rounded double ones on ~1 % of angles, by one ulp)
+  } else {
+    // fast mode: the device's float sincosf for the Gauss-Newton iterations (an ulp in c / s moves a point 30 m out by
+    // 4e-5 cells).  The probability planes stay exact in both modes: the map gradient is a difference of nearly equal
+    // probabilities, where one ulp of exp() is amplified ~1000x.
+    sincosf(angle, &t.s, &t.c);
     t.sin_rot = t.s;
     t.cos_rot = t.c;
   }
