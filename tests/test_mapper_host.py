@@ -142,6 +142,59 @@ def test_pose_graph_solver_recovers_ring(pkg):
     g.close()
 
 
+def test_pose_graph_sparse_ldlt_reaches_the_least_squares_optimum(pkg):
+    """The sparse block LDL^T back end on a noisy multi-lap graph with loop closures (fill-in exercised: the minimum-degree
+    order has to eliminate through the loop edges): its final chi^2 equals the optimum scipy's trust-region least-squares
+    solver finds from the same start, and the poses agree to 1e-5."""
+    import ctypes as C
+    from scipy.optimize import least_squares
+    MP = pkg.load("mapper")
+    n, per_lap = 160, 40
+    th = np.arange(n) * 2 * np.pi / per_lap
+    truth = np.stack([4 * np.cos(th), 4 * np.sin(th), (th + np.pi / 2 + np.pi) % (2 * np.pi) - np.pi], 1)
+    rng = np.random.default_rng(7)
+
+    def rel(a, b):
+        c, sn = np.cos(a[2]), np.sin(a[2])
+        return np.array([c * (b[0] - a[0]) + sn * (b[1] - a[1]), -sn * (b[0] - a[0]) + c * (b[1] - a[1]),
+                         (b[2] - a[2] + np.pi) % (2 * np.pi) - np.pi])
+    guess = truth + np.concatenate([np.zeros((1, 3)), rng.normal(0, [0.05, 0.05, 0.02], (n - 1, 3))])
+    sig = np.array([0.02, 0.02, 0.005])
+    cons = []
+    for i in range(n):
+        for j in [i + 1, i + 2] + ([i - per_lap] if i >= per_lap and i % 3 == 0 else []):
+            if 0 <= j < n and j != i:
+                a, b = (i, j) if j > i else (j, i)
+                cons.append((a, b, rel(truth[a], truth[b]) + rng.normal(0, sig)))
+    g = MP.PoseGraph()
+    s = g.as_scan_solver()
+    dp = C.POINTER(C.c_double)
+    for i in range(n):
+        s.add_node(s.user, i, np.ascontiguousarray(guess[i]).ctypes.data_as(dp))
+    cov = np.ascontiguousarray(np.diag(sig ** 2).ravel())
+    for a, b, d in cons:
+        s.add_constraint(s.user, a, b, np.ascontiguousarray(d).ctypes.data_as(dp), cov.ctypes.data_as(dp))
+    ids, poses = np.zeros(n, np.int32), np.zeros((n, 3))
+    assert s.compute(s.user, n, ids.ctypes.data_as(C.POINTER(C.c_int32)), poses.ctypes.data_as(dp)) == n
+    st = g.stats()
+
+    def residuals(x):
+        P = np.concatenate([guess[:1], x.reshape(-1, 3)])
+        out = []
+        for a, b, d in cons:
+            e = rel(P[a], P[b]) - d
+            e[2] = (e[2] + np.pi) % (2 * np.pi) - np.pi
+            out.append(e / sig)
+        return np.concatenate(out)
+    opt = least_squares(residuals, guess[1:].ravel(), method="trf", xtol=1e-14, ftol=1e-14, gtol=1e-12)
+    chi_opt = float((opt.fun ** 2).sum())
+    assert st["chi2_after"] <= chi_opt * (1 + 1e-6) and st["chi2_after"] < 0.5 * st["chi2_before"]
+    d = poses[1:] - opt.x.reshape(-1, 3)
+    d[:, 2] = (d[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(d).max() < 1e-5
+    g.close()
+
+
 @live
 def test_mapper_with_dropouts(pkg):
     """1 % of the readings replaced by NaN / 0.0 (below min range): unfiltered points, barycenters and every decision
