@@ -359,6 +359,15 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
             float acc = 0.0f;
             const float *col = terms + lane * pitch;
             int i = 0;
+            for (; i + 32 <= n; i += 32) {  // eight 16-byte loads in flight ahead of the 32 dependent adds they feed
+              float4 t[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) t[j] = *reinterpret_cast<const float4 *>(col + i + 4 * j);
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                acc = __fadd_rn(acc, t[j].x); acc = __fadd_rn(acc, t[j].y); acc = __fadd_rn(acc, t[j].z); acc = __fadd_rn(acc, t[j].w);
+              }
+            }
             for (; i + 8 <= n; i += 8) {
               const float4 u = *reinterpret_cast<const float4 *>(col + i), w = *reinterpret_cast<const float4 *>(col + i + 4);
               acc = __fadd_rn(acc, u.x); acc = __fadd_rn(acc, u.y); acc = __fadd_rn(acc, u.z); acc = __fadd_rn(acc, u.w);
