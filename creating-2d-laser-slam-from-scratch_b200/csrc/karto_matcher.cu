@@ -26,6 +26,7 @@
 //   k_angular_cov      fine-stage angular covariance (re-evaluates GetResponse at the best cell)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -877,18 +878,14 @@ struct ReduceArgs {
   const double *tie_in;
 };
 
-// flags bit 2 (value 4): this match's tail already ran inside the sweep kernel (fused path)
-constexpr int32_t FLAG_REDUCED = 4;
 
-__device__ void reduce_match(const int b, const ReduceArgs &A);  // out-of-line copy of the tail for the fused option
-
-template <int STRIDE, bool GEN>
-__global__ void __launch_bounds__(WIN_THREADS, 1)
+template <int STRIDE, bool GEN, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
     k_sweep_window(const uint8_t *__restrict__ grids, size_t grid_pitch, int data_size, int copy_bytes,
                    const int32_t *__restrict__ lists, const int32_t *__restrict__ counts,
                    const int32_t *__restrict__ starts, const int32_t *__restrict__ flags, int batch, int n, int na,
                    int nx, int ny, int width_step, int32_t *__restrict__ sums, int *__restrict__ work_counter,
-                   int band_rows, int nbands, int band_bytes, int neg_bands, int fuse_tail, ReduceArgs RA) {
+                   int band_rows, int nbands, int band_bytes, int neg_bands) {
   // Grids larger than shared memory are swept in `nbands` row bands: a work unit is (match, band, 32-row candidate
   // tile); the image holds the rows that tile of a window whose ORIGIN lies in the band can touch (band_rows +
   // STRIDE * 31 + 2), k_offsets_sorted grouped the beams by the band of their origin (bands [0, neg_bands) hold origins
@@ -897,7 +894,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
   uint8_t *sgrid = smem;  // [WIN_GUARD zeros][band image][WIN_GUARD zeros]
   __shared__ uint64_t bar;
   __shared__ int s_unit, s_item;
-  __shared__ __align__(16) int32_t s_offsets[WIN_THREADS / 32][32];  // per-warp staging of 32 window origins
+  __shared__ __align__(16) int32_t s_offsets[THREADS / 32][32];  // per-warp staging of 32 window origins
 
   const int lane = threadIdx.x & 31;
   int32_t *s_off = s_offsets[threadIdx.x >> 5];
@@ -1016,13 +1013,6 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
       }
     }
     __syncthreads();  // everyone is done with sgrid before the next unit's copy is issued
-    if (fuse_tail) {
-      // The fp64 tail of CorrelateScan for THIS match, while its response volume (just written by this CTA) is still
-      // in L2: no separate k_reduce launch re-reads 700 MB from DRAM after the sweep.  (nbands == 1: a unit is a match.)
-      reduce_match(b, RA);
-      __syncthreads();
-      if (threadIdx.x == 0) RA.flags[b] = f | FLAG_REDUCED;
-    }
   }
 }
 
@@ -1032,8 +1022,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1)
 // (iy, ix, k) with linear index (iy*nx + ix)*na + k; ties are summed sequentially in that order when there are
 // at most RED_MAX_TIES of them (bit-identical to the reference), otherwise by a fixed-order tree.
 // ----------------------------------------------------------------------------------------------
-constexpr int RED_THREADS = 512;   // == WIN_THREADS: the sweep kernel's CTAs run the tail themselves (fused path)
-static_assert(RED_THREADS == WIN_THREADS, "the fused tail runs on the sweep kernel's CTA");
+constexpr int RED_THREADS = 512;
 // (stand-alone k_reduce: 60 registers, two CTAs per SM, so one match's serial tail overlaps another's streaming pass)
 constexpr int RED_MAX_TIES = 512;
 constexpr int RED_UNROLL = 8;
@@ -1389,10 +1378,7 @@ __device__ __forceinline__ void reduce_match_body(const int b, const ReduceArgs 
   res->tie_count = total;
 }
 
-__device__ __noinline__ void reduce_match(const int b, const ReduceArgs &A) { reduce_match_body(b, A); }
-
 __global__ void __launch_bounds__(RED_THREADS, 2) k_reduce(ReduceArgs A) {
-  if (A.flags[blockIdx.x] & FLAG_REDUCED) return;  // the sweep kernel already ran this match's tail
   reduce_match_body(blockIdx.x, A);
 }
 
@@ -1678,7 +1664,7 @@ b2s_status b2s_matcher_grid_info(const b2s_matcher *m, b2s_grid_info *out) {
 }
 
 b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which) {
-  if (!m || which < 0 || which > 4) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad kernel selector");
+  if (!m || which < 0 || which > 3) B2S_FAIL(B2S_ERR_BAD_PARAMS, "bad kernel selector");
   m->force_kernel = which;
   return B2S_OK;
 }
@@ -2239,7 +2225,7 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
   static size_t win_static = 0;
   if (!win_static) {
     cudaFuncAttributes fa;
-    B2S_CUDA_CHECK(cudaFuncGetAttributes(&fa, k_sweep_window<1, false>));
+    B2S_CUDA_CHECK(cudaFuncGetAttributes(&fa, k_sweep_window<1, false, WIN_THREADS>));
     win_static = fa.sharedSizeBytes;
   }
   const long long smem_limit = (long long)m->smem_optin - (long long)win_static - 512;
@@ -2263,9 +2249,9 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
                         (size_t)n * OFF_SMEM_PER_BEAM + 64 <= 200 * 1024 && !m->grid_high_bytes;
   bool use_window = win_fits;
   if (m->force_kernel == 1) use_window = false;
-  if (m->force_kernel >= 2 && m->force_kernel != 4 && !win_fits)
+  if (m->force_kernel >= 2 && !win_fits)
     B2S_FAIL(B2S_ERR_TOO_LARGE, "window kernel forced but not applicable to this lattice / grid / beam count");
-  if (m->force_kernel >= 2 && m->force_kernel != 4) use_window = true;
+  if (m->force_kernel >= 2) use_window = true;
   const bool need_plain_lut = !use_window || s->fine;  // generic sweep and the angular covariance read the plain table
   if (need_plain_lut && (st = ensure_cap(&m->d_lut, &m->lut_cap, (size_t)B * na * std::max(n, 1)))) return st;
 
@@ -2304,25 +2290,30 @@ static b2s_status run_correlate(b2s_matcher *m, const b2s_search *s, bool /*cent
     if (nbands > 1)  // bands accumulate with RED.ADD
       B2S_CUDA_CHECK(cudaMemsetAsync(m->d_sums, 0, sizeof(int32_t) * (size_t)B * na * ncell, m->stream));
     const int ctas = (int)std::min<long long>((long long)B * nbands * (nbands > 1 ? tiles_y_w : 1), m->num_sms);
-    // b2s_matcher_set_kernel(m, 4): the sweep CTA runs each match's fp64 tail itself right after its last tile (volume read
-    // back from L2, no k_reduce pass over DRAM).  Measured SLOWER on cfg 2 (8.80 -> 9.06 ms per 1024 matches): the
-    // sweep kernel owns its SM (127 registers x 512 threads), so the tail's serial stretches are no longer hidden by a
-    // second resident CTA as they are in the stand-alone k_reduce (two 512-thread CTAs per SM).  Kept as an option.
-    const bool fuse_tail = nbands == 1 && mode == 0 && m->force_kernel == 4;
+    // (A variant that ran each match's fp64 tail inside the sweep CTA right after its last tile — volume read back from
+    // L2, no k_reduce pass — was built, parity-tested and measured SLOWER on cfg 2, 8.80 -> 9.06 ms per 1024 matches: the
+    // sweep kernel owns its SM, so the tail's serial stretches are no longer hidden by a second resident CTA as they are
+    // in the stand-alone k_reduce.  Removed again)
     // the GEN = false instantiation assumes exactly two lanes per row-start bank (see win_load)
     const int bank_step = ((m->g.width_step >> 2) * std::max(stride, 1)) & 31;
     const bool gen = (bank_step & 3) != 2;
-    auto launch = [&](auto kern) -> b2s_status {
+    // tuning switch: B2S_WIN_THREADS=384 runs the sweep with 12 warps per SM (leaves registers for co-resident kernels)
+    static const int win_threads = [] { const char *e = getenv("B2S_WIN_THREADS"); return (e && atoi(e) == 384) ? 384 : WIN_THREADS; }();
+    auto launch = [&](auto kern, int threads) -> b2s_status {
       B2S_CUDA_CHECK(raise_dyn_smem(kern, win_smem));
-      kern<<<ctas, WIN_THREADS, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes, m->d_lists,
-                                                       m->d_counts, m->d_starts, m->d_flags, B, n, na, nx, ny,
-                                                       m->g.width_step, m->d_sums, m->d_work, band_rows, nbands,
-                                                       band_bytes, neg_bands, fuse_tail ? 1 : 0,
-                                                       reduce_args(m, *s, nx, ny, na, k_first, mode));
+      kern<<<ctas, threads, win_smem, m->stream>>>(m->d_grids, m->grid_pitch, m->g.data_size, copy_bytes, m->d_lists,
+                                                   m->d_counts, m->d_starts, m->d_flags, B, n, na, nx, ny,
+                                                   m->g.width_step, m->d_sums, m->d_work, band_rows, nbands,
+                                                   band_bytes, neg_bands);
       return B2S_OK;
     };
-    if (stride == 2) st = gen ? launch(k_sweep_window<2, true>) : launch(k_sweep_window<2, false>);
-    else st = gen ? launch(k_sweep_window<1, true>) : launch(k_sweep_window<1, false>);
+    if (win_threads == 384) {
+      if (stride == 2) st = gen ? launch(k_sweep_window<2, true, 384>, 384) : launch(k_sweep_window<2, false, 384>, 384);
+      else st = gen ? launch(k_sweep_window<1, true, 384>, 384) : launch(k_sweep_window<1, false, 384>, 384);
+    } else {
+      if (stride == 2) st = gen ? launch(k_sweep_window<2, true, WIN_THREADS>, WIN_THREADS) : launch(k_sweep_window<2, false, WIN_THREADS>, WIN_THREADS);
+      else st = gen ? launch(k_sweep_window<1, true, WIN_THREADS>, WIN_THREADS) : launch(k_sweep_window<1, false, WIN_THREADS>, WIN_THREADS);
+    }
     if (st) return st;
     // matches whose lattice is not the regular raster (a centre exactly on a rounding tie) fall through;
     // they compute their lookup values on the fly (no table was materialised for them)

@@ -210,8 +210,7 @@ b2s_status b2s_matcher_last_timing(b2s_matcher *m, double out[4]);
 b2s_status b2s_matcher_last_stats(b2s_matcher *m, double out[4]);
 b2s_status b2s_matcher_sync(b2s_matcher *m);
 /* 0 = automatic, 1 = force the generic global-memory gather kernel, 2 = force the shared-memory window kernel,
- * 3 = window kernel without dropping empty windows (every beam is swept), 4 = automatic with the fp64 tail of
- * CorrelateScan run inside the sweep kernel (an option kept for measurement: slower on cfg 2) */
+ * 3 = window kernel without dropping empty windows (every beam is swept) */
 b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which);
 
 /* ---------------------------------------------------------------- lesson6 front end: karto::Mapper / MapperGraph
