@@ -208,10 +208,10 @@ __device__ __noinline__ HsTrig hs_trig(float angle, bool exact, bool use_fma) {
     t.sin_rot = (float)ds;
     t.cos_rot = (float)dc;
   } else {
-    // fast mode: the device's float sincosf for the Gauss-Newton iterations (an ulp in c / s moves a point 30 m out by
-    // 4e-5 cells).  The probability planes stay exact in both modes: the map gradient is a difference of nearly equal
-    // probabilities, where one ulp of exp() is amplified ~1000x.
-    sincosf(angle, &t.s, &t.c);
+    // fast mode: the glibc-exact float sine / cosine also stand in for sinRot / cosRot (they differ from the rounded
+    // double ones on ~1 % of angles, by one ulp).  The device's own sincosf was tried here and broke the 1e-4 contract on
+    // one scan of the test stream: a few Gauss-Newton iterations amplify an ulp of the rotation noticeably.
+    glibc_sincosf(angle, use_fma, &t.s, &t.c);
     t.sin_rot = t.s;
     t.cos_rot = t.c;
   }
