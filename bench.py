@@ -446,6 +446,7 @@ def bench_k2(pkg, local, quick=False):
                        "stream = the whole recording in one b2s_hector_slam_process_stream call (no host round trip between "
                        "scans).  exact = bit-identical to the reference (sequential float32 sums: 14 x 1081 dependent adds per "
                        "scan); fast = tree sums, poses within 1e-4"}
+    stream_poses_by_mode = {}
     for exact in (True, False):
         tag = "exact" if exact else "fast"
         hs = H.HectorSlam(device=local, exact=exact, **kw)
@@ -471,6 +472,7 @@ def bench_k2(pkg, local, quick=False):
         p_all, u_all, _ = hs.process_stream(pts, (0, 0), first_hint=poses[0].astype(np.float32))
         dt = time.perf_counter() - t0
         st = hs.stats()
+        stream_poses_by_mode[tag] = p_all
         hstream[f"stream_{tag}"] = {"scans": n_stream, "scans_per_s": n_stream / dt, "us_per_scan": 1e6 * dt / n_stream,
                                     "map_updates": int(u_all.sum()), "cell_visits": st["cell_visits"],
                                     "cells_per_s": st["cell_visits"] / dt,
@@ -478,6 +480,10 @@ def bench_k2(pkg, local, quick=False):
                                     "h2d_bytes": int(sum(len(p) for p in pts) * 8), "d2h_bytes": n_stream * 64}
         hs.close()
     hstream["scans_per_s"] = hstream["stream_exact"]["scans_per_s"]
+    dpose = np.abs(stream_poses_by_mode["fast"] - stream_poses_by_mode["exact"])
+    dpose[:, 2] = np.abs((dpose[:, 2] + np.pi) % (2 * np.pi) - np.pi)
+    hstream["fast_vs_exact_max_abs_pose_diff"] = {"xy_m": float(dpose[:, :2].max()), "theta_rad": float(dpose[:, 2].max()),
+                                                  "note": "self-driven streams (each mode feeds its own poses back as hints)"}
     out["hector_stream"] = hstream
     stream_ranges, stream_poses = ranges, poses  # reused by the PL-ICP odometry stream below
     # every-scan mapping (gate off): the K2a update rate of ONE map (L2-resident)
