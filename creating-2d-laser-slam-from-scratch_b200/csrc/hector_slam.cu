@@ -524,7 +524,10 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
 #undef HS_PROF
 }
 
-// the update parameters of one level as the gate wrote them; L2 loads (other SMs wrote them during THIS launch)
+// the update parameters of one level as the gate wrote them.  Plain (L1) loads: within the persistent launch every CTA
+// passes the grid barrier between the gate's writes and these reads, and the barrier's gpu-scope acquire drops the SM's
+// L1 (CCTL.IVALL); in the batch path a kernel boundary lies in between.  (With L2 loads the ~dozen dependent state reads
+// at the head of every warp were 47 % of k_hs_apply's stall samples.)
 struct HsUpd {
   int n;
   float c, s, mx, my;
@@ -534,11 +537,11 @@ struct HsUpd {
 };
 __device__ __forceinline__ HsUpd hs_load_upd(const HsState *st, int lv) {
   HsUpd u;
-  u.n = __ldcg(&st->n_pts[lv]);
-  u.c = __ldcg(&st->uc[lv]); u.s = __ldcg(&st->us[lv]); u.mx = __ldcg(&st->umx[lv]); u.my = __ldcg(&st->umy[lv]);
-  u.bx = __ldcg(&st->bx[lv]); u.by = __ldcg(&st->by[lv]);
-  u.ehi = __ldcg(&st->epoch_hi[lv]);
-  u.mark_free = __ldcg(&st->mark_free[lv]); u.mark_occ = __ldcg(&st->mark_occ[lv]);
+  u.n = st->n_pts[lv];
+  u.c = st->uc[lv]; u.s = st->us[lv]; u.mx = st->umx[lv]; u.my = st->umy[lv];
+  u.bx = st->bx[lv]; u.by = st->by[lv];
+  u.ehi = st->epoch_hi[lv];
+  u.mark_free = st->mark_free[lv]; u.mark_occ = st->mark_occ[lv];
   return u;
 }
 
@@ -555,7 +558,7 @@ __device__ unsigned long long hs_mark_pass(const HsBatch &P, int b, int w, int n
   unsigned long long my_visits = 0;
   int first[HS_L + 1];
   first[0] = 0;
-  for (int lv = 0; lv < P.levels; lv++) first[lv + 1] = first[lv] + __ldcg(&st->n_pts[lv]);
+  for (int lv = 0; lv < P.levels; lv++) first[lv + 1] = first[lv] + st->n_pts[lv];
   int lv = 0;
   HsUpd u = hs_load_upd(st, 0);
   for (int j = w; j < first[P.levels]; j += nw) {
@@ -606,9 +609,9 @@ __device__ void hs_apply_pass(const HsBatch &P, int b, int w, int nw, int lane) 
   int first[HS_L + 1], x0[HS_L], y0[HS_L], x1[HS_L], chunks[HS_L];
   first[0] = 0;
   for (int lv = 0; lv < P.levels; lv++) {
-    x0[lv] = __ldcg(&st->bb_x0[lv]); y0[lv] = __ldcg(&st->bb_y0[lv]);
-    x1[lv] = __ldcg(&st->bb_x1[lv]);
-    const int y1 = __ldcg(&st->bb_y1[lv]);
+    x0[lv] = st->bb_x0[lv]; y0[lv] = st->bb_y0[lv];
+    x1[lv] = st->bb_x1[lv];
+    const int y1 = st->bb_y1[lv];
     const bool any = x1[lv] >= x0[lv] && y1 >= y0[lv];
     chunks[lv] = any ? (x1[lv] - x0[lv] + 128) / 128 : 0;
     first[lv + 1] = first[lv] + (any ? (y1 - y0[lv] + 1) * chunks[lv] : 0);
@@ -622,8 +625,8 @@ __device__ void hs_apply_pass(const HsBatch &P, int b, int w, int nw, int lane) 
     float *lo = m.lo + (size_t)b * cells;
     float4 *quad = m.quad + (size_t)b * cells;
     int32_t *ui = m.ui + (size_t)b * cells;
-    const uint32_t ep = __ldcg(&st->epoch_hi[lv]) >> 12;
-    const int mark_free = __ldcg(&st->mark_free[lv]), mark_occ = __ldcg(&st->mark_occ[lv]);
+    const uint32_t ep = st->epoch_hi[lv] >> 12;
+    const int mark_free = st->mark_free[lv], mark_occ = st->mark_occ[lv];
     const int r = j - first[lv];
     const int y = y0[lv] + r / chunks[lv];
     const int xb = x0[lv] + (r % chunks[lv]) * 128 + lane;
