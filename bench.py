@@ -387,11 +387,14 @@ def bench_k2(pkg, local, quick=False):
                      "note": "A2 = 2 x cell bytes x V; single resident maps sit in L2 (atomic-throughput bound), the "
                              "batched Hector case streams B maps larger than L2 through HBM"}
 
-    def roof_row(name, a2_bytes, seconds, kernel, traffic_key=None, batch=None):
+    def roof_row(name, a2_bytes, seconds, kernel, traffic_key=None, batch=None, launches=None):
         ach = a2_bytes / seconds / 1e9
         tr, src = committed_traffic(traffic_key or kernel, batch)
         roof[name] = {"kernel": kernel, "achieved": ach, "frac": ach / peak, "algorithmic_bytes": a2_bytes,
                       "seconds": seconds, "traffic": tr, "traffic_source": src}
+        if tr and launches:  # DRAM bytes per launch (ncu) x launches in the timed region / time: the physical HBM fraction
+            roof[name]["dram_GBps_from_traffic"] = tr * launches / seconds / 1e9
+            roof[name]["dram_frac_from_traffic"] = tr * launches / seconds / 1e9 / peak
 
     # --- K2c: OccupancyGrid::CreateFromScans over a 2000-scan trajectory (what SlamKarto::updateMap rebuilds)
     n_scans = 400 if quick else 2000
@@ -419,7 +422,7 @@ def bench_k2(pkg, local, quick=False):
         "cells_per_s_kernel": visits / ray, "cells_per_s_e2e": visits / wall, "scans_per_s_e2e": n_scans / wall,
         "raytrace_ms": ray * 1e3, "e2e_ms": wall * 1e3,
         "achieved_GBps": 2 * 4 * visits / ray / 1e9}
-    roof_row("karto_occupancy_grid", 2 * 4 * visits, ray, "k_raytrace", batch=n_scans)
+    roof_row("karto_occupancy_grid", 2 * 4 * visits, ray, "k_raytrace", batch=n_scans, launches=1)
     try:  # the reference's own OccupancyGrid::CreateFromScans on a 70-scan sample (survey probe shape), 1 thread
         from oracle import ref
         if ref.available(ndebug=True):
@@ -535,7 +538,7 @@ def bench_k2(pkg, local, quick=False):
                                       "cells_per_s": v / dt, "ms_per_step": 1e3 * dt / (steps - 3),
                                       "map_state_MB": Bm * 1000 * 1000 * 32 * (1 + 0.25 + 0.0625) / 1e6,
                                       "note": "mapping only, given poses; scans already in HBM (b2s_hector_slam_update_batch_device)"}
-        roof_row("hector_batched_maps", 2 * 8 * v, dt, "k_hs_mark + k_hs_apply", traffic_key="k_hs_batched_update", batch=Bm)
+        roof_row("hector_batched_maps", 2 * 8 * v, dt, "k_hs_mark + k_hs_apply", traffic_key="k_hs_batched_update", batch=Bm, launches=steps - 3)
         hb.close()
         # the same B maps fed from a 44 m x 44 m hall (rays up to 30 m): every update sweeps most of the 1000^2 map, so the
         # cell state (B x 26 MB) streams through HBM instead of sitting in L2
@@ -563,7 +566,7 @@ def bench_k2(pkg, local, quick=False):
         out["hector_batched_maps_hall"] = {"maps": Bm, "steps": steps - 3, "scans_per_s": Bm * (steps - 3) / dt, "cell_visits": v,
                                            "cells_per_s": v / dt, "ms_per_step": 1e3 * dt / (steps - 3),
                                            "note": "44 m x 44 m hall, 30 m rays: the swept region of every map is ~800 x 800 cells"}
-        roof_row("hector_batched_maps_hall", 2 * 8 * v, dt, "k_hs_mark + k_hs_apply", traffic_key="k_hs_batched_update_hall", batch=Bm)
+        roof_row("hector_batched_maps_hall", 2 * 8 * v, dt, "k_hs_mark + k_hs_apply", traffic_key="k_hs_batched_update_hall", batch=Bm, launches=steps - 3)
         # the same handle as B SLAM processors (match + gate + update per step)
         hb.close()
         hb = H.HectorSlam(device=local, batch=Bm, max_points=cap, **kw)
@@ -661,16 +664,12 @@ def bench_k2(pkg, local, quick=False):
         out["k1_extras_error"] = repr(e)
     # --- lesson6 front end: karto::Mapper::Process per key frame through b2s_mapper_process with the
     #     shipped indoor yaml (lesson6/config/mapper_params.yaml: 0.3 m / 0.01 m sequential window on a 2431^2 grid,
-    #     110-scan running buffer, 10 m / 0.05 m loop window, response expansion on); near chains / loop candidates batched
+    #     110-scan running buffer, 10 m / 0.05 m loop window, response expansion on); near chains / loop candidates batched.
+    #     Two streams: laps of a 2 m circle in the small room (no loop candidates: every scan stays near-linked), and two
+    #     laps of a 9 m circle in a 28 m x 24 m hall, where the second lap meets the first as loop-closure candidates.
     try:
         MPm = pkg.load("mapper")
         lm = synth.Laser(range_threshold=12.0)
-        n_map = 120 if quick else 520
-        # a 9 m-radius lap in a 28 m x 24 m hall (226 key frames per lap): the second lap meets the first one's scans as
-        # loop-closure candidates (not near-linked: link distance 1.5 m), so TryCloseLoop runs its batched matches
-        _, tru, odo, rng_m = synth.make_loop_trajectory(17, n_map, lm, radius=2.0 if quick else 9.0, step=0.25,
-                                                        half_w=8.0 if quick else 14.0, half_h=6.0 if quick else 12.0,
-                                                        n_boxes=6 if quick else 12)
         yaml = dict(scan_buffer_size=110, scan_buffer_maximum_scan_distance=100.0, link_match_minimum_response_fine=0.1,
                     link_scan_maximum_distance=1.5, loop_search_maximum_distance=10.0, loop_match_minimum_chain_size=5,
                     loop_match_maximum_variance_coarse=9.0, loop_match_minimum_response_coarse=0.35,
@@ -679,35 +678,46 @@ def bench_k2(pkg, local, quick=False):
                     both_fine_search_angle_offset=0.00349, both_coarse_search_angle_offset=0.349,
                     both_coarse_angle_resolution=0.0349, both_use_response_expansion=1)
         prm = MPm.default_params(12.0, **yaml)
-        mp_ = MPm.Mapper(prm, abi.laser_from(lm), device=local)
-        n_warm = 30  # the first frames create the matcher handles (device + pinned allocations, ~0.2-1.5 s once per mapper)
-        for i in range(n_warm):
-            mp_.process(rng_m[i], odo[i], 0.1 * i)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(n_warm, n_map):
-            mp_.process(rng_m[i], odo[i], 0.1 * i)
-        dt = time.perf_counter() - t0
-        stm = mp_.stats()
-        out["karto_mapper_stream"] = {"key_frames": n_map - n_warm, "scans_per_s": (n_map - n_warm) / dt, "ms_per_scan": 1e3 * dt / (n_map - n_warm),
-                                      "untimed_first_frames": n_warm,
-                                      "match_scan_calls": stm["match_calls"], "device_batches": stm["batches"],
-                                      "loop_candidates": stm["loop_candidates"],
-                                      "loops_closed": stm["loops_closed"], "edges": int(len(mp_.edges()[0])),
-                                      "max_xy_err_m": float(np.abs(mp_.poses()[:, :2] - tru[:, :2]).max()),
-                                      "config": "lesson6/config/mapper_params.yaml (no back end), 1081 beams, range threshold 12 m"}
-        mp_.close()
         from oracle import ref as _ref
-        if _ref.available(ndebug=True):
-            n_ref = min(n_map, 150)
-            rm = _ref.RefMapper(prm, lm, ndebug=True)
+        for key, n_map, traj, n_ref in (
+                ("karto_mapper_stream", 120 if quick else 400, dict(radius=2.0, step=0.25), 150),
+                ("karto_mapper_stream_loops", 120 if quick else 520,
+                 dict(radius=2.0, step=0.25) if quick else dict(radius=9.0, step=0.25, half_w=14.0, half_h=12.0, n_boxes=12), 520)):
+            _, tru, odo, rng_m = synth.make_loop_trajectory(17, n_map, lm, **traj)
+            mp_ = MPm.Mapper(prm, abi.laser_from(lm), device=local)
+            n_warm = 30  # the first frames create the matcher handles (device + pinned allocations, ~0.2-1.5 s once per mapper)
+            for i in range(n_warm):
+                mp_.process(rng_m[i], odo[i], 0.1 * i)
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for i in range(n_ref):
-                rm.process(rng_m[i], odo[i], 0.1 * i)
+            for i in range(n_warm, n_map):
+                mp_.process(rng_m[i], odo[i], 0.1 * i)
             dt = time.perf_counter() - t0
-            rm.close()
-            out["karto_mapper_stream"]["cpu_reference"] = {"scans_per_s": n_ref / dt, "sample": f"first {n_ref} key frames of the same "
-                                                           "stream, karto::Mapper::Process, -O2 -DNDEBUG, 1 thread"}
+            stm = mp_.stats()
+            out[key] = {"key_frames": n_map - n_warm, "scans_per_s": (n_map - n_warm) / dt, "ms_per_scan": 1e3 * dt / (n_map - n_warm),
+                        "untimed_first_frames": n_warm, "match_scan_calls": stm["match_calls"], "device_batches": stm["batches"],
+                        "loop_candidates": stm["loop_candidates"], "loops_closed": stm["loops_closed"],
+                        "edges": int(len(mp_.edges()[0])),
+                        "max_xy_err_m": float(np.abs(mp_.poses()[:, :2] - tru[:, :2]).max()),
+                        "config": "lesson6/config/mapper_params.yaml (no back end), 1081 beams, range threshold 12 m; " + repr(traj)}
+            mp_.close()
+            if _ref.available(ndebug=True):  # the reference Mapper on the SAME frames (the timed ones included)
+                n_r = min(n_map, n_ref)
+                rm = _ref.RefMapper(prm, lm, ndebug=True)
+                for i in range(min(n_warm, n_r)):
+                    rm.process(rng_m[i], odo[i], 0.1 * i)
+                t0 = time.perf_counter()
+                done = 0
+                for i in range(n_warm, n_r):
+                    rm.process(rng_m[i], odo[i], 0.1 * i)
+                    done += 1
+                    if time.perf_counter() - t0 > 90.0:
+                        break
+                dt = time.perf_counter() - t0
+                rm.close()
+                out[key]["cpu_reference"] = {"scans_per_s": done / dt, "key_frames": done,
+                                             "sample": f"key frames {n_warm}..{n_warm + done} of the same stream, karto::Mapper::Process, "
+                                                       "-O2 -DNDEBUG, 1 thread (capped at 90 s)"}
     except Exception as e:
         out["karto_mapper_stream"] = {"error": repr(e)}
     # --- K3 (lesson3): batched PL-ICP, 1024 independent scan pairs with odometry-like motion
