@@ -1134,7 +1134,9 @@ def workload_cfg5(ctx, args):
                 br[b, :nb[b]] = br_all[f:f + nb[b]]; bp[b, :nb[b]] = bp_all[f:f + nb[b]]
                 br[b, nb[b]:] = br_all[f]; bp[b, nb[b]:] = bp_all[f]  # pad by repeating a base scan (max-stamp: no change)
                 if which == 1 and rank_log[0]:
-                    jobs.append((r[b].copy(), p[b].copy(), br_all[f:f + nb[b]].copy(), bp_all[f:f + nb[b]].copy()))
+                    seen[0] += 1
+                    if len(jobs) < 1024:  # the replay set is bounded (each chain carries up to ~0.7 MB of readings)
+                        jobs.append((r[b].copy(), p[b].copy(), br_all[f:f + nb[b]].copy(), bp_all[f:f + nb[b]].copy()))
             out = h.match_scan_host(r, p, br, bp, bool(do_pen), bool(do_ref))
             for b in range(batch):
                 cv = out[2][b]
@@ -1157,6 +1159,7 @@ def workload_cfg5(ctx, args):
 
     rank_log = [True]
     conditioned = [0]
+    seen = [0]
     pg = MPm.PoseGraph(lm_iterations=40, cg_iterations=400)
     mapper = MPm.Mapper(prm, al, device=local, match_fn=match_fn)
     mapper.set_scan_solver(pg.as_scan_solver())
@@ -1203,7 +1206,7 @@ def workload_cfg5(ctx, args):
         sweep = hl.last_timing()["sweep_ms"]
         accepted = int(sum(((o[0] > prm.loop_match_minimum_response_coarse) & (o[3] == 0)).sum() for o in results))
         value = len(jobs) * done / (ms_max * 1e-3)
-        row = {"candidate_chains": len(jobs), "chains_this_rank": nj, "max_chain": mxb, "batch": Bc,
+        row = {"candidate_chains": len(jobs), "candidate_chains_seen_by_the_mapper": seen[0], "chains_this_rank": nj, "max_chain": mxb, "batch": Bc,
                "coarse_accepted_this_rank": accepted, "per_rank_ms_per_step": [x / done for x in per_rank],
                "path": hl.last_timing()["path"]}
         hl.close()
