@@ -24,6 +24,7 @@
 #include <list>
 #include <new>
 #include <queue>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -136,7 +137,9 @@ struct MScan {
   std::vector<double> ranges;
   P3 odom, corrected, sensor, bary;
   double time = 0;
-  int id = -1;
+  int id = -1;      // unique id (MapperSensorManager::m_NextScanId): index into b2s_mapper::scans
+  int dev = 0;      // index into b2s_mapper::sensors
+  int state = -1;   // state id: index into that sensor's scan list (ScanManager::AddScan, Mapper.h:1290-1303)
   std::vector<int> edges;  // Vertex::m_Edges: indices into Mapper::edges, in insertion order
 };
 
@@ -144,6 +147,13 @@ struct MEdge {
   int src, dst;
   P3 pose1, pose2, diff;
   M3 cov;
+};
+
+struct SensorState {  // one ScanManager (Mapper.h:1265-1410): the scans, running window and last scan of one sensor
+  std::string name;
+  std::vector<int> ids;      // ScanManager::m_Scans as unique ids, indexed by state id
+  std::vector<int> running;  // ScanManager::m_RunningScans
+  int last_scan = -1;        // ScanManager::m_pLastScan
 };
 
 struct CudaBackend {  // the two ScanMatcher instances a Mapper owns, as b2s_matcher handles
@@ -180,10 +190,11 @@ struct b2s_mapper {
   CudaBackend *cuda = nullptr;
   b2s_scan_solver solver{};
   bool have_solver = false;
-  std::deque<MScan> scans;  // MapperSensorManager scans of the one sensor; deque: stable addresses
+  std::deque<MScan> scans;  // MapperSensorManager::m_Scans (every sensor's scans by unique id); deque: stable addresses
   std::vector<MEdge> edges;
-  std::vector<int> running;  // ScanManager::m_RunningScans
-  int last_scan = -1;        // ScanManager::m_pLastScan
+  std::vector<SensorState> sensors;  // in registration order
+  std::vector<int> by_name;          // sensor indices in the order of std::map<Name, ScanManager*> (Name::operator<, Karto.h:484)
+  int last_sensor = 0;
   double n_match_calls = 0, n_batches = 0, n_loop_candidates = 0, n_loops_closed = 0;
 };
 
@@ -460,14 +471,17 @@ std::vector<std::vector<int>> find_near_chains(const b2s_mapper *m, int scan) {
   std::vector<char> processed(m->scans.size(), 0);
   const std::vector<int> near = find_near_linked_scans(m, scan, m->prm.link_scan_maximum_distance);
   const double lim = sq(m->prm.link_scan_maximum_distance) + KT_TOLERANCE;
-  const int n_scans = (int)m->scans.size();
   for (int near_id : near) {
     if (near_id == scan) continue;
     if (processed[near_id]) continue;
     processed[near_id] = 1;
     bool valid = true;
     std::list<int> chain;
-    for (int c = near_id - 1; c >= 0; c--) {
+    // the chain grows along the state ids of the NEAR scan's own sensor (Mapper.cpp:1208-1262)
+    const std::vector<int> &ids = m->sensors[m->scans[near_id].dev].ids;
+    const int st = m->scans[near_id].state, n_scans = (int)ids.size();
+    for (int cs = st - 1; cs >= 0; cs--) {
+      const int c = ids[cs];
       if (c == scan) valid = false;
       if (sqdist(scan_pose, ref_pose(m, m->scans[c])) < lim) {
         chain.push_front(c);
@@ -477,7 +491,8 @@ std::vector<std::vector<int>> find_near_chains(const b2s_mapper *m, int scan) {
       }
     }
     chain.push_back(near_id);
-    for (int c = near_id + 1; c < n_scans; c++) {
+    for (int cs = st + 1; cs < n_scans; cs++) {
+      const int c = ids[cs];
       if (c == scan) valid = false;
       if (sqdist(scan_pose, ref_pose(m, m->scans[c])) < lim) {
         chain.push_back(c);
@@ -555,17 +570,44 @@ b2s_status link_near_chains(b2s_mapper *m, int scan, std::vector<P3> &means, std
   return B2S_OK;
 }
 
-// MapperGraph::AddEdges (Mapper.cpp:902-973), one sensor
+// MapperGraph::AddEdges (Mapper.cpp:902-973)
 b2s_status add_edges(b2s_mapper *m, int scan, const M3 &cov) {
-  const bool have_last = m->last_scan >= 0;
-  if (have_last) link_scans(m, scan - 1, scan, m->scans[scan].sensor, cov);
+  const int sensor = m->scans[scan].dev;
+  const SensorState &S = m->sensors[sensor];
+  const bool have_last = S.last_scan >= 0;
+  if (have_last) link_scans(m, S.ids[m->scans[scan].state - 1], scan, m->scans[scan].sensor, cov);
   std::vector<P3> means;
   std::vector<M3> covs;
   if (have_last) {
     const P3 scan_pose = m->scans[scan].sensor;
     means.push_back(scan_pose);
     covs.push_back(cov);
-    link_chain_to_scan(m, m->running, scan, scan_pose, cov);
+    link_chain_to_scan(m, S.running, scan, scan_pose, cov);
+  } else {
+    // a sensor's first scan is matched against ALL scans of every other sensor (in name order) and linked to that
+    // sensor's first scan whatever the response (Mapper.cpp:920-952); the matches do not depend on each other
+    std::vector<MatchJob> jobs;
+    std::vector<int> firsts;
+    for (int other : m->by_name) {
+      if (other == sensor || m->sensors[other].ids.empty()) continue;
+      jobs.push_back(MatchJob{m->scans[scan].corrected, &m->scans[scan].ranges, m->sensors[other].ids});
+      firsts.push_back(m->sensors[other].ids[0]);
+    }
+    if (!jobs.empty()) {
+      std::vector<b2s_match_result> res;
+      b2s_status st = run_matches(m, 0, jobs, true, true, res);
+      if (st) return st;
+      for (size_t j = 0; j < jobs.size(); j++) {
+        if (res[j].status) B2S_FAIL((b2s_status)res[j].status, "mapper: first-scan MatchScan against another sensor failed");
+        const P3 best = p3(res[j].pose);
+        const M3 c = cov_of(res[j]);
+        link_scans(m, firsts[j], scan, best, c);
+        if (res[j].response > m->prm.link_match_minimum_response_fine) {
+          means.push_back(best);
+          covs.push_back(c);
+        }
+      }
+    }
   }
   b2s_status st = link_near_chains(m, scan, means, covs);
   if (st) return st;
@@ -580,27 +622,30 @@ b2s_status add_edges(b2s_mapper *m, int scan, const M3 &cov) {
 
 // ScanManager::AddRunningScan (Mapper.h:1365-1386)
 void add_running_scan(b2s_mapper *m, int scan) {
-  m->running.push_back(scan);
-  auto d = [&]() { return sqdist(m->scans[m->running.front()].sensor, m->scans[m->running.back()].sensor); };
+  std::vector<int> &running = m->sensors[m->scans[scan].dev].running;
+  running.push_back(scan);
+  auto d = [&]() { return sqdist(m->scans[running.front()].sensor, m->scans[running.back()].sensor); };
   double sd = d();
-  while (m->running.size() > (size_t)m->prm.scan_buffer_size ||
+  while (running.size() > (size_t)m->prm.scan_buffer_size ||
          sd > sq(m->prm.scan_buffer_maximum_scan_distance) - KT_TOLERANCE) {
-    m->running.erase(m->running.begin());
+    running.erase(running.begin());
     sd = d();
   }
 }
 
 // MapperGraph::FindPossibleLoopClosure (Mapper.cpp:1333-1394)
-std::vector<int> find_possible_loop_closure(const b2s_mapper *m, int scan, const std::vector<char> &near_linked,
+std::vector<int> find_possible_loop_closure(const b2s_mapper *m, int scan, int sensor, const std::vector<char> &near_linked,
                                             unsigned &start) {
   std::vector<int> chain;
   const P3 pose = ref_pose(m, m->scans[scan]);
-  const unsigned n_scans = (unsigned)m->scans.size();
+  const std::vector<int> &ids = m->sensors[sensor].ids;  // the candidate sensor's scans, by state id
+  const unsigned n_scans = (unsigned)ids.size();
   const double lim = sq(m->prm.loop_search_maximum_distance) + KT_TOLERANCE;
   for (; start < n_scans; start++) {
-    if (sqdist(ref_pose(m, m->scans[start]), pose) < lim) {
-      if (near_linked[start]) chain.clear();
-      else chain.push_back((int)start);
+    const int id = ids[start];
+    if (sqdist(ref_pose(m, m->scans[id]), pose) < lim) {
+      if (near_linked[id]) chain.clear();
+      else chain.push_back(id);
     } else {
       if (chain.size() >= (size_t)m->prm.loop_match_minimum_chain_size) return chain;
       chain.clear();
@@ -625,7 +670,7 @@ void correct_poses(b2s_mapper *m) {
 // coarse matches of successive candidates are independent until a loop is actually closed (which moves the scan and,
 // with a solver, every pose), so all candidates that the CURRENT state yields are matched as one batch and then
 // walked in order; after an accepted closure the remaining candidates are re-enumerated from the new state.
-b2s_status try_close_loop(b2s_mapper *m, int scan) {
+b2s_status try_close_loop(b2s_mapper *m, int scan, int sensor) {
   unsigned scan_index = 0;
   for (;;) {
     std::vector<char> near_linked(m->scans.size(), 0);
@@ -633,7 +678,7 @@ b2s_status try_close_loop(b2s_mapper *m, int scan) {
     std::vector<std::vector<int>> chains;
     std::vector<unsigned> index_after;
     for (unsigned idx = scan_index;;) {
-      std::vector<int> chain = find_possible_loop_closure(m, scan, near_linked, idx);
+      std::vector<int> chain = find_possible_loop_closure(m, scan, sensor, near_linked, idx);
       if (chain.empty()) break;
       chains.push_back(std::move(chain));
       index_after.push_back(idx);
@@ -793,24 +838,43 @@ b2s_status b2s_mapper_set_scan_solver(b2s_mapper *m, const b2s_scan_solver *solv
 
 b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double odometric_pose[3], double time,
                               int32_t *out_processed, double out_corrected_pose[3]) {
+  return b2s_mapper_process_sensor(m, "laser", ranges, odometric_pose, time, out_processed, out_corrected_pose);
+}
+
+b2s_status b2s_mapper_process_sensor(b2s_mapper *m, const char *sensor_name, const double *ranges,
+                                     const double odometric_pose[3], double time, int32_t *out_processed,
+                                     double out_corrected_pose[3]) {
   B2S_NVTX("Mapper::Process");
-  if (!m || !ranges || !odometric_pose) B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_mapper_process: null argument");
+  if (!m || !ranges || !odometric_pose || !sensor_name) B2S_FAIL(B2S_ERR_BAD_PARAMS, "b2s_mapper_process: null argument");
   if (out_processed) *out_processed = 0;
   if (m->failed)
     B2S_FAIL(B2S_ERR_BAD_STATE, "b2s_mapper_process: an earlier call failed half-way (the reference aborts there); destroy the handle");
+  // MapperSensorManager::GetLastScan registers an unknown sensor (Mapper.h:1470-1475, Mapper.cpp:45-52)
+  int sensor = -1;
+  for (size_t i = 0; i < m->sensors.size(); i++)
+    if (m->sensors[i].name == sensor_name) sensor = (int)i;
+  if (sensor < 0) {
+    sensor = (int)m->sensors.size();
+    m->sensors.emplace_back();
+    m->sensors.back().name = sensor_name;
+    m->by_name.push_back(sensor);
+    std::sort(m->by_name.begin(), m->by_name.end(), [&](int a, int b) { return m->sensors[a].name < m->sensors[b].name; });
+  }
+  m->last_sensor = sensor;
   MScan scan;
+  scan.dev = sensor;
   scan.ranges.assign(ranges, ranges + m->laser.n_readings);
   scan.odom = p3(odometric_pose);
   scan.corrected = scan.odom;  // karto_slam.cc:437-440 sets both poses from odometry before Process
   scan.time = time;
-  const MScan *last = m->last_scan >= 0 ? &m->scans[m->last_scan] : nullptr;
+  const MScan *last = m->sensors[sensor].last_scan >= 0 ? &m->scans[m->sensors[sensor].last_scan] : nullptr;
   if (last) scan.corrected = Xform(last->odom, last->corrected).apply(scan.odom);  // Mapper.cpp:2021-2026
   if (out_corrected_pose) { out_corrected_pose[0] = scan.corrected.x; out_corrected_pose[1] = scan.corrected.y; out_corrected_pose[2] = scan.corrected.h; }
   if (!has_moved_enough(m, scan, last)) return B2S_OK;
   scan_update(m, scan);
   M3 cov = M3::identity();
   if (m->prm.use_scan_matching && last) {
-    std::vector<MatchJob> job{MatchJob{scan.corrected, &scan.ranges, m->running}};
+    std::vector<MatchJob> job{MatchJob{scan.corrected, &scan.ranges, m->sensors[sensor].running}};
     std::vector<b2s_match_result> res;
     b2s_status st = run_matches(m, 0, job, true, true, res);
     if (st) return st;
@@ -818,9 +882,11 @@ b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double 
     cov = cov_of(res[0]);
     set_sensor_pose(m, scan, p3(res[0].pose));
   }
-  scan.id = (int)m->scans.size();  // ScanManager::AddScan: state id == unique id with one sensor
+  scan.id = (int)m->scans.size();                    // MapperSensorManager::AddScan (Mapper.cpp:75-80): unique id
+  scan.state = (int)m->sensors[sensor].ids.size();   // ScanManager::AddScan: state id within the sensor
   m->scans.push_back(std::move(scan));
   const int id = (int)m->scans.size() - 1;
+  m->sensors[sensor].ids.push_back(id);
   if (m->prm.use_scan_matching) {
     if (m->have_solver && m->solver.add_node) {  // MapperGraph::AddVertex -> ScanSolver::AddNode
       const MScan &s = m->scans[id];
@@ -833,11 +899,13 @@ b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double 
     if (st) { m->failed = true; return st; }
     add_running_scan(m, id);
     if (m->prm.do_loop_closing) {
-      st = try_close_loop(m, id);
-      if (st) { m->failed = true; return st; }
+      for (size_t k = 0; k < m->by_name.size(); k++) {  // against every sensor's scans, in name order (Mapper.cpp:2063-2070)
+        st = try_close_loop(m, id, m->by_name[k]);
+        if (st) { m->failed = true; return st; }
+      }
     }
   }
-  m->last_scan = id;
+  m->sensors[sensor].last_scan = id;
   if (out_processed) *out_processed = 1;
   if (out_corrected_pose) {
     const MScan &s = m->scans[id];
@@ -853,6 +921,16 @@ b2s_status b2s_mapper_get_poses(const b2s_mapper *m, double *out) {
   for (size_t i = 0; i < m->scans.size(); i++) {
     out[3 * i] = m->scans[i].corrected.x; out[3 * i + 1] = m->scans[i].corrected.y; out[3 * i + 2] = m->scans[i].corrected.h;
   }
+  return B2S_OK;
+}
+
+int32_t b2s_mapper_sensor_count(const b2s_mapper *m) { return m ? (int32_t)m->sensors.size() : 0; }
+
+b2s_status b2s_mapper_get_scan_sensors(const b2s_mapper *m, int32_t *out) {
+  if (!m || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  std::vector<int> rank(m->sensors.size());
+  for (size_t k = 0; k < m->by_name.size(); k++) rank[m->by_name[k]] = (int)k;
+  for (size_t i = 0; i < m->scans.size(); i++) out[i] = rank[m->scans[i].dev];
   return B2S_OK;
 }
 
@@ -872,7 +950,7 @@ b2s_status b2s_mapper_get_edges(const b2s_mapper *m, int32_t *ids, double *pose_
 b2s_status b2s_mapper_stats(const b2s_mapper *m, double out[5]) {
   if (!m || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
   out[0] = m->n_match_calls; out[1] = m->n_batches; out[2] = m->n_loop_candidates; out[3] = m->n_loops_closed;
-  out[4] = (double)m->running.size();
+  out[4] = m->sensors.empty() ? 0.0 : (double)m->sensors[m->last_sensor].running.size();  // of the sensor processed last
   return B2S_OK;
 }
 

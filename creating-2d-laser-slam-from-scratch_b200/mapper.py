@@ -54,6 +54,9 @@ def _bind():
     L.b2s_mapper_destroy.restype = None
     L.b2s_mapper_set_scan_solver.argtypes = [vp, C.POINTER(ScanSolver)]
     L.b2s_mapper_process.argtypes = [vp, dp, dp, C.c_double, C.POINTER(C.c_int32), dp]
+    L.b2s_mapper_process_sensor.argtypes = [vp, C.c_char_p, dp, dp, C.c_double, C.POINTER(C.c_int32), dp]
+    L.b2s_mapper_sensor_count.argtypes = [vp]
+    L.b2s_mapper_get_scan_sensors.argtypes = [vp, C.POINTER(C.c_int32)]
     L.b2s_mapper_scan_count.argtypes = [vp]
     L.b2s_mapper_get_poses.argtypes = [vp, dp]
     L.b2s_mapper_edge_count.argtypes = [vp]
@@ -137,12 +140,23 @@ class Mapper:
         self._keep.append(solver)
         check(self.L.b2s_mapper_set_scan_solver(self.h, C.byref(solver)))
 
-    def process(self, ranges, odometric_pose, time=0.0):
+    def process(self, ranges, odometric_pose, time=0.0, sensor=None):
+        """sensor: None = b2s_mapper_process (the sensor named "laser"); a name = b2s_mapper_process_sensor."""
         r = np.ascontiguousarray(ranges, np.float64)
         assert r.size == self.n
         o, out, ok = np.ascontiguousarray(odometric_pose, np.float64), np.zeros(3), C.c_int32(0)
-        check(self.L.b2s_mapper_process(self.h, _d(r), _d(o), float(time), C.byref(ok), _d(out)))
+        if sensor is None:
+            check(self.L.b2s_mapper_process(self.h, _d(r), _d(o), float(time), C.byref(ok), _d(out)))
+        else:
+            check(self.L.b2s_mapper_process_sensor(self.h, str(sensor).encode(), _d(r), _d(o), float(time), C.byref(ok), _d(out)))
         return bool(ok.value), out
+
+    def scan_sensors(self):
+        """Per processed scan (unique-id order): the rank of its sensor in name order."""
+        out = np.zeros(self.L.b2s_mapper_scan_count(self.h), np.int32)
+        if len(out):
+            check(self.L.b2s_mapper_get_scan_sensors(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
 
     def poses(self):
         out = np.zeros((self.L.b2s_mapper_scan_count(self.h), 3))

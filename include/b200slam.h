@@ -218,7 +218,8 @@ b2s_status b2s_matcher_set_kernel(b2s_matcher *m, int which);
  * pose-graph vertices / edges, near-chain links and loop-closure candidates (Mapper.cpp:883-1414, 1999-2125;
  * Mapper.h:1288-1404).  Every MatchScan runs on the device; independent matches of one Process call (all near
  * chains of LinkNearChains, all candidate chains of TryCloseLoop up to the first accepted closure) go out as ONE
- * batch.  One sensor per mapper (the reference's multi-robot first-scan linking, Mapper.cpp:920-952, is not built). */
+ * batch.  Several sensors (robots) may feed one mapper: b2s_mapper_process_sensor (MapperSensorManager semantics, the
+ * first-scan linking of Mapper.cpp:920-952 included). */
 
 /* Values as the Mapper STORES them (Mapper.cpp:1448-1653); the setParam* squaring of distance_variance_penalty,
  * angle_variance_penalty and loop_match_maximum_variance_coarse (Mapper.cpp:1871-1874,1919-1927) is the caller's job. */
@@ -283,15 +284,29 @@ b2s_status b2s_mapper_set_scan_solver(b2s_mapper *m, const b2s_scan_solver *solv
  * must be destroyed. */
 b2s_status b2s_mapper_process(b2s_mapper *m, const double *ranges, const double odometric_pose[3], double time,
                               int32_t *out_processed, double out_corrected_pose[3]);
+/* The same for a scan of the NAMED sensor (LocalizedRangeScan::GetSensorName; karto_slam.cc passes the laser frame id).
+ * MapperSensorManager semantics (Mapper.h:1412-1577, Mapper.cpp:45-100): a sensor is registered by its first scan; each
+ * sensor has its own scan list (state ids), running window and last scan, unique ids count over all sensors; a sensor's
+ * first scan is matched against ALL scans of every other sensor (name order = Name::operator<, Karto.h:484) and linked
+ * to that sensor's first scan (Mapper.cpp:920-952); near chains follow the near scan's own sensor and loop closures are
+ * searched against every sensor's scans in name order (Mapper.cpp:2063-2070).  All sensors share the handle's b2s_laser
+ * (same LaserRangeFinder parameters on every robot).  b2s_mapper_process is this call with the name "laser". */
+b2s_status b2s_mapper_process_sensor(b2s_mapper *m, const char *sensor_name, const double *ranges,
+                                     const double odometric_pose[3], double time, int32_t *out_processed,
+                                     double out_corrected_pose[3]);
+int32_t b2s_mapper_sensor_count(const b2s_mapper *m);
+/* per processed scan (unique-id order): the rank of its sensor in name order, [count] */
+b2s_status b2s_mapper_get_scan_sensors(const b2s_mapper *m, int32_t *out);
 int32_t b2s_mapper_scan_count(const b2s_mapper *m);   /* GetAllProcessedScans().size() */
-/* corrected poses of every processed scan, [count][3] (they move when a loop closes and a solver is set) */
+/* corrected poses of every processed scan in unique-id order, [count][3] (they move when a loop closes and a solver is
+ * set) */
 b2s_status b2s_mapper_get_poses(const b2s_mapper *m, double *out);
 int32_t b2s_mapper_edge_count(const b2s_mapper *m);
 /* graph edges in creation order: ids [count][2] (source, target), LinkInfo pose difference [count][3] and covariance
  * [count][9] (Mapper.h:108-175) */
 b2s_status b2s_mapper_get_edges(const b2s_mapper *m, int32_t *ids, double *pose_difference, double *covariance);
 /* out[0] = MatchScan calls so far, out[1] = device batches they were sent in, out[2] = loop-closure candidate chains
- * examined, out[3] = loops closed, out[4] = running-scan window size */
+ * examined, out[3] = loops closed, out[4] = running-scan window size of the sensor processed last */
 b2s_status b2s_mapper_stats(const b2s_mapper *m, double out[5]);
 
 /* ---------------------------------------------------------------- back end: a ScanSolver for the mapper (host only)

@@ -224,6 +224,10 @@ class OccupancyGrid {
 class MapperScan {
  public:
   MapperScan(const std::vector<double> &readings) : readings_(readings) {}
+  // LocalizedRangeScan(const Name &rSensorName, readings) (Karto.h:5186): scans of different sensors (robots) may feed
+  // one Mapper; all of them share the Mapper's b2s_laser
+  MapperScan(const std::string &sensorName, const std::vector<double> &readings) : readings_(readings), sensor_(sensorName) {}
+  const std::string &GetSensorName() const { return sensor_; }
   void SetOdometricPose(const Pose2 &p) { odometric_ = p; }
   void SetCorrectedPose(const Pose2 &p) { corrected_ = p; }
   void SetTime(double t) { time_ = t; }
@@ -234,6 +238,7 @@ class MapperScan {
 
  private:
   std::vector<double> readings_;
+  std::string sensor_ = "laser";
   Pose2 odometric_, corrected_;
   double time_ = 0;
 };
@@ -255,7 +260,8 @@ class Mapper {
     const double odom[3] = {o.x, o.y, o.heading};
     double corrected[3];
     int32_t ok = 0;
-    check(b2s_mapper_process(h_, pScan->GetRangeReadings().data(), odom, pScan->GetTime(), &ok, corrected));
+    check(b2s_mapper_process_sensor(h_, pScan->GetSensorName().c_str(), pScan->GetRangeReadings().data(), odom, pScan->GetTime(), &ok,
+                                    corrected));
     pScan->SetCorrectedPose(Pose2(corrected[0], corrected[1], corrected[2]));
     return ok != 0;
   }

@@ -294,10 +294,24 @@ class RefMapper:
         self._keep.append(solver)
         self.L.ref_mapper_set_solver(self.h, C.byref(solver))
 
-    def process(self, ranges, odometric_pose, time=0.0):
+    def add_sensor(self, prefix: str) -> int:
+        """Another robot's laser (same parameters); its name is `prefix`_<n>, the session's own is ref_mapper_laser_<n>
+        (the order of the names decides the order sensors are visited in, Karto.h:484).  Returns the sensor index."""
+        return int(self.L.ref_mapper_add_sensor(self.h, prefix.encode()))
+
+    def process(self, ranges, odometric_pose, time=0.0, sensor=0):
         r, o, out = np.ascontiguousarray(ranges, np.float64), np.ascontiguousarray(odometric_pose, np.float64), np.zeros(3)
-        ok = self.L.ref_mapper_process(self.h, _dp(r), self.n, _dp(o), C.c_double(time), _dp(out))
+        if sensor == 0:
+            ok = self.L.ref_mapper_process(self.h, _dp(r), self.n, _dp(o), C.c_double(time), _dp(out))
+        else:
+            ok = self.L.ref_mapper_process_sensor(self.h, int(sensor), _dp(r), self.n, _dp(o), C.c_double(time), _dp(out))
         return bool(ok), out
+
+    def poses_by_id(self):
+        out = np.zeros((self.L.ref_mapper_scan_count(self.h), 3))
+        if len(out):
+            self.L.ref_mapper_get_poses_by_id(self.h, _dp(out))
+        return out
 
     def poses(self):
         out = np.zeros((self.L.ref_mapper_scan_count(self.h), 3))

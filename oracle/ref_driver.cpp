@@ -511,7 +511,39 @@ struct MapperSession {
   CallbackSolver* solver = nullptr;
   Name name;
   std::vector<LocalizedRangeScan*> all;  // every scan handed to Process (rejected ones too), for deletion
+  std::vector<LaserRangeFinder*> extra;  // further sensors (other robots) with the same parameters, ref_mapper_add_sensor
+  std::vector<Name> extra_names;
+  ref_laser_params lp;
 };
+
+LaserRangeFinder* make_lrf(const ref_laser_params* l, const Name& name) {
+  LaserRangeFinder* lrf = LaserRangeFinder::CreateLaserRangeFinder(static_cast<LaserRangeFinderType>(l->type), name);
+  if (l->type == LaserRangeFinder_Custom) {
+    lrf->SetMinimumRange(l->min_range);
+    lrf->SetMaximumRange(l->max_range);
+    lrf->SetMinimumAngle(l->min_angle);
+    lrf->SetMaximumAngle(l->max_angle);
+    lrf->SetAngularResolution(l->angular_resolution);
+  }
+  lrf->SetRangeThreshold(l->range_threshold);
+  lrf->SetOffsetPose(Pose2(l->offset_pose[0], l->offset_pose[1], l->offset_pose[2]));
+  SensorManager::GetInstance()->RegisterSensor(lrf);
+  return lrf;
+}
+
+int process_named(MapperSession* s, const Name& name, const double* ranges, int n, const double* odom, double time,
+                  double* out_corrected) {
+  std::vector<kt_double> r(ranges, ranges + n);
+  LocalizedRangeScan* scan = new LocalizedRangeScan(name, r);
+  scan->SetOdometricPose(Pose2(odom[0], odom[1], odom[2]));
+  scan->SetCorrectedPose(Pose2(odom[0], odom[1], odom[2]));
+  scan->SetTime(time);
+  s->all.push_back(scan);
+  bool ok = s->mapper->Process(scan);
+  Pose2 c = scan->GetCorrectedPose();
+  if (out_corrected) { out_corrected[0] = c.GetX(); out_corrected[1] = c.GetY(); out_corrected[2] = c.GetHeading(); }
+  return ok ? 1 : 0;
+}
 
 }  // namespace
 
@@ -523,17 +555,8 @@ void* ref_mapper_create(const ref_mapper_params* p, const ref_laser_params* l) {
   std::stringstream nm;
   nm << "ref_mapper_laser_" << (g_session_counter++);
   s->name = Name(nm.str());
-  s->lrf = LaserRangeFinder::CreateLaserRangeFinder(static_cast<LaserRangeFinderType>(l->type), s->name);
-  if (l->type == LaserRangeFinder_Custom) {
-    s->lrf->SetMinimumRange(l->min_range);
-    s->lrf->SetMaximumRange(l->max_range);
-    s->lrf->SetMinimumAngle(l->min_angle);
-    s->lrf->SetMaximumAngle(l->max_angle);
-    s->lrf->SetAngularResolution(l->angular_resolution);
-  }
-  s->lrf->SetRangeThreshold(l->range_threshold);
-  s->lrf->SetOffsetPose(Pose2(l->offset_pose[0], l->offset_pose[1], l->offset_pose[2]));
-  SensorManager::GetInstance()->RegisterSensor(s->lrf);
+  s->lp = *l;
+  s->lrf = make_lrf(l, s->name);
   Mapper* m = s->mapper = new Mapper();
   m->m_pUseScanMatching->SetValue(p->use_scan_matching != 0);
   m->m_pUseScanBarycenter->SetValue(p->use_scan_barycenter != 0);
@@ -583,23 +606,52 @@ void ref_mapper_destroy(void* h) {
   delete s->solver;
   SensorManager::GetInstance()->UnregisterSensor(s->lrf);
   delete s->lrf;
+  for (auto* p : s->extra) {
+    SensorManager::GetInstance()->UnregisterSensor(p);
+    delete p;
+  }
   delete s;
 }
 
 // what karto_slam.cc:437-475 does per LaserScan: build the LocalizedRangeScan, set both poses from odometry, Process
+int ref_mapper_scan_count(void* h);
+
 int ref_mapper_process(void* h, const double* ranges, int n, const double* odom, double time, double* out_corrected) {
   CoutSilencer quiet;
   MapperSession* s = static_cast<MapperSession*>(h);
-  std::vector<kt_double> r(ranges, ranges + n);
-  LocalizedRangeScan* scan = new LocalizedRangeScan(s->name, r);
-  scan->SetOdometricPose(Pose2(odom[0], odom[1], odom[2]));
-  scan->SetCorrectedPose(Pose2(odom[0], odom[1], odom[2]));
-  scan->SetTime(time);
-  s->all.push_back(scan);
-  bool ok = s->mapper->Process(scan);
-  Pose2 c = scan->GetCorrectedPose();
-  if (out_corrected) { out_corrected[0] = c.GetX(); out_corrected[1] = c.GetY(); out_corrected[2] = c.GetHeading(); }
-  return ok ? 1 : 0;
+  return process_named(s, s->name, ranges, n, odom, time, out_corrected);
+}
+
+// a further sensor (another robot's laser, same parameters).  `prefix` decides where its name sorts relative to the
+// session's own "ref_mapper_laser_<n>" (Name::operator< compares strings, Karto.h:484).  Returns its index (>= 1).
+int ref_mapper_add_sensor(void* h, const char* prefix) {
+  CoutSilencer quiet;
+  MapperSession* s = static_cast<MapperSession*>(h);
+  std::stringstream nm;
+  nm << prefix << "_" << (g_session_counter++);
+  Name name(nm.str());
+  s->extra.push_back(make_lrf(&s->lp, name));
+  s->extra_names.push_back(name);
+  return static_cast<int>(s->extra.size());
+}
+
+// sensor 0 = the session's own laser, k >= 1 = the k-th added one
+int ref_mapper_process_sensor(void* h, int sensor, const double* ranges, int n, const double* odom, double time,
+                              double* out_corrected) {
+  CoutSilencer quiet;
+  MapperSession* s = static_cast<MapperSession*>(h);
+  return process_named(s, sensor == 0 ? s->name : s->extra_names[sensor - 1], ranges, n, odom, time, out_corrected);
+}
+
+// corrected poses in unique-id order (MapperSensorManager::GetScan(id), Mapper.h:1486-1498); GetAllProcessedScans is
+// sensor-major
+void ref_mapper_get_poses_by_id(void* h, double* out) {
+  MapperSession* s = static_cast<MapperSession*>(h);
+  const int n = ref_mapper_scan_count(h);
+  for (int i = 0; i < n; i++) {
+    Pose2 c = s->mapper->m_pMapperSensorManager->GetScan(i)->GetCorrectedPose();
+    out[3 * i] = c.GetX(); out[3 * i + 1] = c.GetY(); out[3 * i + 2] = c.GetHeading();
+  }
 }
 
 int ref_mapper_scan_count(void* h) {

@@ -212,11 +212,31 @@ def mapper_case():
     r.close()
 
 
+def fleet_case():
+    """Three sensors (robots) feeding one karto::Mapper (MapperSensorManager, Mapper.cpp:45-100, 920-952): poses in
+    unique-id order and graph edges as the reference leaves them."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mapper_cases as mc
+    seed, n = 3, 150
+    laser, prm, true, odom, ranges = mc.workload(pkg, seed, n, drift=mc.FLEET_DRIFT)
+    r = ref.RefMapper(prm, laser)
+    sensors = [0, r.add_sensor("a_robot"), r.add_sensor("z_robot")]
+    flags, _ = mc.run_fleet(r, sensors, odom, ranges)
+    ids, diff, cov = r.edges()
+    np.savez_compressed(os.path.join(HERE, "karto_mapper_fleet.npz"), seed=np.int32(seed), n=np.int32(n), flags=flags,
+                        poses=r.poses_by_id(), edge_ids=ids, edge_diff=diff, edge_cov=cov, ranges_sample=ranges[::17])
+    r.close()
+
+
 if __name__ == "__main__":
     assert ref.available(), "run `make -C oracle ref` first"
     if sys.argv[1:] == ["mapper"]:
         mapper_case()
         print("karto_mapper.npz", os.path.getsize(os.path.join(HERE, "karto_mapper.npz")))
+        sys.exit(0)
+    if sys.argv[1:] == ["fleet"]:
+        fleet_case()
+        print("karto_mapper_fleet.npz", os.path.getsize(os.path.join(HERE, "karto_mapper_fleet.npz")))
         sys.exit(0)
     if sys.argv[1:] == ["hector"]:
         hector_case()
@@ -229,6 +249,7 @@ if __name__ == "__main__":
     gmapping_case()
     hector_case()
     mapper_case()
+    fleet_case()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -23,3 +23,28 @@ def run(mapper, odom, ranges, dt=0.1):
         flags.append(ok)
         firsts.append(c)
     return np.array(flags), np.array(firsts)
+
+
+FLEET_DRIFT = (0.002, 0.0015, 0.0008)
+
+
+def fleet_events(n_per_robot=50, starts=(0, 50, 100), stagger=8):
+    """Three robots on the same lap trajectory, one lap apart, entering `stagger` steps after each other:
+    [(robot, frame)] in processing order."""
+    ev = []
+    for t in range(n_per_robot + stagger * (len(starts) - 1)):
+        for r, s0 in enumerate(starts):
+            k = t - stagger * r
+            if 0 <= k < n_per_robot:
+                ev.append((r, s0 + k))
+    return ev
+
+
+def run_fleet(mapper, sensors, odom, ranges, dt=0.1):
+    """sensors[robot] = what the mapper's process() takes as `sensor`."""
+    flags, firsts = [], []
+    for k, (rob, i) in enumerate(fleet_events()):
+        ok, c = mapper.process(ranges[i], odom[i], dt * k, sensor=sensors[rob])
+        flags.append(ok)
+        firsts.append(c)
+    return np.array(flags), np.array(firsts)

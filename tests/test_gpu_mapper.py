@@ -32,6 +32,25 @@ def test_mapper_cuda_vs_reference_golden(pkg):
     m.close()
 
 
+def test_mapper_cuda_multi_robot_vs_reference_golden(pkg):
+    """Three robots into one mapper (b2s_mapper_process_sensor), every MatchScan on the CUDA matcher — the first-scan
+    matches against another robot's whole scan list included — against the reference's three-sensor run."""
+    MP, abi = pkg.load("mapper"), pkg.abi
+    g = np.load(os.path.join(G, "karto_mapper_fleet.npz"))
+    laser, prm, true, odom, ranges = mc.workload(pkg, int(g["seed"]), int(g["n"]), drift=mc.FLEET_DRIFT)
+    assert np.array_equal(ranges[::17], g["ranges_sample"])
+    m = MP.Mapper(prm, abi.laser_from(laser))
+    flags, _ = mc.run_fleet(m, [None, "a_robot", "z_robot"], odom, ranges)
+    assert np.array_equal(flags, g["flags"]) and np.abs(m.poses() - g["poses"]).max() <= 1e-4
+    ids, diff, cov = m.edges()
+    assert np.array_equal(ids, g["edge_ids"])
+    assert np.abs(diff - g["edge_diff"]).max() <= 1e-4 and np.abs(cov - g["edge_cov"]).max() <= 1e-4
+    sens = m.scan_sensors()
+    assert (sens[ids[:, 0]] != sens[ids[:, 1]]).sum() >= 2 and m.stats()["loops_closed"] >= 1
+    print("fleet pose max |delta| vs reference:", np.abs(m.poses() - g["poses"]).max())
+    m.close()
+
+
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libkarto_ref.so did not travel")
 def test_mapper_cuda_vs_live_reference_with_back_end(pkg):
     MP, abi = pkg.load("mapper"), pkg.abi

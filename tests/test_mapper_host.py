@@ -91,6 +91,63 @@ def test_mapper_key_frame_gate(pkg):
     r.close(), m.close()
 
 
+@live
+@pytest.mark.parametrize("prefixes,solver,seed", [(("a_robot", "z_robot"), False, 3), (("z_robot", "a_robot"), True, 7)])
+def test_mapper_multi_robot_matches_reference(pkg, prefixes, solver, seed):
+    """MapperSensorManager semantics with three sensors (Mapper.cpp:45-100, 920-952, 1170-1275, 1333-1394, 2063-2070):
+    a sensor's first scan is matched against all scans of the other sensors and linked to their first scans, near
+    chains follow the near scan's own sensor, loop closures are searched per sensor in NAME order — the two extra
+    robots' names sort before / after the first one's in both permutations."""
+    MP, abi = pkg.load("mapper"), pkg.abi
+    laser, prm, true, odom, ranges = mc.workload(pkg, seed, 150, drift=mc.FLEET_DRIFT)
+    al = abi.laser_from(laser)
+    r = ref.RefMapper(prm, laser)
+    m = MP.Mapper(prm, al, match_fn=port.mapper_match_hook(prm, al))
+    if solver:
+        g1, g2 = MP.PoseGraph(), MP.PoseGraph()
+        r.set_scan_solver(g1.as_scan_solver())
+        m.set_scan_solver(g2.as_scan_solver())
+    ref_ids = [0] + [r.add_sensor(p) for p in prefixes]
+    names = [None] + list(prefixes)  # None = b2s_mapper_process = the sensor "laser" ("a_robot" < "laser" < "z_robot")
+    for k, (rob, i) in enumerate(mc.fleet_events()):
+        a = r.process(ranges[i], odom[i], 0.1 * k, sensor=ref_ids[rob])
+        b = m.process(ranges[i], odom[i], 0.1 * k, sensor=names[rob])
+        assert a[0] == b[0] and np.abs(a[1] - b[1]).max() <= 1e-9, (k, rob, i)
+    pr, pm = r.poses_by_id(), m.poses()
+    assert pr.shape == pm.shape == (150, 3) and np.abs(pr - pm).max() <= 1e-9
+    (ir, dr, cr), (im, dm, cm) = r.edges(), m.edges()
+    assert np.array_equal(ir, im), "graph edges differ"
+    assert np.abs(dr - dm).max() <= 1e-9 and np.abs(cr - cm).max() <= 1e-9
+    sens = m.scan_sensors()
+    rank = {p: k for k, p in enumerate(sorted(["laser"] + list(prefixes)))}
+    assert sens[0] == rank["laser"] and sens[8] == rank["laser"] and sens[9] == rank[prefixes[0]]
+    # links between different robots exist (first-scan links and near chains), and some loop was examined
+    cross = sens[im[:, 0]] != sens[im[:, 1]]
+    assert cross.sum() >= 2
+    first_b = np.flatnonzero(sens == rank[prefixes[0]])[0]
+    assert any((s_ == 0 and d_ == first_b) for s_, d_ in im), "first scan of robot 2 is linked to the first scan of robot 1"
+    assert m.stats()["loops_closed"] >= 1
+    if solver:
+        assert g1.stats() == g2.stats()
+    r.close(), m.close()
+
+
+def test_mapper_multi_robot_golden(pkg):
+    """The three-robot run as the reference left it (tests/golden/make_golden.py fleet), wherever the library loads."""
+    MP, abi = pkg.load("mapper"), pkg.abi
+    g = np.load(os.path.join(G, "karto_mapper_fleet.npz"))
+    laser, prm, true, odom, ranges = mc.workload(pkg, int(g["seed"]), int(g["n"]), drift=mc.FLEET_DRIFT)
+    assert np.array_equal(ranges[::17], g["ranges_sample"]), "the synthetic workload changed: regenerate the golden file"
+    al = abi.laser_from(laser)
+    m = MP.Mapper(prm, al, match_fn=port.mapper_match_hook(prm, al))
+    flags, _ = mc.run_fleet(m, [None, "a_robot", "z_robot"], odom, ranges)
+    assert np.array_equal(flags, g["flags"]) and np.abs(m.poses() - g["poses"]).max() <= 1e-9
+    ids, diff, cov = m.edges()
+    assert np.array_equal(ids, g["edge_ids"]) and np.abs(diff - g["edge_diff"]).max() <= 1e-9
+    assert np.abs(cov - g["edge_cov"]).max() <= 1e-9
+    m.close()
+
+
 def test_mapper_golden(pkg):
     """Poses and edges the reference Mapper produced for the seeded workload (tests/golden/make_golden.py mapper),
     checked wherever the library loads — e.g. on the GPU box, where /root/reference does not exist."""
