@@ -80,6 +80,7 @@ struct HsState {  // device-resident state of ONE processor
   int bb_x0[HS_L], bb_y0[HS_L], bb_x1[HS_L], bb_y1[HS_L];  // cells the update's rays can touch (inclusive; empty: x1 < x0)
   unsigned long long visits, n_matched, n_updated;
   unsigned long long t_match_ns, t_update_ns;
+  unsigned long long fine[8];  // thread 0's view of the per-point phase: [0] pose read + transform, [1] cell load to use, [2] term arithmetic, [3] warp reduction + store, [4] barrier
   unsigned long long prof[8];  // SM cycles of processor 0's matching CTA: [0] staging, [1] point terms, [2] sums, [3] solve, [4] trig, [5] gate + bbox, [6] iterations
 };
 
@@ -99,15 +100,76 @@ struct HsCall {  // one scan per processor
   const float *hints;   // [b][3] or NULL -> the processor's last scan-match pose (the node's loop)
   float origo_x, origo_y;
   int map_without_matching;
-  float *out;           // [b][16] device: pose[3], cov[9], updated, matched, -, -
+  float *out;           // [b][16] device: pose[3], cov[9], updated, matched, exchange-lost, -
   volatile float *mailbox;  // host-mapped copy of out for processor 0 + sequence word, or NULL
   unsigned int seq;
+  unsigned int tag;     // != 0: published (release, gpu scope) in out[b][15] once the scan's state is complete
 };
 
 __device__ __forceinline__ unsigned long long hs_now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+
+// ---- thread-block cluster exchange of the fast single-stream match (k_hs_stream<false, true>) ----
+// The per-point phase of a Gauss-Newton iteration is issue-bound on ONE SM (2600 of the iteration's 3700 cycles), so the
+// CTAs of cluster 0 split the scan's points: rank 0 (the master) solves, the helpers receive the pose + sine / cosine and
+// return their nine partial sums through distributed shared memory.  Data and signal travel together (st.async with
+// mbarrier complete_tx): no cluster-scope fence, hence no L1 invalidation (CCTL.IVALL) inside the iteration loop.
+constexpr int HS_CLUSTER = 4;
+constexpr int HS_POSE_WORDS = 7;  // e0, e1, cos, sin, sinRot, cosRot, spare
+struct __align__(16) HsXchg {
+  unsigned long long bar_pose, bar_part;  // mbarriers: pose arrived (helpers) / all partial sums arrived (master)
+  float pose[8];
+  float part[8][12];                      // [rank][sum]
+};
+__device__ __forceinline__ uint32_t hs_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t hs_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t hs_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t hs_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void hs_st_async(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void hs_mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hs_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void hs_mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded: a lost exchange must not hang the device (the host reports B2S_ERR_CUDA when the flag is set)
+__device__ __forceinline__ bool hs_mbar_wait(unsigned long long *bar, uint32_t parity) {
+  const uint32_t addr = hs_smem_u32(bar);
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if (clock64() - t0 > (1ll << 25)) return false;  // ~17 ms; a legitimate wait is microseconds
+  }
+}
+__device__ __forceinline__ void hs_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the points [p0, p1) of rank r when n points are split over `size` CTAs
+__device__ __forceinline__ void hs_share(int n, int rank, int size, int &p0, int &p1) {
+  const int chunk = (n + size - 1) / size;
+  p0 = min(n, rank * chunk);
+  p1 = min(n, p0 + chunk);
 }
 
 // interpMapValueWithDerivatives (OccGridMapUtil.h:139-228) in two halves so that the four cell loads of SEVERAL points are
@@ -246,6 +308,56 @@ __device__ __forceinline__ HsLine hs_line(float c, float s, float mx, float my, 
   return L;
 }
 
+// Fast mode, cluster variant: the per-point phase of this CTA's share (points [0, cnt) of `pts`) and the CTA's nine sums.
+// The phase is ISSUE-bound (one SM retires ~500 warp instructions per warp and iteration in the two-points-per-thread
+// form), so: only the warps that own points run it, every thread stores its nine terms as columns (9 STS instead of a
+// 45-shuffle tree per warp), and warps 0..8 then sum one column each.  Returns sum `warp` in every lane of warps 0..8.
+// Contains one __syncthreads.
+struct HsTicks {  // thread 0's cycle stamps (clock reads pinned behind a value by the asm's unused input)
+  unsigned long long fine[8];
+  long long mark;
+  __device__ __forceinline__ void tick(int slot, float dep) {
+    long long c_;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) : "f"(dep) : "memory");
+    if (slot >= 0) fine[slot] += (unsigned long long)(c_ - mark);
+    mark = c_;
+  }
+};
+__device__ __forceinline__ float hs_share_sums(const float4 *__restrict__ prob, int sx, int sy, const float2 *pts, int cnt,
+                                               float factor, float e0, float e1, float c, float s, float sin_rot,
+                                               float cos_rot, bool l2, float *terms, int pitch, int tid, int lane, int warp,
+                                               HsTicks *tk = nullptr) {
+  if (tk && tid == 0) tk->tick(5, e0);  // since the end of the previous solve: publish + barrier + loop head
+  if (warp * 32 < cnt) {
+#pragma unroll 1
+    for (int i = tid; i < cnt; i += HS_THREADS) {
+      const float2 p = make_float2(__fmul_rn(pts[i].x, factor), __fmul_rn(pts[i].y, factor));
+      const HsFetch f = hs_point_fetch(prob, sx, sy, p, c, s, e0, e1, l2);
+      if (tk && tid == 0) { tk->tick(0, f.fx); tk->tick(1, f.i0); }
+      float t[9];
+      hs_point_terms(f, p, sin_rot, cos_rot, t);
+      if (tk && tid == 0) tk->tick(2, t[2] + t[5]);
+#pragma unroll
+      for (int q = 0; q < 9; q++) terms[q * pitch + i] = t[q];
+    }
+  }
+  if (tk && tid == 0) tk->tick(3, e0);
+  __syncthreads();
+  if (tk && tid == 0) tk->tick(4, e0);
+  float v = 0.0f;
+  if (warp < 9) {
+    const float *col = terms + warp * pitch;
+    // (not unrolled on purpose: this runs once per iteration on cold instruction lines — the L0 instruction cache holds
+    // ~6 KB and the iteration loop is larger — so executed code BYTES cost more than instructions)
+#pragma unroll 1
+    for (int i = lane; i < cnt; i += 32) v += col[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  }
+  if (tk && tid == 0) tk->tick(6, v);
+  return v;
+}
+
 // shared memory of the match: [cap] float2 staged scan, then (EXACT) 9 term columns of `pitch` floats / (FAST) per-warp partials
 __host__ __device__ inline int hs_pitch(int cap) { return ((cap + 3) & ~3) + 4; }
 __host__ __device__ inline size_t hs_terms_offset(int cap) { return (sizeof(float2) * (size_t)cap + 15) & ~(size_t)15; }  // float4 reads of the columns
@@ -253,8 +365,12 @@ __host__ __device__ inline size_t hs_smem_bytes(int cap) { return hs_terms_offse
 
 // MapRepMultiMap::matchData (:144-166) on every level, coarsest first, + the gate and the update parameters of
 // HectorSlamProcessor::update (:81-108), by ONE CTA for processor b.
-template <bool EXACT>
-__device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned char *smem) {
+// Returns the gate's verdict (map update or not).  `s_prof`: [16] shared-memory profile counters of the calling kernel
+// (flushed to the state once per launch: sixteen global read-modify-writes per scan were ~0.4 us of the serial tail).
+template <bool EXACT, bool CLUSTER>
+__device__ bool hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned char *smem, unsigned long long *s_prof,
+                             HsXchg *xc = nullptr, uint32_t *xc_parity = nullptr) {
+  static_assert(!(EXACT && CLUSTER), "the bit-exact sums are one sequential chain: nothing to split");
   HsState *st = P.state + b;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = HS_THREADS / 32;
@@ -269,10 +385,44 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
   __shared__ float s_world[3];
   __shared__ int s_do;
   __shared__ int s_bb[HS_L][4];
+  __shared__ int s_lost;
+  const uint32_t csize = CLUSTER ? hs_cluster_size() : 1u;
+  uint32_t part_parity = CLUSTER ? *xc_parity : 0u;
+  int my0 = 0, my1 = n;  // this CTA's share of the points in the per-point phase
+  if (CLUSTER) hs_share(n, 0, (int)csize, my0, my1);
+  if (CLUSTER && tid == 0) s_lost = 0;
+  // master -> helpers: the pose of the next iteration (bc[0..6]) into every helper's HsXchg::pose; one st.async per lane
+  // of warp 0 (the solving thread publishes nothing itself: 21 serial remote stores cost it ~300 cycles)
+  auto publish = [&]() {
+    if constexpr (CLUSTER) {
+      const uint32_t a_pose = hs_smem_u32(xc->pose), a_bar = hs_smem_u32(&xc->bar_pose);
+#pragma unroll 1
+      for (uint32_t l = (uint32_t)lane; l + HS_POSE_WORDS < HS_POSE_WORDS * csize; l += 32) {
+        const uint32_t r = 1 + l / HS_POSE_WORDS, q = l % HS_POSE_WORDS;
+        hs_st_async(hs_mapa(a_pose + 4 * q, r), bc[q], hs_mapa(a_bar, r));
+      }
+    }
+  };
+  // state the serial tail needs, requested now so that the loads' latency hides behind the match (written last by this
+  // same thread, or by an earlier kernel)
+  float lup[3] = {0.0f, 0.0f, 0.0f}, lcov[9];
+  unsigned long long n_matched0 = 0;
+  if (tid == 0) {
+    lup[0] = st->last_update_pose[0]; lup[1] = st->last_update_pose[1]; lup[2] = st->last_update_pose[2];
+    n_matched0 = st->n_matched;
+#pragma unroll
+    for (int q = 0; q < 9; q++) lcov[q] = st->last_cov[q];
+  }
   const unsigned long long t0 = hs_now_ns();
   long long c_mark = clock64();
   unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define HS_PROF(slot) do { if (tid == 0) { const long long c_now = clock64(); pf[slot] += (unsigned long long)(c_now - c_mark); c_mark = c_now; } } while (0)
+  // clock reads pinned behind a value (the asm's unused input), so that they bracket the instruction that produces it
+  HsTicks tk;
+#pragma unroll
+  for (int q = 0; q < 8; q++) tk.fine[q] = 0;
+  tk.mark = clock64();
+#define HS_TICK(slot, dep) do { if (tid == 0) tk.tick((slot), (dep)); } while (0)
   const float2 *gp = reinterpret_cast<const float2 *>(C.pts0) + (size_t)b * C.pts_stride;
   for (int i = tid; i < n; i += HS_THREADS) {
     const float2 p = gp[i];
@@ -303,20 +453,43 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
         const HsTrig tr = hs_trig(world2, exact, use_fma);
         bc[0] = e0; bc[1] = e1; bc[2] = world2; bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
       }
+      if (CLUSTER && warp == 0) {
+        __syncwarp();
+        publish();
+      }
       __syncthreads();
       for (int it = 0; it < m.iterations; it++) {
         const float e0 = bc[0], e1 = bc[1], c = bc[3], s = bc[4], sin_rot = bc[5], cos_rot = bc[6];
+        if constexpr (CLUSTER) {
+          float v = hs_share_sums(prob, m.sx, m.sy, spts, my1, factor, e0, e1, c, s, sin_rot, cos_rot, l2, terms, pitch, tid, lane, warp);
+          HS_PROF(1);
+          if (warp < 9) {
+            if (csize > 1) {  // + the helpers' partial sums, in rank order
+              if (tid == 0) hs_mbar_expect_tx(&xc->bar_part, 36u * (csize - 1));
+              if (!hs_mbar_wait(&xc->bar_part, part_parity)) s_lost = 1;  // every reading thread observes the phase itself
+#pragma unroll 1
+              for (uint32_t r = 1; r < csize; r++) v += xc->part[r][warp];
+            }
+            if (lane == 0) tot[warp] = v;
+          }
+          if (csize > 1) part_parity ^= 1u;
+          __syncthreads();
+        } else {
         float acc[9];
 #pragma unroll
         for (int q = 0; q < 9; q++) acc[q] = 0.0f;
-        for (int base = 0; base < n; base += 2 * HS_THREADS) {  // two points per thread, their eight cell loads in flight together
+        HS_TICK(-1, e0);
+        for (int base = my0; base < my1; base += 2 * HS_THREADS) {  // two points per thread, their eight cell loads in flight together
           const int ia = base + tid, ib = base + tid + HS_THREADS;
+          const int n = my1;  // (shadows the scan length inside the per-point phase: this CTA's share ends at my1)
           float2 pa = make_float2(0.0f, 0.0f), pb = pa;
           HsFetch fa, fb;
           fa.inside = fb.inside = false;
           if (ia < n) { pa = make_float2(__fmul_rn(spts[ia].x, factor), __fmul_rn(spts[ia].y, factor)); fa = hs_point_fetch(prob, m.sx, m.sy, pa, c, s, e0, e1, l2); }
           if (ib < n) { pb = make_float2(__fmul_rn(spts[ib].x, factor), __fmul_rn(spts[ib].y, factor)); fb = hs_point_fetch(prob, m.sx, m.sy, pb, c, s, e0, e1, l2); }
           float ta[9], tb[9];
+          HS_TICK(0, fa.fx);
+          HS_TICK(1, fa.i0);
           if (ia < n) {
             hs_point_terms(fa, pa, sin_rot, cos_rot, ta);
             if (exact) {
@@ -338,6 +511,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
             }
           }
         }
+        HS_TICK(2, acc[8]);
         if (!exact) {
 #pragma unroll
           for (int q = 0; q < 9; q++) {
@@ -349,7 +523,9 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
             for (int q = 0; q < 9; q++) terms[q * NW + warp] = acc[q];
           }
         }
+        HS_TICK(3, acc[8]);
         __syncthreads();
+        HS_TICK(4, acc[0]);
         HS_PROF(1);
         if (exact) {
           // The reference's float32 sums, in point order (OccGridMapUtil.h:99-126): ONE warp instruction advances all nine
@@ -384,6 +560,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
           if (lane < 9) tot[lane] = v;
           __syncwarp();
         }
+        }  // !CLUSTER
         HS_PROF(2);
         if (tid == 0) {  // estimateTransformationLogLh (ScanMatcher.h:107-141)
           const float dTr[3] = {tot[0], tot[1], tot[2]};
@@ -405,7 +582,12 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
             bc[3] = tr.c; bc[4] = tr.s; bc[5] = tr.sin_rot; bc[6] = tr.cos_rot;
           }
           HS_PROF(4);
+          tk.tick(-1, n2);
           pf[6] += 1;
+        }
+        if (CLUSTER && warp == 0 && it + 1 < m.iterations) {
+          __syncwarp();
+          publish();
         }
         __syncthreads();
       }
@@ -424,12 +606,14 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
     // ---- HectorSlamProcessor::update after the match (:88-107) ----
     float est[3] = {world0, world1, world2};
     if (any) {  // covMatrix = H of the last level matched (level 0)
-      st->last_cov[0] = tot[3]; st->last_cov[4] = tot[4]; st->last_cov[8] = tot[5];
-      st->last_cov[1] = st->last_cov[3] = tot[6]; st->last_cov[2] = st->last_cov[6] = tot[7];
-      st->last_cov[5] = st->last_cov[7] = tot[8];
+      lcov[0] = tot[3]; lcov[4] = tot[4]; lcov[8] = tot[5];
+      lcov[1] = lcov[3] = tot[6]; lcov[2] = lcov[6] = tot[7];
+      lcov[5] = lcov[7] = tot[8];
+#pragma unroll
+      for (int q = 0; q < 9; q++) st->last_cov[q] = lcov[q];
     }
     if (!C.map_without_matching) {
-      st->n_matched += 1;
+      st->n_matched = n_matched0 + 1;
       if (n > 0) {
         float factor = 1.0f;
         for (int l = 1; l < P.levels; l++) {
@@ -444,7 +628,7 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
     st->n_pts[0] = n;
     st->origo[0][0] = C.origo_x; st->origo[0][1] = C.origo_y;
     st->last_match_pose[0] = est[0]; st->last_match_pose[1] = est[1]; st->last_match_pose[2] = est[2];
-    const bool do_update = hs_pose_difference_larger_than(est, st->last_update_pose, P.min_dist, P.min_angle) ||
+    const bool do_update = hs_pose_difference_larger_than(est, lup, P.min_dist, P.min_angle) ||
                            C.map_without_matching;
     st->do_update = do_update ? 1 : 0;
     if (do_update) {
@@ -469,11 +653,12 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
     }
     float *o = C.out + 16 * (size_t)b;
     o[0] = est[0]; o[1] = est[1]; o[2] = est[2];
-    for (int q = 0; q < 9; q++) o[3 + q] = st->last_cov[q];
+    for (int q = 0; q < 9; q++) o[3 + q] = lcov[q];
     o[12] = do_update ? 1.0f : 0.0f;
     o[13] = any ? 1.0f : 0.0f;
+    o[14] = (CLUSTER && s_lost) ? 1.0f : 0.0f;  // a cluster exchange timed out: the host fails the call
     if (C.mailbox && b == 0) {
-      for (int q = 0; q < 14; q++) C.mailbox[q] = o[q];
+      for (int q = 0; q < 15; q++) C.mailbox[q] = o[q];
       __threadfence_system();
       reinterpret_cast<volatile unsigned int *>(C.mailbox)[15] = C.seq;
       __threadfence_system();
@@ -517,11 +702,79 @@ __device__ void hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
   }
   HS_PROF(5);
   if (tid == 0) {
-    if (b == 0)
-      for (int q = 0; q < 8; q++) st->prof[q] += pf[q];
+    if (b == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) { s_prof[q] += pf[q]; s_prof[8 + q] += tk.fine[q]; }
+    }
     st->t_match_ns = hs_now_ns() - t0;
   }
+  if (CLUSTER) *xc_parity = part_parity;
+  const bool verdict = s_do != 0;
+  if (C.tag) {
+    __syncthreads();  // the bounding boxes (other threads' stores) are ordered before the release below
+    if (tid == 0)
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(C.out + 16 * (size_t)b + 15), "r"(C.tag) : "memory");
+  }
+  return verdict;
 #undef HS_PROF
+#undef HS_TICK
+}
+
+__device__ __forceinline__ void hs_prof_flush(HsState *st, const unsigned long long *s_prof) {
+  for (int q = 0; q < 8; q++) { st->prof[q] += s_prof[q]; st->fine[q] += s_prof[8 + q]; }
+}
+
+// every CTA but the matching one: wait until scan i's row carries this launch's tag, then read the gate's verdict
+__device__ __forceinline__ bool hs_wait_decision(const float *row, unsigned int tag, int *s_flag) {
+  if (threadIdx.x == 0) {
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(row + 15) : "memory");
+      if (v == tag) break;
+      __nanosleep(40);
+    }
+    *s_flag = __ldcg(row + 12) != 0.0f ? 1 : 0;
+  }
+  __syncthreads();
+  const bool r = *s_flag != 0;
+  __syncthreads();  // s_flag may be rewritten for the next scan
+  return r;
+}
+
+// A helper CTA of cluster 0 (rank >= 1): the same level / iteration loops as hs_match_cta, but only the per-point phase of
+// its share of the scan; the pose comes from the master, the nine partial sums go back to it.
+__device__ void hs_match_helper(const HsBatch &P, const HsCall &C, unsigned char *smem, HsXchg *xc, uint32_t rank,
+                                uint32_t csize, uint32_t &pose_parity) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = C.n0_uniform;
+  if (C.map_without_matching || n <= 0) return;
+  const bool l2 = P.l2_loads != 0;
+  float2 *spts = reinterpret_cast<float2 *>(smem);
+  float *terms = reinterpret_cast<float *>(smem + hs_terms_offset(P.cap));
+  int p0, p1;
+  hs_share(n, (int)rank, (int)csize, p0, p1);
+  const int cnt = p1 - p0;
+  const float2 *gp = reinterpret_cast<const float2 *>(C.pts0);
+  for (int i = tid; i < cnt; i += HS_THREADS) spts[i] = gp[p0 + i];
+  __syncthreads();
+  const int pitch = hs_pitch(P.cap);
+  const uint32_t r_part = hs_mapa(hs_smem_u32(&xc->part[rank][0]), 0), r_bar = hs_mapa(hs_smem_u32(&xc->bar_part), 0);
+  float factor = 1.0f;
+  for (int l = 1; l < P.levels; l++) factor *= 0.5f;
+  for (int lv = P.levels - 1; lv >= 0; lv--, factor *= 2.0f) {
+    const HsLevel &m = P.l[lv];
+    const float4 *prob = m.quad;
+    for (int it = 0; it < m.iterations; it++) {
+      if (tid == 0) hs_mbar_expect_tx(&xc->bar_pose, 4u * HS_POSE_WORDS);
+      hs_mbar_wait(&xc->bar_pose, pose_parity);  // every thread observes the phase itself (a time-out is reported by the master)
+      pose_parity ^= 1u;
+      const float e0 = xc->pose[0], e1 = xc->pose[1], c = xc->pose[3], s = xc->pose[4], sin_rot = xc->pose[5], cos_rot = xc->pose[6];
+      // (no barrier needed here: the master sends the next pose only after it holds all nine of our sums, and those are
+      // sent behind hs_share_sums' barrier, i.e. after every thread has read this pose and the previous columns)
+      const float v = hs_share_sums(prob, m.sx, m.sy, spts, cnt, factor, e0, e1, c, s, sin_rot, cos_rot, l2, terms, pitch, tid, lane, warp);
+      if (warp < 9 && lane == 0) hs_st_async(r_part + 4 * warp, v, r_bar);
+    }
+  }
 }
 
 // the update parameters of one level as the gate wrote them.  Plain (L1) loads: within the persistent launch every CTA
@@ -667,7 +920,11 @@ __device__ void hs_apply_pass(const HsBatch &P, int b, int w, int nw, int lane) 
 template <bool EXACT>
 __global__ void __launch_bounds__(HS_THREADS) k_hs_match(HsBatch P, HsCall C) {
   extern __shared__ __align__(16) unsigned char hs_smem[];
-  hs_match_cta<EXACT>(P, C, blockIdx.x, hs_smem);
+  __shared__ unsigned long long s_prof[16];
+  if (threadIdx.x < 16) s_prof[threadIdx.x] = 0;
+  __syncthreads();
+  hs_match_cta<EXACT, false>(P, C, blockIdx.x, hs_smem, s_prof);
+  if (blockIdx.x == 0 && threadIdx.x == 0) hs_prof_flush(P.state, s_prof);
 }
 __global__ void __launch_bounds__(256) k_hs_mark(HsBatch P) {
   const int b = blockIdx.y;
@@ -715,34 +972,57 @@ struct HsStream {
   volatile float *mailbox;
   unsigned int seq;
   unsigned int *barrier;
+  unsigned int tag;      // this launch's id (never 0): scan i is decided once out[i][15] holds it
 };
 
-template <bool EXACT>
+template <bool EXACT, bool CLUSTER>
 __global__ void __launch_bounds__(HS_THREADS) k_hs_stream(HsBatch P, HsStream S) {
   extern __shared__ __align__(16) unsigned char hs_smem[];
+  __shared__ HsXchg xc;  // same offset in every CTA of the kernel: mapa() of a local address names the peer's copy
+  __shared__ unsigned long long s_prof[16];
+  __shared__ int s_flag;
+  if (threadIdx.x < 16) s_prof[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t crank = 0, csize = 1, pose_parity = 0, part_parity = 0;
+  if (CLUSTER) {
+    crank = hs_cluster_rank();
+    csize = hs_cluster_size();
+    if (threadIdx.x == 0) {
+      hs_mbar_init(&xc.bar_pose, 1);
+      hs_mbar_init(&xc.bar_part, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    hs_cluster_sync();  // no peer signals a barrier that is not initialised yet (once per launch)
+  }
+  const bool helper = CLUSTER && blockIdx.x < csize && crank != 0;  // cluster 0 = CTAs [0, csize)
   unsigned int generation = 0;
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * HS_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * HS_THREADS) >> 5;
   HsState *st = P.state;
   for (int i = 0; i < S.n_scans; i++) {
+    bool update;
+    HsCall C;
+    C.pts0 = S.pts + 2 * (size_t)(S.offsets ? S.offsets[i] : 0);
+    C.n0 = nullptr;
+    C.n0_uniform = S.counts ? S.counts[i] : S.count0;
+    C.pts_stride = 0;
+    C.hints = S.hints ? S.hints + 3 * (size_t)i : ((i == 0 && S.first_hint) ? S.first_hint : nullptr);
+    C.origo_x = S.origo_x; C.origo_y = S.origo_y;
+    C.map_without_matching = S.map_without_matching;
+    C.out = S.out + 16 * (size_t)i;
+    C.mailbox = S.mailbox;
+    C.seq = S.seq;
+    C.tag = S.tag;
+    // The matching CTA never waits for the others unless the map is updated: it publishes the scan's verdict (release) and
+    // goes on to the next scan; the other CTAs follow the verdicts and meet it at the update's barriers.  (A grid barrier
+    // per scan cost the matching CTA ~1 us: two fences and an L2 round trip.)
     if (blockIdx.x == 0) {
-      HsCall C;
-      C.pts0 = S.pts + 2 * (size_t)(S.offsets ? S.offsets[i] : 0);
-      C.n0 = nullptr;
-      C.n0_uniform = S.counts ? S.counts[i] : S.count0;
-      C.pts_stride = 0;
-      C.hints = S.hints ? S.hints + 3 * (size_t)i : ((i == 0 && S.first_hint) ? S.first_hint : nullptr);
-      C.origo_x = S.origo_x; C.origo_y = S.origo_y;
-      C.map_without_matching = S.map_without_matching;
-      C.out = S.out + 16 * (size_t)i;
-      C.mailbox = S.mailbox;
-      C.seq = S.seq;
-      hs_match_cta<EXACT>(P, C, 0, hs_smem);
+      update = hs_match_cta<EXACT, CLUSTER>(P, C, 0, hs_smem, s_prof, &xc, &part_parity);
+    } else {
+      if (helper) hs_match_helper(P, C, hs_smem, &xc, crank, csize, pose_parity);
+      update = hs_wait_decision(C.out, S.tag, &s_flag);
     }
-    hs_grid_barrier(S.barrier, generation);
-    // the gate's decision is read from this scan's own output row: without an update there is no further barrier, so CTA 0
-    // may already be matching scan i + 1 (and rewriting the state) while a slower CTA still looks at scan i's decision
-    if (__ldcg(S.out + 16 * (size_t)i + 12) != 0.0f) {
+    if (update) {
       const unsigned long long t0 = hs_now_ns();
       const unsigned long long v = hs_mark_pass(P, 0, w, nw, lane);
       if (lane == 0 && v) atomicAdd(&st->visits, v);
@@ -752,6 +1032,7 @@ __global__ void __launch_bounds__(HS_THREADS) k_hs_stream(HsBatch P, HsStream S)
       if (blockIdx.x == 0 && threadIdx.x == 0) st->t_update_ns = hs_now_ns() - t0;
     }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) hs_prof_flush(st, s_prof);
 }
 
 __global__ void k_hs_fill(float *__restrict__ p, size_t n, float v) {
@@ -773,6 +1054,7 @@ __global__ void k_hs_state_init(HsState *st, int batch, int reset_maps) {
     s.visits = s.n_matched = s.n_updated = 0;
     s.t_match_ns = s.t_update_ns = 0;
     for (int q = 0; q < 8; q++) s.prof[q] = 0;
+    for (int q = 0; q < 8; q++) s.fine[q] = 0;
     for (int l = 0; l < HS_L; l++) { s.bb_x0[l] = s.bb_y0[l] = 0; s.bb_x1[l] = s.bb_y1[l] = -1; }
   }
 }
@@ -820,6 +1102,8 @@ struct b2s_hector_slam {
   unsigned long long host_updates = 0;  // upper bound of every level's device epoch
   int stream_ctas = HS_STREAM_CTAS;
   bool coop = true;
+  unsigned int launch_tag = 0;  // id of the last stream launch (the kernel publishes per-scan verdicts under it)
+  int cluster = 1;  // CTAs per thread-block cluster of the fast-mode stream kernel (1: no cluster launch)
   cudaEvent_t ev_done = nullptr;
   bool launch_pending = false;  // a per-scan launch may still be running its update passes
 };
@@ -957,16 +1241,39 @@ static b2s_status hs_create(float map_resolution, int map_size_x, int map_size_y
   const size_t smem = hs_smem_bytes(max_points);
   HS_CHECK(raise_dyn_smem(k_hs_match<true>, smem));
   HS_CHECK(raise_dyn_smem(k_hs_match<false>, smem));
-  HS_CHECK(raise_dyn_smem(k_hs_stream<true>, smem));
-  HS_CHECK(raise_dyn_smem(k_hs_stream<false>, smem));
+  HS_CHECK(raise_dyn_smem(k_hs_stream<true, false>, smem));
+  HS_CHECK(raise_dyn_smem(k_hs_stream<false, false>, smem));
+  HS_CHECK(raise_dyn_smem(k_hs_stream<false, true>, smem));
   {
     int coop = 0, sms = 0, per_sm = 0;
     HS_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     HS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    HS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hs_stream<true>, HS_THREADS, smem));
+    HS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hs_stream<true, false>, HS_THREADS, smem));
     p->coop = coop != 0;
-    p->stream_ctas = std::max(1, std::min(HS_STREAM_CTAS, sms * std::max(per_sm, 0)));
+    int want = HS_STREAM_CTAS;
+    if (const char *ec = getenv("B2S_HS_STREAM_CTAS")) want = std::max(1, atoi(ec));  // tuning switch
+    p->stream_ctas = std::max(1, std::min(want, sms * std::max(per_sm, 0)));
     if (!p->coop) p->stream_ctas = 1;  // without a co-residency guarantee a spinning grid barrier could deadlock
+    // fast mode: the matching CTA's cluster (B2S_HS_CLUSTER=0 switches it off).  Needs the whole cooperative grid
+    // co-resident AS clusters.
+    const char *e = getenv("B2S_HS_CLUSTER");
+    if (p->coop && p->stream_ctas >= HS_CLUSTER && !(e && e[0] == '0')) {
+      cudaLaunchConfig_t cfg;
+      std::memset(&cfg, 0, sizeof(cfg));
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = HS_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((p->stream_ctas / HS_CLUSTER) * HS_CLUSTER);
+      cfg.blockDim = dim3(HS_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, k_hs_stream<false, true>, &cfg) == cudaSuccess &&
+          n_clusters * HS_CLUSTER >= (int)cfg.gridDim.x)
+        p->cluster = HS_CLUSTER;
+      else
+        cudaGetLastError();
+    }
   }
   k_hs_state_init<<<ceil_div(batch, 128), 128, 0, p->stream>>>(p->d_state, batch, 2);
   {
@@ -994,14 +1301,36 @@ static b2s_status hs_launch_stream(b2s_hector_slam *p, const HsStream &S) {
   HsBatch P = p->P;
   HsStream Sv = S;
   Sv.barrier = p->d_barrier;
+  p->launch_tag += 1;
+  if (p->launch_tag == 0) p->launch_tag = 1;
+  Sv.tag = p->launch_tag;
   const size_t smem = hs_smem_bytes(p->cap);
+  if (p->coop && !P.exact && p->cluster > 1) {
+    // cooperative (all CTAs co-resident for the grid barrier) AND clustered (CTAs [0, cluster) share the match)
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = (unsigned)p->cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((p->stream_ctas / p->cluster) * p->cluster);
+    cfg.blockDim = dim3(HS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = p->stream;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_hs_stream<false, true>, P, Sv);
+    if (e == cudaSuccess) return B2S_OK;
+    cudaGetLastError();
+    p->cluster = 1;  // this driver refuses the combination: the one-CTA match from now on
+  }
   if (p->coop) {
     void *args[2] = {&P, &Sv};
-    const void *kern = P.exact ? reinterpret_cast<const void *>(k_hs_stream<true>) : reinterpret_cast<const void *>(k_hs_stream<false>);
+    const void *kern = P.exact ? reinterpret_cast<const void *>(k_hs_stream<true, false>) : reinterpret_cast<const void *>(k_hs_stream<false, false>);
     B2S_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(p->stream_ctas), dim3(HS_THREADS), args, smem, p->stream));
   } else {
-    if (P.exact) k_hs_stream<true><<<1, HS_THREADS, smem, p->stream>>>(P, Sv);
-    else k_hs_stream<false><<<1, HS_THREADS, smem, p->stream>>>(P, Sv);
+    if (P.exact) k_hs_stream<true, false><<<1, HS_THREADS, smem, p->stream>>>(P, Sv);
+    else k_hs_stream<false, false><<<1, HS_THREADS, smem, p->stream>>>(P, Sv);
     B2S_CUDA_CHECK(cudaGetLastError());
   }
   return B2S_OK;
@@ -1048,6 +1377,8 @@ b2s_status b2s_hector_slam_set_exact(b2s_hector_slam *p, int exact) {
   p->P.exact = exact ? 1 : 0;
   return B2S_OK;
 }
+
+int32_t b2s_hector_slam_match_cluster_size(const b2s_hector_slam *p) { return p ? (int32_t)p->cluster : 0; }
 
 b2s_status b2s_hector_slam_reset(b2s_hector_slam *p) {
   if (!p) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null handle");
@@ -1102,8 +1433,9 @@ b2s_status b2s_hector_slam_update(b2s_hector_slam *p, const float *points, int n
     }
   }
   std::atomic_thread_fence(std::memory_order_acquire);
-  float r[14];
-  for (int q = 0; q < 14; q++) r[q] = p->h_mail[q];
+  float r[15];
+  for (int q = 0; q < 15; q++) r[q] = p->h_mail[q];
+  if (r[14] != 0.0f) B2S_FAIL(B2S_ERR_CUDA, "b2s_hector_slam_update: a cluster exchange of the match timed out");
   out_pose[0] = r[0]; out_pose[1] = r[1]; out_pose[2] = r[2];
   if (out_cov && !map_without_matching) std::memcpy(out_cov, r + 3, 9 * sizeof(float));
   if (out_map_updated) *out_map_updated = r[12] != 0.0f ? 1 : 0;
@@ -1142,6 +1474,7 @@ b2s_status b2s_hector_slam_process_stream(b2s_hector_slam *p, int n_scans, const
 #define HS_CHECK(expr) B2S_CUDA_CHECK_CLEAN(release(), expr)
   HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_pts), sizeof(float) * 2 * (size_t)std::max<long long>(total, 1), p->stream));
   HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_out), sizeof(float) * 16 * (size_t)n_scans, p->stream));
+  HS_CHECK(cudaMemsetAsync(d_out, 0, sizeof(float) * 16 * (size_t)n_scans, p->stream));  // no stale verdict tags
   HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_offs), sizeof(int) * (size_t)n_scans, p->stream));
   HS_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_cnt), sizeof(int) * (size_t)n_scans, p->stream));
   if (total > 0) HS_CHECK(cudaMemcpyAsync(d_pts, points, sizeof(float) * 2 * (size_t)total, cudaMemcpyHostToDevice, p->stream));
@@ -1168,6 +1501,7 @@ b2s_status b2s_hector_slam_process_stream(b2s_hector_slam *p, int n_scans, const
 #undef HS_CHECK
   release();
   for (int i = 0; i < n_scans; i++) {
+    if (host[16 * (size_t)i + 14] != 0.0f) B2S_FAIL(B2S_ERR_CUDA, "b2s_hector_slam_process_stream: a cluster exchange of the match timed out");
     std::memcpy(out_poses + 3 * (size_t)i, host.data() + 16 * (size_t)i, 3 * sizeof(float));
     if (out_map_updated) out_map_updated[i] = host[16 * (size_t)i + 12] != 0.0f ? 1 : 0;
   }
@@ -1334,6 +1668,17 @@ b2s_status b2s_hector_slam_profile(b2s_hector_slam *p, double out[8]) {
   B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
   p->launch_pending = false;
   for (int q = 0; q < 8; q++) out[q] = (double)s.prof[q];
+  return B2S_OK;
+}
+
+b2s_status b2s_hector_slam_profile_fine(b2s_hector_slam *p, double out[8]) {
+  if (!p || !out) B2S_FAIL(B2S_ERR_BAD_PARAMS, "null argument");
+  B2S_CUDA_CHECK(cudaSetDevice(p->device));
+  HsState s;
+  B2S_CUDA_CHECK(cudaMemcpyAsync(&s, p->d_state, sizeof(HsState), cudaMemcpyDeviceToHost, p->stream));
+  B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+  p->launch_pending = false;
+  for (int q = 0; q < 8; q++) out[q] = (double)s.fine[q];
   return B2S_OK;
 }
 

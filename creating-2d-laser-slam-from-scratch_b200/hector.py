@@ -49,6 +49,8 @@ def _bind():
     L.b2s_hector_slam_last_poses.argtypes = [vp, C.c_int, fp, fp]
     L.b2s_hector_slam_debug_set_epoch.argtypes = [vp, C.c_uint]
     L.b2s_hector_slam_profile.argtypes = [vp, C.POINTER(C.c_double)]
+    L.b2s_hector_slam_match_cluster_size.argtypes = [vp]
+    L.b2s_hector_slam_profile_fine.argtypes = [vp, C.POINTER(C.c_double)]
     _bound = True
     return L
 
@@ -146,6 +148,10 @@ class HectorSlam:
     def set_exact(self, exact):
         check(self.L.b2s_hector_slam_set_exact(self.h, int(bool(exact))))
 
+    def cluster_size(self):
+        """CTAs sharing the fast mode's match (1 = no cluster launch)."""
+        return int(self.L.b2s_hector_slam_match_cluster_size(self.h))
+
     def process_stream(self, scans, origo, first_hint=None, pose_hints=None, map_without_matching=False):
         """A whole stream of LaserScans in one call (hint of scan i = pose of scan i-1, as the node's loop chains them,
         unless pose_hints gives one per scan).  Returns poses [n,3], updated flags [n], last covariance [3,3]."""
@@ -200,8 +206,13 @@ class HectorSlam:
         out = np.zeros(8)
         check(self.L.b2s_hector_slam_profile(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
         it = max(out[6], 1.0)
+        fine = np.zeros(8)
+        check(self.L.b2s_hector_slam_profile_fine(self.h, fine.ctypes.data_as(C.POINTER(C.c_double))))
         return dict(staging=out[0], terms=out[1], sums=out[2], solve=out[3], trig=out[4], gate=out[5], iterations=out[6],
-                    cycles_per_iteration=dict(terms=out[1] / it, sums=out[2] / it, solve=out[3] / it, trig=out[4] / it))
+                    cycles_per_iteration=dict(terms=out[1] / it, sums=out[2] / it, solve=out[3] / it, trig=out[4] / it),
+                    terms_detail_cycles_per_iteration=dict(transform=fine[0] / it, load_to_use=fine[1] / it,
+                                                           arithmetic=fine[2] / it, reduce=fine[3] / it, barrier=fine[4] / it,
+                                                           loop_head=fine[5] / it, column_sum=fine[6] / it))
 
     def debug_set_epoch(self, updates):
         check(self.L.b2s_hector_slam_debug_set_epoch(self.h, int(updates)))

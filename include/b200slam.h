@@ -411,8 +411,8 @@ b2s_status b2s_hector_map_last_timing(b2s_hector_map *m, double out[2]);
  * be handed over at once (b2s_hector_slam_process_stream: no host round trip between scans), and a handle may hold B
  * independent processors (b2s_hector_slam_create_batch).
  * EXACT mode (default): bit-identical poses, Hessians and cells to the reference (sequential float32 sums in point
- * order, glibc's sinf / cosf restated on the device); b2s_hector_slam_set_exact(p, 0) sums with a tree instead
- * (faster; poses within 1e-4). */
+ * order, glibc's sinf / cosf restated on the device); b2s_hector_slam_set_exact(p, 0) sums with a tree instead and
+ * spreads the per-point phase of the match over a 4-CTA cluster (faster; poses within 1e-4). */
 
 typedef struct b2s_hector_slam b2s_hector_slam; /* opaque: replaces hectorslam::HectorSlamProcessor
                                                    (slam_main/HectorSlamProcessor.h:50-150) */
@@ -452,6 +452,10 @@ b2s_status b2s_hector_slam_stats(b2s_hector_slam *p, double out[5]);
 /* 1 (default) = the reference's arithmetic bit for bit; 0 = the nine Gauss-Newton sums are tree-reduced instead of
  * accumulated in point order (everything else unchanged): faster, poses agree to ~1e-6 m */
 b2s_status b2s_hector_slam_set_exact(b2s_hector_slam *p, int exact);
+/* Non-exact mode, single-processor handles: the CTAs of one thread-block cluster share the per-point phase of every
+ * Gauss-Newton iteration (pose out / nine partial sums back through distributed shared memory).  Returns the CTAs per
+ * cluster in use (1: no cluster launch — B2S_HS_CLUSTER=0 or the device cannot co-schedule the grid as clusters). */
+int32_t b2s_hector_slam_match_cluster_size(const b2s_hector_slam *p);
 /* The node's loop over a recorded stream (hector_slam.cc:195-204: update(container, getLastScanMatchPose())) in ONE
  * call: n_scans scans, points concatenated ([sum n_points][2], level-0 map-cell units), hint of scan i = pose of scan
  * i-1 (first_pose_hint for scan 0; NULL = the processor's current last scan-match pose), or pose_hints[i] when given
@@ -486,6 +490,10 @@ b2s_status b2s_hector_slam_last_poses(b2s_hector_slam *p, int processor, float l
 /* SM cycles of processor 0's matching CTA since creation, by phase: staging, per-point terms, the nine sums, 3x3 solve,
  * sine / cosine, gate + update parameters, iterations counted, (unused) */
 b2s_status b2s_hector_slam_profile(b2s_hector_slam *p, double out[8]);
+/* the per-point phase as thread 0 of the matching CTA sees it, SM cycles summed over iterations: [0] pose read +
+ * point transform, [1] probability-cell load to first use, [2] term arithmetic, [3] warp reduction + store, [4] CTA
+ * barrier (waiting for the slowest warp) */
+b2s_status b2s_hector_slam_profile_fine(b2s_hector_slam *p, double out[8]);
 /* test hook: pretend `updates` map updates already consumed per-scan stamp epochs (exercises the 20-bit epoch wrap) */
 b2s_status b2s_hector_slam_debug_set_epoch(b2s_hector_slam *p, unsigned int updates);
 

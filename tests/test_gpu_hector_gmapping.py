@@ -265,6 +265,42 @@ def test_hector_slam_fast_mode_within_contract(pkg, mods):
         assert touched > 1000 and bad <= max(2, touched // 500), (lvl, bad, touched)
 
 
+def test_hector_slam_fast_mode_cluster_match(pkg, mods, monkeypatch):
+    """Fast mode spreads the per-point phase of the match over a 4-CTA thread-block cluster (partial sums through
+    distributed shared memory).  Same stream through the clustered and the one-CTA kernel (B2S_HS_CLUSTER=0): poses
+    within the 1e-4 contract of each other and of the CPU processor, identical gate decisions; the clustered path is
+    deterministic (per-scan calls and the one-call stream agree bit for bit)."""
+    H, _ = mods
+    poses, scans = _stream_case(pkg, H, 33, 60, step_xy=0.1, step_th=3)
+    kw = dict(resolution=0.05, size_x=1000, size_y=1000, start=(0.5, 0.5), levels=3, min_dist=0.2, min_angle=0.1)
+    first = poses[0].astype(np.float32)
+    gc = H.HectorSlam(exact=False, **kw)
+    assert gc.cluster_size() == 4, "the cluster launch is not available: the fast path fell back to one CTA"
+    monkeypatch.setenv("B2S_HS_CLUSTER", "0")
+    g1 = H.HectorSlam(exact=False, **kw)
+    monkeypatch.delenv("B2S_HS_CLUSTER")
+    assert g1.cluster_size() == 1
+    pc, uc, _ = gc.process_stream(scans, (0, 0), first_hint=first)
+    p1, u1, _ = g1.process_stream(scans, (0, 0), first_hint=first)
+    c = port.PortHectorProcessor(**kw)
+    est, ref_poses = first, []
+    for sc in scans:
+        est, _ = c.update(sc, (0, 0), est)
+        ref_poses.append(est.copy())
+    ref_poses = np.stack(ref_poses)
+    assert np.abs(pc - p1).max() <= 1e-4 and np.abs(pc - ref_poses).max() <= 1e-4, (np.abs(pc - p1).max(), np.abs(pc - ref_poses).max())
+    assert list(uc) == list(u1) and 2 <= sum(uc) < len(scans)
+    g2 = H.HectorSlam(exact=False, **kw)
+    est = first
+    for i, sc in enumerate(scans):
+        est, _ = g2.update(sc, (0, 0), est)
+        assert np.array_equal(est.view(np.int32), pc[i].view(np.int32)), i
+    for lvl in range(3):
+        bad, touched = _cell_mismatch(gc.level(lvl), g2.level(lvl))
+        assert touched > 1000 and bad == 0
+    print("cluster vs one-CTA fast match: max |pose diff|", np.abs(pc - p1).max(), "vs CPU processor", np.abs(pc - ref_poses).max())
+
+
 def test_hector_slam_batch_equals_single_processors(pkg, mods):
     """B = 3 independent processors behind one handle (different robots, ragged scans): each equals its own
     single-processor run bit for bit — poses, gate decisions, maps."""
