@@ -80,6 +80,7 @@ struct HsState {  // device-resident state of ONE processor
   int bb_x0[HS_L], bb_y0[HS_L], bb_x1[HS_L], bb_y1[HS_L];  // cells the update's rays can touch (inclusive; empty: x1 < x0)
   unsigned long long visits, n_matched, n_updated;
   unsigned long long t_match_ns, t_update_ns;
+  unsigned long long hfine[8]; // warp 0 of helper CTA 1 (cluster match): [0] waiting for the pose, [1..5] as fine[0..4], [6] column sum, [7] iterations
   unsigned long long fine[8];  // thread 0's view of the per-point phase: [0] pose read + transform, [1] cell load to use, [2] term arithmetic, [3] warp reduction + store, [4] barrier
   unsigned long long prof[8];  // SM cycles of processor 0's matching CTA: [0] staging, [1] point terms, [2] sums, [3] solve, [4] trig, [5] gate + bbox, [6] iterations
 };
@@ -90,6 +91,7 @@ struct HsBatch {  // kernel parameter
   float lo_free, lo_occ, min_dist, min_angle;
   int exact, use_fma;
   int l2_loads;    // 1: the match reads the probability planes with ld.global.cg (tuning switch B2S_HS_L2_LOADS)
+  int master_share;  // cluster match: 1 = the solving CTA also takes a share of the points, 0 = only the helpers do
   HsState *state;  // [batch]
 };
 
@@ -117,6 +119,8 @@ __device__ __forceinline__ unsigned long long hs_now_ns() {
 // CTAs of cluster 0 split the scan's points: rank 0 (the master) solves, the helpers receive the pose + sine / cosine and
 // return their nine partial sums through distributed shared memory.  Data and signal travel together (st.async with
 // mbarrier complete_tx): no cluster-scope fence, hence no L1 invalidation (CCTL.IVALL) inside the iteration loop.
+// (Measured alternative: 8-byte {value, sequence} messages written with plain st.shared::cluster and polled with volatile
+// shared loads — no mbarrier at all — took ~1000 cycles MORE per hop than st.async + try_wait: 21.5 k vs 29.9 k scans/s.)
 constexpr int HS_CLUSTER = 4;
 constexpr int HS_POSE_WORDS = 7;  // e0, e1, cos, sin, sinRot, cosRot, spare
 struct __align__(16) HsXchg {
@@ -327,34 +331,39 @@ __device__ __forceinline__ float hs_share_sums(const float4 *__restrict__ prob, 
                                                float factor, float e0, float e1, float c, float s, float sin_rot,
                                                float cos_rot, bool l2, float *terms, int pitch, int tid, int lane, int warp,
                                                HsTicks *tk = nullptr) {
-  if (tk && tid == 0) tk->tick(5, e0);  // since the end of the previous solve: publish + barrier + loop head
+  if (tk && warp == 0) tk->tick(5, e0);  // since the end of the previous solve: publish + barrier + loop head
   if (warp * 32 < cnt) {
 #pragma unroll 1
     for (int i = tid; i < cnt; i += HS_THREADS) {
       const float2 p = make_float2(__fmul_rn(pts[i].x, factor), __fmul_rn(pts[i].y, factor));
       const HsFetch f = hs_point_fetch(prob, sx, sy, p, c, s, e0, e1, l2);
-      if (tk && tid == 0) { tk->tick(0, f.fx); tk->tick(1, f.i0); }
+      if (tk && warp == 0) { tk->tick(0, f.fx); tk->tick(1, f.i0); }
       float t[9];
       hs_point_terms(f, p, sin_rot, cos_rot, t);
-      if (tk && tid == 0) tk->tick(2, t[2] + t[5]);
+      if (tk && warp == 0) tk->tick(2, t[2] + t[5]);
 #pragma unroll
       for (int q = 0; q < 9; q++) terms[q * pitch + i] = t[q];
     }
   }
-  if (tk && tid == 0) tk->tick(3, e0);
+  if (tk && warp == 0) tk->tick(3, e0);
   __syncthreads();
-  if (tk && tid == 0) tk->tick(4, e0);
+  if (tk && warp == 0) tk->tick(4, e0);
   float v = 0.0f;
   if (warp < 9) {
     const float *col = terms + warp * pitch;
     // (not unrolled on purpose: this runs once per iteration on cold instruction lines — the L0 instruction cache holds
     // ~6 KB and the iteration loop is larger — so executed code BYTES cost more than instructions)
+    float v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;  // four loads in flight: the loop is a latency chain, not a throughput one
+    int i = lane;
 #pragma unroll 1
-    for (int i = lane; i < cnt; i += 32) v += col[i];
+    for (; i + 96 < cnt; i += 128) { v += col[i]; v1 += col[i + 32]; v2 += col[i + 64]; v3 += col[i + 96]; }
+#pragma unroll 1
+    for (; i < cnt; i += 32) v += col[i];
+    v = (v + v1) + (v2 + v3);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   }
-  if (tk && tid == 0) tk->tick(6, v);
+  if (tk && warp == 0) tk->tick(6, v);
   return v;
 }
 
@@ -389,7 +398,10 @@ __device__ bool hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
   const uint32_t csize = CLUSTER ? hs_cluster_size() : 1u;
   uint32_t part_parity = CLUSTER ? *xc_parity : 0u;
   int my0 = 0, my1 = n;  // this CTA's share of the points in the per-point phase
-  if (CLUSTER) hs_share(n, 0, (int)csize, my0, my1);
+  if (CLUSTER) {
+    if (P.master_share || csize < 2) hs_share(n, 0, (int)csize, my0, my1);
+    else my1 = 0;  // the helpers cover the whole scan; this CTA only solves
+  }
   if (CLUSTER && tid == 0) s_lost = 0;
   // master -> helpers: the pose of the next iteration (bc[0..6]) into every helper's HsXchg::pose; one st.async per lane
   // of warp 0 (the solving thread publishes nothing itself: 21 serial remote stores cost it ~300 cycles)
@@ -461,7 +473,8 @@ __device__ bool hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
       for (int it = 0; it < m.iterations; it++) {
         const float e0 = bc[0], e1 = bc[1], c = bc[3], s = bc[4], sin_rot = bc[5], cos_rot = bc[6];
         if constexpr (CLUSTER) {
-          float v = hs_share_sums(prob, m.sx, m.sy, spts, my1, factor, e0, e1, c, s, sin_rot, cos_rot, l2, terms, pitch, tid, lane, warp);
+          float v = 0.0f;
+          if (my1 > 0) v = hs_share_sums(prob, m.sx, m.sy, spts, my1, factor, e0, e1, c, s, sin_rot, cos_rot, l2, terms, pitch, tid, lane, warp);
           HS_PROF(1);
           if (warp < 9) {
             if (csize > 1) {  // + the helpers' partial sums, in rank order
@@ -752,12 +765,18 @@ __device__ void hs_match_helper(const HsBatch &P, const HsCall &C, unsigned char
   float2 *spts = reinterpret_cast<float2 *>(smem);
   float *terms = reinterpret_cast<float *>(smem + hs_terms_offset(P.cap));
   int p0, p1;
-  hs_share(n, (int)rank, (int)csize, p0, p1);
+  if (P.master_share) hs_share(n, (int)rank, (int)csize, p0, p1);
+  else hs_share(n, (int)rank - 1, (int)csize - 1, p0, p1);
   const int cnt = p1 - p0;
   const float2 *gp = reinterpret_cast<const float2 *>(C.pts0);
   for (int i = tid; i < cnt; i += HS_THREADS) spts[i] = gp[p0 + i];
   __syncthreads();
   const int pitch = hs_pitch(P.cap);
+  HsTicks htk;
+#pragma unroll
+  for (int q = 0; q < 8; q++) htk.fine[q] = 0;
+  htk.mark = clock64();
+  int n_it = 0;
   const uint32_t r_part = hs_mapa(hs_smem_u32(&xc->part[rank][0]), 0), r_bar = hs_mapa(hs_smem_u32(&xc->bar_part), 0);
   float factor = 1.0f;
   for (int l = 1; l < P.levels; l++) factor *= 0.5f;
@@ -768,12 +787,21 @@ __device__ void hs_match_helper(const HsBatch &P, const HsCall &C, unsigned char
       if (tid == 0) hs_mbar_expect_tx(&xc->bar_pose, 4u * HS_POSE_WORDS);
       hs_mbar_wait(&xc->bar_pose, pose_parity);  // every thread observes the phase itself (a time-out is reported by the master)
       pose_parity ^= 1u;
+      if (warp == 0) { htk.tick(7, xc->pose[0]); n_it++; }
       const float e0 = xc->pose[0], e1 = xc->pose[1], c = xc->pose[3], s = xc->pose[4], sin_rot = xc->pose[5], cos_rot = xc->pose[6];
       // (no barrier needed here: the master sends the next pose only after it holds all nine of our sums, and those are
       // sent behind hs_share_sums' barrier, i.e. after every thread has read this pose and the previous columns)
-      const float v = hs_share_sums(prob, m.sx, m.sy, spts, cnt, factor, e0, e1, c, s, sin_rot, cos_rot, l2, terms, pitch, tid, lane, warp);
+      const float v = hs_share_sums(prob, m.sx, m.sy, spts, cnt, factor, e0, e1, c, s, sin_rot, cos_rot, l2, terms, pitch, tid, lane, warp, &htk);
       if (warp < 9 && lane == 0) hs_st_async(r_part + 4 * warp, v, r_bar);
+      if (warp == 0) htk.tick(-1, v);
     }
+  }
+  if (rank == 1 && tid == 0) {  // the helper's view of an iteration, for b2s_hector_slam_profile_fine
+    HsState *st = P.state;
+    st->hfine[0] += htk.fine[7];
+    for (int q = 0; q < 5; q++) st->hfine[1 + q] += htk.fine[q];
+    st->hfine[6] += htk.fine[6];
+    st->hfine[7] += (unsigned long long)n_it;
   }
 }
 
@@ -1055,6 +1083,7 @@ __global__ void k_hs_state_init(HsState *st, int batch, int reset_maps) {
     s.t_match_ns = s.t_update_ns = 0;
     for (int q = 0; q < 8; q++) s.prof[q] = 0;
     for (int q = 0; q < 8; q++) s.fine[q] = 0;
+    for (int q = 0; q < 8; q++) s.hfine[q] = 0;
     for (int l = 0; l < HS_L; l++) { s.bb_x0[l] = s.bb_y0[l] = 0; s.bb_x1[l] = s.bb_y1[l] = -1; }
   }
 }
@@ -1188,6 +1217,7 @@ static b2s_status hs_create(float map_resolution, int map_size_x, int map_size_y
   p->P.min_dist = 0.4f; p->P.min_angle = 0.13f;  // HectorSlamProcessor.h:63-64
   p->P.exact = 1;
   { const char *e = getenv("B2S_HS_L2_LOADS"); p->P.l2_loads = (e && e[0] == '1') ? 1 : 0; }
+  { const char *e = getenv("B2S_HS_MASTER_SHARE"); p->P.master_share = (e && e[0] == '0') ? 0 : 1; }
   const int variant = glibc_sincosf_variant_of_host();
   p->P.use_fma = variant == 0 ? 0 : 1;
   // MapRepMultiMap ctor (MapRepMultiMap.h:56-89): one offset for every level, dims halve, cell length doubles
@@ -1257,20 +1287,22 @@ static b2s_status hs_create(float map_resolution, int map_size_x, int map_size_y
     // fast mode: the matching CTA's cluster (B2S_HS_CLUSTER=0 switches it off).  Needs the whole cooperative grid
     // co-resident AS clusters.
     const char *e = getenv("B2S_HS_CLUSTER");
-    if (p->coop && p->stream_ctas >= HS_CLUSTER && !(e && e[0] == '0')) {
+    int want_cluster = HS_CLUSTER;
+    if (e && (e[0] == '2' || e[0] == '4' || e[0] == '8')) want_cluster = e[0] - '0';  // tuning switch; 0 switches it off
+    if (p->coop && p->stream_ctas >= want_cluster && !(e && e[0] == '0')) {
       cudaLaunchConfig_t cfg;
       std::memset(&cfg, 0, sizeof(cfg));
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = HS_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.gridDim = dim3((p->stream_ctas / HS_CLUSTER) * HS_CLUSTER);
+      at[0].val.clusterDim.x = (unsigned)want_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((p->stream_ctas / want_cluster) * want_cluster);
       cfg.blockDim = dim3(HS_THREADS);
       cfg.dynamicSmemBytes = smem;
       cfg.attrs = at; cfg.numAttrs = 1;
       int n_clusters = 0;
       if (cudaOccupancyMaxActiveClusters(&n_clusters, k_hs_stream<false, true>, &cfg) == cudaSuccess &&
-          n_clusters * HS_CLUSTER >= (int)cfg.gridDim.x)
-        p->cluster = HS_CLUSTER;
+          n_clusters * want_cluster >= (int)cfg.gridDim.x)
+        p->cluster = want_cluster;
       else
         cudaGetLastError();
     }
@@ -1679,6 +1711,8 @@ b2s_status b2s_hector_slam_profile_fine(b2s_hector_slam *p, double out[8]) {
   B2S_CUDA_CHECK(cudaStreamSynchronize(p->stream));
   p->launch_pending = false;
   for (int q = 0; q < 8; q++) out[q] = (double)s.fine[q];
+  if (p->P.exact == 0 && p->cluster > 1)
+    for (int q = 0; q < 8; q++) out[q] = (double)s.hfine[q];  // the helper's view when the cluster match is in use
   return B2S_OK;
 }
 

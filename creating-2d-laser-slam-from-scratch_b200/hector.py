@@ -210,6 +210,7 @@ class HectorSlam:
         check(self.L.b2s_hector_slam_profile_fine(self.h, fine.ctypes.data_as(C.POINTER(C.c_double))))
         return dict(staging=out[0], terms=out[1], sums=out[2], solve=out[3], trig=out[4], gate=out[5], iterations=out[6],
                     cycles_per_iteration=dict(terms=out[1] / it, sums=out[2] / it, solve=out[3] / it, trig=out[4] / it),
+                    raw_fine=[float(x) for x in fine],
                     terms_detail_cycles_per_iteration=dict(transform=fine[0] / it, load_to_use=fine[1] / it,
                                                            arithmetic=fine[2] / it, reduce=fine[3] / it, barrier=fine[4] / it,
                                                            loop_head=fine[5] / it, column_sum=fine[6] / it))

@@ -19,12 +19,12 @@ kw = dict(resolution=0.05, size_x=1000, size_y=1000, start=(0.5, 0.5), levels=3,
           min_dist=0.4, min_angle=0.9)
 first = poses[0].astype(np.float32)
 out, traces = {"scans": n}, {}
-CONFIGS = [("fast_cluster", {}, False), ("fast_cluster_148ctas", {"B2S_HS_STREAM_CTAS": "148"}, False),
+CONFIGS = [("fast_cluster", {}, False), ("fast_cluster8", {"B2S_HS_CLUSTER": "8"}, False), ("fast_cluster2", {"B2S_HS_CLUSTER": "2"}, False), ("fast_cluster_master_share", {"B2S_HS_MASTER_SHARE": "1"}, False), ("fast_cluster_148ctas", {"B2S_HS_STREAM_CTAS": "148"}, False),
            ("fast_one_cta", {"B2S_HS_CLUSTER": "0"}, False), ("exact", {}, True)]
 if len(sys.argv) > 2:
     CONFIGS = [c for c in CONFIGS if c[0] in sys.argv[2].split(",")]
 for tag, env, exact in CONFIGS:
-    for k in ("B2S_HS_CLUSTER", "B2S_HS_STREAM_CTAS"):
+    for k in ("B2S_HS_CLUSTER", "B2S_HS_STREAM_CTAS", "B2S_HS_MASTER_SHARE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     hs = H.HectorSlam(exact=exact, **kw)
