@@ -106,6 +106,7 @@ struct HsCall {  // one scan per processor
   volatile float *mailbox;  // host-mapped copy of out for processor 0 + sequence word, or NULL
   unsigned int seq;
   unsigned int tag;     // != 0: published (release, gpu scope) in out[b][15] once the scan's state is complete
+  float *carry;         // shared-memory [3] or NULL: receives the scan-match pose (the next scan's hint in a stream)
 };
 
 __device__ __forceinline__ unsigned long long hs_now_ns() {
@@ -254,7 +255,17 @@ __device__ __forceinline__ void hs_point_terms(const HsFetch &f, float2 p, float
 // util::normalize_angle (UtilFunctions.h:36-48): double fmod, float result
 __device__ __noinline__ float hs_normalize_angle(float e2) {
   const double two_pi = 2.0f * 3.14159265358979323846;
-  float a = (float)fmod(fmod((double)e2, two_pi) + two_pi, two_pi);
+  const double d = (double)e2;
+  double r;
+  if (fabs(d) < two_pi) {
+    // fmod(d, 2pi) = d here, and for x = d + 2pi in (0, 4pi): fmod(x, 2pi) = x - 2pi when x >= 2pi (exact: Sterbenz), else x.
+    // Bit for bit the reference's two fmod calls, without the two software remainder loops (~1000 cycles per scan).
+    const double x = d + two_pi;
+    r = x >= two_pi ? x - two_pi : x;
+  } else {
+    r = fmod(fmod(d, two_pi) + two_pi, two_pi);
+  }
+  float a = (float)r;
   if ((double)a > 3.14159265358979323846) a = (float)((double)a - two_pi);  // `a -= 2.0f*M_PI` promotes to double
   return a;
 }
@@ -641,6 +652,7 @@ __device__ bool hs_match_cta(const HsBatch &P, const HsCall &C, int b, unsigned 
     st->n_pts[0] = n;
     st->origo[0][0] = C.origo_x; st->origo[0][1] = C.origo_y;
     st->last_match_pose[0] = est[0]; st->last_match_pose[1] = est[1]; st->last_match_pose[2] = est[2];
+    if (C.carry) { C.carry[0] = est[0]; C.carry[1] = est[1]; C.carry[2] = est[2]; }
     const bool do_update = hs_pose_difference_larger_than(est, lup, P.min_dist, P.min_angle) ||
                            C.map_without_matching;
     st->do_update = do_update ? 1 : 0;
@@ -1027,14 +1039,22 @@ __global__ void __launch_bounds__(HS_THREADS) k_hs_stream(HsBatch P, HsStream S)
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * HS_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * HS_THREADS) >> 5;
   HsState *st = P.state;
+  __shared__ float s_last[3];  // the matching CTA's last scan-match pose: the next scan's hint without a global round trip
+  int next_off = (S.offsets && S.n_scans > 0) ? S.offsets[0] : 0, next_cnt = (S.counts && S.n_scans > 0) ? S.counts[0] : S.count0;
   for (int i = 0; i < S.n_scans; i++) {
     bool update;
     HsCall C;
-    C.pts0 = S.pts + 2 * (size_t)(S.offsets ? S.offsets[i] : 0);
+    const int off = next_off, cnt_i = next_cnt;
+    if (i + 1 < S.n_scans) {  // requested a whole scan ahead of their use
+      if (S.offsets) next_off = S.offsets[i + 1];
+      if (S.counts) next_cnt = S.counts[i + 1];
+    }
+    C.pts0 = S.pts + 2 * (size_t)off;
     C.n0 = nullptr;
-    C.n0_uniform = S.counts ? S.counts[i] : S.count0;
+    C.n0_uniform = cnt_i;
     C.pts_stride = 0;
-    C.hints = S.hints ? S.hints + 3 * (size_t)i : ((i == 0 && S.first_hint) ? S.first_hint : nullptr);
+    C.hints = S.hints ? S.hints + 3 * (size_t)i : ((i == 0 && S.first_hint) ? S.first_hint : (i > 0 ? s_last : nullptr));
+    C.carry = s_last;
     C.origo_x = S.origo_x; C.origo_y = S.origo_y;
     C.map_without_matching = S.map_without_matching;
     C.out = S.out + 16 * (size_t)i;

@@ -19,3 +19,12 @@ def test_restated_sincosf_equals_host_libm(tmp_path):
     assert out["host_variant"] in (0, 1), out
     key = "mismatch_fma" if out["host_variant"] == 1 else "mismatch_plain"
     assert out[key] == 0, out
+
+
+def test_normalize_angle_shortcut_equals_fmod(tmp_path):
+    """hs_normalize_angle's |a| < 2 pi path (one add, one compare, one subtract in double) against the two fmod calls of
+    util::normalize_angle on this machine's C library: identical bits."""
+    exe = str(tmp_path / "normalize_angle_check")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", os.path.join(HERE, "normalize_angle_check.c"), "-o", exe, "-lm"])
+    out = json.loads(subprocess.check_output([exe, "20000000"], text=True))
+    assert out["inputs"] > 20_000_000 and out["mismatches"] == 0, out
