@@ -775,6 +775,48 @@ def bench_k2(pkg, local, quick=False):
                                         "note": "pure scan-to-scan odometry, no map: drift accumulates; parity unpinned"}
     except Exception as e:
         out["plicp_odometry_stream"] = {"error": repr(e)}
+    # --- lesson5 pre-stage: motion de-skew of a batch of scans (LidarUndistortion::CorrectLaserScan, one thread per beam)
+    try:
+        DS = pkg.load("deskew")
+        nb_d, nbeam = (256 if quick else 2048), 1081
+        rg = np.random.default_rng(5)
+        rr = rg.uniform(0.5, 25.0, (nb_d, nbeam)).astype(np.float32)
+        t0s = 100.0 + 0.1 * np.arange(nb_d)
+        infos, T, X, Y, Z = [], [], [], [], []
+        for b in range(nb_d):
+            stamps = t0s[b] - 0.05 + np.arange(45) * 0.005
+            t_end = t0s[b] + 0.1 / nbeam * (nbeam - 1)
+            last, t, x, y, z = DS.integrate_imu(stamps, np.tile([0.1, -0.05, 0.8], (45, 1)), t0s[b], t_end, capacity=64)
+            inf = DS.DeskewScan()
+            inf.time_start, inf.time_increment, inf.range_min, inf.range_max = t0s[b], 0.1 / nbeam, 0.1, 30.0
+            inf.use_imu = inf.use_odom = 1
+            inf.imu_last, inf.odom_start_time, inf.odom_end_time = last, t0s[b] - 0.01, t_end - 0.004
+            inc = DS.odom_increment([0, 0, 0, 0, 0, 0.1], [0.08, 0.01, 0, 0, 0, 0.18])
+            inf.odom_incre[0], inf.odom_incre[1], inf.odom_incre[2] = inc
+            infos.append(inf); T.append(t); X.append(x); Y.append(y); Z.append(z)
+        T, X, Y, Z = (np.stack(a) for a in (T, X, Y, Z))
+        a_min, a_inc = -2.35619449, 4.71238898 / (nbeam - 1)
+        DS.undistort(rr[:8], a_min, a_inc, infos[:8], T[:8], X[:8], Y[:8], Z[:8], device=local)
+        t0 = time.perf_counter()
+        cloud = DS.undistort(rr, a_min, a_inc, infos, T, X, Y, Z, device=local)
+        dt = time.perf_counter() - t0
+        out["lidar_undistortion_batch"] = {"scans": nb_d, "beams": nbeam, "scans_per_s_e2e": nb_d / dt, "ms": dt * 1e3,
+                                           "points_per_s": nb_d * nbeam / dt,
+                                           "note": "host buffers in (ranges, IMU tables), corrected clouds out (H2D + kernel + D2H); "
+                                                   "parity unpinned (PCL / Eigen are not in the reference tree)"}
+        from oracle import port as _port
+        n_c = 64
+        t0 = time.perf_counter()
+        ok = True
+        for i in range(n_c):
+            ref_cloud = _port.deskew_scan(rr[i], a_min, a_inc, infos[i], T[i], X[i], Y[i], Z[i])
+            ok = ok and np.array_equal(ref_cloud.view(np.int32), cloud[i].view(np.int32))
+        dt = time.perf_counter() - t0
+        out["lidar_undistortion_batch"]["cpu_reference"] = {"scans_per_s": n_c / dt, "identical_to_device": bool(ok),
+                                                            "kind": "port (oracle/deskew_oracle.c; PARITY UNPINNED)",
+                                                            "sample": f"{n_c} scans, 1 thread, -O2 (ctypes call per scan)"}
+    except Exception as e:
+        out["lidar_undistortion_batch"] = {"error": repr(e)}
     return out, roof
 
 

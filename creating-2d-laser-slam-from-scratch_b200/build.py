@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libb200slam.so")
-SOURCES = ["karto_matcher.cu", "karto_occgrid.cu", "hector_map.cu", "hector_slam.cu", "gmapping_map.cu", "plicp.cu", "karto_mapper.cu", "pose_graph.cu", "ros_io.cu"]
+SOURCES = ["karto_matcher.cu", "karto_occgrid.cu", "hector_map.cu", "hector_slam.cu", "gmapping_map.cu", "plicp.cu", "karto_mapper.cu", "pose_graph.cu", "ros_io.cu", "lidar_undistortion.cu"]
 HEADERS = ["common.cuh", "scan_kernels.cuh", "glibc_math.cuh", os.path.join("..", "..", "include", "b200slam.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -578,6 +578,39 @@ b2s_status b2s_plicp_match(const b2s_icp_params *params, int batch, int n, const
                            const double *sens_ranges, const double *theta, double range_min, double range_max,
                            const double *first_guess, int device, void *cuda_stream, b2s_icp_result *results);
 
+/* ---------------------------------------------------------------- lesson5: motion de-skew pre-stage
+ * LidarUndistortion (lesson5/src/lidar_undistortion.cc): every reading of a LaserScan is moved into the sensor frame
+ * of the scan's first valid reading, using IMU angles integrated over the scan and the odometry increment across it.
+ * The per-beam loop (CorrectLaserScan, :339-393) runs on the device for a batch of scans; the per-scan preparation is
+ * host arithmetic.  PARITY UNPINNED: pcl::getTransformation and Eigen::Affine3f inverse / product are third-party
+ * header code absent from the reference tree (PCL 1.8, Eigen 3.3); their published algorithms are restated. */
+typedef struct b2s_deskew_scan {
+  double time_start, time_increment;   /* header.stamp (start of the sweep), LaserScan::time_increment */
+  float range_min, range_max;          /* readings outside [range_min, range_max] or non-finite are skipped (:349-352) */
+  int32_t use_imu, use_odom;           /* the node's use_imu_ / use_odom_ */
+  int32_t imu_last, reserved;          /* current_imu_index_ after PruneImuDeque: index of the last table entry */
+  double odom_start_time, odom_end_time; /* stamps of start_odom_msg_ / end_odom_msg_ */
+  float odom_incre[3];                 /* odom_incre_x_/y_/z_ */
+  float reserved2;
+} b2s_deskew_scan;
+
+/* PruneImuDeque's integration (:196-238) over the IMU messages of the (already pruned) queue: stamp[n_imu],
+ * angular_velocity[n_imu][3]; fills imu_time / rot_x / rot_y / rot_z [capacity] (zeroed first, as ResetParameters does)
+ * and returns current_imu_index_ (the last entry), or -2 where the node would run outside its arrays. */
+int32_t b2s_deskew_integrate_imu(int n_imu, const double *stamp, const double *angular_velocity, double scan_time_start,
+                                 double scan_time_end, int capacity, double *imu_time, double *rot_x, double *rot_y,
+                                 double *rot_z);
+/* PruneOdomDeque's increment (:296-333): start / end pose as (x, y, z, roll, pitch, yaw) — the position of the
+ * odometry message and tf::Matrix3x3(orientation).getRPY — gives odom_incre_x_/y_/z_. */
+void b2s_deskew_odom_increment(const double start_pose[6], const double end_pose[6], float out_increment[3]);
+/* CorrectLaserScan for `batch` scans: ranges [batch][n_beams] (host), beam angles angle_min + i * angle_increment
+ * (CreateAngleCache, :160-172), per-scan parameters, IMU tables [batch][imu_stride]; out_xyz [batch][n_beams][3] (host):
+ * the corrected point cloud, skipped readings as (0, 0, 0) (the cloud is cleared and resized per scan). */
+b2s_status b2s_lidar_undistort(int batch, int n_beams, const float *ranges, double angle_min, double angle_increment,
+                               const b2s_deskew_scan *scans, const double *imu_time, const double *imu_rot_x,
+                               const double *imu_rot_y, const double *imu_rot_z, int imu_stride, float *out_xyz, int device,
+                               void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("karto_oracle.c", "gmapping_oracle.c", "hector_oracle.c", "plicp_oracle.c",
+    srcs = [os.path.join(_HERE, f) for f in ("karto_oracle.c", "gmapping_oracle.c", "hector_oracle.c", "plicp_oracle.c", "deskew_oracle.c",
                                              "oracle_common.h", "Makefile")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libslam_oracle.so"])
@@ -327,3 +327,36 @@ def plicp_match(params, ref_ranges, sens_ranges, theta, range_min, range_max, fi
     lib().orc_plicp_match(C.byref(params), len(t), _d(r), _d(s_), _d(t), C.c_double(range_min), C.c_double(range_max),
                           _d(f64(first_guess)), C.byref(res))
     return res
+
+
+# ---------------------------------------------------------------- lesson5 de-skew (deskew_oracle.c) — PARITY UNPINNED
+
+def deskew_integrate_imu(stamps, angular_velocity, scan_start, scan_end, capacity=2000):
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.orc_deskew_integrate_imu.argtypes = [C.c_int, dp, dp, C.c_double, C.c_double, C.c_int, dp, dp, dp, dp]
+    L.orc_deskew_integrate_imu.restype = C.c_int32
+    st, av = f64(stamps), f64(angular_velocity).reshape(-1, 3)
+    t, x, y, z = (np.zeros(capacity) for _ in range(4))
+    last = L.orc_deskew_integrate_imu(len(st), _d(st), _d(av), float(scan_start), float(scan_end), capacity, _d(t), _d(x), _d(y), _d(z))
+    return int(last), t, x, y, z
+
+
+def deskew_odom_increment(start_pose, end_pose):
+    L = lib()
+    out = np.zeros(3, np.float32)
+    L.orc_deskew_odom_increment.restype = None
+    L.orc_deskew_odom_increment(_d(f64(start_pose)), _d(f64(end_pose)), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def deskew_scan(ranges, angle_min, angle_increment, info, imu_time, rot_x, rot_y, rot_z):
+    """info: any ctypes struct laid out as b2s_deskew_scan.  -> corrected cloud [n, 3] float32."""
+    L = lib()
+    L.orc_deskew_scan.restype = None
+    r = np.ascontiguousarray(ranges, np.float32)
+    out = np.zeros((len(r), 3), np.float32)
+    fp = C.POINTER(C.c_float)
+    L.orc_deskew_scan(len(r), r.ctypes.data_as(fp), C.c_double(angle_min), C.c_double(angle_increment), C.byref(info),
+                      _d(f64(imu_time)), _d(f64(rot_x)), _d(f64(rot_y)), _d(f64(rot_z)), out.ctypes.data_as(fp))
+    return out
