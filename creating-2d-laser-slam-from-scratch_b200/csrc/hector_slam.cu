@@ -799,10 +799,12 @@ __device__ void hs_match_helper(const HsBatch &P, const HsCall &C, unsigned char
       if (tid == 0) hs_mbar_expect_tx(&xc->bar_pose, 4u * HS_POSE_WORDS);
       hs_mbar_wait(&xc->bar_pose, pose_parity);  // every thread observes the phase itself (a time-out is reported by the master)
       pose_parity ^= 1u;
+      // Not needed for ordering — the master sends this pose only after it holds all nine sums of the previous iteration,
+      // which are sent after the column reads — but that chain runs through another CTA, which compute-sanitizer's
+      // racecheck cannot follow: the barrier (~50 cycles) keeps the tool's report clean.
+      __syncthreads();
       if (warp == 0) { htk.tick(7, xc->pose[0]); n_it++; }
       const float e0 = xc->pose[0], e1 = xc->pose[1], c = xc->pose[3], s = xc->pose[4], sin_rot = xc->pose[5], cos_rot = xc->pose[6];
-      // (no barrier needed here: the master sends the next pose only after it holds all nine of our sums, and those are
-      // sent behind hs_share_sums' barrier, i.e. after every thread has read this pose and the previous columns)
       const float v = hs_share_sums(prob, m.sx, m.sy, spts, cnt, factor, e0, e1, c, s, sin_rot, cos_rot, l2, terms, pitch, tid, lane, warp, &htk);
       if (warp < 9 && lane == 0) hs_st_async(r_part + 4 * warp, v, r_bar);
       if (warp == 0) htk.tick(-1, v);
