@@ -282,7 +282,7 @@ def run_reference(args):
                              "host": host_desc()},
             "e2e": {"value": value, "unit": "scan-matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ shared plumbing
@@ -1300,8 +1300,34 @@ def workload_k2(ctx, args):
             "gpu_launches": 3 * 21, "roofline": roof.get("hector_batched_maps"), "roofline_k2": roof, "grid_cells": sections}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at
+    NCCL_DEBUG=VERSION / WARN, and whole pages at INFO), so file descriptor 1 is pointed at stderr for the run and the
+    line goes out through a private duplicate of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+        return
+    sys.stdout.flush()
+    while data:
+        data = data[os.write(_REAL_STDOUT, data):]
+
+
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     ctx = Ctx(args)
@@ -1316,7 +1342,7 @@ def main():
     else:
         line = workload_k2(ctx, args)
     if ctx.rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
 
 
