@@ -91,3 +91,21 @@ def test_device_stage_equals_restatement(pkg):
                     ranges[31] * np.sin(cases[0]["angle_min"] + np.arange(1081) * cases[0]["angle_increment"])], 1)
     v31 = valid[31]
     assert np.abs(got[31][v31, :2] - raw[v31]).max() < 1e-5  # nothing to correct: the measured points
+
+
+def test_undistort_rejects_bad_arguments_before_touching_a_device(pkg):
+    """Argument errors are reported as B2S_ERR_BAD_PARAMS whether or not a GPU is present (imu_last outside the table,
+    an odometry interval of zero length, empty scans)."""
+    DS, M, abi = pkg.load("deskew"), pkg.load("matcher"), pkg.abi
+    case = dc.make_case(pkg, 7, n=64)
+    info = case["info"]
+    tabs = [np.zeros((1, 16))] * 4
+    info.imu_last = 16  # one past the table
+    with pytest.raises(M.B2SError) as e:
+        DS.undistort(case["ranges"][None, :], case["angle_min"], case["angle_increment"], [info], *tabs)
+    assert e.value.status == abi.B2S_ERR_BAD_PARAMS
+    info.imu_last = 3
+    info.odom_start_time = info.odom_end_time = 5.0
+    with pytest.raises(M.B2SError) as e:
+        DS.undistort(case["ranges"][None, :], case["angle_min"], case["angle_increment"], [info], *tabs)
+    assert e.value.status == abi.B2S_ERR_BAD_PARAMS
