@@ -109,3 +109,25 @@ def test_undistort_rejects_bad_arguments_before_touching_a_device(pkg):
     with pytest.raises(M.B2SError) as e:
         DS.undistort(case["ranges"][None, :], case["angle_min"], case["angle_increment"], [info], *tabs)
     assert e.value.status == abi.B2S_ERR_BAD_PARAMS
+
+
+def test_odometry_increment_is_the_relative_pose_in_the_start_frame(pkg):
+    """transBegin.inverse() * transEnd (:320-327): the translation of the end pose expressed in the start frame — checked
+    against double-precision rotation matrices built independently (roll, pitch, yaw about x, y, z; R = Rz Ry Rx)."""
+    DS = pkg.load("deskew")
+
+    def rot(r, p, y):
+        cx, sx, cy, sy, cz, sz = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+        rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        return rz @ ry @ rx
+
+    rng = np.random.default_rng(4)
+    for _ in range(50):
+        a = np.concatenate([rng.uniform(-5, 5, 3), rng.uniform(-0.4, 0.4, 2), rng.uniform(-3, 3, 1)])
+        b = a + np.concatenate([rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.05, 0.05, 3)])
+        want = rot(*a[3:]).T @ (b[:3] - a[:3])
+        for got in (DS.odom_increment(a, b), port.deskew_odom_increment(a, b)):
+            assert np.abs(got - want).max() < 5e-6, (got, want)
+    assert np.array_equal(DS.odom_increment([1, 2, 3, 0, 0, 0], [1.5, 2.25, 3, 0, 0, 0]), np.array([0.5, 0.25, 0.0], np.float32))
